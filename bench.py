@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — contact windows/s at batch=4096 per B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16x3|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (contact_cnn forward + argmax + contact
+bits) over one batch of 4096 synthetic z-scored
+150x54 fp32 windows per GPU (BASELINE.json configs[1]).  Weak scaling: every
+rank classifies its own 4096 windows; the only collective is the one-time NCCL
+broadcast of the packed weights, outside the timed region.
+
+One JSON line on stdout (rank 0):
+  value        whole-job windows/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through ContactEngine.classify_host(): pinned HOST windows in,
+               host class/bits out, H2D + D2H inside the timed region
+  roofline     dominant kernel: algorithmic FLOPs / its CUDA-event duration vs measured bf16 peak
+  cpu_baseline the oracle (torch CPU restatement of the reference forward) on this box's host cores
+--impl reference times that CPU path alone, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_WINDOW = 39_368_192          # SURVEY.md §8d / BASELINE.md §3 (algorithmic; split passes count once)
+BYTES_PER_WINDOW = 150 * 54 * 4 + 64  # batch mode: window read + logits written
+LAYER_FLOP = {                        # per window, BASELINE.md §3
+    "conv": 3_110_400 + 3_686_400 + 3_686_400 + 7_372_800,
+    "conv1": 3_110_400, "conv2": 3_686_400, "conv3": 3_686_400, "conv4": 7_372_800,
+    "fc1": 19_398_656, "fc2": 2_097_152, "fc3": 16_384,
+}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.1] or [r for _, r in self.rows]
+        sm, smax, reasons, power = [], [], set(), []
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_forward_baseline(batch: int, budget_s: float = 20.0, max_runs: int = 5):
+    """The reference's CPU forward (oracle port: same ATen ops) on all host cores."""
+    import torch
+    from deep_contact_estimator_b200 import synth
+    from oracle import contact_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = synth.make_params(0)
+    x = synth.make_windows(batch, seed=1)
+    with torch.no_grad():
+        oracle.forward_torch(params, x[:256])                 # warm-up
+        times, t_begin = [], time.perf_counter()
+        while len(times) < max_runs and (time.perf_counter() - t_begin < budget_s or not times):
+            t0 = time.perf_counter()
+            y = oracle.forward_torch(params, x)
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": batch / med, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} x forward of {batch} windows (oracle.forward_torch = reference contact_cnn ops, fp32, "
+                      f"torch {torch.__version__} CPU), median {med * 1e3:.1f} ms",
+            "ms_per_batch": med * 1e3}, y
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (the
+    oracle port: /root/reference is Python and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from deep_contact_estimator_b200 import synth
+    from oracle import contact_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = synth.make_params(0)
+    batch = args.batch
+    x = synth.make_windows(batch, seed=1)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            oracle.forward_torch(params, x[: min(batch, 512)])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            logits = oracle.forward_torch(params, x)
+            cls = oracle.argmax_class(logits)
+            oracle.decimal2binary(cls)
+        dt = time.perf_counter() - t0
+    v = batch * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "contact windows/sec at batch=4096", "value": v, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch={batch} synthetic z-scored 150x54 fp32 windows, contact_cnn forward + argmax + bits",
+                   "host": f"{cores} CPU threads, torch {torch.__version__}"},
+        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} windows through oracle.forward_torch (reference ops on CPU)"},
+        "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def dominant_kernel(profile_runs):
+    """profile_runs: list of [(name, ms)] per profiled step -> (avg ms per kernel name, launches per step)."""
+    agg, count = {}, {}
+    for run in profile_runs:
+        for name, ms in run:
+            agg[name] = agg.get(name, 0.0) + ms
+            count[name] = count.get(name, 0) + 1
+    n = max(len(profile_runs), 1)
+    per_step = {k: v / n for k, v in agg.items()}
+    launches = {k: count[k] / n for k in count}
+    return per_step, launches
+
+
+def kernel_flops(name: str) -> int:
+    """Algorithmic FLOPs per window a kernel covers, from its name."""
+    for key in ("conv1", "conv2", "conv3", "conv4", "fc1", "fc2", "fc3"):
+        if key in name:
+            return LAYER_FLOP[key]
+    if "conv" in name:
+        return LAYER_FLOP["conv"]
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
+    ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import deep_contact_estimator_b200 as dce
+    from deep_contact_estimator_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision or dce.default_precision()
+    B = args.batch
+
+    # weights: rank 0 packs (K0), one NCCL broadcast of the packed buffer, outside the timed region
+    eng = dce.ContactEngine(synth.make_params(0) if rank == 0 else None, dev, precision)
+    bcast_ms = None
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        eng.broadcast_weights(src=0)
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+
+    # inputs: NBUF distinct batches resident in HBM, rotated so every step reads data no longer in L2
+    NBUF = 4
+    host = [synth.make_windows(B, seed=1000 * (rank + 1) + i) for i in range(NBUF)]
+    xs = [h.to(dev) for h in host]
+    pinned = [h.pin_memory() for h in host]
+    out_bits_host = torch.empty((B, 4), dtype=torch.uint8).pin_memory()
+    out_cls_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (`value`) ---------------------------------
+    for i in range(args.warmup):
+        eng.classify(xs[i % NBUF], want_logits=True)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    sync_all()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        eng.classify(xs[i % NBUF], want_logits=True)
+        launches += eng.last_launches
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel durations for the roofline (CUDA events around every launch) ----
+    prof_runs = [eng.profile_forward(xs[i % NBUF]) for i in range(args.steps)]
+    per_kernel_ms, per_kernel_launches = dominant_kernel(prof_runs)
+
+    # ---- end to end from pinned host memory (`e2e`) --------------------------------
+    for i in range(2):
+        eng.classify_host(pinned[i % NBUF], out_bits_host, out_cls_host)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_launches = 0
+    for i in range(args.steps):
+        eng.classify_host(pinned[i % NBUF], out_bits_host, out_cls_host)     # returns after the D2H read completed
+        e2e_launches += eng.last_launches
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    dom = max(per_kernel_ms, key=per_kernel_ms.get) if per_kernel_ms else None
+    roofline = None
+    if dom:
+        step_kernel_ms = sum(per_kernel_ms.values())
+        n_launch = per_kernel_launches[dom]
+        avg_launch_ms = per_kernel_ms[dom] / n_launch
+        flops_per_launch = kernel_flops(dom) * B / n_launch
+        achieved_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        roofline = {
+            "bound": "tensor", "kernel": dom, "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved_tflops / peak, "traffic": None,
+            "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
+            "note": "algorithmic FLOPs (bf16x3 split passes count once; ceiling of frac is 1/3 in bf16x3 mode)",
+            "kernel_share_of_step": per_kernel_ms[dom] / step_kernel_ms,
+            "kernels_ms_per_step": {k: round(v, 4) for k, v in per_kernel_ms.items()},
+            "whole_step": {"achieved_tflops": value / world * FLOP_PER_WINDOW / 1e12,
+                           "hbm_read_gbs": value / world * BYTES_PER_WINDOW / 1e9,
+                           "hbm_frac": value / world * BYTES_PER_WINDOW / 1e9 / peaks["hbm_gbs"]},
+        }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_forward_baseline(B)
+
+    line = {
+        "metric": "contact windows/sec at batch=4096", "value": value, "unit": "windows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3_f32acc" if precision == "bf16x3" else "f32", "data": "synthetic",
+        "config": {"workload": f"batch={B} synthetic z-scored 150x54 fp32 windows per GPU -> 16 logits + class + 4 contact bits "
+                               f"(BASELINE configs[1])",
+                   "precision": precision, "weights": "seeded random init (synth.make_params(0))",
+                   "l2": f"inputs rotate over {NBUF} resident batches of {B * 32400 / 1e6:.1f} MB each (> 126 MB L2 in total)",
+                   "parallelism": f"window-range shards x{world}, one-time NCCL weight broadcast"
+                                  + (f" ({bcast_ms:.1f} ms, untimed)" if bcast_ms else "")},
+        "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * 32400, "d2h_bytes_per_step": B * 8,
+                "ms_per_step": e2e_ms / args.steps, "api": "ContactEngine.classify_host (pinned host windows -> host cls+bits)"},
+        "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,327 @@
+// libdce_b200.so — C ABI (include/dce.h) over the sm_100a kernels.
+//
+// Replaces, for the contact-classification hot path only:
+//   contact_cnn.forward            /root/reference/src/contact_cnn.py:60-66
+//   window extract + z-score       /root/reference/utils/data_handler.py:55-57
+//   argmax + decimal2binary        /root/reference/src/inference_one_seq.py:26-27,59-62
+// No torch types here: plain device pointers, sizes and a stream.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <new>
+
+#include "../../include/dce.h"
+#include "dce_common.cuh"
+#include "dce_fp32.cuh"
+#include "dce_tc.cuh"
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+thread_local int g_launches = 0;
+
+inline int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return DCE_ECUDA; }
+#define DCE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
+using dce::align_up;
+using dce::Ctx;
+
+// ---- packed-weight buffer layout (one allocation so it can be broadcast) ----
+struct Fp32Layout {
+    size_t w1, w2, w3, w4;          // conv [3][cin][cout]
+    size_t f1, f2, f3;              // fc [K][N], [K][N], [16][512]
+    size_t b[7];                    // biases in layer order
+    size_t end;
+};
+
+Fp32Layout make_fp32_layout(size_t base) {
+    Fp32Layout L; size_t o = base;
+    auto take = [&](size_t floats) { size_t r = o; o = align_up(o + floats * 4, 256); return r; };
+    L.w1 = take(3 * 54 * 64);  L.w2 = take(3 * 64 * 64);  L.w3 = take(3 * 64 * 128);  L.w4 = take(3 * 128 * 128);
+    L.f1 = take((size_t)4736 * 2048);  L.f2 = take((size_t)2048 * 512);  L.f3 = take(16 * 512);
+    const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
+    for (int i = 0; i < 7; ++i) L.b[i] = take(bn[i]);
+    L.end = o;
+    return L;
+}
+
+}  // namespace
+
+struct dce_weights {
+    int device = -1;
+    int sm_count = 0;
+    bool packed = false;
+    char* buf = nullptr;            // device
+    size_t bytes = 0;
+    Fp32Layout f32;
+    dce::tc::PackedLayout tc;
+};
+
+namespace {
+
+constexpr int64_t kChunkFp32 = 4096;   // windows per internal pass (bounds the workspace)
+
+struct Fp32Workspace { size_t act4, h1, h2, end; };
+Fp32Workspace fp32_workspace(int64_t n) {
+    Fp32Workspace W; size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    W.act4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.h2 = take((size_t)n * 512 * 4);
+    W.end = o; return W;
+}
+
+template <class T> const T* at(const dce_weights* w, size_t off) { return reinterpret_cast<const T*>(w->buf + off); }
+template <class T> T* at_mut(dce_weights* w, size_t off) { return reinterpret_cast<T*>(w->buf + off); }
+
+int pack_fp32(dce_weights* w, const float* const p[DCE_NUM_PARAMS], Ctx& ctx) {
+    cudaStream_t s = ctx.stream;
+    using namespace dce::fp32;
+    const Fp32Layout& L = w->f32;
+    struct { int idx, cout, cin; size_t off; } convs[4] = {
+        {0, 64, 54, L.w1}, {2, 64, 64, L.w2}, {4, 128, 64, L.w3}, {6, 128, 128, L.w4}};
+    for (auto& c : convs) {
+        int n = 3 * c.cin * c.cout;
+        DCE_KL(ctx, "pack_conv", pack_conv_kernel<<<(n + 255) / 256, 256, 0, s>>>(p[c.idx], at_mut<float>(w, c.off), c.cout, c.cin));
+    }
+    DCE_KL(ctx, "pack_fc1", pack_fc_kernel<<<dim3(4736 / 32, 2048 / 32), dim3(32, 8), 0, s>>>(p[8], at_mut<float>(w, L.f1), 2048, 4736, 1));
+    DCE_KL(ctx, "pack_fc2", pack_fc_kernel<<<dim3(2048 / 32, 512 / 32), dim3(32, 8), 0, s>>>(p[10], at_mut<float>(w, L.f2), 512, 2048, 0));
+    DCE_CUDA(cudaMemcpyAsync(at_mut<float>(w, L.f3), p[12], 16 * 512 * 4, cudaMemcpyDeviceToDevice, s));
+    const int bidx[7] = {1, 3, 5, 7, 9, 11, 13};
+    const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
+    for (int i = 0; i < 7; ++i)
+        DCE_CUDA(cudaMemcpyAsync(at_mut<float>(w, L.b[i]), p[bidx[i]], bn[i] * 4, cudaMemcpyDeviceToDevice, s));
+    return DCE_OK;
+}
+
+// fp32 mode: conv stack (one CTA per window) -> fc.0 SGEMM -> fc.3 SGEMM -> fc.6 + argmax + bits
+int run_fp32(const dce_weights* w, const float* x, bool normalize, int64_t first, int64_t n,
+             float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+    cudaStream_t s = ctx.stream;
+    using namespace dce::fp32;
+    const Fp32Layout& L = w->f32;
+    static thread_local bool attr_done[2] = {false, false};
+    if (!attr_done[0]) {
+        DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+        DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+        attr_done[0] = true;
+    }
+    ConvParams cp{at<float>(w, L.w1), at<float>(w, L.b[0]), at<float>(w, L.w2), at<float>(w, L.b[1]),
+                  at<float>(w, L.w3), at<float>(w, L.b[2]), at<float>(w, L.w4), at<float>(w, L.b[3])};
+    for (int64_t c0 = 0; c0 < n; c0 += kChunkFp32) {
+        const int64_t m = (n - c0 < kChunkFp32) ? n - c0 : kChunkFp32;
+        Fp32Workspace W = fp32_workspace(m);
+        float* act4 = reinterpret_cast<float*>(ws + W.act4);
+        float* h1 = reinterpret_cast<float*>(ws + W.h1);
+        float* h2 = reinterpret_cast<float*>(ws + W.h2);
+        const int grid = (int)((m < (int64_t)w->sm_count * 8) ? m : (int64_t)w->sm_count * 8);
+        if (normalize)
+            DCE_KL(ctx, "fp32_conv_stack_norm", conv_stack_kernel<true><<<grid, 256, kConvSmemBytes, s>>>(x, first + c0, m, cp, act4));
+        else
+            DCE_KL(ctx, "fp32_conv_stack", conv_stack_kernel<false><<<grid, 256, kConvSmemBytes, s>>>(x + c0 * (150 * 54), 0, m, cp, act4));
+        DCE_KL(ctx, "fp32_fc1_sgemm", sgemm_bias_kernel<true><<<dim3(2048 / 128, (unsigned)((m + 127) / 128)), 256, 0, s>>>(
+            act4, at<float>(w, L.f1), at<float>(w, L.b[4]), h1, (int)m, 2048, 4736));
+        DCE_KL(ctx, "fp32_fc2_sgemm", sgemm_bias_kernel<true><<<dim3(512 / 128, (unsigned)((m + 127) / 128)), 256, 0, s>>>(
+            h1, at<float>(w, L.f2), at<float>(w, L.b[5]), h2, (int)m, 512, 2048));
+        const int g3 = (int)((m + 7) / 8 < (int64_t)w->sm_count * 4 ? (m + 7) / 8 : (int64_t)w->sm_count * 4);
+        DCE_KL(ctx, "fp32_fc3_argmax", fc3_argmax_kernel<<<g3, 256, 0, s>>>(h2, at<float>(w, L.f3), at<float>(w, L.b[6]), m,
+                                            logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,
+                                            bits ? bits + c0 * 4 : nullptr));
+    }
+    return DCE_OK;
+}
+
+int check_common(const dce_weights* w, const void* ws, size_t ws_bytes, int64_t n, int precision) {
+    if (!w) return DCE_EINVAL;
+    if (!w->packed) return DCE_ENOTPACKED;
+    if (n < 0) return DCE_EINVAL;
+    if (precision != DCE_PREC_FP32 && precision != DCE_PREC_BF16X3) return DCE_EINVAL;
+    if (n > 0) {
+        if (!ws) return DCE_EINVAL;
+        if ((uintptr_t)ws % 256) return DCE_EALIGN;
+        if (ws_bytes < dce_workspace_bytes(n, precision)) return DCE_EWORKSPACE;
+    }
+    return DCE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dce_version(void) { return DCE_VERSION; }
+
+const char* dce_strerror(int code) {
+    switch (code) {
+        case DCE_OK: return "ok";
+        case DCE_EINVAL: return "invalid argument";
+        case DCE_EALIGN: return "misaligned pointer";
+        case DCE_EARCH: return "device is not sm_100 (B200)";
+        case DCE_ECUDA: return "CUDA runtime error (see dce_last_cuda_error)";
+        case DCE_ENOTPACKED: return "weights not packed";
+        case DCE_EWORKSPACE: return "workspace too small";
+        case DCE_EUNSUPPORTED: return "unsupported precision/mode";
+        default: return "unknown error";
+    }
+}
+
+int dce_last_cuda_error(void) { return g_last_cuda_error; }
+int dce_last_launch_count(void) { return g_launches; }
+
+int dce_weights_create(dce_weights** out, int device) {
+    if (!out) return DCE_EINVAL;
+    *out = nullptr;
+    cudaDeviceProp prop;
+    DCE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return DCE_EARCH;
+    dce_weights* w = new (std::nothrow) dce_weights();
+    if (!w) return DCE_EINVAL;
+    w->device = device;
+    w->sm_count = prop.multiProcessorCount;
+    w->f32 = make_fp32_layout(0);
+    w->tc = dce::tc::make_packed_layout(w->f32.end);
+    w->bytes = w->tc.end;
+    int prev = 0;
+    DCE_CUDA(cudaGetDevice(&prev));
+    DCE_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(&w->buf, w->bytes);
+    if (e == cudaSuccess) e = cudaMemset(w->buf, 0, w->bytes);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { delete w; return cuda_fail(e); }
+    *out = w;
+    return DCE_OK;
+}
+
+int dce_weights_destroy(dce_weights* w) {
+    if (!w) return DCE_OK;
+    if (w->buf) cudaFree(w->buf);
+    delete w;
+    return DCE_OK;
+}
+
+int dce_weights_pack(dce_weights* w, const float* const params_dev[DCE_NUM_PARAMS], void* stream) {
+    if (!w || !params_dev) return DCE_EINVAL;
+    for (int i = 0; i < DCE_NUM_PARAMS; ++i) {
+        if (!params_dev[i]) return DCE_EINVAL;
+        if ((uintptr_t)params_dev[i] % 4) return DCE_EALIGN;
+    }
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    int rc = pack_fp32(w, params_dev, ctx);
+    if (rc == DCE_OK) rc = dce::tc::pack(w->buf, w->tc, params_dev, ctx);
+    g_launches = ctx.launches;
+    if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
+    if (rc != DCE_OK) return rc;
+    w->packed = true;
+    return DCE_OK;
+}
+
+size_t dce_weights_packed_bytes(const dce_weights* w) { return w ? w->bytes : 0; }
+void* dce_weights_packed_ptr(dce_weights* w) { return w ? (void*)w->buf : nullptr; }
+int dce_weights_adopt(dce_weights* w) { if (!w) return DCE_EINVAL; w->packed = true; return DCE_OK; }
+
+size_t dce_workspace_bytes(int64_t max_windows, int precision) {
+    if (max_windows <= 0) return 256;
+    if (precision == DCE_PREC_FP32) {
+        const int64_t n = max_windows < kChunkFp32 ? max_windows : kChunkFp32;
+        return fp32_workspace(n).end;
+    }
+    if (precision == DCE_PREC_BF16X3) return dce::tc::workspace_bytes(max_windows);
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// shared body of dce_forward / dce_stream / their profiling variants
+int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, int64_t first, int64_t n,
+            float* logits, int32_t* cls, uint8_t* bits, void* ws, size_t ws_bytes, int precision, Ctx& ctx) {
+    int rc = check_common(w, ws, ws_bytes, n, precision);
+    if (rc != DCE_OK) return rc;
+    if (is_stream) {
+        if (first < 0 || T < 0) return DCE_EINVAL;
+        if (n > 0 && first + n + (DCE_WINDOW - 1) > T) return DCE_EINVAL;      // utils/data_handler.py:24
+    }
+    if (n == 0) return DCE_OK;
+    if (!src) return DCE_EINVAL;
+    if ((uintptr_t)src % 16 || (logits && (uintptr_t)logits % 16) || (bits && (uintptr_t)bits % 4) || (cls && (uintptr_t)cls % 4))
+        return DCE_EALIGN;
+    if (precision == DCE_PREC_FP32)
+        rc = run_fp32(w, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
+    else
+        rc = dce::tc::run(w->buf, w->tc, w->sm_count, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
+    if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dce_forward(const dce_weights* w, const float* x_dev, int64_t B,
+                float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev,
+                void* workspace_dev, size_t workspace_bytes, int precision, void* stream) {
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    int rc = run_any(w, x_dev, false, 0, 0, B, logits_dev, cls_dev, bits_dev, workspace_dev, workspace_bytes, precision, ctx);
+    g_launches = ctx.launches;
+    return rc;
+}
+
+int dce_stream(const dce_weights* w, const float* data_dev, int64_t T,
+               int64_t first_window, int64_t n_windows,
+               float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev,
+               void* workspace_dev, size_t workspace_bytes, int precision, void* stream) {
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    int rc = run_any(w, data_dev, true, T, first_window, n_windows, logits_dev, cls_dev, bits_dev,
+                     workspace_dev, workspace_bytes, precision, ctx);
+    g_launches = ctx.launches;
+    return rc;
+}
+
+int dce_forward_profile(const dce_weights* w, const float* x_dev, int64_t B,
+                        float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev,
+                        void* workspace_dev, size_t workspace_bytes, int precision, void* stream,
+                        int max_kernels, float* ms_out, const char** names_out, int* n_out) {
+    if (!ms_out || !names_out || !n_out || max_kernels <= 0) return DCE_EINVAL;
+    dce::Profiler prof;
+    Ctx ctx; ctx.stream = (cudaStream_t)stream; ctx.prof = &prof;
+    int rc = run_any(w, x_dev, false, 0, 0, B, logits_dev, cls_dev, bits_dev, workspace_dev, workspace_bytes, precision, ctx);
+    g_launches = ctx.launches;
+    cudaError_t se = cudaStreamSynchronize(ctx.stream);
+    int n = 0;
+    for (int i = 0; i < prof.n; ++i) {
+        float ms = 0.f;
+        if (se == cudaSuccess) cudaEventElapsedTime(&ms, prof.start[i], prof.stop[i]);
+        if (n < max_kernels) { ms_out[n] = ms; names_out[n] = prof.names[i]; ++n; }
+        cudaEventDestroy(prof.start[i]); cudaEventDestroy(prof.stop[i]);
+    }
+    *n_out = n;
+    if (rc == DCE_OK && se != cudaSuccess) return cuda_fail(se);
+    return rc;
+}
+
+int dce_decimal2binary(const int64_t* cls_dev, int64_t n, uint8_t* bits_dev, void* stream) {
+    if (n < 0) return DCE_EINVAL;
+    if (n == 0) return DCE_OK;
+    if (!cls_dev || !bits_dev) return DCE_EINVAL;
+    if ((uintptr_t)cls_dev % 8 || (uintptr_t)bits_dev % 4) return DCE_EALIGN;
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    ctx.begin("decimal2binary");
+    dce::fp32::decimal2binary_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(cls_dev, n, bits_dev);
+    const bool ok = ctx.end();
+    g_launches = ctx.launches;
+    return ok ? DCE_OK : cuda_fail(ctx.err);
+}
+
+int dce_accuracy_counts(const int32_t* cls_dev, const int64_t* labels_dev, int64_t n, int64_t* counts_dev, void* stream) {
+    if (n < 0) return DCE_EINVAL;
+    if (n == 0) return DCE_OK;
+    if (!cls_dev || !labels_dev || !counts_dev) return DCE_EINVAL;
+    if ((uintptr_t)cls_dev % 4 || (uintptr_t)labels_dev % 8 || (uintptr_t)counts_dev % 8) return DCE_EALIGN;
+    int64_t blocks = (n + 255) / 256; if (blocks > 1184) blocks = 1184;
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    ctx.begin("accuracy_counts");
+    dce::fp32::accuracy_counts_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(
+        cls_dev, labels_dev, n, reinterpret_cast<unsigned long long*>(counts_dev));
+    const bool ok = ctx.end();
+    g_launches = ctx.launches;
+    return ok ? DCE_OK : cuda_fail(ctx.err);
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Launch context shared by the fp32 and tensor-core paths: the stream, a launch
+// counter, and an optional per-kernel CUDA-event profiler (dce_forward_profile).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dce.h"
+
+namespace dce {
+
+constexpr int kMaxProfiled = 64;
+
+struct Profiler {
+    int n = 0;
+    const char* names[kMaxProfiled];
+    cudaEvent_t start[kMaxProfiled], stop[kMaxProfiled];
+};
+
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    int launches = 0;
+    cudaError_t err = cudaSuccess;
+    Profiler* prof = nullptr;
+
+    // bracket one kernel launch: KL_BEGIN(ctx, "name"); kernel<<<...>>>(...); KL_END(ctx);
+    inline void begin(const char* name) {
+        if (prof && prof->n < kMaxProfiled) {
+            prof->names[prof->n] = name;
+            cudaEventCreate(&prof->start[prof->n]);
+            cudaEventCreate(&prof->stop[prof->n]);
+            cudaEventRecord(prof->start[prof->n], stream);
+        }
+    }
+    inline bool end() {
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (prof && prof->n < kMaxProfiled) { cudaEventRecord(prof->stop[prof->n], stream); ++prof->n; }
+        if (e != cudaSuccess) { err = e; return false; }
+        return true;
+    }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace dce
+
+#define DCE_KL(ctx, name, ...) do { (ctx).begin(name); __VA_ARGS__; if (!(ctx).end()) return DCE_ECUDA; } while (0)

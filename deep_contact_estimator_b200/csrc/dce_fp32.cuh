@@ -1,0 +1,358 @@
+// fp32 FFMA kernels: the DCE_PREC_FP32 arithmetic mode.
+//
+// This mode keeps every product in fp32 on the CUDA cores.  It is the
+// full-precision arm of the library (error vs. the fp64 arbiter ~3e-7, the
+// same as the reference's own fp32 forward) and the on-device cross-check for
+// the tensor-core mode; its roofline is the fp32 FMA pipe, ~74 TFLOP/s.
+//
+// Layouts (all channels-last so a conv tap is a contiguous row of the input):
+//   conv weights   wp[tap][cin][cout]           from W[cout][cin][tap]   src/contact_cnn.py:11-40
+//   fc.0 weight    w1p[t*128 + c][n]            from W[n][c*37 + t]      src/contact_cnn.py:48,64
+//   fc.3 weight    w2p[k][n]                    from W[n][k]             src/contact_cnn.py:52
+//   fc.6 weight    unchanged [16][512]                                   src/contact_cnn.py:56
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dce {
+namespace fp32 {
+
+// ---------------------------------------------------------------------------
+// K0 (fp32 part): repack
+// ---------------------------------------------------------------------------
+__global__ void pack_conv_kernel(const float* __restrict__ w, float* __restrict__ wp, int cout, int cin) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;          // index into wp[tap][cin][cout]
+    int n = 3 * cin * cout;
+    if (i >= n) return;
+    int o = i % cout, c = (i / cout) % cin, k = i / (cout * cin);
+    wp[i] = w[(o * cin + c) * 3 + k];
+}
+
+// dst[k'][n] = src[n][perm(k')]; flat == 1: perm(k') = k'; else k' = t*128+c -> c*37+t
+__global__ void pack_fc_kernel(const float* __restrict__ w, float* __restrict__ wp, int N, int K, int permute) {
+    __shared__ float tile[32][33];
+    int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    int tx = threadIdx.x, ty = threadIdx.y;                 // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        int n = n0 + j, k = k0 + tx;                        // read along k' (dst order)
+        float v = 0.f;
+        if (n < N && k < K) {
+            int ks = k;
+            if (permute) { int t = k / 128, c = k % 128; ks = c * 37 + t; }
+            v = w[(size_t)n * K + ks];
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int k = k0 + j, n = n0 + tx;
+        if (n < N && k < K) wp[(size_t)k * N + n] = tile[tx][j];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one conv layer on a smem-resident window, thread tile = PT positions x 4 couts
+// in : smem rows r = position + 1 (row 0 and rows > T are zero), stride CIN
+// out: POOL ? pooled rows : rows, same row convention, stride COUT
+// ---------------------------------------------------------------------------
+template <int CIN, int CIN_STRIDE, int COUT, int T, bool POOL, bool TO_GLOBAL>
+__device__ __forceinline__ void conv3_relu_layer(const float* __restrict__ in, float* __restrict__ out,
+                                                 const float* __restrict__ wp, const float* __restrict__ bias) {
+    constexpr int PT = 10;                         // positions per thread
+    constexpr int CG = COUT / 4;                   // cout groups (float4)
+    constexpr int PG = 256 / CG;                   // position groups
+    static_assert(PG * PT >= T, "tile does not cover the window");
+    const int cg = threadIdx.x % CG, pg = threadIdx.x / CG;
+    const int p0 = pg * PT, co = cg * 4;
+
+    float acc[PT][4];
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + co);
+#pragma unroll
+    for (int i = 0; i < PT; ++i) { acc[i][0] = b4.x; acc[i][1] = b4.y; acc[i][2] = b4.z; acc[i][3] = b4.w; }
+
+    const float* xin = in + p0 * CIN_STRIDE;       // row p0 = position p0-1
+#pragma unroll 2
+    for (int c = 0; c < CIN; ++c) {
+        float xv[PT + 2];
+#pragma unroll
+        for (int i = 0; i < PT + 2; ++i) xv[i] = xin[i * CIN_STRIDE + c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)k * CIN + c) * COUT + co));
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+                acc[i][0] = fmaf(xv[i + k], w4.x, acc[i][0]);
+                acc[i][1] = fmaf(xv[i + k], w4.y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i + k], w4.z, acc[i][2]);
+                acc[i][3] = fmaf(xv[i + k], w4.w, acc[i][3]);
+            }
+        }
+    }
+    if (POOL) {
+        // MaxPool1d(2,2) after ReLU (src/contact_cnn.py:22-25): max(relu(a),relu(b)) = relu(max(a,b))
+#pragma unroll
+        for (int i = 0; i < PT; i += 2) {
+            const int tp = (p0 + i) / 2;                     // pooled position
+            if (p0 + i + 1 < T) {                            // floor: an unpaired last sample is dropped
+                float4 v;
+                v.x = fmaxf(fmaxf(acc[i][0], acc[i + 1][0]), 0.f);
+                v.y = fmaxf(fmaxf(acc[i][1], acc[i + 1][1]), 0.f);
+                v.z = fmaxf(fmaxf(acc[i][2], acc[i + 1][2]), 0.f);
+                v.w = fmaxf(fmaxf(acc[i][3], acc[i + 1][3]), 0.f);
+                // fmaxf drops NaN operands; the reference propagates them.
+                if (acc[i][0] != acc[i][0] || acc[i + 1][0] != acc[i + 1][0]) v.x = __int_as_float(0x7fc00000);
+                if (acc[i][1] != acc[i][1] || acc[i + 1][1] != acc[i + 1][1]) v.y = __int_as_float(0x7fc00000);
+                if (acc[i][2] != acc[i][2] || acc[i + 1][2] != acc[i + 1][2]) v.z = __int_as_float(0x7fc00000);
+                if (acc[i][3] != acc[i][3] || acc[i + 1][3] != acc[i + 1][3]) v.w = __int_as_float(0x7fc00000);
+                float* dst = TO_GLOBAL ? out + tp * COUT + co : out + (tp + 1) * COUT + co;
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            if (p0 + i < T) {
+                float4 v;
+                v.x = acc[i][0] > 0.f || acc[i][0] != acc[i][0] ? acc[i][0] : 0.f;
+                v.y = acc[i][1] > 0.f || acc[i][1] != acc[i][1] ? acc[i][1] : 0.f;
+                v.z = acc[i][2] > 0.f || acc[i][2] != acc[i][2] ? acc[i][2] : 0.f;
+                v.w = acc[i][3] > 0.f || acc[i][3] != acc[i][3] ? acc[i][3] : 0.f;
+                *reinterpret_cast<float4*>(out + (p0 + i + 1) * COUT + co) = v;
+            }
+        }
+    }
+}
+
+struct ConvParams {
+    const float* w1; const float* b1;   // [3][54][64]
+    const float* w2; const float* b2;   // [3][64][64]
+    const float* w3; const float* b3;   // [3][64][128]
+    const float* w4; const float* b4;   // [3][128][128]
+};
+
+constexpr int kRows150 = 162;           // 1 + 160 + 1 rows (tile covers 160 positions)
+constexpr int kRows75  = 82;            // 1 + 80 + 1
+constexpr int kBuf0Floats = kRows150 * 54 > kRows75 * 64 ? kRows150 * 54 : kRows75 * 64;   // X0 / X2
+constexpr int kBuf1Floats = kRows150 * 64 > kRows75 * 128 ? kRows150 * 64 : kRows75 * 128; // X1 / X3
+constexpr int kConvSmemBytes = (kBuf0Floats + kBuf1Floats) * 4;
+
+// One CTA per window.  NORMALIZE: x is the raw [T][54] log and window w starts
+// at row first + w (utils/data_handler.py:55-56 fused into the load);
+// otherwise x is [B][150][54] already-normalised windows.
+// act4: [B][37*128] fp32, index t*128 + c.
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256, 2)
+conv_stack_kernel(const float* __restrict__ x, int64_t first, int64_t n_windows, ConvParams p, float* __restrict__ act4) {
+    extern __shared__ __align__(16) float smem[];
+    float* buf0 = smem;
+    float* buf1 = smem + kBuf0Floats;
+    __shared__ float s_mean[64], s_rstd[64];
+
+    for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        const float* src = NORMALIZE ? x + (first + w) * 54 : x + w * (150 * 54);
+        __syncthreads();                                     // previous window's readers are done
+        for (int i = threadIdx.x; i < kBuf0Floats; i += 256) buf0[i] = 0.f;
+        for (int i = threadIdx.x; i < kBuf1Floats; i += 256) buf1[i] = 0.f;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 150 * 54; i += 256) buf0[54 + i] = __ldg(src + i);
+        __syncthreads();
+        if (NORMALIZE) {
+            // two-pass mean / unbiased std per channel (utils/data_handler.py:55-56)
+            // 4 threads per channel; threads past channel 53 redo channel 53 so the
+            // full-warp shuffles stay convergent, and simply do not publish.
+            const int cr = threadIdx.x >> 2, q = threadIdx.x & 3;
+            const int c = cr < 54 ? cr : 53;
+            float s = 0.f;
+            for (int t = q; t < 150; t += 4) s += buf0[54 + t * 54 + c];
+            s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+            const float mean = s / 150.f;
+            float v = 0.f;
+            for (int t = q; t < 150; t += 4) { float d = buf0[54 + t * 54 + c] - mean; v = fmaf(d, d, v); }
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (q == 0 && cr < 54) { s_mean[c] = mean; s_rstd[c] = sqrtf(v / 149.f); }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 150 * 54; i += 256) {
+                const int c = i % 54;
+                buf0[54 + i] = (buf0[54 + i] - s_mean[c]) / s_rstd[c];   // division, as the reference does
+            }
+            __syncthreads();
+        }
+        conv3_relu_layer<54, 54, 64, 150, false, false>(buf0, buf1, p.w1, p.b1);   // src/contact_cnn.py:11-16
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBuf0Floats; i += 256) buf0[i] = 0.f;
+        __syncthreads();
+        conv3_relu_layer<64, 64, 64, 150, true, false>(buf1, buf0, p.w2, p.b2);    // :17-25
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBuf1Floats; i += 256) buf1[i] = 0.f;
+        __syncthreads();
+        conv3_relu_layer<64, 64, 128, 75, false, false>(buf0, buf1, p.w3, p.b3);   // :29-34
+        __syncthreads();
+        conv3_relu_layer<128, 128, 128, 75, true, true>(buf1, act4 + w * 4736, p.w4, p.b4);   // :35-43
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C[M][N] = relu?(A[M][K] * Bp[K][N] + bias[N]); 128x128x16 tiles, 8x8 per thread
+// ---------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+sgemm_bias_kernel(const float* __restrict__ A, const float* __restrict__ Bp, const float* __restrict__ bias,
+                  float* __restrict__ C, int M, int N, int K) {
+    constexpr int BM = 128, BN = 128, BK = 16;
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid % 16, ty = tid / 16;                  // 16 x 16 threads, each 8x8 (split 4+4)
+
+    // A tile loader: 128 rows x 16 k = 512 float4; 2 per thread
+    const int a_row = tid / 4, a_k4 = (tid % 4) * 4;         // rows a_row, a_row + 64
+    // B tile loader: 16 k x 128 n = 512 float4; 2 per thread
+    const int b_k = tid / 32, b_n4 = (tid % 32) * 4;         // k rows b_k, b_k + 8
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + a_row + h * 64;
+            ra[h] = (m < M) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)m * K + k0 + a_k4)) : make_float4(0, 0, 0, 0);
+            const int n = n0 + b_n4;
+            rb[h] = (n < N) ? __ldg(reinterpret_cast<const float4*>(Bp + (size_t)(k0 + b_k + h * 8) * N + n)) : make_float4(0, 0, 0, 0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = a_row + h * 64;
+            As[buf][a_k4 + 0][r] = ra[h].x; As[buf][a_k4 + 1][r] = ra[h].y;
+            As[buf][a_k4 + 2][r] = ra[h].z; As[buf][a_k4 + 3][r] = ra[h].w;
+            *reinterpret_cast<float4*>(&Bs[buf][b_k + h * 8][b_n4]) = rb[h];
+        }
+    };
+
+    gload(0); sstore(0); __syncthreads();
+    const int nk = K / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) { sstore(buf ^ 1); }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int n = n0 + jh * 64 + tx * 4;
+            if (n >= N) continue;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+            float4 v = make_float4(acc[i][jh * 4 + 0] + b4.x, acc[i][jh * 4 + 1] + b4.y,
+                                   acc[i][jh * 4 + 2] + b4.z, acc[i][jh * 4 + 3] + b4.w);
+            if (RELU) {
+                v.x = v.x > 0.f || v.x != v.x ? v.x : 0.f; v.y = v.y > 0.f || v.y != v.y ? v.y : 0.f;
+                v.z = v.z > 0.f || v.z != v.z ? v.z : 0.f; v.w = v.w > 0.f || v.w != v.w ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(C + (size_t)m * N + n) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fc.6 (512 -> 16) + argmax + decimal2binary; one warp per window
+//   src/contact_cnn.py:56-57, src/inference_one_seq.py:26-27,59-62
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void argmax_bits_store(const float (&y)[16], int64_t w, float* logits, int32_t* cls, uint8_t* bits) {
+    // torch.max semantics: first maximal index; a NaN is "greater" than everything and the first NaN wins.
+    int best = 0; float bv = y[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+        const bool better = (y[j] > bv) || (y[j] != y[j] && bv == bv);
+        if (better) { bv = y[j]; best = j; }
+    }
+    if (logits) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(logits + w * 16 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    }
+    if (cls) cls[w] = best;
+    if (bits) {
+        uchar4 b4 = make_uchar4((best >> 3) & 1, (best >> 2) & 1, (best >> 1) & 1, best & 1);   // MSB first = leg 0
+        *reinterpret_cast<uchar4*>(bits + w * 4) = b4;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3, const float* __restrict__ b3,
+                  int64_t n_windows, float* __restrict__ logits, int32_t* __restrict__ cls, uint8_t* __restrict__ bits) {
+    __shared__ float ws[16 * 512];
+    for (int i = threadIdx.x; i < 16 * 512; i += blockDim.x) ws[i] = __ldg(w3 + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int64_t w = (int64_t)blockIdx.x * nwarp + warp; w < n_windows; w += (int64_t)gridDim.x * nwarp) {
+        float hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = __ldg(h2 + w * 512 + i * 32 + lane);
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s = fmaf(hv[i], ws[j * 512 + i * 32 + lane], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            y[j] = s + __ldg(b3 + j);
+        }
+        if (lane == 0) argmax_bits_store(y, w, logits, cls, bits);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// decimal2binary on labels; accuracy counters
+// ---------------------------------------------------------------------------
+__global__ void decimal2binary_kernel(const int64_t* __restrict__ cls, int64_t n, uint8_t* __restrict__ bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t v = cls[i];
+    *reinterpret_cast<uchar4*>(bits + i * 4) = make_uchar4((v & 8) != 0, (v & 4) != 0, (v & 2) != 0, (v & 1) != 0);
+}
+
+__global__ void accuracy_counts_kernel(const int32_t* __restrict__ cls, const int64_t* __restrict__ labels, int64_t n,
+                                       unsigned long long* __restrict__ counts) {
+    unsigned int c[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = cls[i], g = labels[i];
+        c[0] += (p == g);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) c[1 + l] += (((p >> (3 - l)) & 1) == ((g >> (3 - l)) & 1));
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        unsigned int v = c[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(counts + j, (unsigned long long)v);
+    }
+}
+
+}  // namespace fp32
+}  // namespace dce

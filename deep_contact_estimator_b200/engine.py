@@ -1,0 +1,265 @@
+"""ContactEngine: the host-side owner of a ``dce_weights`` handle on one B200.
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, workspace)
+and the stream; the arithmetic is in libdce_b200.so (include/dce.h).
+
+Replaces the per-batch body of the reference loops:
+    output = model(input_data); _, prediction = torch.max(output, 1);
+    bin_pred = decimal2binary(prediction)
+(/root/reference/src/inference_one_seq.py:25-27, src/test.py:87-94) and, for a
+device-resident log, the whole ``for sample in dataloader`` loop
+(src/inference_one_seq.py:23-28) including ``contact_dataset.__getitem__``
+(utils/data_handler.py:55-57).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Mapping, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .synth import PARAM_NAMES, PARAM_SHAPES, WINDOW, CHANNELS, CLASSES
+
+
+def default_precision() -> str:
+    return os.environ.get("DCE_PRECISION", "bf16x3")
+
+
+class ContactEngine:
+    """Packed weights + workspace on one CUDA device.
+
+    ``params``: mapping with the reference's 14 ``state_dict`` keys
+    (src/contact_cnn.py:10-58); tensors may live anywhere, they are copied to
+    ``device`` as fp32 and repacked once (K0).
+    """
+
+    def __init__(self, params: Optional[Mapping[str, torch.Tensor]], device, precision: Optional[str] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ContactEngine needs a CUDA (B200) device; CPU tensors use the stock PyTorch module")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.precision = precision or default_precision()
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self._handle = ctypes.c_void_p()
+        _lib.check(self.lib.dce_weights_create(ctypes.byref(self._handle), self.device.index), "dce_weights_create")
+        self._workspace: Optional[torch.Tensor] = None
+        self.last_launches = 0
+        if params is not None:
+            self.pack(params)
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.dce_weights_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- K0 ---------------------------------------------------------------
+    def pack(self, params: Mapping[str, torch.Tensor]):
+        missing = [k for k in PARAM_NAMES if k not in params]
+        if missing:
+            raise KeyError(f"state_dict is missing {missing}")
+        dev = []
+        for k in PARAM_NAMES:
+            t = params[k].detach()
+            if tuple(t.shape) != PARAM_SHAPES[k]:
+                raise ValueError(f"{k}: expected shape {PARAM_SHAPES[k]}, got {tuple(t.shape)}")
+            dev.append(t.to(device=self.device, dtype=torch.float32).contiguous())
+        arr = (ctypes.c_void_p * len(dev))(*[t.data_ptr() for t in dev])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.dce_weights_pack(self._handle, arr, ctypes.c_void_p(stream.cuda_stream)), "dce_weights_pack")
+            stream.synchronize()            # the fp32 staging copies in `dev` may be freed after this
+        return self
+
+    def packed_view(self) -> torch.Tensor:
+        """The packed-weight buffer as a uint8 tensor sharing memory with the
+        handle (for ``torch.distributed.broadcast`` over NCCL)."""
+        n = self.lib.dce_weights_packed_bytes(self._handle)
+        ptr = self.lib.dce_weights_packed_ptr(self._handle)
+        iface = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+        holder = type("_DcePacked", (), {"__cuda_array_interface__": iface})()
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(holder, device=self.device)
+
+    def broadcast_weights(self, src: int = 0, group=None):
+        """One-time NCCL broadcast of the packed weights from rank ``src``
+        (SURVEY.md §8e).  No steady-state collective exists on this path."""
+        import torch.distributed as dist
+        view = self.packed_view()
+        dist.broadcast(view, src=src, group=group)
+        _lib.check(self.lib.dce_weights_adopt(self._handle), "dce_weights_adopt")
+        return self
+
+    # -- workspace ----------------------------------------------------------
+    def _ws(self, n: int) -> torch.Tensor:
+        need = self.lib.dce_workspace_bytes(n, _lib.PRECISIONS[self.precision])
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _outs(self, n: int, want_logits: bool, want_cls: bool, want_bits: bool):
+        logits = torch.empty((n, CLASSES), dtype=torch.float32, device=self.device) if want_logits else None
+        cls = torch.empty((n,), dtype=torch.int32, device=self.device) if want_cls else None
+        bits = torch.empty((n, 4), dtype=torch.uint8, device=self.device) if want_bits else None
+        return logits, cls, bits
+
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]):
+        return ctypes.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
+
+    # -- K1 -------------------------------------------------------------------
+    def classify(self, x: torch.Tensor, want_logits: bool = True, want_cls: bool = True, want_bits: bool = True
+                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """``(B,150,54)`` fp32 CUDA windows -> ``(logits (B,16) f32, cls (B,) i32, bits (B,4) u8)``."""
+        if x.dim() != 3 or tuple(x.shape[1:]) != (WINDOW, CHANNELS):
+            raise ValueError(f"expected (B,{WINDOW},{CHANNELS}), got {tuple(x.shape)}")
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError(f"expected float32 on {self.device}, got {x.dtype} on {x.device}")
+        x = x.contiguous()
+        n = x.shape[0]
+        logits, cls, bits = self._outs(n, want_logits, want_cls, want_bits)
+        if n == 0:
+            return logits, cls, bits
+        ws = self._ws(n)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_forward(self._handle, self._p(x), n, self._p(logits), self._p(cls), self._p(bits),
+                                      self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
+                                      ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dce_forward")
+        self.last_launches = self.lib.dce_last_launch_count()
+        return logits, cls, bits
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.classify(x, True, False, False)[0]
+
+    def profile_forward(self, x: torch.Tensor):
+        """Per-kernel CUDA-event durations of one ``dce_forward`` (synchronises):
+        ``[(kernel name, ms), ...]`` in launch order."""
+        x = x.contiguous()
+        n = x.shape[0]
+        logits, cls, bits = self._outs(n, True, True, True)
+        ws = self._ws(n)
+        cap = 64
+        ms = (ctypes.c_float * cap)()
+        names = (ctypes.c_char_p * cap)()
+        cnt = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_forward_profile(self._handle, self._p(x), n, self._p(logits), self._p(cls), self._p(bits),
+                                              self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
+                                              ctypes.c_void_p(stream.cuda_stream), cap, ms, names, ctypes.byref(cnt))
+        _lib.check(rc, "dce_forward_profile")
+        return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
+
+    # -- host-buffer entry point (what a user with numpy / pinned data calls) ----
+    def classify_host(self, x_host: torch.Tensor, out_bits_host: Optional[torch.Tensor] = None,
+                      out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024):
+        """``x_host``: ``(B,150,54)`` fp32 on the HOST (pinned for full speed).
+        Copies chunk by chunk on a side stream so the host->device transfer of
+        chunk i+1 overlaps the kernels of chunk i; returns host ``(cls, bits)``
+        after the device->host read of the results has completed."""
+        n = x_host.shape[0]
+        if out_bits_host is None:
+            out_bits_host = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+        if out_cls_host is None:
+            out_cls_host = torch.empty((n,), dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.device):
+            compute = torch.cuda.current_stream(self.device)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+                self._stage = [torch.empty((chunk, WINDOW, CHANNELS), dtype=torch.float32, device=self.device) for _ in range(2)]
+                self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            if self._stage[0].shape[0] != chunk:
+                self._stage = [torch.empty((chunk, WINDOW, CHANNELS), dtype=torch.float32, device=self.device) for _ in range(2)]
+            copy = self._copy_stream
+            copy.wait_stream(compute)
+            bits_dev = torch.empty((n, 4), dtype=torch.uint8, device=self.device)
+            cls_dev = torch.empty((n,), dtype=torch.int32, device=self.device)
+            ws = self._ws(min(n, chunk))
+            launches = 0
+            for i, s0 in enumerate(range(0, n, chunk)):
+                m = min(chunk, n - s0)
+                buf = self._stage[i & 1]
+                with torch.cuda.stream(copy):
+                    copy.wait_event(self._stage_free[i & 1])          # kernels of chunk i-2 are done with this buffer
+                    buf[:m].copy_(x_host[s0:s0 + m], non_blocking=True)
+                    ready = torch.cuda.Event(); ready.record(copy)
+                compute.wait_event(ready)
+                rc = self.lib.dce_forward(self._handle, self._p(buf), m, None, ctypes.c_void_p(cls_dev[s0:].data_ptr()),
+                                          ctypes.c_void_p(bits_dev[s0:].data_ptr()), self._p(ws), ws.numel(),
+                                          _lib.PRECISIONS[self.precision], ctypes.c_void_p(compute.cuda_stream))
+                _lib.check(rc, "dce_forward")
+                launches += self.lib.dce_last_launch_count()
+                self._stage_free[i & 1].record(compute)
+            out_bits_host.copy_(bits_dev, non_blocking=True)
+            out_cls_host.copy_(cls_dev, non_blocking=True)
+            compute.synchronize()
+        self.last_launches = launches
+        return out_cls_host, out_bits_host
+
+    # -- K2 -------------------------------------------------------------------
+    def stream(self, data: torch.Tensor, first_window: int = 0, n_windows: Optional[int] = None,
+               want_logits: bool = False, want_cls: bool = True, want_bits: bool = True):
+        """Whole-log inference: ``data`` is the device-resident ``(T,54)`` fp32
+        sensor log (utils/data_handler.py:26); returns results for windows
+        ``first_window .. first_window + n_windows``."""
+        if data.dim() != 2 or data.shape[1] != CHANNELS:
+            raise ValueError(f"expected (T,{CHANNELS}), got {tuple(data.shape)}")
+        if data.device != self.device or data.dtype != torch.float32:
+            raise ValueError(f"expected float32 on {self.device}, got {data.dtype} on {data.device}")
+        data = data.contiguous()
+        T = data.shape[0]
+        total = max(T - WINDOW + 1, 0)
+        if n_windows is None:
+            n_windows = total - first_window
+        if first_window < 0 or n_windows < 0 or first_window + n_windows > total:
+            raise ValueError(f"window range [{first_window}, {first_window + n_windows}) outside [0, {total})")
+        logits, cls, bits = self._outs(n_windows, want_logits, want_cls, want_bits)
+        if n_windows == 0:
+            return logits, cls, bits
+        ws = self._ws(n_windows)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_stream(self._handle, self._p(data), T, first_window, n_windows,
+                                     self._p(logits), self._p(cls), self._p(bits), self._p(ws), ws.numel(),
+                                     _lib.PRECISIONS[self.precision], ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dce_stream")
+        self.last_launches = self.lib.dce_last_launch_count()
+        return logits, cls, bits
+
+    # -- small helpers on the same ABI ------------------------------------------
+    def decimal2binary(self, x: torch.Tensor) -> torch.Tensor:
+        flat = x.reshape(-1).to(torch.int64).contiguous()
+        out = torch.empty((flat.numel(), 4), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_decimal2binary(self._p(flat), flat.numel(), self._p(out), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dce_decimal2binary")
+        return out.reshape(*x.shape, 4)
+
+    def accuracy_counts(self, cls: torch.Tensor, labels: torch.Tensor, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """counts[0] += #(cls == label); counts[1+l] += #(bit l agrees)  (int64[5], on device)."""
+        if counts is None:
+            counts = torch.zeros(5, dtype=torch.int64, device=self.device)
+        cls = cls.to(torch.int32).contiguous()
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        if cls.numel() != labels.numel():
+            raise ValueError("cls and labels differ in length")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_accuracy_counts(self._p(cls), self._p(labels), cls.numel(), self._p(counts),
+                                              ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dce_accuracy_counts")
+        return counts

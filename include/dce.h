@@ -1,0 +1,157 @@
+/*
+ * dce.h — C ABI of libdce_b200.so: the B200-native contact-classification path.
+ *
+ * The reference (UMich-CURLY/deep-contact-estimator) has no FFI / plugin layer
+ * of its own; its hot path is the Python `contact_cnn` nn.Module plus three
+ * tiny torch helpers.  This header is the boundary a binding would target.
+ * Each entry point names the reference interface it replaces (file:line under
+ * /root/reference).  The Python host side (deep_contact_estimator_b200/) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross the boundary;
+ *   - every pointer named *_dev is a DEVICE pointer on the handle's device;
+ *     the caller owns all input/output/workspace buffers (the library only
+ *     owns the packed-weight buffer inside a dce_weights handle);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises, nothing allocates: calls are CUDA-graph capturable;
+ *   - return value: 0 = DCE_OK, negative = DCE_E*; never throws or aborts;
+ *   - a handle is immutable after dce_weights_pack() and may be shared by
+ *     host threads; dce_forward / dce_stream are re-entrant given distinct
+ *     workspaces.
+ */
+#ifndef DCE_H_
+#define DCE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCE_VERSION 100          /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define DCE_API __attribute__((visibility("default")))
+#else
+#define DCE_API
+#endif
+
+/* model geometry — src/contact_cnn.py:10-58, config/*.yaml window_size */
+#define DCE_WINDOW   150
+#define DCE_CHANNELS 54
+#define DCE_CLASSES  16
+#define DCE_LEGS     4
+#define DCE_NUM_PARAMS 14
+
+/* error codes */
+#define DCE_OK            0
+#define DCE_EINVAL       -1      /* bad argument / shape / null pointer      */
+#define DCE_EALIGN       -2      /* pointer not aligned as documented        */
+#define DCE_EARCH        -3      /* device is not sm_100 (B200)              */
+#define DCE_ECUDA        -4      /* CUDA runtime error; see dce_last_cuda_error */
+#define DCE_ENOTPACKED   -5      /* handle has no packed weights yet         */
+#define DCE_EWORKSPACE   -6      /* workspace too small                      */
+#define DCE_EUNSUPPORTED -7      /* precision / mode not built               */
+
+/* arithmetic mode of the forward pass */
+#define DCE_PREC_FP32    0       /* fp32 FFMA kernels (exact-order-free fp32) */
+#define DCE_PREC_BF16X3  1       /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
+
+typedef struct dce_weights dce_weights;
+
+/* library / error introspection */
+DCE_API int         dce_version(void);
+DCE_API const char *dce_strerror(int code);
+DCE_API int         dce_last_cuda_error(void);           /* cudaError_t of the last DCE_ECUDA on this thread */
+
+/*
+ * Weights handle — replaces `model = contact_cnn(); model.load_state_dict(...);
+ * model.eval().to(device)` (src/inference_one_seq.py:153-156, src/test.py:130-134).
+ */
+DCE_API int dce_weights_create(dce_weights **out, int device);
+DCE_API int dce_weights_destroy(dce_weights *w);
+
+/*
+ * K0: repack the 14 fp32 state_dict tensors (device pointers, contiguous, in
+ * state_dict order: block1.0.weight, block1.0.bias, block1.2.weight,
+ * block1.2.bias, block2.0.weight, block2.0.bias, block2.2.weight,
+ * block2.2.bias, fc.0.weight, fc.0.bias, fc.3.weight, fc.3.bias, fc.6.weight,
+ * fc.6.bias — src/contact_cnn.py:10-58) into the kernels' layouts: tap-major
+ * conv weights, fc.0 columns permuted from c*37+t to t*128+c
+ * (src/contact_cnn.py:64), bf16 hi/lo split images for the tensor-core path.
+ */
+DCE_API int dce_weights_pack(dce_weights *w, const float *const params_dev[DCE_NUM_PARAMS], void *stream);
+
+/* The packed buffer, for a one-time ncclBroadcast to the other ranks.  After
+ * writing the buffer externally call dce_weights_adopt() to mark it packed. */
+DCE_API size_t dce_weights_packed_bytes(const dce_weights *w);
+DCE_API void  *dce_weights_packed_ptr(dce_weights *w);
+DCE_API int    dce_weights_adopt(dce_weights *w);
+
+/* Scratch the caller must provide to dce_forward / dce_stream for up to
+ * `max_windows` windows per call (the library chunks internally, so this
+ * saturates at a fixed size). 256-byte aligned device memory. */
+DCE_API size_t dce_workspace_bytes(int64_t max_windows, int precision);
+
+/*
+ * K1: logits = contact_cnn.forward(x)  (src/contact_cnn.py:60-66), optionally
+ * followed by `torch.max(output, 1)` (src/inference_one_seq.py:26) and
+ * `decimal2binary` (src/inference_one_seq.py:59-62).
+ *   x_dev       [B][150][54] fp32, contiguous (the DataLoader batch,
+ *               src/inference_one_seq.py:24), 16-byte aligned
+ *   logits_dev  [B][16] fp32 or NULL
+ *   cls_dev     [B] int32 class 0..15 or NULL (first maximal index; NaN wins)
+ *   bits_dev    [B][4] uint8 contact bits, MSB first = leg 0 (RF), or NULL
+ */
+DCE_API int dce_forward(const dce_weights *w, const float *x_dev, int64_t B,
+                float *logits_dev, int32_t *cls_dev, uint8_t *bits_dev,
+                void *workspace_dev, size_t workspace_bytes, int precision, void *stream);
+
+/*
+ * K2: the body of `inference(dataloader, model, device)`
+ * (src/inference_one_seq.py:19-30) over a device-resident sensor log: for
+ * window i in [first_window, first_window + n_windows): rows i..i+149 of
+ * `data_dev` ([T][54] fp32, utils/data_handler.py:26), minus the column mean,
+ * divided by the unbiased column std (utils/data_handler.py:55-56), forward,
+ * argmax, bits.  Overlapping windows are read once per tile from the
+ * contiguous stream.  Outputs are indexed from 0 (= first_window).
+ */
+DCE_API int dce_stream(const dce_weights *w, const float *data_dev, int64_t T,
+               int64_t first_window, int64_t n_windows,
+               float *logits_dev, int32_t *cls_dev, uint8_t *bits_dev,
+               void *workspace_dev, size_t workspace_bytes, int precision, void *stream);
+
+/*
+ * Profiling twin of dce_forward: the same launches with a cudaEvent pair around
+ * every kernel; synchronises `stream`, then reports each kernel's duration.
+ * names_out[i] are static strings.  Used by bench.py for the roofline figure.
+ */
+DCE_API int dce_forward_profile(const dce_weights *w, const float *x_dev, int64_t B,
+                        float *logits_dev, int32_t *cls_dev, uint8_t *bits_dev,
+                        void *workspace_dev, size_t workspace_bytes, int precision, void *stream,
+                        int max_kernels, float *ms_out, const char **names_out, int *n_out);
+
+/*
+ * `decimal2binary(x)` alone (src/inference_one_seq.py:59-62, src/test.py:109-111):
+ * cls_dev [n] int64 -> bits_dev [n][4] uint8 (used for ground-truth labels).
+ */
+DCE_API int dce_decimal2binary(const int64_t *cls_dev, int64_t n, uint8_t *bits_dev, void *stream);
+
+/*
+ * Fused accuracy counters of `inference_and_compute_acc` / `compute_accuracy`
+ * (src/inference_one_seq.py:33-57, src/test.py:72-107): given predicted
+ * classes and labels, accumulate counts_dev[0] += #(pred == label),
+ * counts_dev[1..4] += per-leg bit agreement.  counts_dev is int64[5].
+ */
+DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_dev, int64_t n,
+                        int64_t *counts_dev, void *stream);
+
+/* How many kernel launches the last dce_forward / dce_stream on this thread enqueued. */
+DCE_API int dce_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCE_H_ */

@@ -1,0 +1,52 @@
+"""The C-ABI library builds, loads, and exports every symbol include/dce.h
+declares.  No compute calls (no GPU here)."""
+import ctypes
+import os
+
+import pytest
+
+from deep_contact_estimator_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_library()
+    return _lib.load()
+
+
+def test_library_is_in_tree(lib):
+    assert os.path.dirname(_lib.LIB_PATH).endswith("deep_contact_estimator_b200")
+    assert os.path.exists(_lib.LIB_PATH)
+
+
+def test_exports_every_header_symbol(lib):
+    names = _lib.header_symbols()
+    assert len(names) >= 15 and set(names) == set(_lib._SIGNATURES)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_version_and_strerror(lib):
+    assert lib.dce_version() == 100
+    assert lib.dce_strerror(0) == b"ok"
+    for code in range(-7, 0):
+        assert lib.dce_strerror(code) not in (b"ok", b"unknown error")
+    assert lib.dce_strerror(-99) == b"unknown error"
+
+
+def test_argument_errors_without_gpu(lib):
+    # argument validation happens before any CUDA call
+    assert lib.dce_weights_create(None, 0) == -1
+    assert lib.dce_forward(None, None, 1, None, None, None, None, 0, 0, None) == -1
+    assert lib.dce_weights_pack(None, None, None) == -1
+    assert lib.dce_workspace_bytes(0, 0) == 256
+    assert lib.dce_workspace_bytes(4096, 0) > 4096 * 4736 * 4
+    assert lib.dce_decimal2binary(None, -1, None, None) == -1
+    assert lib.dce_weights_destroy(None) == 0
+
+
+def test_no_cpu_fallback_on_missing_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no fallback"):
+        _lib.load()

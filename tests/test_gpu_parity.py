@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on a B200.
+
+Tolerances (BASELINE.json north_star): logits within 1e-4 norm-wise relative
+(max|d| / max|logit| per window), argmax classes and contact bits bit-exact.
+We hold the kernels to tighter internal bars: 1e-5 for the fp32 mode and 3e-5
+for the bf16x3 tensor-core mode (SURVEY.md §0.4 measured 4e-6 for the scheme).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+import deep_contact_estimator_b200 as dce
+from deep_contact_estimator_b200 import synth, _lib
+from oracle import contact_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+NORTH_STAR_TOL = 1e-4
+TOL = {"fp32": 1e-5, "bf16x3": 3e-5}
+PRECISIONS = ["fp32", "bf16x3"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a GPU"
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def params0():
+    return synth.make_params(0)
+
+
+_engines = {}
+
+
+def engine(dev, precision, seed=0, scale=1.0):
+    key = (precision, seed, scale)
+    if key not in _engines:
+        _engines[key] = dce.ContactEngine(synth.make_params(seed, logit_scale=scale), dev, precision)
+    return _engines[key]
+
+
+def oracle_logits(params, x, bs=256):
+    with torch.no_grad():
+        return torch.cat([oracle.forward_torch(params, x[i:i + bs]) for i in range(0, x.shape[0], bs)]).numpy()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("golden", ["forward_seed0.npz", "forward_scaled.npz"])
+def test_forward_vs_reference_golden(dev, golden_dir, precision, golden):
+    g = np.load(os.path.join(golden_dir, golden))
+    eng = engine(dev, precision, int(g["param_seed"]), float(g["logit_scale"]))
+    x = synth.make_windows(int(g["batch"]), seed=int(g["input_seed"])).to(dev)
+    logits, cls, bits = eng.classify(x)
+    torch.cuda.synchronize()
+    err = oracle.normwise_rel_err(logits.cpu().numpy(), g["logits"])
+    assert err <= TOL[precision] <= NORTH_STAR_TOL, err
+    assert np.array_equal(cls.cpu().numpy(), g["cls"])
+    assert np.array_equal(bits.cpu().numpy(), oracle.decimal2binary_numpy(g["cls"]))
+    assert eng.last_launches > 0
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("batch", [1, 2, 30, 127, 300])
+def test_forward_vs_oracle_ragged_batches(dev, params0, precision, batch):
+    eng = engine(dev, precision)
+    x = synth.make_windows(batch, seed=100 + batch)
+    want = oracle_logits(params0, x)
+    logits, cls, bits = eng.classify(x.to(dev))
+    err = oracle.normwise_rel_err(logits.cpu().numpy(), want)
+    assert err <= TOL[precision], err
+    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
+    assert np.array_equal(bits.cpu().numpy(), oracle.decimal2binary_numpy(want.argmax(1)))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_forward_unnormalised_inputs_and_big_logits(dev, precision):
+    """Raw (not z-scored) windows with offsets, and a weight set with O(1) logits."""
+    params = synth.make_params(7, logit_scale=50.0)
+    eng = engine(dev, precision, 7, 50.0)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(96, 150, 54, generator=g) * 3.0 + 1.5
+    want = oracle_logits(params, x)
+    logits, cls, _ = eng.classify(x.to(dev))
+    assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL[precision]
+    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_batch_properties(dev, params0, precision):
+    """BASELINE config 2 (B=4096): checked through size-independent properties —
+    batch invariance (same window, same answer wherever it sits in the batch),
+    bits == decimal2binary(cls), cls == argmax(logits) — plus the oracle on a
+    512-window sample."""
+    eng = engine(dev, precision)
+    x = synth.make_windows(4096, seed=1).to(dev)
+    logits, cls, bits = eng.classify(x)
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(3)).to(dev)
+    logits_p, cls_p, _ = eng.classify(x[perm].contiguous())
+    assert torch.equal(logits[perm], logits_p) and torch.equal(cls[perm], cls_p)
+    lo, cl, bi = eng.classify(x[1000:1003].contiguous())
+    assert torch.equal(lo, logits[1000:1003]) and torch.equal(cl, cls[1000:1003])
+    assert torch.equal(cls.long(), logits.argmax(1))
+    assert torch.equal(bits, dce.decimal2binary(cls.long()))
+    idx = torch.arange(0, 4096, 8)
+    want = oracle_logits(params0, x[idx.to(dev)].cpu())
+    assert oracle.normwise_rel_err(logits[idx.to(dev)].cpu().numpy(), want) <= TOL[precision]
+    assert np.array_equal(cls[idx.to(dev)].cpu().numpy(), want.argmax(1))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_stream_vs_reference_golden(dev, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "stream_seed2.npz"))
+    eng = engine(dev, precision, int(g["param_seed"]))
+    log = synth.make_sensor_log(int(g["steps"]), seed=int(g["log_seed"])).to(dev)
+    logits, cls, bits = eng.stream(log, want_logits=True)
+    assert oracle.normwise_rel_err(logits.cpu().numpy(), g["logits"]) <= TOL[precision] * 2   # + z-score rounding
+    assert np.array_equal(cls.cpu().numpy(), g["cls"])
+    assert np.array_equal(bits.cpu().numpy(), g["bits"])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_stream_ranges_and_alignment(dev, params0, precision):
+    """Odd/even first rows (a window starts 216 B after its neighbour, so only
+    even rows are 16-byte aligned), sub-ranges, and stream == forward(extract)."""
+    eng = engine(dev, precision)
+    log = synth.make_sensor_log(1500, seed=21)
+    n = oracle.num_windows(1500)
+    want_logits, want_cls, want_bits = oracle.inference_stream(params0, log, batch_size=256)
+    logd = log.to(dev)
+    lg, cl, bi = eng.stream(logd, want_logits=True)
+    assert lg.shape == (n, 16)
+    assert oracle.normwise_rel_err(lg.cpu().numpy(), want_logits.numpy()) <= TOL[precision] * 2
+    assert np.array_equal(cl.cpu().numpy(), want_cls.numpy()) and np.array_equal(bi.cpu().numpy(), want_bits.numpy())
+    for first, cnt in ((0, 1), (1, 1), (3, 130), (n - 1, 1), (777, 0), (640, 257)):
+        lg2, cl2, bi2 = eng.stream(logd, first, cnt, want_logits=True)
+        assert torch.equal(lg2, lg[first:first + cnt]) and torch.equal(cl2, cl[first:first + cnt])
+        assert torch.equal(bi2, bi[first:first + cnt])
+    with pytest.raises(ValueError):
+        eng.stream(logd, n - 1, 2)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_empty_and_error_paths(dev, precision):
+    eng = engine(dev, precision)
+    lo, cl, bi = eng.classify(torch.empty(0, 150, 54, device=dev))
+    assert lo.shape == (0, 16) and cl.shape == (0,) and bi.shape == (0, 4)
+    with pytest.raises(ValueError):
+        eng.classify(torch.zeros(2, 149, 54, device=dev))
+    with pytest.raises(ValueError):
+        eng.classify(torch.zeros(2, 150, 54, device=dev, dtype=torch.float64))
+    # misaligned input pointer is rejected by the ABI, not silently accepted
+    import ctypes
+    buf = torch.zeros(150 * 54 + 1, device=dev)
+    ws = eng._ws(1)
+    out = torch.empty(16, device=dev)
+    rc = eng.lib.dce_forward(eng._handle, ctypes.c_void_p(buf.data_ptr() + 4), 1, ctypes.c_void_p(out.data_ptr()), None, None,
+                             ctypes.c_void_p(ws.data_ptr()), ws.numel(), _lib.PRECISIONS[precision], None)
+    assert rc == -2
+    rc = eng.lib.dce_forward(eng._handle, ctypes.c_void_p(buf.data_ptr()), 1, ctypes.c_void_p(out.data_ptr()), None, None,
+                             ctypes.c_void_p(ws.data_ptr()), 16, _lib.PRECISIONS[precision], None)
+    assert rc == -6
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_nan_window_propagates_like_reference(dev, params0, precision):
+    """A constant channel makes the reference z-score 0/0 = NaN; logits are NaN
+    and torch.max picks index 0 (utils/data_handler.py:55-56)."""
+    eng = engine(dev, precision)
+    log = synth.make_sensor_log(400, seed=5)
+    log[100:260, 3] = 1.25                        # windows 100..110 see a constant channel
+    lg, cl, bi = eng.stream(log.to(dev), want_logits=True)
+    wl, wc, wb = oracle.inference_stream(params0, log, batch_size=64)
+    nan_rows = torch.isnan(wl).any(1)
+    assert nan_rows.sum() == 11
+    assert torch.equal(torch.isnan(lg.cpu()).any(1), nan_rows)
+    assert np.array_equal(cl.cpu().numpy(), wc.numpy()) and np.array_equal(bi.cpu().numpy(), wb.numpy())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_module_and_loops_use_native_path(dev, golden_dir, precision, monkeypatch):
+    monkeypatch.setenv("DCE_PRECISION", precision)
+    g = np.load(os.path.join(golden_dir, "stream_seed2.npz"))
+    m = dce.contact_cnn(); m.load_state_dict(synth.make_params(0)); m = m.eval().to(dev)
+    x = synth.make_windows(30, seed=1).to(dev)
+    with torch.no_grad():
+        y = m(x)
+    assert m._engine is not None and m._engine.last_launches > 0 and m._engine.precision == precision
+    assert oracle.normwise_rel_err(y.cpu().numpy(), oracle_logits(synth.make_params(0), x.cpu())) <= TOL[precision]
+    # grad-enabled call keeps autograd (stock path), same numbers within fp32 drift
+    y2 = m(x)
+    assert y2.requires_grad and oracle.normwise_rel_err(y2.detach().cpu().numpy(), y.cpu().numpy()) <= TOL[precision] * 2
+    # loops: one dce_stream call over the resident log
+    log, lab = synth.make_sensor_log(420, seed=2), synth.make_labels(420, seed=3)
+    ds = dce.contact_dataset(data=log, label=lab.reshape(-1, 1), window_size=150, device=dev)
+    loader = DataLoader(ds, batch_size=30)
+    bits = dce.inference(loader, m, dev)
+    assert bits.is_cuda and np.array_equal(bits.cpu().numpy(), g["bits"])
+    bits2, acc, per_leg = dce.inference_and_compute_acc(loader, m, dev)
+    assert np.array_equal(bits2.cpu().numpy(), g["bits"])
+    assert abs(acc - float((g["cls"] == g["labels"]).mean())) < 1e-12
+    assert np.allclose(per_leg, (g["bits"] == oracle.decimal2binary_numpy(g["labels"])).mean(axis=0))
+    acc3, per_leg3, bp, bg, pa, ga = dce.compute_accuracy(loader, m)
+    assert acc3 == acc and np.array_equal(pa, g["cls"]) and np.array_equal(bp, g["bits"])
+    # weights changed in place -> engine repacks
+    with torch.no_grad():
+        m.fc[6].bias.add_(1.0)
+        y3 = m(x)
+    assert torch.allclose(y3, y + 1.0, atol=1e-5)
+
+
+def test_decimal2binary_and_counts_kernels(dev, golden_dir):
+    eng = engine(dev, "fp32")
+    tbl = np.load(os.path.join(golden_dir, "bits_table.npz"))["table"]
+    assert np.array_equal(eng.decimal2binary(torch.arange(16, device=dev)).cpu().numpy(), tbl)
+    g = torch.Generator().manual_seed(0)
+    cls = torch.randint(0, 16, (100003,), generator=g)
+    lab = torch.randint(0, 16, (100003,), generator=g)
+    c = eng.accuracy_counts(cls.to(dev), lab.to(dev)).cpu().numpy()
+    assert c[0] == int((cls == lab).sum())
+    assert np.array_equal(c[1:], (oracle.decimal2binary(cls) == oracle.decimal2binary(lab)).sum(0).numpy())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_cuda_graph_capture(dev, precision):
+    """No hidden allocation or sync: dce_forward is graph-capturable (latency mode)."""
+    eng = engine(dev, precision)
+    x = synth.make_windows(4, seed=8).to(dev)
+    want = eng.classify(x)[0].clone()
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        eng.classify(x)                       # warm-up on the side stream (workspace sized)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            out = eng.classify(x)[0]
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+
+
+def test_two_gpu_shards_equal_single(dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deep_contact_estimator_b200 import sharding
+    log = synth.make_sensor_log(3000, seed=2)
+    n = oracle.num_windows(3000)
+    single = engine(dev, "fp32").stream(log.to(dev))[2].cpu()
+    parts = []
+    for r in range(2):
+        d = torch.device("cuda", r)
+        eng = dce.ContactEngine(synth.make_params(0), d, "fp32")
+        s, e = sharding.window_range(n, r, 2)
+        r0, r1 = sharding.rows_for_windows(s, e)
+        parts.append(eng.stream(log[r0:r1].to(d))[2].cpu())
+    assert torch.equal(torch.cat(parts), single)
