@@ -245,7 +245,13 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
     if (precision == DCE_PREC_FP32)
         rc = run_fp32(w, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
     else
-        rc = dce::tc::run(w->buf, w->tc, w->sm_count, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
+    {
+        const Fp32Layout& L = w->f32;
+        dce::tc::BiasPtrs bp;
+        for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
+        bp.w3 = at<float>(w, L.f3);
+        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
+    }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
     return rc;
 }

@@ -1,18 +1,550 @@
-// tcgen05 bf16x3 path (DCE_PREC_BF16X3) — placeholder until the kernels land.
+// DCE_PREC_BF16X3: the tcgen05 tensor-core path.
+//
+// Every layer of contact_cnn (/root/reference/src/contact_cnn.py:10-58) is one
+// launch of the same persistent, warp-specialised kernel `tapgemm_kernel`:
+//
+//     D[row][n] = sum_{tap < TAPS} sum_{c} A[row + tap - 1][c] * W[n][tap][c]
+//
+// with TAPS = 3 for the Conv1d(k=3, pad=1) layers and TAPS = 1 for the Linear
+// layers.  Arithmetic is split-bf16 ("bf16x3"): every fp32 operand x is stored as
+// hi = bf16(x), lo = bf16(x - hi) and each K-step issues three tcgen05.mma
+// (hi*hi + hi*lo + lo*hi) accumulating in fp32 in TMEM.  Plain bf16 or TF32 miss
+// the 1e-4 parity bar; the dropped lo*lo term is ~2^-16 relative.
+//
+// Activation "tapes".  Activations live channels-last, as bf16 hi/lo, in
+//     tape[part][kchunk = c / 8][row][8]                       (16 bytes per (kchunk,row))
+// where for conv layers all windows of a chunk are stacked along `row` with
+// RW rows per window (150 samples + 2 zero guard rows -> 152; after pooling
+// 75 + 1 -> 76), so a conv tap is a shift by one row and window-edge padding
+// is a guard row.  A 128-row M-tile plus its one-row halo is, per kchunk, ONE
+// contiguous 2080-byte span: it is fetched with 1-D bulk TMA (cp.async.bulk)
+// straight into the UMMA SWIZZLE_NONE K-major layout, and the three taps read
+// the same staged slab through descriptors whose start address differs by
+// 16 bytes (the folded im2col).  Weights are pre-packed (K0) into the exact
+// shared-memory image of each (n-tile, k-stage) so a stage's B operand is one
+// bulk copy.
+//
+// Roles per CTA (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   : TMA producer  (one lane)      smem ring, full/empty mbarriers
+//   warp 1   : MMA issuer    (one lane)      tcgen05.mma + tcgen05.commit; owns TMEM alloc
+//   warps 2-5: epilogue      (128 threads)   tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
+// TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include "dce_common.cuh"
+#include "dce_tc_ptx.cuh"
+#include "dce_fp32.cuh"
 
 namespace dce {
 namespace tc {
 
-struct PackedLayout { size_t begin, end; };
-inline PackedLayout make_packed_layout(size_t base) { return PackedLayout{base, base}; }
-inline int pack(char*, const PackedLayout&, const float* const*, Ctx&) { return DCE_OK; }
-inline size_t workspace_bytes(int64_t) { return 256; }
-inline int run(const char*, const PackedLayout&, int, const float*, bool, int64_t, int64_t, float*, int32_t*, uint8_t*,
-               char*, Ctx&) { return DCE_EUNSUPPORTED; }
+constexpr int kRW1 = 152;            // tape rows per window, T = 150 layers
+constexpr int kRW2 = 76;             // tape rows per window, T = 75 layers
+constexpr int kGuard = 8;            // leading guard rows of every tape (row r lives at index r + 8)
+constexpr int kSlabRows = 130;       // 1 + 128 + 1
+constexpr int kSlabBytes = kSlabRows * 16;
+constexpr int64_t kChunk = 4096;     // windows per internal pass
+
+enum Epi { EPI_TAPE = 0, EPI_POOL_TAPE = 1, EPI_POOL_FC = 2, EPI_FC_TAPE = 3, EPI_FC_F32 = 4 };
+
+struct TapGemmParams {
+    const uint8_t* a_tape;       // part 0 (hi); lo at + a_part_stride
+    size_t a_part_stride;
+    size_t a_kch_stride;         // bytes between consecutive kchunks = row capacity * 16
+    const uint8_t* w_packed;     // [n_tile][stage][hi|lo][tap][j][BN][8] bf16
+    const float* bias;           // [N]
+    int m_tiles, n_tiles, stages;
+    // epilogue
+    uint8_t* out;                // tape outputs: part 0
+    size_t out_part_stride, out_kch_stride;
+    int out_rows_cap;            // rows the output tape can hold (excluding guards)
+    float* out_f32;              // EPI_FC_F32: [n_valid][N]
+    int N;                       // total output features
+    int rw, tv;                  // rows per window / valid rows per window of the INPUT tape (conv modes)
+    int n_valid;                 // EPI_FC_F32: valid rows
+};
+
+struct Tape {
+    int rows, m_tiles, cap;      // logical rows, 128-row tiles, row capacity incl. guards
+    int kch;
+    size_t kch_stride, part_stride, bytes;
+};
+inline Tape make_tape(int64_t rows, int kch) {
+    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.cap = kGuard + t.m_tiles * 128 + 8; t.kch = kch;
+    t.kch_stride = (size_t)t.cap * 16; t.part_stride = t.kch_stride * kch; t.bytes = align_up(t.part_stride * 2, 256);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hb);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }                 // keeps NaN
+__device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }  // NaN wins
+
+template <int BN, int TAPS, int KSA, int NSTAGE>
+struct TapGemmCfg {
+    static constexpr int A_PART = KSA * kSlabBytes;
+    static constexpr int A_BYTES = 2 * A_PART;
+    static constexpr int B_TAPCH = BN * 16;
+    static constexpr int B_PART = TAPS * KSA * B_TAPCH;
+    static constexpr int B_BYTES = 2 * B_PART;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + (2 * NSTAGE + 4) * 8 + 16;
+    static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
+    static_assert(STAGE_BYTES % 16 == 0, "bulk copies are 16-byte granular");
+    static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+};
+
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
+__global__ void __launch_bounds__(192, 1)
+tapgemm_kernel(const TapGemmParams p) {
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* tfull = empty + NSTAGE;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m = tile / p.n_tiles, n = tile % p.n_tiles;
+                const uint8_t* a_row = p.a_tape + (size_t)(128 * m + kGuard - 1) * 16;
+                const uint8_t* wsrc = p.w_packed + (size_t)n * p.stages * Cfg::B_BYTES;
+                for (int s = 0; s < p.stages; ++s, ++it) {
+                    const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                    ptx::mbar_wait(&empty[slot], ph ^ 1);
+                    uint8_t* st = smem + slot * Cfg::STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int part = 0; part < 2; ++part)
+#pragma unroll
+                        for (int j = 0; j < KSA; ++j)
+                            ptx::bulk_g2s(st + part * Cfg::A_PART + j * kSlabBytes,
+                                          a_row + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                          kSlabBytes, &full[slot]);
+                    ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
+                ptx::mbar_wait(&tempty[buf], tph ^ 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t d = tmem_base + buf * BN;
+                for (int s = 0; s < p.stages; ++s, ++it) {
+                    const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                    ptx::mbar_wait(&full[slot], ph);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES);
+                    const uint32_t b0 = a0 + Cfg::A_BYTES;
+#pragma unroll
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
+#pragma unroll
+                        for (int kk = 0; kk < KSA / 2; ++kk) {
+                            const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
+                            const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
+                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                            const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
+                            const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
+                            const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                            ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
+                            ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                            ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                        }
+                    }
+                    ptx::umma_commit(&empty[slot]);          // frees the smem slot when these MMAs retire
+                }
+                ptx::umma_commit(&tfull[buf]);               // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias / ReLU / pool -> bf16 hi/lo -> next layer's tape =====
+        const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+        const int row_in_tile = q * 32 + lane;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int m = tile / p.n_tiles, n = tile % p.n_tiles;
+            const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
+            const int row = 128 * m + row_in_tile;
+            const int n0 = n * BN;
+            ptx::mbar_wait(&tfull[buf], tph);
+            ptx::tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+
+            // per-mode row bookkeeping
+            bool valid = true; size_t out_off = 0; bool zero_prev = false;
+            if (EPI == EPI_TAPE) {
+                const int t = row % p.rw;
+                valid = t < p.tv;
+                out_off = (size_t)(row + kGuard) * 16;
+                zero_prev = (row == 0);
+            } else if (EPI == EPI_POOL_TAPE) {
+                const int t = row % p.rw;
+                valid = (t >> 1) < (p.tv >> 1);
+                const int orow = row >> 1;
+                out_off = (size_t)(orow + kGuard) * 16;
+                zero_prev = (orow == 0);
+                if (orow >= p.out_rows_cap) out_off = (size_t)-1;
+            } else if (EPI == EPI_POOL_FC) {
+                const int w = row / p.rw, t = row % p.rw;
+                const int to = t >> 1;
+                valid = to < (p.tv >> 1);
+                out_off = (valid && w < p.out_rows_cap) ? (size_t)(to * (BN / 8)) * p.out_kch_stride + (size_t)(w + kGuard) * 16 : (size_t)-1;
+            } else if (EPI == EPI_FC_TAPE) {
+                out_off = (size_t)(row + kGuard) * 16;
+            }
+
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld32(taddr + c0, v);
+                ptx::tmem_ld_wait();
+                float y[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]) + __ldg(p.bias + n0 + c0 + i);
+
+                if (EPI == EPI_FC_F32) {
+                    if (row < p.n_valid) {
+                        float* dst = p.out_f32 + (size_t)row * p.N + n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) =
+                                make_float4(relu_nan(y[i]), relu_nan(y[i + 1]), relu_nan(y[i + 2]), relu_nan(y[i + 3]));
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = relu_nan(y[i]);
+                if (EPI == EPI_POOL_TAPE || EPI == EPI_POOL_FC) {
+                    // MaxPool1d(2,2): rows (2i, 2i+1) are adjacent lanes (src/contact_cnn.py:24-25,42-43)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
+                }
+                if (EPI != EPI_FC_TAPE && EPI != EPI_POOL_FC) {
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) y[i] = 0.f;                  // guard rows stay zero
+                    }
+                }
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 hi, lo;
+                    split8(y + qd * 8, hi, lo);
+                    const int kch = (n0 + c0) / 8 + qd;
+                    if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
+                        uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off;
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
+                        if (EPI == EPI_TAPE && zero_prev) {
+                            *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
+                        }
+                    } else {
+                        // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
+                        if (out_off != (size_t)-1) {
+                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off + ((lane & 1) ? p.out_part_stride : 0);
+                            *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
+                            if (EPI == EPI_POOL_TAPE && zero_prev) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0 (tensor-core part): weights -> bf16 hi/lo shared-memory images, one block per (n_tile, stage)
+// kind 0: conv  W[n][cin][3]      K index (tap, c), c padded to 8*KSA*stages
+// kind 1: fc.0  W[n][c*37 + t]    K index k' = t*128 + c      (src/contact_cnn.py:64)
+// kind 2: fc.3  W[n][k]
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
+                              int BN, int TAPS, int KSA, int kind, int cin) {
+    const size_t per_part = (size_t)TAPS * KSA * BN * 8;            // elements in one part of one block
+    const size_t total = (size_t)n_tiles * stages * per_part;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const int e = r % 8; r /= 8;
+        const int nn = r % BN; r /= BN;
+        const int j = r % KSA; r /= KSA;
+        const int tap = r % TAPS; r /= TAPS;
+        const int s = r % stages; r /= stages;
+        const int nt = (int)r;
+        const int n = nt * BN + nn;
+        const int c = (s * KSA + j) * 8 + e;
+        float v;
+        if (kind == 0) v = (c < cin) ? W[((size_t)n * cin + c) * 3 + tap] : 0.f;
+        else if (kind == 1) { const int t = c / 128, ch = c % 128; v = W[(size_t)n * 4736 + ch * 37 + t]; }
+        else v = W[(size_t)n * cin + c];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        const size_t blk = ((size_t)nt * stages + s) * (2 * per_part * 2);      // bytes
+        const size_t within = ((((size_t)tap * KSA + j) * BN + nn) * 8 + e) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
+        *reinterpret_cast<__nv_bfloat16*>(out + blk + per_part * 2 + within) = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ingest: fp32 windows -> layer-0 tape (54 channels padded to 64, bf16 hi/lo, guard rows zero)
+//   batch mode : x = [B][150][54]                                 (DataLoader batch, src/inference_one_seq.py:24)
+//   stream mode: x = [T][54] log; window w = rows first+w .. +149, z-scored with stats[w]
+//                (utils/data_handler.py:55-56)
+// block = 8 warps = 8 kchunks x 32 consecutive tape rows
+// ---------------------------------------------------------------------------------------------
+template <bool STREAM>
+__global__ void __launch_bounds__(256)
+ingest_kernel(const float* __restrict__ x, int64_t first, int n_windows, const float* __restrict__ mean,
+              const float* __restrict__ sdev, uint8_t* __restrict__ tape, size_t part_stride, size_t kch_stride) {
+    const int kch = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 32 + lane;
+    const int w = row / kRW1, t = row % kRW1;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = 0.f;
+    if (w < n_windows && t < 150 && kch < 7) {
+        const float* src = STREAM ? x + (size_t)(first + w + t) * 54 + kch * 8 : x + ((size_t)w * 150 + t) * 54 + kch * 8;
+        const int nv = (kch == 6) ? 6 : 8;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            if (i < nv) {
+                const float2 f = __ldg(reinterpret_cast<const float2*>(src + i));
+                y[i] = f.x; y[i + 1] = f.y;
+            }
+        }
+        if (STREAM) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nv) y[i] = (y[i] - __ldg(mean + (size_t)w * 64 + kch * 8 + i)) / __ldg(sdev + (size_t)w * 64 + kch * 8 + i);
+        }
+    }
+    uint4 hi, lo;
+    split8(y, hi, lo);
+    uint8_t* dst = tape + (size_t)kch * kch_stride + (size_t)(row + kGuard) * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + part_stride) = lo;
+    if (row == 0) {
+        *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + part_stride - 16) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// per-window, per-channel mean and unbiased std, two-pass in fp32 (utils/data_handler.py:55-56)
+__global__ void __launch_bounds__(256)
+window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, float* __restrict__ mean, float* __restrict__ sdev) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = idx / 64, c = idx % 64;
+    if (w >= n_windows || c >= 54) return;
+    const float* src = x + (size_t)(first + w) * 54 + c;
+    float s = 0.f;
+    for (int t = 0; t < 150; ++t) s += __ldg(src + (size_t)t * 54);
+    const float mu = s / 150.f;
+    float v = 0.f;
+    for (int t = 0; t < 150; ++t) { const float d = __ldg(src + (size_t)t * 54) - mu; v = fmaf(d, d, v); }
+    mean[(size_t)w * 64 + c] = mu;
+    sdev[(size_t)w * 64 + c] = sqrtf(v / 149.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: packed layout, workspace, launch sequence
+// ---------------------------------------------------------------------------------------------
+struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
+//                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
+constexpr LayerCfg kLayers[6] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
+                                 {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
+                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0
+                                 {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
+                                 {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
+                                 {128, 1, 4, 64, 4, 2, 2048, 10}}; // fc.3
+inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
+
+struct PackedLayout { size_t w[6]; size_t begin, end; };
+inline PackedLayout make_packed_layout(size_t base) {
+    PackedLayout L; L.begin = base; size_t o = base;
+    for (int i = 0; i < 6; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }
+    L.end = o;
+    return L;
+}
+
+inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ctx& ctx) {
+    for (int i = 0; i < 6; ++i) {
+        const LayerCfg& c = kLayers[i];
+        const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
+        const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        DCE_KL(ctx, "tc_pack_b", pack_b_kernel<<<blocks, 256, 0, ctx.stream>>>(
+            params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin));
+    }
+    return DCE_OK;
+}
+
+struct Workspace {
+    Tape x0, x1, x2, x3, x4, h1;
+    size_t o_x0, o_x1, o_x2, o_x3, o_x4, o_h1, o_h2, o_mean, o_sdev, end;
+};
+inline Workspace make_workspace(int64_t n) {
+    Workspace W; size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    W.x0 = make_tape(n * kRW1, 8);   W.o_x0 = take(W.x0.bytes);
+    W.x1 = make_tape(n * kRW1, 8);   W.o_x1 = take(W.x1.bytes);
+    W.x2 = make_tape(n * kRW2, 8);   W.o_x2 = take(W.x2.bytes);
+    W.x3 = make_tape(n * kRW2, 16);  W.o_x3 = take(W.x3.bytes);
+    W.x4 = make_tape(n, 592);        W.o_x4 = take(W.x4.bytes);
+    W.h1 = make_tape(n, 256);        W.o_h1 = take(W.h1.bytes);
+    W.o_h2 = take((size_t)n * 512 * 4);
+    W.o_mean = take((size_t)n * 64 * 4);
+    W.o_sdev = take((size_t)n * 64 * 4);
+    W.end = o;
+    return W;
+}
+inline size_t workspace_bytes(int64_t max_windows) {
+    return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
+}
+
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
+inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI>;
+    static thread_local bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+        attr_done = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    DCE_KL(ctx, name, kern<<<grid, 192, Cfg::SMEM_BYTES, ctx.stream>>>(p));
+    return DCE_OK;
+}
+
+// bias offsets inside the fp32 section are passed in by dce.cu
+struct BiasPtrs { const float* b[7]; const float* w3; };
+
+inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
+               int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+    cudaStream_t s = ctx.stream;
+    for (int64_t c0 = 0; c0 < n; c0 += kChunk) {
+        const int m = (int)((n - c0 < kChunk) ? n - c0 : kChunk);
+        const Workspace W = make_workspace(m);
+        uint8_t* x0 = reinterpret_cast<uint8_t*>(ws + W.o_x0);
+        uint8_t* x1 = reinterpret_cast<uint8_t*>(ws + W.o_x1);
+        uint8_t* x2 = reinterpret_cast<uint8_t*>(ws + W.o_x2);
+        uint8_t* x3 = reinterpret_cast<uint8_t*>(ws + W.o_x3);
+        uint8_t* x4 = reinterpret_cast<uint8_t*>(ws + W.o_x4);
+        uint8_t* h1 = reinterpret_cast<uint8_t*>(ws + W.o_h1);
+        float* h2 = reinterpret_cast<float*>(ws + W.o_h2);
+        float* mean = reinterpret_cast<float*>(ws + W.o_mean);
+        float* sdev = reinterpret_cast<float*>(ws + W.o_sdev);
+
+        // ---- ingest (a2/a3/a4): windows -> X0 tape
+        const int iblocks = W.x0.m_tiles * 4;
+        if (stream_mode) {
+            DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev));
+            DCE_KL(ctx, "tc_ingest_stream", ingest_kernel<true><<<iblocks, 256, 0, s>>>(
+                src, first + c0, m, mean, sdev, x0, W.x0.part_stride, W.x0.kch_stride));
+        } else {
+            DCE_KL(ctx, "tc_ingest", ingest_kernel<false><<<iblocks, 256, 0, s>>>(
+                src + (size_t)c0 * 150 * 54, 0, m, nullptr, nullptr, x0, W.x0.part_stride, W.x0.kch_stride));
+        }
+        int rc;
+        TapGemmParams p{};
+        // ---- conv1 (a5): X0 -> X1
+        p = TapGemmParams{};
+        p.a_tape = x0; p.a_part_stride = W.x0.part_stride; p.a_kch_stride = W.x0.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[0]); p.bias = bp.b[0];
+        p.m_tiles = W.x0.m_tiles; p.n_tiles = 1; p.stages = kLayers[0].stages;
+        p.out = x1; p.out_part_stride = W.x1.part_stride; p.out_kch_stride = W.x1.kch_stride; p.out_rows_cap = W.x1.m_tiles * 128;
+        p.N = 64; p.rw = kRW1; p.tv = 150;
+        if ((rc = launch_layer<64, 3, 4, 4, EPI_TAPE>(ctx, "tc_conv1", sm_count, p)) != DCE_OK) return rc;
+        // ---- conv2 + pool (a6): X1 -> X2
+        p.a_tape = x1; p.a_part_stride = W.x1.part_stride; p.a_kch_stride = W.x1.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[1]); p.bias = bp.b[1];
+        p.m_tiles = W.x1.m_tiles; p.stages = kLayers[1].stages;
+        p.out = x2; p.out_part_stride = W.x2.part_stride; p.out_kch_stride = W.x2.kch_stride; p.out_rows_cap = W.x2.m_tiles * 128;
+        if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
+        // ---- conv3 (a7): X2 -> X3
+        p.a_tape = x2; p.a_part_stride = W.x2.part_stride; p.a_kch_stride = W.x2.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[2]); p.bias = bp.b[2];
+        p.m_tiles = W.x2.m_tiles; p.stages = kLayers[2].stages;
+        p.out = x3; p.out_part_stride = W.x3.part_stride; p.out_kch_stride = W.x3.kch_stride; p.out_rows_cap = W.x3.m_tiles * 128;
+        p.N = 128; p.rw = kRW2; p.tv = 75;
+        if ((rc = launch_layer<128, 3, 2, 6, EPI_TAPE>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
+        // ---- conv4 + pool + flatten (a8, a9): X3 -> X4 (fc.0 operand layout, k' = t*128 + c)
+        p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
+        p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
+        p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
+        if ((rc = launch_layer<128, 3, 2, 6, EPI_POOL_FC>(ctx, "tc_conv4_pool", sm_count, p)) != DCE_OK) return rc;
+        // ---- fc.0 + ReLU (a10): X4 -> H1
+        p = TapGemmParams{};
+        p.a_tape = x4; p.a_part_stride = W.x4.part_stride; p.a_kch_stride = W.x4.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[4]); p.bias = bp.b[4];
+        p.m_tiles = W.x4.m_tiles; p.n_tiles = kLayers[4].n_tiles; p.stages = kLayers[4].stages;
+        p.out = h1; p.out_part_stride = W.h1.part_stride; p.out_kch_stride = W.h1.kch_stride; p.out_rows_cap = W.h1.m_tiles * 128;
+        p.N = 2048; p.rw = 1; p.tv = 1;
+        if ((rc = launch_layer<256, 1, 4, 4, EPI_FC_TAPE>(ctx, "tc_fc1", sm_count, p)) != DCE_OK) return rc;
+        // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
+        p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;
+        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[5]); p.bias = bp.b[5];
+        p.m_tiles = W.h1.m_tiles; p.n_tiles = kLayers[5].n_tiles; p.stages = kLayers[5].stages;
+        p.out = nullptr; p.out_f32 = h2; p.N = 512; p.n_valid = m;
+        if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
+        // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
+        const int g3 = (int)((m + 7) / 8 < sm_count * 4 ? (m + 7) / 8 : sm_count * 4);
+        DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<g3, 256, 0, s>>>(
+            h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
+    }
+    return DCE_OK;
+}
 
 }  // namespace tc
 }  // namespace dce
