@@ -24,10 +24,10 @@
 // shared-memory image of each (n-tile, k-stage) so a stage's B operand is one
 // bulk copy.
 //
-// Roles per CTA (192 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0   : TMA producer  (one lane)      smem ring, full/empty mbarriers
-//   warp 1   : MMA issuer    (one lane)      tcgen05.mma + tcgen05.commit; owns TMEM alloc
-//   warps 2-5: epilogue      (128 threads)   tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
+// Roles per CTA (320 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-7: epilogue      (256 threads)   tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
+//   warp 8   : TMA producer  (one lane)      smem ring, full/empty mbarriers
+//   warp 9   : MMA issuer    (one lane)      tcgen05.mma + tcgen05.commit; owns TMEM alloc
 // TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda_runtime.h>
@@ -93,8 +93,18 @@ __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }                 // keeps NaN
-__device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }  // NaN wins
+// NaN-propagating max (FMNMX.NAN): torch's ReLU and MaxPool1d both propagate NaN.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float relu_nan(float v) { return max_nan(v, 0.f); }
+
+constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant: column halves
+constexpr int kProducerWarp = kEpiWarps;           // warp 8
+constexpr int kMmaWarp = kEpiWarps + 1;            // warp 9
+constexpr int kThreads = (kEpiWarps + 2) * 32;     // 320
 
 template <int BN, int TAPS, int KSA, int NSTAGE>
 struct TapGemmCfg {
@@ -105,7 +115,8 @@ struct TapGemmCfg {
     static constexpr int B_BYTES = 2 * B_PART;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + (2 * NSTAGE + 4) * 8 + 16;
+    static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + kEpiWarps * (BN / 2) * 4;
     static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
     static_assert(STAGE_BYTES % 16 == 0, "bulk copies are 16-byte granular");
@@ -113,7 +124,7 @@ struct TapGemmCfg {
 };
 
 template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const TapGemmParams p) {
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -122,22 +133,23 @@ tapgemm_kernel(const TapGemmParams p) {
     uint64_t* tfull = empty + NSTAGE;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], kEpiWarps); }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp == kMmaWarp) { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
@@ -161,7 +173,7 @@ tapgemm_kernel(const TapGemmParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
@@ -201,17 +213,24 @@ tapgemm_kernel(const TapGemmParams p) {
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias / ReLU / pool -> bf16 hi/lo -> next layer's tape =====
-        const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+        // warp e: TMEM lane quadrant q = e % 4 (hardware restriction), column half h = e / 4.
+        constexpr int HALF = BN / 2;
+        const int q = warp & 3, h = warp >> 2;
         const int row_in_tile = q * 32 + lane;
+        float* my_bias = s_bias + warp * HALF;               // warp-private copy of this warp's bias slice
         uint32_t tcount = 0;
+        int last_n = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int m = tile / p.n_tiles, n = tile % p.n_tiles;
             const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
             const int row = 128 * m + row_in_tile;
-            const int n0 = n * BN;
-            ptx::mbar_wait(&tfull[buf], tph);
-            ptx::tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+            const int n0 = n * BN + h * HALF;                // first output feature this warp owns
+            if (n != last_n) {                               // stage this warp's bias slice (warp-private copy)
+                __syncwarp();
+                for (int i = lane; i < HALF; i += 32) my_bias[i] = __ldg(p.bias + n0 + i);
+                __syncwarp();
+                last_n = n;
+            }
 
             // per-mode row bookkeeping
             bool valid = true; size_t out_off = 0; bool zero_prev = false;
@@ -236,57 +255,63 @@ tapgemm_kernel(const TapGemmParams p) {
                 out_off = (size_t)(row + kGuard) * 16;
             }
 
+            ptx::mbar_wait(&tfull[buf], tph);
+            ptx::tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + buf * BN + h * HALF + ((uint32_t)(q * 32) << 16);
+
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < HALF; c0 += 32) {
                 uint32_t v[32];
                 ptx::tmem_ld32(taddr + c0, v);
                 ptx::tmem_ld_wait();
                 float y[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]) + __ldg(p.bias + n0 + c0 + i);
-
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c0 + i);     // smem broadcast
+                    y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
+                    y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
+                    y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
+                    y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
+                }
                 if (EPI == EPI_FC_F32) {
                     if (row < p.n_valid) {
                         float* dst = p.out_f32 + (size_t)row * p.N + n0 + c0;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(dst + i) =
-                                make_float4(relu_nan(y[i]), relu_nan(y[i + 1]), relu_nan(y[i + 2]), relu_nan(y[i + 3]));
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
                     }
-                    continue;
-                }
+                } else {
+                    if (EPI == EPI_POOL_TAPE || EPI == EPI_POOL_FC) {
+                        // MaxPool1d(2,2): rows (2i, 2i+1) are adjacent lanes (src/contact_cnn.py:24-25,42-43)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = relu_nan(y[i]);
-                if (EPI == EPI_POOL_TAPE || EPI == EPI_POOL_FC) {
-                    // MaxPool1d(2,2): rows (2i, 2i+1) are adjacent lanes (src/contact_cnn.py:24-25,42-43)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
-                }
-                if (EPI != EPI_FC_TAPE && EPI != EPI_POOL_FC) {
-                    if (!valid) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) y[i] = 0.f;                  // guard rows stay zero
+                        for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
                     }
-                }
+                    if (EPI == EPI_TAPE || EPI == EPI_POOL_TAPE) {
+                        if (!valid) {
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    uint4 hi, lo;
-                    split8(y + qd * 8, hi, lo);
-                    const int kch = (n0 + c0) / 8 + qd;
-                    if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
-                        uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off;
-                        *reinterpret_cast<uint4*>(dst) = hi;
-                        *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
-                        if (EPI == EPI_TAPE && zero_prev) {
-                            *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
-                            *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
+                            for (int i = 0; i < 32; ++i) y[i] = 0.f;              // guard rows stay zero
                         }
-                    } else {
-                        // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
-                        if (out_off != (size_t)-1) {
-                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off + ((lane & 1) ? p.out_part_stride : 0);
-                            *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
-                            if (EPI == EPI_POOL_TAPE && zero_prev) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 hi, lo;
+                        split8(y + qd * 8, hi, lo);
+                        const int kch = (n0 + c0) / 8 + qd;
+                        if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
+                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off;
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
+                            if (EPI == EPI_TAPE && zero_prev) {
+                                *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                                *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
+                            }
+                        } else {
+                            // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
+                            if (out_off != (size_t)-1) {
+                                uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off + ((lane & 1) ? p.out_part_stride : 0);
+                                *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
+                                if (EPI == EPI_POOL_TAPE && zero_prev) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                            }
                         }
                     }
                 }
@@ -299,7 +324,7 @@ tapgemm_kernel(const TapGemmParams p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -462,7 +487,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    DCE_KL(ctx, name, kern<<<grid, 192, Cfg::SMEM_BYTES, ctx.stream>>>(p));
+    DCE_KL(ctx, name, kern<<<grid, kThreads, Cfg::SMEM_BYTES, ctx.stream>>>(p));
     return DCE_OK;
 }
 
