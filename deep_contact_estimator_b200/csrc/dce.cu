@@ -8,12 +8,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <new>
 
 #include "../../include/dce.h"
 #include "dce_common.cuh"
 #include "dce_fp32.cuh"
 #include "dce_tc.cuh"
+#include "dce_tc_run.cuh"
 
 namespace {
 
@@ -300,6 +302,12 @@ int dce_forward_profile(const dce_weights* w, const float* x_dev, int64_t B,
     *n_out = n;
     if (rc == DCE_OK && se != cudaSuccess) return cuda_fail(se);
     return rc;
+}
+
+int dce_set_option(const char* key, int value) {
+    if (!key) return DCE_EINVAL;
+    if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
+    return DCE_EINVAL;
 }
 
 int dce_decimal2binary(const int64_t* cls_dev, int64_t n, uint8_t* bits_dev, void* stream) {

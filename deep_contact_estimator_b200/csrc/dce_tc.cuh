@@ -491,85 +491,5 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     return DCE_OK;
 }
 
-// bias offsets inside the fp32 section are passed in by dce.cu
-struct BiasPtrs { const float* b[7]; const float* w3; };
-
-inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
-               int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
-    cudaStream_t s = ctx.stream;
-    for (int64_t c0 = 0; c0 < n; c0 += kChunk) {
-        const int m = (int)((n - c0 < kChunk) ? n - c0 : kChunk);
-        const Workspace W = make_workspace(m);
-        uint8_t* x0 = reinterpret_cast<uint8_t*>(ws + W.o_x0);
-        uint8_t* x1 = reinterpret_cast<uint8_t*>(ws + W.o_x1);
-        uint8_t* x2 = reinterpret_cast<uint8_t*>(ws + W.o_x2);
-        uint8_t* x3 = reinterpret_cast<uint8_t*>(ws + W.o_x3);
-        uint8_t* x4 = reinterpret_cast<uint8_t*>(ws + W.o_x4);
-        uint8_t* h1 = reinterpret_cast<uint8_t*>(ws + W.o_h1);
-        float* h2 = reinterpret_cast<float*>(ws + W.o_h2);
-        float* mean = reinterpret_cast<float*>(ws + W.o_mean);
-        float* sdev = reinterpret_cast<float*>(ws + W.o_sdev);
-
-        // ---- ingest (a2/a3/a4): windows -> X0 tape
-        const int iblocks = W.x0.m_tiles * 4;
-        if (stream_mode) {
-            DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev));
-            DCE_KL(ctx, "tc_ingest_stream", ingest_kernel<true><<<iblocks, 256, 0, s>>>(
-                src, first + c0, m, mean, sdev, x0, W.x0.part_stride, W.x0.kch_stride));
-        } else {
-            DCE_KL(ctx, "tc_ingest", ingest_kernel<false><<<iblocks, 256, 0, s>>>(
-                src + (size_t)c0 * 150 * 54, 0, m, nullptr, nullptr, x0, W.x0.part_stride, W.x0.kch_stride));
-        }
-        int rc;
-        TapGemmParams p{};
-        // ---- conv1 (a5): X0 -> X1
-        p = TapGemmParams{};
-        p.a_tape = x0; p.a_part_stride = W.x0.part_stride; p.a_kch_stride = W.x0.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[0]); p.bias = bp.b[0];
-        p.m_tiles = W.x0.m_tiles; p.n_tiles = 1; p.stages = kLayers[0].stages;
-        p.out = x1; p.out_part_stride = W.x1.part_stride; p.out_kch_stride = W.x1.kch_stride; p.out_rows_cap = W.x1.m_tiles * 128;
-        p.N = 64; p.rw = kRW1; p.tv = 150;
-        if ((rc = launch_layer<64, 3, 4, 4, EPI_TAPE>(ctx, "tc_conv1", sm_count, p)) != DCE_OK) return rc;
-        // ---- conv2 + pool (a6): X1 -> X2
-        p.a_tape = x1; p.a_part_stride = W.x1.part_stride; p.a_kch_stride = W.x1.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[1]); p.bias = bp.b[1];
-        p.m_tiles = W.x1.m_tiles; p.stages = kLayers[1].stages;
-        p.out = x2; p.out_part_stride = W.x2.part_stride; p.out_kch_stride = W.x2.kch_stride; p.out_rows_cap = W.x2.m_tiles * 128;
-        if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
-        // ---- conv3 (a7): X2 -> X3
-        p.a_tape = x2; p.a_part_stride = W.x2.part_stride; p.a_kch_stride = W.x2.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[2]); p.bias = bp.b[2];
-        p.m_tiles = W.x2.m_tiles; p.stages = kLayers[2].stages;
-        p.out = x3; p.out_part_stride = W.x3.part_stride; p.out_kch_stride = W.x3.kch_stride; p.out_rows_cap = W.x3.m_tiles * 128;
-        p.N = 128; p.rw = kRW2; p.tv = 75;
-        if ((rc = launch_layer<128, 3, 2, 6, EPI_TAPE>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
-        // ---- conv4 + pool + flatten (a8, a9): X3 -> X4 (fc.0 operand layout, k' = t*128 + c)
-        p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
-        p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
-        p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
-        if ((rc = launch_layer<128, 3, 2, 6, EPI_POOL_FC>(ctx, "tc_conv4_pool", sm_count, p)) != DCE_OK) return rc;
-        // ---- fc.0 + ReLU (a10): X4 -> H1
-        p = TapGemmParams{};
-        p.a_tape = x4; p.a_part_stride = W.x4.part_stride; p.a_kch_stride = W.x4.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[4]); p.bias = bp.b[4];
-        p.m_tiles = W.x4.m_tiles; p.n_tiles = kLayers[4].n_tiles; p.stages = kLayers[4].stages;
-        p.out = h1; p.out_part_stride = W.h1.part_stride; p.out_kch_stride = W.h1.kch_stride; p.out_rows_cap = W.h1.m_tiles * 128;
-        p.N = 2048; p.rw = 1; p.tv = 1;
-        if ((rc = launch_layer<256, 1, 4, 4, EPI_FC_TAPE>(ctx, "tc_fc1", sm_count, p)) != DCE_OK) return rc;
-        // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
-        p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;
-        p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[5]); p.bias = bp.b[5];
-        p.m_tiles = W.h1.m_tiles; p.n_tiles = kLayers[5].n_tiles; p.stages = kLayers[5].stages;
-        p.out = nullptr; p.out_f32 = h2; p.N = 512; p.n_valid = m;
-        if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
-        // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
-        const int g3 = (int)((m + 7) / 8 < sm_count * 4 ? (m + 7) / 8 : sm_count * 4);
-        DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<g3, 256, 0, s>>>(
-            h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
-    }
-    return DCE_OK;
-}
-
 }  // namespace tc
 }  // namespace dce

@@ -1,0 +1,322 @@
+// Fused block1: window ingest (+ optional z-score) -> Conv1d 54->64 + ReLU -> Conv1d 64->64 + ReLU
+// -> MaxPool1d(2,2), one persistent kernel; activations between the two convolutions never
+// leave the SM.   /root/reference/src/contact_cnn.py:10-26, utils/data_handler.py:55-56
+//
+// Tiling ("recompute nothing, shrink the valid range"): a tile produces 124 rows of conv2
+// output.  With b = 124*i:
+//      slab0 row s  <->  X0 row b-3+s   (s = 0..129)   fp32 input -> bf16 hi/lo, written by converter warps
+//      conv1 MMA row k  <->  X1 row b-2+k  (k = 0..127), reads slab0 rows k..k+2; result -> slab1 row k+1
+//      conv2 MMA row j  <->  out row b-2+j (j = 0..127), reads slab1 rows j..j+2; rows j in [2,126) are exact
+// so each tile is two 128-row UMMA passes for 124 useful rows (96.9 %), pool pairs (j, j+1) with j
+// even sit in adjacent lanes, and both conv weight images (2 x 48 KB bf16 hi/lo) stay resident in
+// shared memory for the life of the CTA.
+//
+// Warp roles (13 warps, 1 CTA/SM):
+//   warps 0-3  : converters   global fp32 rows -> (z-score) -> bf16 hi/lo -> slab0[buf] (UMMA K-major layout)
+//   warps 4-11 : epilogue     epi1: TMEM D1 -> bias/ReLU/guard -> bf16 hi/lo -> slab1 (smem, feeds conv2)
+//                             epi2: TMEM D2 -> bias/ReLU/pool/guard -> bf16 hi/lo -> X2 tape (global)
+//   warp 12    : MMA issuer   weights via bulk TMA once; conv1(k+1) is issued before conv2(k) so the
+//                             tensor pipe works on the next tile's conv1 while epi1(k) fills slab1
+#pragma once
+#include "dce_tc.cuh"
+
+namespace dce {
+namespace tc {
+
+constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
+constexpr int kB1Threads = 13 * 32;
+constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
+constexpr int kB1WBytes = 49152;                   // one conv weight image: [stage 2][part 2][tap 3][j 4][64][8] bf16
+constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 128 + 2 * 64 * 4;
+
+struct Block1Params {
+    const float* x;              // batch: [W][150][54]; stream: [T][54]
+    int64_t first;               // stream: first window row
+    int n_windows;
+    const float* mean;           // stream: [W][64]
+    const float* sdev;
+    const uint8_t* w1; const uint8_t* w2;     // packed images (tc::pack layout, layers 0 and 1)
+    const float* b1; const float* b2;
+    uint8_t* out;                // X2 tape (part 0)
+    size_t out_part_stride, out_kch_stride;
+    int out_rows_cap;
+    int n_tiles;
+};
+
+__device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kB1Threads, 1)
+block1_kernel(const Block1Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w1s = smem;
+    uint8_t* w2s = smem + kB1WBytes;
+    uint8_t* slab0 = smem + 2 * kB1WBytes;                  // two buffers
+    uint8_t* slab1 = slab0 + 2 * kB1SlabBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + kB1SlabBytes);
+    uint64_t* x0_full = bars;        // [2] 128 converter threads arrive
+    uint64_t* x0_empty = bars + 2;   // [2] tcgen05.commit
+    uint64_t* d1_full = bars + 4;    // [2] commit
+    uint64_t* d1_empty = bars + 6;   // [2] 8 epilogue warps arrive
+    uint64_t* d2_full = bars + 8;    // [2] commit
+    uint64_t* d2_empty = bars + 10;  // [2] 8 epilogue warps arrive
+    uint64_t* x1_full = bars + 12;   // 256 epilogue threads arrive
+    uint64_t* x1_empty = bars + 13;  // commit
+    uint64_t* wbar = bars + 14;      // weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // b1[64], b2[64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NR = p.n_windows * kRW1;
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&x0_full[i], 128); ptx::mbar_init(&x0_empty[i], 1);
+            ptx::mbar_init(&d1_full[i], 1);   ptx::mbar_init(&d1_empty[i], 8);
+            ptx::mbar_init(&d2_full[i], 1);   ptx::mbar_init(&d2_empty[i], 8);
+        }
+        ptx::mbar_init(x1_full, 256); ptx::mbar_init(x1_empty, 1); ptx::mbar_init(wbar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 12) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    // zero the activation slabs once: kchunk 7 of slab0 (channels 56..63 do not exist) and the
+    // never-written halo rows of slab1 must not hold NaN bit patterns
+    for (int i = threadIdx.x; i < 3 * kB1SlabBytes / 16; i += kB1Threads)
+        reinterpret_cast<uint4*>(slab0)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 128) s_bias[threadIdx.x] = __ldg((threadIdx.x < 64 ? p.b1 : p.b2 - 64) + threadIdx.x);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== converters: fp32 rows -> slab0[buf] =====
+        // Thread t owns slab row s = t: one contiguous 216-byte input row, fetched with 27
+        // independent 8-byte loads issued back to back (one memory latency per tile, and it
+        // overlaps the wait for the slab to drain).  Rows 128/129 are split over threads 0..13.
+        const int tid = threadIdx.x;
+        auto row_src = [&](int r, int& w) -> const float* {        // nullptr: guard / out-of-range row -> zeros
+            if (r < 0 || r >= NR) return nullptr;
+            w = r / kRW1;
+            const int t = r - w * kRW1;
+            if (t >= 150) return nullptr;
+            return STREAM ? p.x + (size_t)(p.first + w + t) * 54 : p.x + ((size_t)w * 150 + t) * 54;
+        };
+        for (int k = 0; k < my_tiles; ++k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            const int b = tile * kB1Rows;
+            const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+            // ---- issue every load of this tile first
+            float2 f[27];
+            int w0 = 0;
+            const float* src0 = row_src(b - 3 + tid, w0);
+#pragma unroll
+            for (int i = 0; i < 27; ++i) f[i] = src0 ? __ldg(reinterpret_cast<const float2*>(src0) + i) : make_float2(0.f, 0.f);
+            float2 g[4];
+            int w1 = 0;
+            const int s1 = 128 + tid / 7, kch1 = tid % 7;
+            const float* src1 = (tid < 14) ? row_src(b - 3 + s1, w1) : nullptr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                g[i] = (src1 && (kch1 < 6 || i < 3)) ? __ldg(reinterpret_cast<const float2*>(src1 + kch1 * 8) + i) : make_float2(0.f, 0.f);
+            if (STREAM) {
+                if (src0) {
+                    const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w0 * 64);
+                    const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w0 * 64);
+#pragma unroll
+                    for (int i = 0; i < 27; ++i) {                 // utils/data_handler.py:55-56
+                        const float2 m2 = __ldg(mu + i), s2 = __ldg(sd + i);
+                        f[i].x = (f[i].x - m2.x) / s2.x; f[i].y = (f[i].y - m2.y) / s2.y;
+                    }
+                }
+                if (src1) {
+                    const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w1 * 64 + kch1 * 8);
+                    const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w1 * 64 + kch1 * 8);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (kch1 < 6 || i < 3) {
+                            const float2 m2 = __ldg(mu + i), s2 = __ldg(sd + i);
+                            g[i].x = (g[i].x - m2.x) / s2.x; g[i].y = (g[i].y - m2.y) / s2.y;
+                        }
+                    }
+                }
+            }
+            ptx::mbar_wait(&x0_empty[buf], ph ^ 1);
+            uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
+#pragma unroll
+            for (int kch = 0; kch < 7; ++kch) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool have = (kch < 6 || i < 3);              // channels 54, 55 do not exist
+                    y[2 * i] = have ? f[(kch * 4 + i) % 27].x : 0.f;
+                    y[2 * i + 1] = have ? f[(kch * 4 + i) % 27].y : 0.f;
+                }
+                uint4 hi, lo;
+                split8(y, hi, lo);
+                uint8_t* d = dst0 + kch * kSlabBytes + tid * 16;
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+            }
+            if (tid < 14) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { y[2 * i] = g[i].x; y[2 * i + 1] = g[i].y; }
+                uint4 hi, lo;
+                split8(y, hi, lo);
+                uint8_t* d = dst0 + kch1 * kSlabBytes + s1 * 16;
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+            }
+            ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
+            ptx::mbar_arrive(&x0_full[buf]);
+        }
+    } else if (warp == 12) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
+            ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
+            ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
+            ptx::mbar_wait(wbar, 0);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64);
+            const uint32_t w1a = ptx::smem_u32(w1s), w2a = ptx::smem_u32(w2s);
+            const uint32_t s0a = ptx::smem_u32(slab0), s1a = ptx::smem_u32(slab1);
+
+            // 36 MMAs: 3 taps x 4 kchunk pairs x (hi*lo, lo*hi, hi*hi)
+            auto conv_mmas = [&](uint32_t a_base, uint32_t w_base, uint32_t d) {
+#pragma unroll
+                for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t a_hi = a_base + (2 * kk) * kSlabBytes + tap * 16;
+                        const uint32_t b_hi = w_base + (kk >> 1) * 24576 + (tap * 4 + (2 * kk & 3)) * 1024;
+                        const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                        const uint64_t da_lo = ptx::make_smem_desc(a_hi + 8 * kSlabBytes, kSlabBytes, 128);
+                        const uint64_t db_hi = ptx::make_smem_desc(b_hi, 1024, 128);
+                        const uint64_t db_lo = ptx::make_smem_desc(b_hi + 12288, 1024, 128);
+                        ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, (tap | kk) ? 1u : 0u);
+                        ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                        ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                    }
+                }
+            };
+            auto issue_c1 = [&](int k) {
+                const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+                ptx::mbar_wait(&x0_full[buf], ph);
+                ptx::mbar_wait(&d1_empty[buf], ph ^ 1);
+                ptx::tc_fence_after_sync();
+                conv_mmas(s0a + buf * kB1SlabBytes, w1a, tmem_base + buf * 64);
+                ptx::umma_commit(&x0_empty[buf]);
+                ptx::umma_commit(&d1_full[buf]);
+            };
+            auto issue_c2 = [&](int k) {
+                const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+                ptx::mbar_wait(x1_full, k & 1);
+                ptx::mbar_wait(&d2_empty[buf], ph ^ 1);
+                ptx::tc_fence_after_sync();
+                conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64);
+                ptx::umma_commit(x1_empty);
+                ptx::umma_commit(&d2_full[buf]);
+            };
+            if (my_tiles > 0) issue_c1(0);
+            for (int k = 0; k < my_tiles; ++k) {
+                if (k + 1 < my_tiles) issue_c1(k + 1);
+                issue_c2(k);
+            }
+        }
+    } else {
+        // ===== epilogue warps 4..11 =====
+        const int q = warp & 3, h = (warp - 4) >> 2;          // TMEM lane quadrant, column half
+        const int rit = q * 32 + lane;                        // MMA row this thread owns
+        const float* bias1 = s_bias + h * 32;
+        const float* bias2 = s_bias + 64 + h * 32;
+
+        auto epi1 = [&](int k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+            const int r = tile * kB1Rows - 2 + rit;           // X1 row
+            const bool valid = r >= 0 && pos_mod(r, kRW1) < 150;
+            ptx::mbar_wait(&d1_full[buf], ph);
+            ptx::tc_fence_after_sync();
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);  // accumulator is in registers now
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias1 + i);
+                y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
+                y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
+                y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
+                y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
+            }
+            ptx::mbar_wait(x1_empty, (k & 1) ^ 1);            // conv2 of the previous tile has finished reading slab1
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                uint4 hi, lo;
+                split8(y + qd * 8, hi, lo);
+                uint8_t* d = slab1 + (h * 4 + qd) * kSlabBytes + (rit + 1) * 16;
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(x1_full);
+        };
+        auto epi2 = [&](int k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+            const int r = tile * kB1Rows - 2 + rit;           // conv2 output row (X1 row space)
+            const int orow = r >> 1;                          // pooled row (arithmetic shift: -2,-1 -> -1)
+            const bool valid = r >= 0 && (pos_mod(r, kRW1) >> 1) < 75;
+            const bool store = ((rit >= 2 && rit < 126) || (tile == 0 && rit < 2)) && orow < p.out_rows_cap;
+            ptx::mbar_wait(&d2_full[buf], ph);
+            ptx::tc_fence_after_sync();
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + 128 + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&d2_empty[buf]);
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias2 + i);
+                y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
+                y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
+                y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
+                y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
+                y[i] = valid ? m : 0.f;
+            }
+            if (store) {
+                uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 hi, lo;
+                    split8(y + qd * 8, hi, lo);
+                    *reinterpret_cast<uint4*>(base + (size_t)(h * 4 + qd) * p.out_kch_stride) = (lane & 1) ? lo : hi;
+                }
+            }
+        };
+        for (int k = 0; k < my_tiles; ++k) {
+            epi1(k);
+            if (k > 0) epi2(k - 1);
+        }
+        if (my_tiles > 0) epi2(my_tiles - 1);
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 12) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace tc
+}  // namespace dce

@@ -148,6 +148,14 @@ DCE_API int dce_decimal2binary(const int64_t *cls_dev, int64_t n, uint8_t *bits_
 DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_dev, int64_t n,
                         int64_t *counts_dev, void *stream);
 
+/*
+ * Ablation / debugging switches (process-wide).  Keys:
+ *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
+ *                  0: one kernel per layer (activations round-trip through HBM).
+ * Returns DCE_EINVAL for an unknown key.
+ */
+DCE_API int dce_set_option(const char *key, int value);
+
 /* How many kernel launches the last dce_forward / dce_stream on this thread enqueued. */
 DCE_API int dce_last_launch_count(void);
 

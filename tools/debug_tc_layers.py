@@ -52,10 +52,12 @@ def report(name, got, want):
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    layerwise = "--layerwise" in sys.argv
     dev = torch.device("cuda", 0)
     params = synth.make_params(0)
     x = synth.make_windows(B, seed=1)
     eng = dce.ContactEngine(params, dev, "bf16x3")
+    eng.lib.dce_set_option(b"fuse_block1", 0 if layerwise else 1)
     logits, cls, bits = eng.classify(x.to(dev))
     torch.cuda.synchronize()
     ws = eng._workspace
@@ -77,10 +79,11 @@ def main():
         print(f"{name}: guard rows max |v| = {guard:.3e}")
         return report(name, got[:, :tv, :ch], act.permute(0, 2, 1))
 
-    x0 = decode(ws, W["x0"]).reshape(B, 152, 64)
-    report("x0", x0[:, :150, :54], x)
-    print("x0 pad channels / guard rows:", x0[:, :, 54:].abs().max().item(), x0[:, 150:, :].abs().max().item())
-    conv_tape("x1", a1, 152, 150, 64)
+    if layerwise:
+        x0 = decode(ws, W["x0"]).reshape(B, 152, 64)
+        report("x0", x0[:, :150, :54], x)
+        print("x0 pad channels / guard rows:", x0[:, :, 54:].abs().max().item(), x0[:, 150:, :].abs().max().item())
+        conv_tape("x1", a1, 152, 150, 64)
     conv_tape("x2", a2, 76, 75, 64)
     conv_tape("x3", a3, 76, 75, 128)
     x4 = decode(ws, W["x4"])                                  # [B][592*8], k' = t*128 + c
