@@ -307,6 +307,7 @@ int dce_forward_profile(const dce_weights* w, const float* x_dev, int64_t B,
 int dce_set_option(const char* key, int value) {
     if (!key) return DCE_EINVAL;
     if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
     return DCE_EINVAL;
 }
 

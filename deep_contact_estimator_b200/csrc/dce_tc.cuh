@@ -150,8 +150,8 @@ tapgemm_kernel(const TapGemmParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == kProducerWarp) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (warp-uniform loop; one elected lane issues) =====
+        {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m = tile / p.n_tiles, n = tile % p.n_tiles;
@@ -161,21 +161,24 @@ tapgemm_kernel(const TapGemmParams p) {
                     const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
                     ptx::mbar_wait(&empty[slot], ph ^ 1);
                     uint8_t* st = smem + slot * Cfg::STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int part = 0; part < 2; ++part)
+                        for (int part = 0; part < 2; ++part)
 #pragma unroll
-                        for (int j = 0; j < KSA; ++j)
-                            ptx::bulk_g2s(st + part * Cfg::A_PART + j * kSlabBytes,
-                                          a_row + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
-                                          kSlabBytes, &full[slot]);
-                    ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
+                            for (int j = 0; j < KSA; ++j)
+                                ptx::bulk_g2s(st + part * Cfg::A_PART + j * kSlabBytes,
+                                              a_row + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                              kSlabBytes, &full[slot]);
+                        ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (warp-uniform loop; one elected lane issues) =====
+        {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -189,26 +192,29 @@ tapgemm_kernel(const TapGemmParams p) {
                     ptx::tc_fence_after_sync();
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES);
                     const uint32_t b0 = a0 + Cfg::A_BYTES;
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
 #pragma unroll
-                        for (int kk = 0; kk < KSA / 2; ++kk) {
-                            const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
-                            const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
-                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
-                            const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
-                            const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
-                            const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                            ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
-                            ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
-                            ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                            for (int kk = 0; kk < KSA / 2; ++kk) {
+                                const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
+                                const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
+                                const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                                const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                                const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
+                                const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
+                                const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                                ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
+                                ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                                ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                            }
                         }
+                        ptx::umma_commit(&empty[slot]);          // frees the smem slot when these MMAs retire
+                        if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // accumulator complete
                     }
-                    ptx::umma_commit(&empty[slot]);          // frees the smem slot when these MMAs retire
+                    __syncwarp();
                 }
-                ptx::umma_commit(&tfull[buf]);               // accumulator complete
             }
         }
     } else {

@@ -41,6 +41,7 @@ struct Block1Params {
     size_t out_part_stride, out_kch_stride;
     int out_rows_cap;
     int n_tiles;
+    int dbg;                     // timing ablations only (results invalid when non-zero)
 };
 
 __device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -93,36 +94,65 @@ block1_kernel(const Block1Params p) {
 
     if (warp < 4) {
         // ===== converters: fp32 rows -> slab0[buf] =====
-        // Thread t owns slab row s = t: one contiguous 216-byte input row, fetched with 27
-        // independent 8-byte loads issued back to back (one memory latency per tile, and it
-        // overlaps the wait for the slab to drain).  Rows 128/129 are split over threads 0..13.
+        // Raw rows are staged with coalesced 8-byte cp.async (LDGSTS; rows are only 8-byte aligned:
+        // 54 floats = 216 B) INTO the slab buffer itself, one tile ahead of the conversion; then
+        // thread t reads row t back (27 x 8 B), the converter warps synchronise on a named barrier,
+        // and the bf16 hi/lo image is written in place in the UMMA K-major layout.
         const int tid = threadIdx.x;
-        auto row_src = [&](int r, int& w) -> const float* {        // nullptr: guard / out-of-range row -> zeros
-            if (r < 0 || r >= NR) return nullptr;
-            w = r / kRW1;
-            const int t = r - w * kRW1;
-            if (t >= 150) return nullptr;
-            return STREAM ? p.x + (size_t)(p.first + w + t) * 54 : p.x + ((size_t)w * 150 + t) * 54;
+        auto issue_raw = [&](int k) {
+            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
+            const uint32_t stage = ptx::smem_u32(slab0 + (k & 1) * kB1SlabBytes);
+            const int wf = (r0 >= 0) ? r0 / kRW1 : -1;
+#pragma unroll
+            for (int wi = wf; wi <= wf + 1; ++wi) {
+                int lo = r0 > wi * kRW1 ? r0 : wi * kRW1;
+                int hi = (r0 + kSlabRows) < (wi * kRW1 + 150) ? (r0 + kSlabRows) : (wi * kRW1 + 150);
+                if (wi < 0 || wi >= p.n_windows || hi <= lo) continue;
+                const int t0 = lo - wi * kRW1;
+                const char* src = reinterpret_cast<const char*>(
+                    STREAM ? p.x + (size_t)(p.first + wi + t0) * 54 : p.x + ((size_t)wi * 150 + t0) * 54);
+                const int units = (hi - lo) * 27;
+                const uint32_t dst = stage + (lo - r0) * 216;
+                for (int u = tid; u < units; u += 128)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * u), "l"(src + 8 * u) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        auto row_window = [&](int r, int& w) -> bool {           // false: guard / out-of-range row -> zeros
+            if (r < 0 || r >= NR) return false;
+            w = r / kRW1;
+            return r - w * kRW1 < 150;
+        };
+        if (my_tiles > 0) issue_raw(0);
         for (int k = 0; k < my_tiles; ++k) {
-            const int tile = blockIdx.x + k * gridDim.x;
-            const int b = tile * kB1Rows;
-            const uint32_t buf = k & 1, ph = (k >> 1) & 1;
-            // ---- issue every load of this tile first
+            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
+            const uint32_t buf = k & 1;
+            if (k + 1 < my_tiles) {
+                ptx::mbar_wait(&x0_empty[(k + 1) & 1], (((k + 1) >> 1) & 1) ^ 1);    // conv1(k-1) has drained that buffer
+                issue_raw(k + 1);
+            } else {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            if (p.dbg & 4) { asm volatile("cp.async.wait_group 0;" ::: "memory"); ptx::mbar_arrive(&x0_full[buf]); continue; }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");                   // this thread's copies of tile k landed
+            asm volatile("bar.sync 1, 128;" ::: "memory");                           // ... and everybody else's
+            uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
             float2 f[27];
             int w0 = 0;
-            const float* src0 = row_src(b - 3 + tid, w0);
+            const bool v0 = row_window(r0 + tid, w0);
 #pragma unroll
-            for (int i = 0; i < 27; ++i) f[i] = src0 ? __ldg(reinterpret_cast<const float2*>(src0) + i) : make_float2(0.f, 0.f);
+            for (int i = 0; i < 27; ++i)
+                f[i] = v0 ? *reinterpret_cast<const float2*>(dst0 + tid * 216 + 8 * i) : make_float2(0.f, 0.f);
             float2 g[4];
             int w1 = 0;
             const int s1 = 128 + tid / 7, kch1 = tid % 7;
-            const float* src1 = (tid < 14) ? row_src(b - 3 + s1, w1) : nullptr;
+            const bool v1 = (tid < 14) && row_window(r0 + s1, w1);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                g[i] = (src1 && (kch1 < 6 || i < 3)) ? __ldg(reinterpret_cast<const float2*>(src1 + kch1 * 8) + i) : make_float2(0.f, 0.f);
+                g[i] = (v1 && (kch1 < 6 || i < 3)) ? *reinterpret_cast<const float2*>(dst0 + s1 * 216 + kch1 * 32 + 8 * i)
+                                                   : make_float2(0.f, 0.f);
             if (STREAM) {
-                if (src0) {
+                if (v0) {
                     const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w0 * 64);
                     const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w0 * 64);
 #pragma unroll
@@ -131,7 +161,7 @@ block1_kernel(const Block1Params p) {
                         f[i].x = (f[i].x - m2.x) / s2.x; f[i].y = (f[i].y - m2.y) / s2.y;
                     }
                 }
-                if (src1) {
+                if (v1) {
                     const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w1 * 64 + kch1 * 8);
                     const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w1 * 64 + kch1 * 8);
 #pragma unroll
@@ -143,8 +173,7 @@ block1_kernel(const Block1Params p) {
                     }
                 }
             }
-            ptx::mbar_wait(&x0_empty[buf], ph ^ 1);
-            uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
+            asm volatile("bar.sync 1, 128;" ::: "memory");                           // all raw reads done: overwrite in place
 #pragma unroll
             for (int kch = 0; kch < 7; ++kch) {
                 float y[8];
@@ -160,6 +189,8 @@ block1_kernel(const Block1Params p) {
                 *reinterpret_cast<uint4*>(d) = hi;
                 *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
             }
+            // channels 56..63 do not exist: the hi image of kchunk 7 was clobbered by the raw rows
+            *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + tid * 16) = make_uint4(0, 0, 0, 0);
             if (tid < 14) {
                 float y[8];
 #pragma unroll
@@ -170,55 +201,60 @@ block1_kernel(const Block1Params p) {
                 *reinterpret_cast<uint4*>(d) = hi;
                 *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
             }
+            if (tid < 2) *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + (128 + tid) * 16) = make_uint4(0, 0, 0, 0);
             ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
             ptx::mbar_arrive(&x0_full[buf]);
         }
     } else if (warp == 12) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
-            ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
-            ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
+        // ===== MMA issuer (warp-uniform control flow; one elected lane issues) =====
+        {
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
+                ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
+                ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
+            }
+            __syncwarp();
             ptx::mbar_wait(wbar, 0);
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64);
             const uint32_t w1a = ptx::smem_u32(w1s), w2a = ptx::smem_u32(w2s);
             const uint32_t s0a = ptx::smem_u32(slab0), s1a = ptx::smem_u32(slab1);
 
-            // 36 MMAs: 3 taps x 4 kchunk pairs x (hi*lo, lo*hi, hi*hi)
-            auto conv_mmas = [&](uint32_t a_base, uint32_t w_base, uint32_t d) {
+            // 36 MMAs: 3 taps x 4 kchunk pairs x (hi*lo, lo*hi, hi*hi); then the two completion commits
+            auto conv_mmas = [&](uint32_t a_base, uint32_t w_base, uint32_t d, uint64_t* bar_a, uint64_t* bar_b) {
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int tap = 0; tap < 3; ++tap) {
+                    for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a_hi = a_base + (2 * kk) * kSlabBytes + tap * 16;
-                        const uint32_t b_hi = w_base + (kk >> 1) * 24576 + (tap * 4 + (2 * kk & 3)) * 1024;
-                        const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                        const uint64_t da_lo = ptx::make_smem_desc(a_hi + 8 * kSlabBytes, kSlabBytes, 128);
-                        const uint64_t db_hi = ptx::make_smem_desc(b_hi, 1024, 128);
-                        const uint64_t db_lo = ptx::make_smem_desc(b_hi + 12288, 1024, 128);
-                        ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, (tap | kk) ? 1u : 0u);
-                        ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
-                        ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t a_hi = a_base + (2 * kk) * kSlabBytes + tap * 16;
+                            const uint32_t b_hi = w_base + (kk >> 1) * 24576 + (tap * 4 + (2 * kk & 3)) * 1024;
+                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + 8 * kSlabBytes, kSlabBytes, 128);
+                            const uint64_t db_hi = ptx::make_smem_desc(b_hi, 1024, 128);
+                            const uint64_t db_lo = ptx::make_smem_desc(b_hi + 12288, 1024, 128);
+                            ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, (tap | kk) ? 1u : 0u);
+                            ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                            ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                        }
                     }
+                    ptx::umma_commit(bar_a);
+                    ptx::umma_commit(bar_b);
                 }
+                __syncwarp();
             };
             auto issue_c1 = [&](int k) {
                 const uint32_t buf = k & 1, ph = (k >> 1) & 1;
                 ptx::mbar_wait(&x0_full[buf], ph);
                 ptx::mbar_wait(&d1_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
-                conv_mmas(s0a + buf * kB1SlabBytes, w1a, tmem_base + buf * 64);
-                ptx::umma_commit(&x0_empty[buf]);
-                ptx::umma_commit(&d1_full[buf]);
+                conv_mmas(s0a + buf * kB1SlabBytes, w1a, tmem_base + buf * 64, &x0_empty[buf], &d1_full[buf]);
             };
             auto issue_c2 = [&](int k) {
                 const uint32_t buf = k & 1, ph = (k >> 1) & 1;
                 ptx::mbar_wait(x1_full, k & 1);
                 ptx::mbar_wait(&d2_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
-                conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64);
-                ptx::umma_commit(x1_empty);
-                ptx::umma_commit(&d2_full[buf]);
+                conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64, x1_empty, &d2_full[buf]);
             };
             if (my_tiles > 0) issue_c1(0);
             for (int k = 0; k < my_tiles; ++k) {
@@ -256,6 +292,7 @@ block1_kernel(const Block1Params p) {
                 y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
             }
             ptx::mbar_wait(x1_empty, (k & 1) ^ 1);            // conv2 of the previous tile has finished reading slab1
+            if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
                 uint4 hi, lo;
@@ -282,6 +319,7 @@ block1_kernel(const Block1Params p) {
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&d2_empty[buf]);
+            if (p.dbg & 8) return;
             float y[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -296,7 +334,7 @@ block1_kernel(const Block1Params p) {
                 const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
                 y[i] = valid ? m : 0.f;
             }
-            if (store) {
+            if (store && !(p.dbg & 1)) {
                 uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {

@@ -8,6 +8,7 @@ namespace tc {
 
 // debug/ablation switch: 0 = one kernel per layer (ingest, conv1, conv2 as separate launches)
 inline int& fuse_block1_flag() { static int v = 1; return v; }
+inline int& block1_dbg_flag() { static int v = 0; return v; }
 
 // bias offsets inside the fp32 section are passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; };
@@ -48,6 +49,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
+            b.dbg = block1_dbg_flag();
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
             if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", block1_kernel<true><<<grid, kB1Threads, kB1SmemBytes, s>>>(b));
