@@ -251,7 +251,7 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
         const Fp32Layout& L = w->f32;
         dce::tc::BiasPtrs bp;
         for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
-        bp.w3 = at<float>(w, L.f3);
+        bp.w3 = at<float>(w, L.f3); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
         rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
     }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
@@ -282,26 +282,41 @@ int dce_stream(const dce_weights* w, const float* data_dev, int64_t T,
     return rc;
 }
 
+static int profile_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, int64_t first, int64_t n,
+                       float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev, void* workspace_dev, size_t workspace_bytes,
+                       int precision, void* stream, int max_kernels, float* ms_out, const char** names_out, int* n_out) {
+    if (!ms_out || !names_out || !n_out || max_kernels <= 0) return DCE_EINVAL;
+    dce::Profiler prof;
+    Ctx ctx; ctx.stream = (cudaStream_t)stream; ctx.prof = &prof;
+    int rc = run_any(w, src, is_stream, T, first, n, logits_dev, cls_dev, bits_dev, workspace_dev, workspace_bytes, precision, ctx);
+    g_launches = ctx.launches;
+    cudaError_t se = cudaStreamSynchronize(ctx.stream);
+    int cnt = 0;
+    for (int i = 0; i < prof.n; ++i) {
+        float ms = 0.f;
+        if (se == cudaSuccess) cudaEventElapsedTime(&ms, prof.start[i], prof.stop[i]);
+        if (cnt < max_kernels) { ms_out[cnt] = ms; names_out[cnt] = prof.names[i]; ++cnt; }
+        cudaEventDestroy(prof.start[i]); cudaEventDestroy(prof.stop[i]);
+    }
+    *n_out = cnt;
+    if (rc == DCE_OK && se != cudaSuccess) return cuda_fail(se);
+    return rc;
+}
+
 int dce_forward_profile(const dce_weights* w, const float* x_dev, int64_t B,
                         float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev,
                         void* workspace_dev, size_t workspace_bytes, int precision, void* stream,
                         int max_kernels, float* ms_out, const char** names_out, int* n_out) {
-    if (!ms_out || !names_out || !n_out || max_kernels <= 0) return DCE_EINVAL;
-    dce::Profiler prof;
-    Ctx ctx; ctx.stream = (cudaStream_t)stream; ctx.prof = &prof;
-    int rc = run_any(w, x_dev, false, 0, 0, B, logits_dev, cls_dev, bits_dev, workspace_dev, workspace_bytes, precision, ctx);
-    g_launches = ctx.launches;
-    cudaError_t se = cudaStreamSynchronize(ctx.stream);
-    int n = 0;
-    for (int i = 0; i < prof.n; ++i) {
-        float ms = 0.f;
-        if (se == cudaSuccess) cudaEventElapsedTime(&ms, prof.start[i], prof.stop[i]);
-        if (n < max_kernels) { ms_out[n] = ms; names_out[n] = prof.names[i]; ++n; }
-        cudaEventDestroy(prof.start[i]); cudaEventDestroy(prof.stop[i]);
-    }
-    *n_out = n;
-    if (rc == DCE_OK && se != cudaSuccess) return cuda_fail(se);
-    return rc;
+    return profile_any(w, x_dev, false, 0, 0, B, logits_dev, cls_dev, bits_dev, workspace_dev, workspace_bytes, precision,
+                       stream, max_kernels, ms_out, names_out, n_out);
+}
+
+int dce_stream_profile(const dce_weights* w, const float* data_dev, int64_t T, int64_t first_window, int64_t n_windows,
+                       float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev,
+                       void* workspace_dev, size_t workspace_bytes, int precision, void* stream,
+                       int max_kernels, float* ms_out, const char** names_out, int* n_out) {
+    return profile_any(w, data_dev, true, T, first_window, n_windows, logits_dev, cls_dev, bits_dev, workspace_dev,
+                       workspace_bytes, precision, stream, max_kernels, ms_out, names_out, n_out);
 }
 
 int dce_set_option(const char* key, int value) {

@@ -412,7 +412,8 @@ ingest_kernel(const float* __restrict__ x, int64_t first, int n_windows, const f
 
 // per-window, per-channel mean and unbiased std, two-pass in fp32 (utils/data_handler.py:55-56)
 __global__ void __launch_bounds__(256)
-window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, float* __restrict__ mean, float* __restrict__ sdev) {
+window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, float* __restrict__ mean, float* __restrict__ sdev,
+                    int reciprocal) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = idx / 64, c = idx % 64;
     if (w >= n_windows || c >= 54) return;
@@ -423,7 +424,8 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, f
     float v = 0.f;
     for (int t = 0; t < 150; ++t) { const float d = __ldg(src + (size_t)t * 54) - mu; v = fmaf(d, d, v); }
     mean[(size_t)w * 64 + c] = mu;
-    sdev[(size_t)w * 64 + c] = sqrtf(v / 149.f);
+    const float sd = sqrtf(v / 149.f);
+    sdev[(size_t)w * 64 + c] = reciprocal ? 1.f / sd : sd;     // std == 0 -> inf -> (x - mean) * inf = NaN, as 0/0 in the reference
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,14 +27,14 @@ constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
 constexpr int kB1Threads = 13 * 32;
 constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
 constexpr int kB1WBytes = 49152;                   // one conv weight image: [stage 2][part 2][tap 3][j 4][64][8] bf16
-constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 128 + 2 * 64 * 4;
+constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 128 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
 
 struct Block1Params {
     const float* x;              // batch: [W][150][54]; stream: [T][54]
     int64_t first;               // stream: first window row
     int n_windows;
     const float* mean;           // stream: [W][64]
-    const float* sdev;
+    const float* rstd;           // 1 / unbiased std
     const uint8_t* w1; const uint8_t* w2;     // packed images (tc::pack layout, layers 0 and 1)
     const float* b1; const float* b2;
     uint8_t* out;                // X2 tape (part 0)
@@ -66,6 +66,7 @@ block1_kernel(const Block1Params p) {
     uint64_t* wbar = bars + 14;      // weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // b1[64], b2[64]
+    float* s_nrm = s_bias + 128;     // stream mode: [2 windows][mean 64 | 1/std 64] of the tile being converted
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NR = p.n_windows * kRW1;
@@ -135,6 +136,13 @@ block1_kernel(const Block1Params p) {
             }
             if (p.dbg & 4) { asm volatile("cp.async.wait_group 0;" ::: "memory"); ptx::mbar_arrive(&x0_full[buf]); continue; }
             asm volatile("cp.async.wait_group 1;" ::: "memory");                   // this thread's copies of tile k landed
+            const int wbase = (r0 > 0 ? r0 : 0) / kRW1;                              // first window this tile touches
+            if (STREAM) {                                                            // its z-score constants -> smem
+                const int wi = wbase + (tid >> 6), c = tid & 63;
+                const bool in = wi < p.n_windows;
+                s_nrm[(tid >> 6) * 128 + c] = in ? __ldg(p.mean + (size_t)wi * 64 + c) : 0.f;
+                s_nrm[(tid >> 6) * 128 + 64 + c] = in ? __ldg(p.rstd + (size_t)wi * 64 + c) : 1.f;
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");                           // ... and everybody else's
             uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
             float2 f[27];
@@ -153,22 +161,22 @@ block1_kernel(const Block1Params p) {
                                                    : make_float2(0.f, 0.f);
             if (STREAM) {
                 if (v0) {
-                    const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w0 * 64);
-                    const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w0 * 64);
+                    const float2* mu = reinterpret_cast<const float2*>(s_nrm + (w0 - wbase) * 128);
+                    const float2* sd = mu + 32;
 #pragma unroll
-                    for (int i = 0; i < 27; ++i) {                 // utils/data_handler.py:55-56
-                        const float2 m2 = __ldg(mu + i), s2 = __ldg(sd + i);
-                        f[i].x = (f[i].x - m2.x) / s2.x; f[i].y = (f[i].y - m2.y) / s2.y;
+                    for (int i = 0; i < 27; ++i) {                 // utils/data_handler.py:55-56: (x - mean) / std, as (x - mean) * (1 / std)
+                        const float2 m2 = mu[i], s2 = sd[i];
+                        f[i].x = (f[i].x - m2.x) * s2.x; f[i].y = (f[i].y - m2.y) * s2.y;
                     }
                 }
                 if (v1) {
-                    const float2* mu = reinterpret_cast<const float2*>(p.mean + (size_t)w1 * 64 + kch1 * 8);
-                    const float2* sd = reinterpret_cast<const float2*>(p.sdev + (size_t)w1 * 64 + kch1 * 8);
+                    const float2* mu = reinterpret_cast<const float2*>(s_nrm + (w1 - wbase) * 128 + kch1 * 8);
+                    const float2* sd = mu + 32;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (kch1 < 6 || i < 3) {
-                            const float2 m2 = __ldg(mu + i), s2 = __ldg(sd + i);
-                            g[i].x = (g[i].x - m2.x) / s2.x; g[i].y = (g[i].y - m2.y) / s2.y;
+                            const float2 m2 = mu[i], s2 = sd[i];
+                            g[i].x = (g[i].x - m2.x) * s2.x; g[i].y = (g[i].y - m2.y) * s2.y;
                         }
                     }
                 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "dce_tc.cuh"
 #include "dce_tc_block1.cuh"
+#include "dce_small.cuh"
 
 namespace dce {
 namespace tc {
@@ -10,8 +11,8 @@ namespace tc {
 inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 
-// bias offsets inside the fp32 section are passed in by dce.cu
-struct BiasPtrs { const float* b[7]; const float* w3; };
+// pointers into the fp32 section of the packed buffer, passed in by dce.cu
+struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
 
 inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
                int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
@@ -32,7 +33,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         int rc;
         TapGemmParams p{};
         if (stream_mode)
-            DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev));
+            DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev, fuse_block1_flag() ? 1 : 0));
         if (fuse_block1_flag()) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static thread_local bool attr_done = false;
@@ -44,7 +45,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             }
             Block1Params b{};
             b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m;
-            b.mean = mean; b.sdev = sdev;
+            b.mean = mean; b.rstd = sdev;   // window_stats_kernel<true> writes 1/std
             b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[0]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[1]);
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
@@ -95,6 +96,24 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
         p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
         if ((rc = launch_layer<128, 3, 2, 6, EPI_POOL_FC>(ctx, "tc_conv4_pool", sm_count, p)) != DCE_OK) return rc;
+        if (m <= small::kMaxB) {
+            // ---- latency mode (K3): fc.0 / fc.3 as split-N fp32 GEMVs over the fp32 weight images
+            using namespace small;
+            float* h1f = reinterpret_cast<float*>(h1);            // [m][2048] fp32 (aliases the unused H1 tape)
+            static thread_local bool gemv_attr = false;
+            auto k1 = gemv_bias_relu_kernel<4736, 2048, 16, true>;
+            auto k2 = gemv_bias_relu_kernel<2048, 512, 8, false>;
+            if (!gemv_attr) {
+                cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxB * 4736 * 4);
+                if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+                gemv_attr = true;
+            }
+            DCE_KL(ctx, "fc1_gemv", k1<<<2048 / 16, 256, m * 4736 * 4, s>>>(x4, W.x4.part_stride, W.x4.kch_stride, m, bp.f1, bp.b[4], h1f));
+            DCE_KL(ctx, "fc2_gemv", k2<<<512 / 8, 256, m * 2048 * 4, s>>>(h1f, 0, 0, m, bp.f2, bp.b[5], h2));
+            DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<1, 256, 0, s>>>(
+                h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
+            continue;
+        }
         // ---- fc.0 + ReLU (a10): X4 -> H1
         p = TapGemmParams{};
         p.a_tape = x4; p.a_part_stride = W.x4.part_stride; p.a_kch_stride = W.x4.kch_stride;

@@ -163,6 +163,22 @@ class ContactEngine:
         _lib.check(rc, "dce_forward_profile")
         return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
 
+    def profile_stream(self, data: torch.Tensor, first_window: int, n_windows: int):
+        """Per-kernel CUDA-event durations of one ``dce_stream`` call (synchronises)."""
+        data = data.contiguous()
+        logits, cls, bits = self._outs(n_windows, False, True, True)
+        ws = self._ws(n_windows)
+        cap = 64
+        ms = (ctypes.c_float * cap)(); names = (ctypes.c_char_p * cap)(); cnt = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            rc = self.lib.dce_stream_profile(self._handle, self._p(data), data.shape[0], first_window, n_windows, None,
+                                             self._p(cls), self._p(bits), self._p(ws), ws.numel(),
+                                             _lib.PRECISIONS[self.precision], ctypes.c_void_p(stream.cuda_stream),
+                                             cap, ms, names, ctypes.byref(cnt))
+        _lib.check(rc, "dce_stream_profile")
+        return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
+
     # -- host-buffer entry point (what a user with numpy / pinned data calls) ----
     def classify_host(self, x_host: torch.Tensor, out_bits_host: Optional[torch.Tensor] = None,
                       out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024):

@@ -133,6 +133,12 @@ DCE_API int dce_forward_profile(const dce_weights *w, const float *x_dev, int64_
                         void *workspace_dev, size_t workspace_bytes, int precision, void *stream,
                         int max_kernels, float *ms_out, const char **names_out, int *n_out);
 
+DCE_API int dce_stream_profile(const dce_weights *w, const float *data_dev, int64_t T,
+                        int64_t first_window, int64_t n_windows,
+                        float *logits_dev, int32_t *cls_dev, uint8_t *bits_dev,
+                        void *workspace_dev, size_t workspace_bytes, int precision, void *stream,
+                        int max_kernels, float *ms_out, const char **names_out, int *n_out);
+
 /*
  * `decimal2binary(x)` alone (src/inference_one_seq.py:59-62, src/test.py:109-111):
  * cls_dev [n] int64 -> bits_dev [n][4] uint8 (used for ground-truth labels).

@@ -102,8 +102,13 @@ def test_full_size_batch_properties(dev, params0, precision):
     perm = torch.randperm(4096, generator=torch.Generator().manual_seed(3)).to(dev)
     logits_p, cls_p, _ = eng.classify(x[perm].contiguous())
     assert torch.equal(logits[perm], logits_p) and torch.equal(cls[perm], cls_p)
+    lo, cl, bi = eng.classify(x[1000:1040].contiguous())
+    assert torch.equal(lo, logits[1000:1040]) and torch.equal(cl, cls[1000:1040])
+    # batches of <= 4 windows take the latency path (fp32 GEMV fully-connected layers): same answer
+    # to rounding, identical classes
     lo, cl, bi = eng.classify(x[1000:1003].contiguous())
-    assert torch.equal(lo, logits[1000:1003]) and torch.equal(cl, cls[1000:1003])
+    assert oracle.normwise_rel_err(lo.cpu().numpy(), logits[1000:1003].cpu().numpy()) <= TOL[precision]
+    assert torch.equal(cl, cls[1000:1003])
     assert torch.equal(cls.long(), logits.argmax(1))
     assert torch.equal(bits, dce.decimal2binary(cls.long()))
     idx = torch.arange(0, 4096, 8)
@@ -136,10 +141,13 @@ def test_stream_ranges_and_alignment(dev, params0, precision):
     assert lg.shape == (n, 16)
     assert oracle.normwise_rel_err(lg.cpu().numpy(), want_logits.numpy()) <= TOL[precision] * 2
     assert np.array_equal(cl.cpu().numpy(), want_cls.numpy()) and np.array_equal(bi.cpu().numpy(), want_bits.numpy())
-    for first, cnt in ((0, 1), (1, 1), (3, 130), (n - 1, 1), (777, 0), (640, 257)):
+    for first, cnt in ((0, 1), (1, 1), (3, 130), (n - 1, 1), (777, 0), (640, 257), (10, 4), (11, 5)):
         lg2, cl2, bi2 = eng.stream(logd, first, cnt, want_logits=True)
-        assert torch.equal(lg2, lg[first:first + cnt]) and torch.equal(cl2, cl[first:first + cnt])
-        assert torch.equal(bi2, bi[first:first + cnt])
+        if 0 < cnt <= 4:      # latency path: fp32 GEMV fully-connected layers, equal to rounding
+            assert oracle.normwise_rel_err(lg2.cpu().numpy(), lg[first:first + cnt].cpu().numpy()) <= TOL[precision]
+        else:
+            assert torch.equal(lg2, lg[first:first + cnt])
+        assert torch.equal(cl2, cl[first:first + cnt]) and torch.equal(bi2, bi[first:first + cnt])
     with pytest.raises(ValueError):
         eng.stream(logd, n - 1, 2)
 

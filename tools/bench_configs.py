@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Secondary BASELINE.json configs (bench.py covers configs[1] and the scaling run):
+   --stream   configs[2]: inference over a 10M-step contiguous synthetic sensor log, 1 GPU
+   --latency  configs[4]: batch=1 latency, CUDA-graph replay, p50/p99 per-window microseconds
+Prints one JSON line per config.  Parity for both is asserted on a prefix against the oracle."""
+import argparse, json, os, sys, time
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import deep_contact_estimator_b200 as dce
+from deep_contact_estimator_b200 import synth
+from oracle import contact_oracle as oracle
+
+
+def stream(args, dev, eng):
+    T = args.steps_log
+    log = synth.make_sensor_log(T, seed=2)
+    logd = log.to(dev)
+    n = T - 149
+    eng.stream(logd, 0, min(n, 8192))                       # warm-up (workspace, attributes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, cls, bits = eng.stream(logd)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # parity on the first windows vs the oracle (reference inference() semantics)
+    k = 512
+    _, wc, wb = oracle.inference_stream(synth.make_params(0), log[: k + 149], batch_size=128)
+    ok = bool(np.array_equal(bits[:k].cpu().numpy(), wb.numpy()))
+    # end to end from a pinned host log: H2D of the whole log + kernels + D2H of the bits
+    pinned = log.pin_memory()
+    out = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    d = pinned.to(dev, non_blocking=True)
+    _, _, b2 = eng.stream(d)
+    out.copy_(b2, non_blocking=True); torch.cuda.synchronize()
+    e2e = time.perf_counter() - t0
+    print(json.dumps({"config": "stream", "steps": T, "windows": n, "ms": ms, "windows_per_s": n / ms * 1e3,
+                      "launches": eng.last_launches, "bits_match_oracle_prefix": ok,
+                      "e2e_s": e2e, "e2e_windows_per_s": n / e2e, "h2d_bytes": T * 216, "d2h_bytes": n * 4,
+                      "hbm_read_bytes_per_window_algorithmic": 216}))
+
+
+def latency(args, dev, eng):
+    x = synth.make_windows(1, seed=5).to(dev)
+    want = oracle.forward_torch(synth.make_params(0), x.cpu()).numpy()
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            eng.classify(x)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            logits, cls, bits = eng.classify(x)
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    err = oracle.normwise_rel_err(logits.cpu().numpy(), want)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.calls)]
+    host = []
+    xh = synth.make_windows(1, seed=5).pin_memory()
+    for a, b in ev:
+        t0 = time.perf_counter()
+        a.record()
+        x.copy_(xh, non_blocking=True)            # the new window arrives from the host (32.4 KB)
+        g.replay()
+        b.record()
+        b.synchronize()
+        _ = bits.cpu()                             # 4 contact bits back to the control loop
+        host.append((time.perf_counter() - t0) * 1e6)
+    dev_us = np.array([a.elapsed_time(b) * 1e3 for a, b in ev])
+    host = np.array(host)
+    print(json.dumps({"config": "latency", "batch": 1, "calls": args.calls, "precision": eng.precision,
+                      "gpu_us_p50": float(np.percentile(dev_us, 50)), "gpu_us_p99": float(np.percentile(dev_us, 99)),
+                      "host_us_p50": float(np.percentile(host, 50)), "host_us_p99": float(np.percentile(host, 99)),
+                      "launches_per_call": eng.last_launches, "normwise_err": err,
+                      "bits": bits.cpu().numpy().tolist()}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stream", action="store_true"); ap.add_argument("--latency", action="store_true")
+    ap.add_argument("--steps-log", type=int, default=10_000_000); ap.add_argument("--calls", type=int, default=1000)
+    ap.add_argument("--precision", default=None)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    eng = dce.ContactEngine(synth.make_params(0), dev, args.precision)
+    if args.stream or not args.latency:
+        stream(args, dev, eng)
+    if args.latency or not args.stream:
+        latency(args, dev, eng)
+
+
+if __name__ == "__main__":
+    main()
