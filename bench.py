@@ -299,9 +299,14 @@ def main():
         flops_per_launch = kernel_flops(dom) * B / n_launch
         achieved_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and B == 4096:
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom)
         roofline = {
             "bound": "tensor", "kernel": dom, "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved_tflops / peak, "traffic": None,
+            "frac": achieved_tflops / peak, "traffic": traffic,
             "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
             "note": "algorithmic FLOPs (bf16x3 split passes count once; ceiling of frac is 1/3 in bf16x3 mode)",
             "kernel_share_of_step": per_kernel_ms[dom] / step_kernel_ms,
