@@ -99,11 +99,10 @@ int run_fp32(const dce_weights* w, const float* x, bool normalize, int64_t first
     cudaStream_t s = ctx.stream;
     using namespace dce::fp32;
     const Fp32Layout& L = w->f32;
-    static thread_local bool attr_done[2] = {false, false};
-    if (!attr_done[0]) {
+    static dce::DeviceOnce attr_once;
+    if (attr_once.need()) {
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
-        attr_done[0] = true;
     }
     ConvParams cp{at<float>(w, L.w1), at<float>(w, L.b[0]), at<float>(w, L.w2), at<float>(w, L.b[1]),
                   at<float>(w, L.w3), at<float>(w, L.b[2]), at<float>(w, L.w4), at<float>(w, L.b[3])};

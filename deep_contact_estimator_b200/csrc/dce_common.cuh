@@ -39,6 +39,19 @@ struct Ctx {
     }
 };
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel's attributes were set on.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace dce

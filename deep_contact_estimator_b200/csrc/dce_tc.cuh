@@ -487,11 +487,10 @@ template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
     auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI>;
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
-        attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;

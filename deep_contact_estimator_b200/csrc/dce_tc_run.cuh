@@ -36,12 +36,11 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev, fuse_block1_flag() ? 1 : 0));
         if (fuse_block1_flag()) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
-            static thread_local bool attr_done = false;
-            if (!attr_done) {
+            static DeviceOnce attr_once;
+            if (attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
-                attr_done = true;
             }
             Block1Params b{};
             b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m;
@@ -100,13 +99,12 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             // ---- latency mode (K3): fc.0 / fc.3 as split-N fp32 GEMVs over the fp32 weight images
             using namespace small;
             float* h1f = reinterpret_cast<float*>(h1);            // [m][2048] fp32 (aliases the unused H1 tape)
-            static thread_local bool gemv_attr = false;
+            static DeviceOnce gemv_once;
             auto k1 = gemv_bias_relu_kernel<4736, 2048, 16, true>;
             auto k2 = gemv_bias_relu_kernel<2048, 512, 8, false>;
-            if (!gemv_attr) {
+            if (gemv_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxB * 4736 * 4);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
-                gemv_attr = true;
             }
             DCE_KL(ctx, "fc1_gemv", k1<<<2048 / 16, 256, m * 4736 * 4, s>>>(x4, W.x4.part_stride, W.x4.kch_stride, m, bp.f1, bp.b[4], h1f));
             DCE_KL(ctx, "fc2_gemv", k2<<<512 / 8, 256, m * 2048 * 4, s>>>(h1f, 0, 0, m, bp.f2, bp.b[5], h2));

@@ -104,6 +104,26 @@ def main():
     np.savez(os.path.join(out_dir, "bits_table.npz"), table=tbl.numpy())
     print("bits_table: ok")
 
+    # ---- LCM wire bytes from the reference's generated Python types (lcm_types/python) ----------
+    from lcm_types.python import contact_t, leg_control_data_lcmt, microstrain_lcmt   # (reference)
+    rng = np.random.RandomState(0)
+    c = contact_t(); c.num_legs = 4; c.timestamp = 12.5; c.contact = [1, 0, 0, 1]
+    leg = leg_control_data_lcmt()
+    vals = {k: rng.randn(12).astype(np.float32) for k in ("q", "qd", "p", "v", "tau_est")}
+    for k, v in vals.items():
+        setattr(leg, k, v.tolist())
+    imu = microstrain_lcmt()
+    iv = {"quat": rng.randn(4).astype(np.float32), "rpy": rng.randn(3).astype(np.float32),
+          "omega": rng.randn(3).astype(np.float32), "acc": rng.randn(3).astype(np.float32)}
+    for k, v in iv.items():
+        setattr(imu, k, v.tolist())
+    imu.good_packets, imu.bad_packets = 7, 2
+    np.savez(os.path.join(out_dir, "lcm_bytes.npz"),
+             contact=np.frombuffer(c.encode(), dtype=np.uint8), leg=np.frombuffer(leg.encode(), dtype=np.uint8),
+             imu=np.frombuffer(imu.encode(), dtype=np.uint8),
+             **{"leg_" + k: v for k, v in vals.items()}, **{"imu_" + k: v for k, v in iv.items()})
+    print("lcm_bytes: ok")
+
 
 if __name__ == "__main__":
     main()

@@ -269,3 +269,26 @@ def test_two_gpu_shards_equal_single(dev):
         r0, r1 = sharding.rows_for_windows(s, e)
         parts.append(eng.stream(log[r0:r1].to(d))[2].cpu())
     assert torch.equal(torch.cat(parts), single)
+
+
+def test_entrypoint_script_on_gpu(dev, tmp_path):
+    """scripts/inference_one_seq.main() end to end on the GPU: yaml config -> dataset on device ->
+    checkpoint -> one dce_stream call -> .mat and LCM log on disk."""
+    import yaml
+    from deep_contact_estimator_b200 import lcm_wire
+    from deep_contact_estimator_b200.scripts import inference_one_seq as ios
+    from tests.test_entrypoints_cpu import _make_files
+    log, lab = _make_files(tmp_path, steps=600)
+    cfg = {"data_path": str(tmp_path / "data.npy"), "label_path": str(tmp_path / "label.npy"),
+           "mat_data_path": str(tmp_path / "raw.mat"), "model_load_path": str(tmp_path / "model.pt"),
+           "window_size": 150, "batch_size": 1, "calculate_accuracy": False, "save_mat": False,
+           "save_lcm": True, "lcm_save_path": str(tmp_path / "out.lcm")}
+    with open(tmp_path / "cfg.yaml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    pred = ios.main(["--config_name", str(tmp_path / "cfg.yaml")])
+    assert pred.is_cuda
+    _, _, want = oracle.inference_stream(synth.make_params(0), log, batch_size=64)
+    assert np.array_equal(pred.cpu().numpy(), want.numpy())
+    events = list(lcm_wire.read_events(str(tmp_path / "out.lcm")))
+    assert len(events) == 3 * 451
+    assert lcm_wire.decode_contact(events[-2][3])[2] == want[-1].tolist()
