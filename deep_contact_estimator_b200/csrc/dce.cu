@@ -251,7 +251,7 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
         dce::tc::BiasPtrs bp;
         for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
         bp.w3 = at<float>(w, L.f3); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
-        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
+        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx);
     }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
     return rc;
@@ -322,7 +322,19 @@ int dce_set_option(const char* key, int value) {
     if (!key) return DCE_EINVAL;
     if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
     if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "block1_trace")) {          // value != 0: allocate (once) and arm a 60-tile x 16-event clock64 trace of CTA 0
+        long long*& t = dce::tc::block1_trace_ptr();
+        if (value && !t) { if (cudaMalloc(&t, 60 * 16 * 8) != cudaSuccess) return DCE_ECUDA; cudaMemset(t, 0, 60 * 16 * 8); }
+        if (!value && t) { cudaFree(t); t = nullptr; }
+        return DCE_OK;
+    }
     return DCE_EINVAL;
+}
+
+int dce_debug_read_trace(long long* host_out, int n) {
+    long long* t = dce::tc::block1_trace_ptr();
+    if (!t || !host_out || n <= 0 || n > 60 * 16) return DCE_EINVAL;
+    return cudaMemcpy(host_out, t, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? DCE_OK : DCE_ECUDA;
 }
 
 int dce_decimal2binary(const int64_t* cls_dev, int64_t n, uint8_t* bits_dev, void* stream) {

@@ -11,10 +11,11 @@
 // even sit in adjacent lanes, and both conv weight images (2 x 48 KB bf16 hi/lo) stay resident in
 // shared memory for the life of the CTA.
 //
-// Warp roles (13 warps, 1 CTA/SM):
-//   warps 0-3  : converters   global fp32 rows -> (z-score) -> bf16 hi/lo -> slab0[buf] (UMMA K-major layout)
+// Warp roles (14 warps, 1 CTA/SM):
+//   warps 0-3  : converters   staged fp32 rows -> (z-score) -> bf16 hi/lo, in place in slab0[buf] (UMMA K-major layout)
 //   warps 4-11 : epilogue     epi1: TMEM D1 -> bias/ReLU/guard -> bf16 hi/lo -> slab1 (smem, feeds conv2)
 //                             epi2: TMEM D2 -> bias/ReLU/pool/guard -> bf16 hi/lo -> X2 tape (global)
+//   warp 13    : loader       raw fp32 rows of a tile -> slab buffer by bulk TMA (<= 2 copies), L2 prefetch ahead
 //   warp 12    : MMA issuer   weights via bulk TMA once; conv1(k+1) is issued before conv2(k) so the
 //                             tensor pipe works on the next tile's conv1 while epi1(k) fills slab1
 #pragma once
@@ -24,10 +25,10 @@ namespace dce {
 namespace tc {
 
 constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
-constexpr int kB1Threads = 13 * 32;
+constexpr int kB1Threads = 14 * 32;
 constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
 constexpr int kB1WBytes = 49152;                   // one conv weight image: [stage 2][part 2][tap 3][j 4][64][8] bf16
-constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 128 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
+constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
 
 struct Block1Params {
     const float* x;              // batch: [W][150][54]; stream: [T][54]
@@ -41,10 +42,52 @@ struct Block1Params {
     size_t out_part_stride, out_kch_stride;
     int out_rows_cap;
     int n_tiles;
+    int64_t total_rows;          // stream: rows T of the log (to keep the 16-byte-rounded bulk copies in bounds)
     int dbg;                     // timing ablations only (results invalid when non-zero)
+    long long* trace;            // optional: CTA 0 records clock64() per role per tile ([tile][16])
 };
 
+#define B1_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
+
 __device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+// The raw fp32 rows a tile needs form at most two contiguous runs in global memory (one per window
+// it touches; the guard rows between windows have no source).  Rows are 216 B, so a run starts on
+// an 8-byte boundary only: each run is fetched with ONE bulk TMA copy of the enclosing 16-byte
+// aligned range and lands at `off` (its first row at off, i.e. aligned base + phase).
+struct TileSegs {
+    int s_lo[2], n[2];           // first slab row / row count of each run (n == 0: absent)
+    uint32_t off[2];             // byte offset, inside the staging buffer, of the run's first row
+    uint32_t dst_al[2];          // 16-byte aligned staging offset the bulk copy writes to
+    const char* src_al[2];       // 16-byte aligned global source
+    uint32_t bytes[2];           // bulk copy size (multiple of 16)
+    bool tail8[2];               // stream mode, run ends at the end of the log on an 8-byte boundary:
+                                 //   the last 16-byte chunk is not bulk-copied; its 8 valid bytes are copied by hand
+};
+template <bool STREAM>
+__device__ __forceinline__ TileSegs tile_segs(const Block1Params& p, int r0) {
+    TileSegs g;
+    const int wf = (r0 >= 0) ? r0 / kRW1 : -1;
+    uint32_t cursor = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int wi = wf + j;
+        const int lo = r0 > wi * kRW1 ? r0 : wi * kRW1;
+        const int hi = (r0 + kSlabRows) < (wi * kRW1 + 150) ? (r0 + kSlabRows) : (wi * kRW1 + 150);
+        g.s_lo[j] = lo - r0; g.n[j] = 0; g.off[j] = 0; g.dst_al[j] = 0; g.src_al[j] = nullptr; g.bytes[j] = 0; g.tail8[j] = false;
+        if (wi < 0 || wi >= p.n_windows || hi <= lo) continue;
+        const int t0 = lo - wi * kRW1;
+        const int64_t row = STREAM ? (p.first + wi + t0) : ((int64_t)wi * 150 + t0);
+        const char* src = reinterpret_cast<const char*>(p.x) + row * 216;
+        const uint32_t ps = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint32_t len = (uint32_t)(hi - lo) * 216;
+        uint32_t bytes = (ps + len + 15) & ~15u;
+        if (STREAM && ((ps + len) & 15) && row + (hi - lo) == p.total_rows) { bytes -= 16; g.tail8[j] = true; }
+        g.n[j] = hi - lo; g.dst_al[j] = cursor; g.off[j] = cursor + ps; g.src_al[j] = src - ps; g.bytes[j] = bytes;
+        cursor += ((ps + len + 15) & ~15u);
+    }
+    return g;
+}
 
 template <bool STREAM>
 __global__ void __launch_bounds__(kB1Threads, 1)
@@ -64,8 +107,9 @@ block1_kernel(const Block1Params p) {
     uint64_t* x1_full = bars + 12;   // 256 epilogue threads arrive
     uint64_t* x1_empty = bars + 13;  // commit
     uint64_t* wbar = bars + 14;      // weights landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // b1[64], b2[64]
+    uint64_t* raw_full = bars + 15;  // [2] raw fp32 rows of a tile landed (bulk TMA, bytes)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // b1[64], b2[64]
     float* s_nrm = s_bias + 128;     // stream mode: [2 windows][mean 64 | 1/std 64] of the tile being converted
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,6 +123,7 @@ block1_kernel(const Block1Params p) {
             ptx::mbar_init(&d2_full[i], 1);   ptx::mbar_init(&d2_empty[i], 8);
         }
         ptx::mbar_init(x1_full, 256); ptx::mbar_init(x1_empty, 1); ptx::mbar_init(wbar, 1);
+        ptx::mbar_init(&raw_full[0], 1); ptx::mbar_init(&raw_full[1], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 12) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
@@ -95,69 +140,52 @@ block1_kernel(const Block1Params p) {
 
     if (warp < 4) {
         // ===== converters: fp32 rows -> slab0[buf] =====
-        // Raw rows are staged with coalesced 8-byte cp.async (LDGSTS; rows are only 8-byte aligned:
-        // 54 floats = 216 B) INTO the slab buffer itself, one tile ahead of the conversion; then
-        // thread t reads row t back (27 x 8 B), the converter warps synchronise on a named barrier,
-        // and the bf16 hi/lo image is written in place in the UMMA K-major layout.
+        // The loader warp has bulk-copied the tile's raw rows INTO the slab buffer itself; thread t
+        // reads row t back (27 x 8 B), the converter warps synchronise on a named barrier, and the
+        // bf16 hi/lo image is written in place in the UMMA K-major layout.
         const int tid = threadIdx.x;
-        auto issue_raw = [&](int k) {
-            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
-            const uint32_t stage = ptx::smem_u32(slab0 + (k & 1) * kB1SlabBytes);
-            const int wf = (r0 >= 0) ? r0 / kRW1 : -1;
-#pragma unroll
-            for (int wi = wf; wi <= wf + 1; ++wi) {
-                int lo = r0 > wi * kRW1 ? r0 : wi * kRW1;
-                int hi = (r0 + kSlabRows) < (wi * kRW1 + 150) ? (r0 + kSlabRows) : (wi * kRW1 + 150);
-                if (wi < 0 || wi >= p.n_windows || hi <= lo) continue;
-                const int t0 = lo - wi * kRW1;
-                const char* src = reinterpret_cast<const char*>(
-                    STREAM ? p.x + (size_t)(p.first + wi + t0) * 54 : p.x + ((size_t)wi * 150 + t0) * 54);
-                const int units = (hi - lo) * 27;
-                const uint32_t dst = stage + (lo - r0) * 216;
-                for (int u = tid; u < units; u += 128)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * u), "l"(src + 8 * u) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
         auto row_window = [&](int r, int& w) -> bool {           // false: guard / out-of-range row -> zeros
             if (r < 0 || r >= NR) return false;
             w = r / kRW1;
             return r - w * kRW1 < 150;
         };
-        if (my_tiles > 0) issue_raw(0);
         for (int k = 0; k < my_tiles; ++k) {
             const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
             const uint32_t buf = k & 1;
-            if (k + 1 < my_tiles) {
-                ptx::mbar_wait(&x0_empty[(k + 1) & 1], (((k + 1) >> 1) & 1) ^ 1);    // conv1(k-1) has drained that buffer
-                issue_raw(k + 1);
-            } else {
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-            if (p.dbg & 4) { asm volatile("cp.async.wait_group 0;" ::: "memory"); ptx::mbar_arrive(&x0_full[buf]); continue; }
-            asm volatile("cp.async.wait_group 1;" ::: "memory");                   // this thread's copies of tile k landed
+            if (warp == 0) B1_TRACE(k, 0);
+            const TileSegs sg = tile_segs<STREAM>(p, r0);
+            ptx::mbar_wait(&raw_full[buf], (k >> 1) & 1);                           // raw rows of tile k have landed
+            if (warp == 0) B1_TRACE(k, 1);
+            if (p.dbg & 4) { ptx::mbar_arrive(&x0_full[buf]); continue; }
             const int wbase = (r0 > 0 ? r0 : 0) / kRW1;                              // first window this tile touches
             if (STREAM) {                                                            // its z-score constants -> smem
                 const int wi = wbase + (tid >> 6), c = tid & 63;
                 const bool in = wi < p.n_windows;
                 s_nrm[(tid >> 6) * 128 + c] = in ? __ldg(p.mean + (size_t)wi * 64 + c) : 0.f;
                 s_nrm[(tid >> 6) * 128 + 64 + c] = in ? __ldg(p.rstd + (size_t)wi * 64 + c) : 1.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");                           // ... and everybody else's
+            if (warp == 0) B1_TRACE(k, 2);
+            auto row_ptr = [&](int srow) -> const uint8_t* {                         // where slab row srow's raw data sits
+                const int j = (sg.n[1] > 0 && srow >= sg.s_lo[1]) ? 1 : 0;
+                return slab0 + buf * kB1SlabBytes + sg.off[j] + (srow - sg.s_lo[j]) * 216;
+            };
             uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
             float2 f[27];
             int w0 = 0;
             const bool v0 = row_window(r0 + tid, w0);
+            const uint8_t* src_row0 = row_ptr(tid);
 #pragma unroll
             for (int i = 0; i < 27; ++i)
-                f[i] = v0 ? *reinterpret_cast<const float2*>(dst0 + tid * 216 + 8 * i) : make_float2(0.f, 0.f);
+                f[i] = v0 ? *reinterpret_cast<const float2*>(src_row0 + 8 * i) : make_float2(0.f, 0.f);
             float2 g[4];
             int w1 = 0;
             const int s1 = 128 + tid / 7, kch1 = tid % 7;
             const bool v1 = (tid < 14) && row_window(r0 + s1, w1);
+            const uint8_t* src_row1 = row_ptr(s1);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                g[i] = (v1 && (kch1 < 6 || i < 3)) ? *reinterpret_cast<const float2*>(dst0 + s1 * 216 + kch1 * 32 + 8 * i)
+                g[i] = (v1 && (kch1 < 6 || i < 3)) ? *reinterpret_cast<const float2*>(src_row1 + kch1 * 32 + 8 * i)
                                                    : make_float2(0.f, 0.f);
             if (STREAM) {
                 if (v0) {
@@ -212,6 +240,45 @@ block1_kernel(const Block1Params p) {
             if (tid < 2) *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + (128 + tid) * 16) = make_uint4(0, 0, 0, 0);
             ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
             ptx::mbar_arrive(&x0_full[buf]);
+            if (warp == 0) B1_TRACE(k, 3);
+        }
+    } else if (warp == 13) {
+        // ===== loader: raw fp32 rows of tile k -> slab0[k & 1] by bulk TMA, as soon as conv1(k-2) has drained it =====
+        for (int k = 0; k < my_tiles; ++k) {
+            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
+            const uint32_t buf = k & 1;
+            const TileSegs sg = tile_segs<STREAM>(p, r0);
+            ptx::mbar_wait(&x0_empty[buf], ((k >> 1) & 1) ^ 1);
+            if (ptx::elect_one()) {
+                B1_TRACE(k, 14);
+                uint8_t* stage = slab0 + buf * kB1SlabBytes;
+                uint32_t total = 0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (sg.n[j] > 0 && sg.tail8[j]) {        // 8 valid bytes at the very end of the log, copied by hand
+                        const unsigned long long v = *reinterpret_cast<const unsigned long long*>(sg.src_al[j] + sg.bytes[j]);
+                        *reinterpret_cast<unsigned long long*>(stage + sg.dst_al[j] + sg.bytes[j]) = v;
+                    }
+                    total += sg.bytes[j];
+                }
+                if (total > 0) {
+                    ptx::mbar_arrive_expect_tx(&raw_full[buf], total);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (sg.bytes[j] > 0) ptx::bulk_g2s(stage + sg.dst_al[j], sg.src_al[j], sg.bytes[j], &raw_full[buf]);
+                } else {
+                    ptx::mbar_arrive(&raw_full[buf]);
+                }
+                // warm L2 with the tile that will use this buffer next
+                if (k + 2 < my_tiles) {
+                    const TileSegs nx = tile_segs<STREAM>(p, (int)(blockIdx.x + (k + 2) * gridDim.x) * kB1Rows - 3);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (nx.bytes[j] > 0)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.src_al[j]), "r"(nx.bytes[j]) : "memory");
+                }
+            }
+            __syncwarp();
         }
     } else if (warp == 12) {
         // ===== MMA issuer (warp-uniform control flow; one elected lane issues) =====
@@ -255,6 +322,7 @@ block1_kernel(const Block1Params p) {
                 ptx::mbar_wait(&x0_full[buf], ph);
                 ptx::mbar_wait(&d1_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
+                B1_TRACE(k, 4);
                 conv_mmas(s0a + buf * kB1SlabBytes, w1a, tmem_base + buf * 64, &x0_empty[buf], &d1_full[buf]);
             };
             auto issue_c2 = [&](int k) {
@@ -262,6 +330,7 @@ block1_kernel(const Block1Params p) {
                 ptx::mbar_wait(x1_full, k & 1);
                 ptx::mbar_wait(&d2_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
+                B1_TRACE(k, 5);
                 conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64, x1_empty, &d2_full[buf]);
             };
             if (my_tiles > 0) issue_c1(0);
@@ -282,7 +351,9 @@ block1_kernel(const Block1Params p) {
             const uint32_t buf = k & 1, ph = (k >> 1) & 1;
             const int r = tile * kB1Rows - 2 + rit;           // X1 row
             const bool valid = r >= 0 && pos_mod(r, kRW1) < 150;
+            if (warp == 4) B1_TRACE(k, 6);
             ptx::mbar_wait(&d1_full[buf], ph);
+            if (warp == 4) B1_TRACE(k, 7);
             ptx::tc_fence_after_sync();
             uint32_t v[32];
             ptx::tmem_ld32(tmem_base + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
@@ -299,7 +370,9 @@ block1_kernel(const Block1Params p) {
                 y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
                 y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
             }
+            if (warp == 4) B1_TRACE(k, 8);
             ptx::mbar_wait(x1_empty, (k & 1) ^ 1);            // conv2 of the previous tile has finished reading slab1
+            if (warp == 4) B1_TRACE(k, 9);
             if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
@@ -311,6 +384,7 @@ block1_kernel(const Block1Params p) {
             }
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(x1_full);
+            if (warp == 4) B1_TRACE(k, 10);
         };
         auto epi2 = [&](int k) {
             const int tile = blockIdx.x + k * gridDim.x;
@@ -319,7 +393,9 @@ block1_kernel(const Block1Params p) {
             const int orow = r >> 1;                          // pooled row (arithmetic shift: -2,-1 -> -1)
             const bool valid = r >= 0 && (pos_mod(r, kRW1) >> 1) < 75;
             const bool store = ((rit >= 2 && rit < 126) || (tile == 0 && rit < 2)) && orow < p.out_rows_cap;
+            if (warp == 4) B1_TRACE(k, 11);
             ptx::mbar_wait(&d2_full[buf], ph);
+            if (warp == 4) B1_TRACE(k, 12);
             ptx::tc_fence_after_sync();
             uint32_t v[32];
             ptx::tmem_ld32(tmem_base + 128 + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
@@ -351,6 +427,7 @@ block1_kernel(const Block1Params p) {
                     *reinterpret_cast<uint4*>(base + (size_t)(h * 4 + qd) * p.out_kch_stride) = (lane & 1) ? lo : hi;
                 }
             }
+            if (warp == 4) B1_TRACE(k, 13);
         };
         for (int k = 0; k < my_tiles; ++k) {
             epi1(k);

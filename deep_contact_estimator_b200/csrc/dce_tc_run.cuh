@@ -10,12 +10,13 @@ namespace tc {
 // debug/ablation switch: 0 = one kernel per layer (ingest, conv1, conv2 as separate launches)
 inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& block1_dbg_flag() { static int v = 0; return v; }
+inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 
 // pointers into the fp32 section of the packed buffer, passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
 
 inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
-               int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+               int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
     cudaStream_t s = ctx.stream;
     for (int64_t c0 = 0; c0 < n; c0 += kChunk) {
         const int m = (int)((n - c0 < kChunk) ? n - c0 : kChunk);
@@ -43,13 +44,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
-            b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m;
+            b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m; b.total_rows = total_rows;
             b.mean = mean; b.rstd = sdev;   // window_stats_kernel<true> writes 1/std
             b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[0]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[1]);
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
-            b.dbg = block1_dbg_flag();
+            b.dbg = block1_dbg_flag(); b.trace = block1_trace_ptr();
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
             if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", block1_kernel<true><<<grid, kB1Threads, kB1SmemBytes, s>>>(b));

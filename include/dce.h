@@ -156,11 +156,15 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
 
 /*
  * Ablation / debugging switches (process-wide).  Keys:
+ *   "block1_dbg"   bit mask of timing ablations inside the fused block1 kernel (results invalid);
+ *   "block1_trace" 1: record a per-role clock64 timeline of CTA 0 (tools/trace_block1.py);
  *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
  *                  0: one kernel per layer (activations round-trip through HBM).
  * Returns DCE_EINVAL for an unknown key.
  */
 DCE_API int dce_set_option(const char *key, int value);
+/* "block1_trace" armed: copy the first n clock64 samples ([tile][16 events]) of CTA 0 to the host. */
+DCE_API int dce_debug_read_trace(long long *host_out, int n);
 
 /* How many kernel launches the last dce_forward / dce_stream on this thread enqueued. */
 DCE_API int dce_last_launch_count(void);
