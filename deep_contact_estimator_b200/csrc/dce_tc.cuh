@@ -72,7 +72,8 @@ struct Tape {
     size_t kch_stride, part_stride, bytes;
 };
 inline Tape make_tape(int64_t rows, int kch) {
-    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.cap = kGuard + t.m_tiles * 128 + 8; t.kch = kch;
+    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;   // even: MT = 2 tiles
+    t.cap = kGuard + t.m_tiles * 128 + 8; t.kch = kch;
     t.kch_stride = (size_t)t.cap * 16; t.part_stride = t.kch_stride * kch; t.bytes = align_up(t.part_stride * 2, 256);
     return t;
 }
@@ -106,15 +107,19 @@ constexpr int kProducerWarp = kEpiWarps;           // warp 8
 constexpr int kMmaWarp = kEpiWarps + 1;            // warp 9
 constexpr int kThreads = (kEpiWarps + 2) * 32;     // 320
 
-template <int BN, int TAPS, int KSA, int NSTAGE>
+// MT = 128-row M-tiles per CTA tile: MT = 2 runs two accumulators against every staged B block, which
+// halves the L2 -> smem weight traffic per MMA (the fc.0 / conv3 / conv4 / fc.3 tiles are L2-bound at MT = 1).
+template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1>
 struct TapGemmCfg {
     static constexpr int A_PART = KSA * kSlabBytes;
-    static constexpr int A_BYTES = 2 * A_PART;
+    static constexpr int A_TILE = 2 * A_PART;                 // hi + lo slabs of one M-tile
+    static constexpr int A_BYTES = MT * A_TILE;
     static constexpr int B_TAPCH = BN * 16;
     static constexpr int B_PART = TAPS * KSA * B_TAPCH;
     static constexpr int B_BYTES = 2 * B_PART;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int NBUF = (2 * MT * BN <= 512) ? 2 : 1;   // accumulator buffers (epilogue / MMA overlap)
+    static constexpr int TMEM_COLS = NBUF * MT * BN;
     static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + kEpiWarps * (BN / 2) * 4;
     static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
@@ -123,10 +128,11 @@ struct TapGemmCfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const TapGemmParams p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT>;
+    constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE_BYTES);
     uint64_t* empty = full + NSTAGE;
@@ -136,7 +142,7 @@ tapgemm_kernel(const TapGemmParams p) {
     float* s_bias = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
@@ -154,7 +160,7 @@ tapgemm_kernel(const TapGemmParams p) {
         {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m = tile / p.n_tiles, n = tile % p.n_tiles;
+                const int m = (tile / p.n_tiles) * MT, n = tile % p.n_tiles;
                 const uint8_t* a_row = p.a_tape + (size_t)(128 * m + kGuard - 1) * 16;
                 const uint8_t* wsrc = p.w_packed + (size_t)n * p.stages * Cfg::B_BYTES;
                 for (int s = 0; s < p.stages; ++s, ++it) {
@@ -164,12 +170,14 @@ tapgemm_kernel(const TapGemmParams p) {
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES);
 #pragma unroll
-                        for (int part = 0; part < 2; ++part)
+                        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                            for (int j = 0; j < KSA; ++j)
-                                ptx::bulk_g2s(st + part * Cfg::A_PART + j * kSlabBytes,
-                                              a_row + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
-                                              kSlabBytes, &full[slot]);
+                            for (int part = 0; part < 2; ++part)
+#pragma unroll
+                                for (int j = 0; j < KSA; ++j)
+                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                                  a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                                  kSlabBytes, &full[slot]);
                         ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
                     }
                     __syncwarp();
@@ -182,10 +190,10 @@ tapgemm_kernel(const TapGemmParams p) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
+                const uint32_t buf = tcount % NBUF, tph = (tcount / NBUF) & 1;
                 ptx::mbar_wait(&tempty[buf], tph ^ 1);
                 ptx::tc_fence_after_sync();
-                const uint32_t d = tmem_base + buf * BN;
+                const uint32_t d0 = tmem_base + buf * (MT * BN);
                 for (int s = 0; s < p.stages; ++s, ++it) {
                     const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
                     ptx::mbar_wait(&full[slot], ph);
@@ -198,16 +206,20 @@ tapgemm_kernel(const TapGemmParams p) {
                             const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
 #pragma unroll
                             for (int kk = 0; kk < KSA / 2; ++kk) {
-                                const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
                                 const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
-                                const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                                const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
                                 const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
                                 const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
                                 const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                                ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
-                                ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
-                                ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt) {
+                                    const uint32_t a_hi = a0 + mt * Cfg::A_TILE + (2 * kk) * kSlabBytes + arow * 16;
+                                    const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                                    const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                                    const uint32_t d = d0 + mt * BN;
+                                    ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
+                                    ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                                    ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                                }
                             }
                         }
                         ptx::umma_commit(&empty[slot]);          // frees the smem slot when these MMAs retire
@@ -227,9 +239,8 @@ tapgemm_kernel(const TapGemmParams p) {
         uint32_t tcount = 0;
         int last_n = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const int m = tile / p.n_tiles, n = tile % p.n_tiles;
-            const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
-            const int row = 128 * m + row_in_tile;
+            const int m0 = (tile / p.n_tiles) * MT, n = tile % p.n_tiles;
+            const uint32_t buf = tcount % NBUF, tph = (tcount / NBUF) & 1;
             const int n0 = n * BN + h * HALF;                // first output feature this warp owns
             if (n != last_n) {                               // stage this warp's bias slice (warp-private copy)
                 __syncwarp();
@@ -238,6 +249,11 @@ tapgemm_kernel(const TapGemmParams p) {
                 last_n = n;
             }
 
+            ptx::mbar_wait(&tfull[buf], tph);
+            ptx::tc_fence_after_sync();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+            const int row = 128 * (m0 + mt) + row_in_tile;
             // per-mode row bookkeeping
             bool valid = true; size_t out_off = 0; bool zero_prev = false;
             if (EPI == EPI_TAPE) {
@@ -261,9 +277,7 @@ tapgemm_kernel(const TapGemmParams p) {
                 out_off = (size_t)(row + kGuard) * 16;
             }
 
-            ptx::mbar_wait(&tfull[buf], tph);
-            ptx::tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + buf * BN + h * HALF + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + buf * (MT * BN) + mt * BN + h * HALF + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
             for (int c0 = 0; c0 < HALF; c0 += 32) {
@@ -322,6 +336,7 @@ tapgemm_kernel(const TapGemmParams p) {
                     }
                 }
             }
+            }   // mt
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
@@ -483,16 +498,16 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT>;
     static DeviceOnce attr_once;
     if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
     }
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
     DCE_KL(ctx, name, kern<<<grid, kThreads, Cfg::SMEM_BYTES, ctx.stream>>>(p));
     return DCE_OK;

@@ -105,7 +105,7 @@ class ContactEngine:
     def _ws(self, n: int) -> torch.Tensor:
         need = self.lib.dce_workspace_bytes(n, _lib.PRECISIONS[self.precision])
         if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._workspace = torch.zeros(need, dtype=torch.uint8, device=self.device)   # tape padding rows start finite
         return self._workspace
 
     def _outs(self, n: int, want_logits: bool, want_cls: bool, want_bits: bool):

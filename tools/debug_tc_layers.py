@@ -23,6 +23,7 @@ def align(v, a=256):
 
 def tape(rows, kch):
     m_tiles = (rows + 127) // 128
+    m_tiles += m_tiles & 1
     cap = GUARD + m_tiles * 128 + 8
     return dict(rows=rows, m_tiles=m_tiles, cap=cap, kch=kch, bytes=align(cap * 16 * kch * 2))
 

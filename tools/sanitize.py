@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Small-shape run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+   compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import deep_contact_estimator_b200 as dce
+from deep_contact_estimator_b200 import synth
+from oracle import contact_oracle as oracle
+dev = torch.device("cuda", 0)
+params = synth.make_params(0)
+for precision in ("bf16x3", "fp32"):
+    eng = dce.ContactEngine(params, dev, precision)
+    for B in (1, 3, 37, 260):
+        x = synth.make_windows(B, seed=B)
+        lo, cl, bi = eng.classify(x.to(dev)); torch.cuda.synchronize()
+        want = oracle.forward_torch(params, x).detach().numpy()
+        assert np.array_equal(cl.cpu().numpy(), want.argmax(1)), (precision, B)
+    log = synth.make_sensor_log(150 + 333, seed=2)          # odd row count: exercises the unaligned stream tail
+    _, cl, bi = eng.stream(log.to(dev)); torch.cuda.synchronize()
+    _, wc, wb = oracle.inference_stream(params, log)
+    assert np.array_equal(bi.cpu().numpy(), wb.numpy()), precision
+    eng.lib.dce_set_option(b"fuse_block1", 0)
+    lo, cl, bi = eng.classify(synth.make_windows(37, seed=37).to(dev)); torch.cuda.synchronize()
+    eng.lib.dce_set_option(b"fuse_block1", 1)
+print("sanitize run ok")
