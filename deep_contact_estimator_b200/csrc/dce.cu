@@ -322,6 +322,8 @@ int dce_set_option(const char* key, int value) {
     if (!key) return DCE_EINVAL;
     if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
     if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "tapgemm_dbg")) { dce::tc::tapgemm_dbg_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "trace_layer")) { dce::tc::tapgemm_trace_layer() = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3
     if (!strcmp(key, "block1_trace")) {          // value != 0: allocate (once) and arm a 60-tile x 16-event clock64 trace of CTA 0
         long long*& t = dce::tc::block1_trace_ptr();
         if (value && !t) { if (cudaMalloc(&t, 60 * 16 * 8) != cudaSuccess) return DCE_ECUDA; cudaMemset(t, 0, 60 * 16 * 8); }

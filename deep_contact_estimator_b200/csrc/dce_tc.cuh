@@ -24,10 +24,10 @@
 // shared-memory image of each (n-tile, k-stage) so a stage's B operand is one
 // bulk copy.
 //
-// Roles per CTA (320 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-7: epilogue      (256 threads)   tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
-//   warp 8   : TMA producer  (one lane)      smem ring, full/empty mbarriers
-//   warp 9   : MMA issuer    (one lane)      tcgen05.mma + tcgen05.commit; owns TMEM alloc
+// Roles per CTA (416 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-7 : epilogue      (256 threads)  tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
+//   warp 8    : MMA issuer    (one lane)     tcgen05.mma + tcgen05.commit; owns TMEM alloc
+//   warps 9-12: TMA producers (one lane each) smem ring, full/empty mbarriers
 // TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda_runtime.h>
@@ -64,6 +64,8 @@ struct TapGemmParams {
     int N;                       // total output features
     int rw, tv;                  // rows per window / valid rows per window of the INPUT tape (conv modes)
     int n_valid;                 // EPI_FC_F32: valid rows
+    long long* trace;            // optional clock64 timeline of CTA 0: [tile][8] (tools/trace_tapgemm.py)
+    int dbg;                     // timing ablations (results invalid): 1 = every tile loads the A slabs of tile 0; 2 = skip epilogue stores
 };
 
 struct Tape {
@@ -103,13 +105,18 @@ __device__ __forceinline__ float max_nan(float a, float b) {
 __device__ __forceinline__ float relu_nan(float v) { return max_nan(v, 0.f); }
 
 constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant: column halves
-constexpr int kProducerWarp = kEpiWarps;           // warp 8
-constexpr int kMmaWarp = kEpiWarps + 1;            // warp 9
-constexpr int kThreads = (kEpiWarps + 2) * 32;     // 320
+constexpr int kMmaWarp = kEpiWarps;                // warp 8
+constexpr int kProdWarps = 4;                      // warps 9..12: bulk-copy issue is ~100 cycles per copy from one
+                                                   // thread, so the copies of a stage are dealt round-robin to 4 warps
+constexpr int kProducerWarp0 = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 416
 
 // MT = 128-row M-tiles per CTA tile: MT = 2 runs two accumulators against every staged B block, which
 // halves the L2 -> smem weight traffic per MMA (the fc.0 / conv3 / conv4 / fc.3 tiles are L2-bound at MT = 1).
-template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1>
+// WST > 0: the layer has WST k-stages and a single n-tile, and its whole weight image (WST * B_BYTES)
+// stays resident in shared memory for the life of the CTA (conv3: 96 KB) — otherwise all 148 CTAs
+// re-stream the same few weight blocks from the same L2 lines for every tile, which hot-spots L2.
+template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1, int WST = 0>
 struct TapGemmCfg {
     static constexpr int A_PART = KSA * kSlabBytes;
     static constexpr int A_TILE = 2 * A_PART;                 // hi + lo slabs of one M-tile
@@ -117,36 +124,43 @@ struct TapGemmCfg {
     static constexpr int B_TAPCH = BN * 16;
     static constexpr int B_PART = TAPS * KSA * B_TAPCH;
     static constexpr int B_BYTES = 2 * B_PART;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + (WST ? 0 : B_BYTES);
+    static constexpr int WRES_BYTES = WST * B_BYTES;
     static constexpr int NBUF = (2 * MT * BN <= 512) ? 2 : 1;   // accumulator buffers (epilogue / MMA overlap)
     static constexpr int TMEM_COLS = NBUF * MT * BN;
-    static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + kEpiWarps * (BN / 2) * 4;
+    static constexpr int BAR_BYTES = (2 * NSTAGE + 5) * 8 + 8;
+    static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = RING_BYTES + WRES_BYTES + BAR_BYTES + kEpiWarps * (BN / 2) * 4;
     static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
     static_assert(STAGE_BYTES % 16 == 0, "bulk copies are 16-byte granular");
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1>
+#define TG_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
+
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const TapGemmParams p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE_BYTES);
+    uint8_t* wres = smem + Cfg::RING_BYTES;                       // resident weight image (WST > 0)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::WRES_BYTES);
     uint64_t* empty = full + NSTAGE;
     uint64_t* tfull = empty + NSTAGE;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::WRES_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], 1); }
         for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], kEpiWarps); }
+        ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == kMmaWarp) { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
@@ -155,30 +169,48 @@ tapgemm_kernel(const TapGemmParams p) {
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == kProducerWarp) {
-        // ===== TMA producer (warp-uniform loop; one elected lane issues) =====
+    if (warp >= kProducerWarp0) {
+        // ===== TMA producers (warp-uniform loops; one elected lane per warp issues) =====
+        // copy c of a stage: c < NA -> A slab (mt, part, j) of 2080 B; c == NA -> the B block.  Warp pw issues c = pw, pw+4, ...
         {
+            constexpr int NA = MT * 2 * KSA;
+            const int pw = warp - kProducerWarp0;
+            uint32_t my_bytes = 0;
+            for (int c = pw; c <= NA; c += kProdWarps) my_bytes += (c < NA) ? kSlabBytes : (WST ? 0 : Cfg::B_BYTES);
+            if (WST && pw == 0) {                              // one-time load of the whole weight image
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(wbar, Cfg::WRES_BYTES);
+#pragma unroll
+                    for (int s = 0; s < (WST ? WST : 1); ++s)
+                        ptx::bulk_g2s(wres + s * Cfg::B_BYTES, p.w_packed + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, wbar);
+                }
+                __syncwarp();
+            }
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m = (tile / p.n_tiles) * MT, n = tile % p.n_tiles;
-                const uint8_t* a_row = p.a_tape + (size_t)(128 * m + kGuard - 1) * 16;
+                const uint8_t* a_row = p.a_tape + (size_t)(128 * ((p.dbg & 1) ? 0 : m) + kGuard - 1) * 16;
                 const uint8_t* wsrc = p.w_packed + (size_t)n * p.stages * Cfg::B_BYTES;
                 for (int s = 0; s < p.stages; ++s, ++it) {
                     const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
-                    ptx::mbar_wait(&empty[slot], ph ^ 1);
+                    ptx::mbar_wait_relaxed(&empty[slot], ph ^ 1);
+                    if (pw == 0 && s == 0) TG_TRACE(it / p.stages, 0);
+                    if (pw == 0 && s == p.stages - 1) TG_TRACE(it / p.stages, 1);
                     uint8_t* st = smem + slot * Cfg::STAGE_BYTES;
                     if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES);
+                        ptx::mbar_arrive_expect_tx(&full[slot], my_bytes);
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                            for (int part = 0; part < 2; ++part)
-#pragma unroll
-                                for (int j = 0; j < KSA; ++j)
-                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
-                                                  a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
-                                                  kSlabBytes, &full[slot]);
-                        ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
+                        for (int c0 = 0; c0 <= NA; c0 += kProdWarps) {
+                            const int c = c0 + pw;
+                            if (c < NA) {
+                                const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
+                                ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                              a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                              kSlabBytes, &full[slot]);
+                            } else if (c == NA && !WST) {
+                                ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
+                            }
+                        }
                     }
                     __syncwarp();
                 }
@@ -189,17 +221,22 @@ tapgemm_kernel(const TapGemmParams p) {
         {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
             uint32_t it = 0, tcount = 0;
+            if (WST) ptx::mbar_wait(wbar, 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount % NBUF, tph = (tcount / NBUF) & 1;
+                TG_TRACE(tcount, 2);
                 ptx::mbar_wait(&tempty[buf], tph ^ 1);
+                TG_TRACE(tcount, 3);
                 ptx::tc_fence_after_sync();
                 const uint32_t d0 = tmem_base + buf * (MT * BN);
                 for (int s = 0; s < p.stages; ++s, ++it) {
                     const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
                     ptx::mbar_wait(&full[slot], ph);
+                    if (s == 0) TG_TRACE(tcount, 4);
+                    if (s == p.stages - 1) TG_TRACE(tcount, 5);
                     ptx::tc_fence_after_sync();
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES);
-                    const uint32_t b0 = a0 + Cfg::A_BYTES;
+                    const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : a0 + Cfg::A_BYTES;
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
@@ -249,13 +286,16 @@ tapgemm_kernel(const TapGemmParams p) {
                 last_n = n;
             }
 
-            ptx::mbar_wait(&tfull[buf], tph);
+            if (warp == 0) TG_TRACE(tcount, 6);
+            ptx::mbar_wait_relaxed(&tfull[buf], tph);
+            if (warp == 0) TG_TRACE(tcount, 7);
             ptx::tc_fence_after_sync();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
             const int row = 128 * (m0 + mt) + row_in_tile;
             // per-mode row bookkeeping
             bool valid = true; size_t out_off = 0; bool zero_prev = false;
+            if (p.dbg & 2) continue;
             if (EPI == EPI_TAPE) {
                 const int t = row % p.rw;
                 valid = t < p.tv;
@@ -337,6 +377,7 @@ tapgemm_kernel(const TapGemmParams p) {
                 }
             }
             }   // mt
+            if (warp == 0) TG_TRACE(tcount, 8);
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
@@ -498,10 +539,11 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST>;
+    if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
     static DeviceOnce attr_once;
     if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);

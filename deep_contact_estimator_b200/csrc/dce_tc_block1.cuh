@@ -154,7 +154,7 @@ block1_kernel(const Block1Params p) {
             const uint32_t buf = k & 1;
             if (warp == 0) B1_TRACE(k, 0);
             const TileSegs sg = tile_segs<STREAM>(p, r0);
-            ptx::mbar_wait(&raw_full[buf], (k >> 1) & 1);                           // raw rows of tile k have landed
+            ptx::mbar_wait_relaxed(&raw_full[buf], (k >> 1) & 1);                           // raw rows of tile k have landed
             if (warp == 0) B1_TRACE(k, 1);
             if (p.dbg & 4) { ptx::mbar_arrive(&x0_full[buf]); continue; }
             const int wbase = (r0 > 0 ? r0 : 0) / kRW1;                              // first window this tile touches
@@ -248,7 +248,7 @@ block1_kernel(const Block1Params p) {
             const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
             const uint32_t buf = k & 1;
             const TileSegs sg = tile_segs<STREAM>(p, r0);
-            ptx::mbar_wait(&x0_empty[buf], ((k >> 1) & 1) ^ 1);
+            ptx::mbar_wait_relaxed(&x0_empty[buf], ((k >> 1) & 1) ^ 1, 256);
             if (ptx::elect_one()) {
                 B1_TRACE(k, 14);
                 uint8_t* stage = slab0 + buf * kB1SlabBytes;
@@ -352,7 +352,7 @@ block1_kernel(const Block1Params p) {
             const int r = tile * kB1Rows - 2 + rit;           // X1 row
             const bool valid = r >= 0 && pos_mod(r, kRW1) < 150;
             if (warp == 4) B1_TRACE(k, 6);
-            ptx::mbar_wait(&d1_full[buf], ph);
+            ptx::mbar_wait_relaxed(&d1_full[buf], ph);
             if (warp == 4) B1_TRACE(k, 7);
             ptx::tc_fence_after_sync();
             uint32_t v[32];
@@ -371,7 +371,7 @@ block1_kernel(const Block1Params p) {
                 y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
             }
             if (warp == 4) B1_TRACE(k, 8);
-            ptx::mbar_wait(x1_empty, (k & 1) ^ 1);            // conv2 of the previous tile has finished reading slab1
+            ptx::mbar_wait_relaxed(x1_empty, (k & 1) ^ 1);    // conv2 of the previous tile has finished reading slab1
             if (warp == 4) B1_TRACE(k, 9);
             if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
 #pragma unroll
@@ -394,7 +394,7 @@ block1_kernel(const Block1Params p) {
             const bool valid = r >= 0 && (pos_mod(r, kRW1) >> 1) < 75;
             const bool store = ((rit >= 2 && rit < 126) || (tile == 0 && rit < 2)) && orow < p.out_rows_cap;
             if (warp == 4) B1_TRACE(k, 11);
-            ptx::mbar_wait(&d2_full[buf], ph);
+            ptx::mbar_wait_relaxed(&d2_full[buf], ph);
             if (warp == 4) B1_TRACE(k, 12);
             ptx::tc_fence_after_sync();
             uint32_t v[32];

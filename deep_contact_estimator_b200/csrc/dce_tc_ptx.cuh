@@ -48,6 +48,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// For warps that wait a long time (epilogue on a whole tile, producers on a free slot): every failed
+// probe is a shared-memory access that competes with the tensor core's operand fetch, so back off.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 128) {
+    if (mbar_try_wait(bar, parity)) return;
+    do { __nanosleep(ns); } while (!mbar_try_wait(bar, parity));
+}
 
 // ---- 1-D bulk TMA: global -> shared, completion counted in bytes on an mbarrier ----
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

@@ -11,6 +11,8 @@ namespace tc {
 inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
+inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
+inline int& tapgemm_trace_layer() { static int v = -1; return v; }   // which layer (2..5) records into the trace buffer
 
 // pointers into the fp32 section of the packed buffer, passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
@@ -50,7 +52,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
-            b.dbg = block1_dbg_flag(); b.trace = block1_trace_ptr();
+            b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
             if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", block1_kernel<true><<<grid, kB1Threads, kB1SmemBytes, s>>>(b));
@@ -89,12 +91,15 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.x2.m_tiles; p.stages = kLayers[2].stages;
         p.out = x3; p.out_part_stride = W.x3.part_stride; p.out_kch_stride = W.x3.kch_stride; p.out_rows_cap = W.x3.m_tiles * 128;
         p.N = 128; p.rw = kRW2; p.tv = 75;
-        if ((rc = launch_layer<128, 3, 2, 4, EPI_TAPE, 2>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
+        p.dbg = tapgemm_dbg_flag();
+        p.trace = (tapgemm_trace_layer() == 2) ? block1_trace_ptr() : nullptr;
+        if ((rc = launch_layer<128, 3, 2, 6, EPI_TAPE, 2, 4>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
         // ---- conv4 + pool + flatten (a8, a9): X3 -> X4 (fc.0 operand layout, k' = t*128 + c)
         p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
         p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
         p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
+        p.trace = (tapgemm_trace_layer() == 3) ? block1_trace_ptr() : nullptr;
         if ((rc = launch_layer<128, 3, 2, 4, EPI_POOL_FC, 2>(ctx, "tc_conv4_pool", sm_count, p)) != DCE_OK) return rc;
         if (m <= small::kMaxB) {
             // ---- latency mode (K3): fc.0 / fc.3 as split-N fp32 GEMVs over the fp32 weight images
@@ -120,12 +125,15 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.x4.m_tiles; p.n_tiles = kLayers[4].n_tiles; p.stages = kLayers[4].stages;
         p.out = h1; p.out_part_stride = W.h1.part_stride; p.out_kch_stride = W.h1.kch_stride; p.out_rows_cap = W.h1.m_tiles * 128;
         p.N = 2048; p.rw = 1; p.tv = 1;
+        p.dbg = tapgemm_dbg_flag();
+        p.trace = (tapgemm_trace_layer() == 4) ? block1_trace_ptr() : nullptr;
         if ((rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p)) != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
         p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[5]); p.bias = bp.b[5];
         p.m_tiles = W.h1.m_tiles; p.n_tiles = kLayers[5].n_tiles; p.stages = kLayers[5].stages;
         p.out = nullptr; p.out_f32 = h2; p.N = 512; p.n_valid = m;
+        p.trace = (tapgemm_trace_layer() == 5) ? block1_trace_ptr() : nullptr;
         if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32, 1>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
         // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
         const int g3 = (int)((m + 7) / 8 < sm_count ? (m + 7) / 8 : sm_count);      // one 32 KB weight stage-in per SM

@@ -10,12 +10,13 @@ from deep_contact_estimator_b200 import synth
 dev = torch.device("cuda", 0)
 eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 xs = [synth.make_windows(4096, seed=10 + i).to(dev) for i in range(3)]
-for dbg in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 8, 9, 11, 15]:
-    eng.lib.dce_set_option(b"block1_dbg", dbg)
+key = b"tapgemm_dbg" if "--tapgemm" in sys.argv else b"block1_dbg"
+for dbg in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [0, 1, 2, 4, 8, 9, 11, 15]:
+    eng.lib.dce_set_option(key, dbg)
     for i in range(3):
         eng.classify(xs[i % 3])
     tot = {}
     for i in range(10):
         for name, ms in eng.profile_forward(xs[i % 3]):
             tot[name] = tot.get(name, 0) + ms / 10
-    print(f"dbg={dbg:2d}  block1 {tot['tc_block1']*1e3:7.1f} us")
+    print(f"dbg={dbg:2d}  " + "  ".join(f"{k} {v*1e3:6.1f}" for k, v in tot.items()))

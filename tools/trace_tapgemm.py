@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""clock64 timeline of CTA 0 of one tapgemm layer: python tools/trace_tapgemm.py <layer 2..5>"""
+import ctypes, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import deep_contact_estimator_b200 as dce
+from deep_contact_estimator_b200 import synth
+layer = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+dev = torch.device("cuda", 0)
+eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
+x = synth.make_windows(4096, seed=1).to(dev)
+for _ in range(3): eng.classify(x)
+eng.lib.dce_set_option(b"block1_trace", 1); eng.lib.dce_set_option(b"trace_layer", layer)
+eng.classify(x); torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (60 * 16))()
+assert eng.lib.dce_debug_read_trace(buf, 60 * 16) == 0
+t = np.array(buf, dtype=np.int64).reshape(60, 16)
+t0 = t[t > 0].min()
+names = ["ld:first", "ld:last", "mma:start", "mma:tempty", "mma:full0", "mma:fullL", "ep:start", "ep:tfull", "ep:done"]
+print("tile " + " ".join(f"{n:>10s}" for n in names))
+for k in range(0, 10):
+    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(9)))
+d = np.diff(t[2:14, 4]); print("tile period (cycles):", d.mean(), d.min(), d.max())
