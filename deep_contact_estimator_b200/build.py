@@ -42,7 +42,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/dce.cu -> libdce_b200.so; returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = ["-DDCE_TRACE=1"] if os.environ.get("DCE_TRACE") == "1" else []      # clock64 timelines (tools/trace_*.py)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -26,8 +26,8 @@
 //
 // Roles per CTA (416 threads, 1 CTA/SM, persistent over tiles):
 //   warps 0-7 : epilogue      (256 threads)  tcgen05.ld -> bias/ReLU/pool -> bf16 hi/lo -> next tape
-//   warp 8    : MMA issuer    (one lane)     tcgen05.mma + tcgen05.commit; owns TMEM alloc
-//   warps 9-12: TMA producers (one lane each) smem ring, full/empty mbarriers
+//   warps 8.. : MMA issuers   (one lane each, one warp per accumulator) tcgen05.mma + tcgen05.commit; warp 8 owns TMEM alloc
+//   last 4    : TMA producers (one lane each) smem ring, full/empty mbarriers
 // TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda_runtime.h>
@@ -105,11 +105,13 @@ __device__ __forceinline__ float max_nan(float a, float b) {
 __device__ __forceinline__ float relu_nan(float v) { return max_nan(v, 0.f); }
 
 constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant: column halves
-constexpr int kMmaWarp = kEpiWarps;                // warp 8
-constexpr int kProdWarps = 4;                      // warps 9..12: bulk-copy issue is ~100 cycles per copy from one
-                                                   // thread, so the copies of a stage are dealt round-robin to 4 warps
-constexpr int kProducerWarp0 = kEpiWarps + 1;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 416
+constexpr int kMmaWarp = kEpiWarps;                // warps 8 .. 8+MT-1: one MMA issuer per accumulator.  Between two stages an
+                                                   // issuer spends ~500 cycles in its own serial code (mbarrier probe, fences,
+                                                   // descriptors) while the tensor pipe's short queue drains; with one issuer per
+                                                   // accumulator the other issuer's MMAs fill that bubble, and every accumulator
+                                                   // still sees its MMAs in one fixed order (bit-reproducible).
+constexpr int kProdWarps = 4;                      // the bulk copies of a stage are dealt round-robin to 4 producer warps
+__host__ __device__ constexpr int tapgemm_threads(int MT) { return (kEpiWarps + MT + kProdWarps) * 32; }
 
 // MT = 128-row M-tiles per CTA tile: MT = 2 runs two accumulators against every staged B block, which
 // halves the L2 -> smem weight traffic per MMA (the fc.0 / conv3 / conv4 / fc.3 tiles are L2-bound at MT = 1).
@@ -137,11 +139,15 @@ struct TapGemmCfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 };
 
-#define TG_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
+#ifndef DCE_TRACE
+#define DCE_TRACE 0
+#endif
+#define TG_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
 template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(tapgemm_threads(MT), 1)
 tapgemm_kernel(const TapGemmParams p) {
+    constexpr int kProducerWarp0 = kEpiWarps + MT;
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -158,8 +164,8 @@ tapgemm_kernel(const TapGemmParams p) {
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], 1); }
-        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], kEpiWarps); }
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], MT); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], MT); ptx::mbar_init(&tempty[b], kEpiWarps); }
         ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
     }
@@ -197,6 +203,11 @@ tapgemm_kernel(const TapGemmParams p) {
                     if (pw == 0 && s == 0) TG_TRACE(it / p.stages, 0);
                     if (pw == 0 && s == p.stages - 1) TG_TRACE(it / p.stages, 1);
                     uint8_t* st = smem + slot * Cfg::STAGE_BYTES;
+                    if ((p.dbg & 4) && it >= NSTAGE) {            // ablation: no TMA traffic after the ring is primed
+                        if (ptx::elect_one()) ptx::mbar_arrive(&full[slot]);
+                        __syncwarp();
+                        continue;
+                    }
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&full[slot], my_bytes);
 #pragma unroll
@@ -216,27 +227,33 @@ tapgemm_kernel(const TapGemmParams p) {
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ===== MMA issuer (warp-uniform loop; one elected lane issues) =====
+    } else if (warp >= kMmaWarp) {
+        // ===== MMA issuers: warp kMmaWarp + mt owns accumulator mt (warp-uniform loop; one elected lane issues) =====
         {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
+            const int mt = warp - kMmaWarp;
             uint32_t it = 0, tcount = 0;
             if (WST) ptx::mbar_wait(wbar, 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount % NBUF, tph = (tcount / NBUF) & 1;
-                TG_TRACE(tcount, 2);
+                if (mt == 0) TG_TRACE(tcount, 2);
+                if (DCE_TRACE && p.trace && mt == 0 && blockIdx.x == 0 && tcount < 60 && (threadIdx.x & 31) == 0) {
+                    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.trace[tcount * 16 + 15] = (long long)gt;
+                }
                 ptx::mbar_wait(&tempty[buf], tph ^ 1);
-                TG_TRACE(tcount, 3);
+                if (mt == 0) TG_TRACE(tcount, 3);
                 ptx::tc_fence_after_sync();
-                const uint32_t d0 = tmem_base + buf * (MT * BN);
+                const uint32_t d = tmem_base + buf * (MT * BN) + mt * BN;
                 for (int s = 0; s < p.stages; ++s, ++it) {
                     const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                    if (mt == 0 && s >= 1 && s <= 3) TG_TRACE(tcount, 7 + 2 * s);     // 9, 11, 13: before the wait
                     ptx::mbar_wait(&full[slot], ph);
-                    if (s == 0) TG_TRACE(tcount, 4);
-                    if (s == p.stages - 1) TG_TRACE(tcount, 5);
+                    if (mt == 0 && s >= 1 && s <= 3) TG_TRACE(tcount, 8 + 2 * s);     // 10, 12, 14: after
+                    if (mt == 0 && s == 0) TG_TRACE(tcount, 4);
+                    if (mt == 0 && s == p.stages - 1) TG_TRACE(tcount, 5);
                     ptx::tc_fence_after_sync();
-                    const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES);
-                    const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : a0 + Cfg::A_BYTES;
+                    const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + mt * Cfg::A_TILE;
+                    const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
@@ -247,20 +264,16 @@ tapgemm_kernel(const TapGemmParams p) {
                                 const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
                                 const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
                                 const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-#pragma unroll
-                                for (int mt = 0; mt < MT; ++mt) {
-                                    const uint32_t a_hi = a0 + mt * Cfg::A_TILE + (2 * kk) * kSlabBytes + arow * 16;
-                                    const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                                    const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
-                                    const uint32_t d = d0 + mt * BN;
-                                    ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
-                                    ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
-                                    ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
-                                }
+                                const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
+                                const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                                const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                                ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
+                                ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
+                                ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
                             }
                         }
-                        ptx::umma_commit(&empty[slot]);          // frees the smem slot when these MMAs retire
-                        if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // accumulator complete
+                        ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
+                        if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
                     }
                     __syncwarp();
                 }
@@ -491,7 +504,7 @@ struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
 constexpr LayerCfg kLayers[6] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
-                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0
+                                 {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10}}; // fc.3
@@ -551,7 +564,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    DCE_KL(ctx, name, kern<<<grid, kThreads, Cfg::SMEM_BYTES, ctx.stream>>>(p));
+    DCE_KL(ctx, name, kern<<<grid, tapgemm_threads(MT), Cfg::SMEM_BYTES, ctx.stream>>>(p));
     return DCE_OK;
 }
 

@@ -11,13 +11,14 @@
 // even sit in adjacent lanes, and both conv weight images (2 x 48 KB bf16 hi/lo) stay resident in
 // shared memory for the life of the CTA.
 //
-// Warp roles (14 warps, 1 CTA/SM):
+// Warp roles (15 warps, 1 CTA/SM):
 //   warps 0-3  : converters   staged fp32 rows -> (z-score) -> bf16 hi/lo, in place in slab0[buf] (UMMA K-major layout)
 //   warps 4-11 : epilogue     epi1: TMEM D1 -> bias/ReLU/guard -> bf16 hi/lo -> slab1 (smem, feeds conv2)
 //                             epi2: TMEM D2 -> bias/ReLU/pool/guard -> bf16 hi/lo -> X2 tape (global)
 //   warp 13    : loader       raw fp32 rows of a tile -> slab buffer by bulk TMA (<= 2 copies), L2 prefetch ahead
-//   warp 12    : MMA issuer   weights via bulk TMA once; conv1(k+1) is issued before conv2(k) so the
-//                             tensor pipe works on the next tile's conv1 while epi1(k) fills slab1
+//   warp 12    : conv1 MMA issuer (+ weights via bulk TMA once)
+//   warp 14    : conv2 MMA issuer — separate issuers, so the tensor pipe always has the other conv's MMAs queued
+//                             while one issuer is between tiles or waiting for epi1 to fill slab1
 #pragma once
 #include "dce_tc.cuh"
 
@@ -25,7 +26,7 @@ namespace dce {
 namespace tc {
 
 constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
-constexpr int kB1Threads = 14 * 32;
+constexpr int kB1Threads = 15 * 32;
 constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
 constexpr int kB1WBytes = 49152;                   // one conv weight image: [stage 2][part 2][tap 3][j 4][64][8] bf16
 constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
@@ -280,10 +281,12 @@ block1_kernel(const Block1Params p) {
             }
             __syncwarp();
         }
-    } else if (warp == 12) {
-        // ===== MMA issuer (warp-uniform control flow; one elected lane issues) =====
+    } else if (warp == 12 || warp == 14) {
+        // ===== MMA issuers (warp-uniform control flow; one elected lane issues): warp 12 = conv1, warp 14 = conv2.
+        // Two issuers so that one's serial code between tiles (mbarrier probes, fences, descriptors: ~500 cycles, more
+        // than the tensor pipe's short queue covers) is filled by the other's MMAs; each accumulator keeps one issuer.
         {
-            if (ptx::elect_one()) {
+            if (warp == 12 && ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
                 ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
                 ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
@@ -333,11 +336,8 @@ block1_kernel(const Block1Params p) {
                 B1_TRACE(k, 5);
                 conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64, x1_empty, &d2_full[buf]);
             };
-            if (my_tiles > 0) issue_c1(0);
-            for (int k = 0; k < my_tiles; ++k) {
-                if (k + 1 < my_tiles) issue_c1(k + 1);
-                issue_c2(k);
-            }
+            if (warp == 12) { for (int k = 0; k < my_tiles; ++k) issue_c1(k); }
+            else            { for (int k = 0; k < my_tiles; ++k) issue_c2(k); }
         }
     } else {
         // ===== epilogue warps 4..11 =====

@@ -93,7 +93,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.N = 128; p.rw = kRW2; p.tv = 75;
         p.dbg = tapgemm_dbg_flag();
         p.trace = (tapgemm_trace_layer() == 2) ? block1_trace_ptr() : nullptr;
-        if ((rc = launch_layer<128, 3, 2, 6, EPI_TAPE, 2, 4>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
+        if ((rc = launch_layer<128, 3, 4, 3, EPI_TAPE, 2, 2>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
         // ---- conv4 + pool + flatten (a8, a9): X3 -> X4 (fc.0 operand layout, k' = t*128 + c)
         p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];

@@ -14,7 +14,12 @@ __global__ void __launch_bounds__(416, 1) mix(int flags, int reps, const uint8_t
     __shared__ uint64_t bar, tbar[8], stop_flag;
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += 416) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += 416) {
+        uint32_t h = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+        // flags bit4: random bf16 operands in [-2, 2] instead of zeros (switching power)
+        uint32_t w = (flags & 16) ? ((h & 0x807f807fu) | 0x3f803f80u) : 0u;
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(w, w * 3u | ((flags & 16) ? 0x3f003f00u : 0u) & 0xbfffbfffu, w, w);
+    }
     if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&tbar[i], 1); fence_barrier_init(); *(volatile uint64_t*)&stop_flag = 0; }
     if (warp == 8) { tmem_alloc(&slot, 512); tmem_relinquish(); }
     fence_proxy_async_smem(); tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
@@ -28,6 +33,9 @@ __global__ void __launch_bounds__(416, 1) mix(int flags, int reps, const uint8_t
         long long t0 = clock64();
         if (elect_one()) {
             for (int r = 0; r < reps; ++r) {
+                if ((flags & 32) && r) umma_commit(&tbar[1]);          // bit5: a tcgen05.commit after every 18 MMAs
+                if ((flags & 64) && r) { umma_commit(&tbar[1]); umma_commit(&tbar[2]); }
+                if (flags & 128) tc_fence_after_sync();
                 const uint32_t a0 = a0b + (r & 3) * 16640, b0 = b0b + (r & 1) * 24576;
 #pragma unroll
                 for (int tap = 0; tap < 3; ++tap) {
@@ -89,7 +97,7 @@ int main() {
     uint8_t *gsrc, *gdst; cudaMalloc(&gsrc, 8 << 20); cudaMemset(gsrc, 0, 8 << 20); cudaMalloc(&gdst, 148 * 256 * 128 + 1024);
     cudaFuncSetAttribute(mix, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int reps = 256;
-    for (int flags : {0, 1, 2, 3, 4, 12, 7, 15}) {
+    for (int flags : {0, 32, 64, 128, 32 + 15}) {
         for (int it = 0; it < 2; ++it) { mix<<<148, 416, 200 * 1024>>>(flags, reps, gsrc, gdst, d_out); cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("err %s\n", cudaGetErrorString(e)); return 1; } }
         long long h = 0; cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
         printf("flags=%2d  cycles per MMA (N=128) = %.1f\n", flags, (double)h / (reps * 18));

@@ -16,8 +16,9 @@ buf = (ctypes.c_longlong * (60 * 16))()
 assert eng.lib.dce_debug_read_trace(buf, 60 * 16) == 0
 t = np.array(buf, dtype=np.int64).reshape(60, 16)
 t0 = t[t > 0].min()
-names = ["ld:first", "ld:last", "mma:start", "mma:tempty", "mma:full0", "mma:fullL", "ep:start", "ep:tfull", "ep:done"]
+names = ["ld:first", "ld:last", "mma:start", "mma:tempty", "mma:full0", "mma:fullL", "ep:start", "ep:tfull", "ep:done", "s1:pre", "s1:post", "s2:pre", "s2:post", "s3:pre", "s3:post"]
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for k in range(0, 10):
-    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(9)))
-d = np.diff(t[2:14, 4]); print("tile period (cycles):", d.mean(), d.min(), d.max())
+    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(15)))
+k1 = max(k for k in range(60) if t[k, 2] > 0)
+print("tiles", k1 + 1, "SM clock during kernel: %.3f GHz" % ((t[k1, 2] - t[1, 2]) / (t[k1, 15] - t[1, 15])), " tile period cycles %.0f, ns %.0f" % ((t[k1, 2] - t[1, 2]) / (k1 - 1), (t[k1, 15] - t[1, 15]) / (k1 - 1)))
