@@ -30,7 +30,7 @@ using dce::Ctx;
 // ---- packed-weight buffer layout (one allocation so it can be broadcast) ----
 struct Fp32Layout {
     size_t w1, w2, w3, w4;          // conv [3][cin][cout]
-    size_t f1, f2, f3;              // fc [K][N], [K][N], [16][512]
+    size_t f1, f2, f3, f3t;         // fc [K][N], [K][N], [16][512], [512][16]
     size_t b[7];                    // biases in layer order
     size_t end;
 };
@@ -39,7 +39,7 @@ Fp32Layout make_fp32_layout(size_t base) {
     Fp32Layout L; size_t o = base;
     auto take = [&](size_t floats) { size_t r = o; o = align_up(o + floats * 4, 256); return r; };
     L.w1 = take(3 * 54 * 64);  L.w2 = take(3 * 64 * 64);  L.w3 = take(3 * 64 * 128);  L.w4 = take(3 * 128 * 128);
-    L.f1 = take((size_t)4736 * 2048);  L.f2 = take((size_t)2048 * 512);  L.f3 = take(16 * 512);
+    L.f1 = take((size_t)4736 * 2048);  L.f2 = take((size_t)2048 * 512);  L.f3 = take(16 * 512); L.f3t = take(16 * 512);
     const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
     for (int i = 0; i < 7; ++i) L.b[i] = take(bn[i]);
     L.end = o;
@@ -86,6 +86,7 @@ int pack_fp32(dce_weights* w, const float* const p[DCE_NUM_PARAMS], Ctx& ctx) {
     DCE_KL(ctx, "pack_fc1", pack_fc_kernel<<<dim3(4736 / 32, 2048 / 32), dim3(32, 8), 0, s>>>(p[8], at_mut<float>(w, L.f1), 2048, 4736, 1));
     DCE_KL(ctx, "pack_fc2", pack_fc_kernel<<<dim3(2048 / 32, 512 / 32), dim3(32, 8), 0, s>>>(p[10], at_mut<float>(w, L.f2), 512, 2048, 0));
     DCE_CUDA(cudaMemcpyAsync(at_mut<float>(w, L.f3), p[12], 16 * 512 * 4, cudaMemcpyDeviceToDevice, s));
+    DCE_KL(ctx, "pack_fc3", pack_fc_kernel<<<dim3(512 / 32, 1), dim3(32, 8), 0, s>>>(p[12], at_mut<float>(w, L.f3t), 16, 512, 0));
     const int bidx[7] = {1, 3, 5, 7, 9, 11, 13};
     const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
     for (int i = 0; i < 7; ++i)
@@ -103,6 +104,7 @@ int run_fp32(const dce_weights* w, const float* x, bool normalize, int64_t first
     if (attr_once.need()) {
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+        DCE_CUDA(cudaFuncSetAttribute(fc3_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFc3SmemBytes));
     }
     ConvParams cp{at<float>(w, L.w1), at<float>(w, L.b[0]), at<float>(w, L.w2), at<float>(w, L.b[1]),
                   at<float>(w, L.w3), at<float>(w, L.b[2]), at<float>(w, L.w4), at<float>(w, L.b[3])};
@@ -121,8 +123,8 @@ int run_fp32(const dce_weights* w, const float* x, bool normalize, int64_t first
             act4, at<float>(w, L.f1), at<float>(w, L.b[4]), h1, (int)m, 2048, 4736));
         DCE_KL(ctx, "fp32_fc2_sgemm", sgemm_bias_kernel<true><<<dim3(512 / 128, (unsigned)((m + 127) / 128)), 256, 0, s>>>(
             h1, at<float>(w, L.f2), at<float>(w, L.b[5]), h2, (int)m, 512, 2048));
-        const int g3 = (int)((m + 7) / 8 < (int64_t)w->sm_count * 4 ? (m + 7) / 8 : (int64_t)w->sm_count * 4);
-        DCE_KL(ctx, "fp32_fc3_argmax", fc3_argmax_kernel<<<g3, 256, 0, s>>>(h2, at<float>(w, L.f3), at<float>(w, L.b[6]), m,
+        const int g3 = (int)((m + 15) / 16 < (int64_t)w->sm_count * 2 ? (m + 15) / 16 : (int64_t)w->sm_count * 2);
+        DCE_KL(ctx, "fp32_fc3_argmax", fc3_argmax_kernel<<<g3, 256, kFc3SmemBytes, s>>>(h2, at<float>(w, L.f3t), at<float>(w, L.b[6]), m,
                                             logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,
                                             bits ? bits + c0 * 4 : nullptr));
     }
@@ -250,7 +252,7 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
         const Fp32Layout& L = w->f32;
         dce::tc::BiasPtrs bp;
         for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
-        bp.w3 = at<float>(w, L.f3); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
+        bp.w3 = at<float>(w, L.f3t); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
         rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx);
     }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;

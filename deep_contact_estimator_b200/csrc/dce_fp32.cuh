@@ -301,30 +301,46 @@ __device__ __forceinline__ void argmax_bits_store(const float (&y)[16], int64_t 
     }
 }
 
+// block = 16 windows x 16 outputs (one thread per logit); weights k-major in smem so the 16 output
+// threads of a window read 64 contiguous bytes and different windows broadcast
 __global__ void __launch_bounds__(256)
-fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3, const float* __restrict__ b3,
+fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3t, const float* __restrict__ b3,
                   int64_t n_windows, float* __restrict__ logits, int32_t* __restrict__ cls, uint8_t* __restrict__ bits) {
-    __shared__ float ws[16 * 512];
-    for (int i = threadIdx.x; i < 16 * 512; i += blockDim.x) ws[i] = __ldg(w3 + i);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int64_t w = (int64_t)blockIdx.x * nwarp + warp; w < n_windows; w += (int64_t)gridDim.x * nwarp) {
-        float hv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hv[i] = __ldg(h2 + w * 512 + i * 32 + lane);
+    extern __shared__ __align__(16) float fc3_smem[];
+    float* ws = fc3_smem;                  // [512][16]
+    float* hs = fc3_smem + 512 * 16;       // [16][516]
+    const int tid = threadIdx.x, o = tid & 15, wl = tid >> 4;
+    for (int i = tid; i < 16 * 512 / 4; i += 256)                     // w3t is already k-major [512][16]
+        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w3t) + i);
+    const float bias = __ldg(b3 + o);
+    for (int64_t w0 = (int64_t)blockIdx.x * 16; w0 < n_windows; w0 += (int64_t)gridDim.x * 16) {
+        __syncthreads();
+        for (int i = tid; i < 16 * 128; i += 256) {                       // 16 rows x 128 float4
+            const int r = i >> 7, c4 = i & 127;
+            const float4 v = (w0 + r < n_windows) ? __ldg(reinterpret_cast<const float4*>(h2 + (w0 + r) * 512) + c4) : make_float4(0, 0, 0, 0);
+            *reinterpret_cast<float4*>(hs + r * 516 + c4 * 4) = v;
+        }
+        __syncthreads();
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};                                // 4 partial sums: shorter dependency chains
+        const float* hrow = hs + wl * 516;
+#pragma unroll 8
+        for (int k = 0; k < 512; k += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
+            acc[0] = fmaf(hv.x, ws[(k + 0) * 16 + o], acc[0]);
+            acc[1] = fmaf(hv.y, ws[(k + 1) * 16 + o], acc[1]);
+            acc[2] = fmaf(hv.z, ws[(k + 2) * 16 + o], acc[2]);
+            acc[3] = fmaf(hv.w, ws[(k + 3) * 16 + o], acc[3]);
+        }
+        const float y_mine = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + bias;
+        // gather the window's 16 logits into its first lane (lanes 0 and 16 of each warp)
         float y[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) s = fmaf(hv[i], ws[j * 512 + i * 32 + lane], s);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            y[j] = s + __ldg(b3 + j);
-        }
-        if (lane == 0) argmax_bits_store(y, w, logits, cls, bits);
+        for (int j = 0; j < 16; ++j) y[j] = __shfl_sync(0xffffffffu, y_mine, (threadIdx.x & 16) + j);
+        const int64_t w = w0 + wl;
+        if (o == 0 && w < n_windows) argmax_bits_store(y, w, logits, cls, bits);
     }
 }
+constexpr int kFc3SmemBytes = (512 * 16 + 16 * 516) * 4;
 
 // ---------------------------------------------------------------------------
 // decimal2binary on labels; accuracy counters

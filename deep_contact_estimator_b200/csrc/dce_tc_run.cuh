@@ -20,6 +20,13 @@ struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const flo
 inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
                int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
     cudaStream_t s = ctx.stream;
+    {
+        static DeviceOnce fc3_once;
+        if (fc3_once.need()) {
+            cudaError_t e = cudaFuncSetAttribute(fp32::fc3_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fp32::kFc3SmemBytes);
+            if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+        }
+    }
     for (int64_t c0 = 0; c0 < n; c0 += kChunk) {
         const int m = (int)((n - c0 < kChunk) ? n - c0 : kChunk);
         const Workspace W = make_workspace(m);
@@ -93,14 +100,21 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.N = 128; p.rw = kRW2; p.tv = 75;
         p.dbg = tapgemm_dbg_flag();
         p.trace = (tapgemm_trace_layer() == 2) ? block1_trace_ptr() : nullptr;
-        if ((rc = launch_layer<128, 3, 4, 3, EPI_TAPE, 2, 2>(ctx, "tc_conv3", sm_count, p)) != DCE_OK) return rc;
+        const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
+        if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
+        rc = tiny ? launch_layer<128, 3, 4, 3, EPI_TAPE, 1, 2>(ctx, "tc_conv3", sm_count, p)
+                  : launch_layer<128, 3, 4, 3, EPI_TAPE, 2, 2>(ctx, "tc_conv3", sm_count, p);
+        if (rc != DCE_OK) return rc;
         // ---- conv4 + pool + flatten (a8, a9): X3 -> X4 (fc.0 operand layout, k' = t*128 + c)
         p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
         p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
         p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
         p.trace = (tapgemm_trace_layer() == 3) ? block1_trace_ptr() : nullptr;
-        if ((rc = launch_layer<128, 3, 2, 4, EPI_POOL_FC, 2>(ctx, "tc_conv4_pool", sm_count, p)) != DCE_OK) return rc;
+        if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
+        rc = tiny ? launch_layer<128, 3, 2, 6, EPI_POOL_FC, 1>(ctx, "tc_conv4_pool", sm_count, p)
+                  : launch_layer<128, 3, 2, 4, EPI_POOL_FC, 2>(ctx, "tc_conv4_pool", sm_count, p);
+        if (rc != DCE_OK) return rc;
         if (m <= small::kMaxB) {
             // ---- latency mode (K3): fc.0 / fc.3 as split-N fp32 GEMVs over the fp32 weight images
             using namespace small;
@@ -114,7 +128,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             }
             DCE_KL(ctx, "fc1_gemv", k1<<<2048 / 16, 256, m * 4736 * 4, s>>>(x4, W.x4.part_stride, W.x4.kch_stride, m, bp.f1, bp.b[4], h1f));
             DCE_KL(ctx, "fc2_gemv", k2<<<512 / 8, 256, m * 2048 * 4, s>>>(h1f, 0, 0, m, bp.f2, bp.b[5], h2));
-            DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<1, 256, 0, s>>>(
+            DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<1, 256, fp32::kFc3SmemBytes, s>>>(
                 h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
             continue;
         }
@@ -136,8 +150,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.trace = (tapgemm_trace_layer() == 5) ? block1_trace_ptr() : nullptr;
         if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32, 1>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
         // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
-        const int g3 = (int)((m + 7) / 8 < sm_count ? (m + 7) / 8 : sm_count);      // one 32 KB weight stage-in per SM
-        DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<g3, 256, 0, s>>>(
+        const int g3 = (int)((m + 15) / 16 < sm_count * 2 ? (m + 15) / 16 : sm_count * 2);
+        DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<g3, 256, fp32::kFc3SmemBytes, s>>>(
             h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
     }
     return DCE_OK;
