@@ -228,54 +228,67 @@ tapgemm_kernel(const TapGemmParams p) {
             }
         }
     } else if (warp >= kMmaWarp) {
-        // ===== MMA issuers: warp kMmaWarp + mt owns accumulator mt (warp-uniform loop; one elected lane issues) =====
+        // ===== MMA issuers: warp kMmaWarp + mt owns accumulator mt =====
+        // The tensor pipe queues only an MMA or two ahead of the issuing thread, so every cycle the issuer spends
+        // between two stages (mbarrier probe ~90 cycles, fences, elect, descriptor arithmetic) is a pipe bubble
+        // (tools/microbench/umma_mix.cu: 80 vs 65 cycles per N=128 MMA).  Hence: the leader lane is elected once,
+        // and the probe of the NEXT stage's barrier (and of the next tile's accumulator) sits in the middle of the
+        // current stage's MMAs, where the pipe still has queued work.
         {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
             const int mt = warp - kMmaWarp;
-            uint32_t it = 0, tcount = 0;
+            const bool leader = ptx::elect_one();
+            const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const uint32_t total_stages = (uint32_t)my_tiles * p.stages;
             if (WST) ptx::mbar_wait(wbar, 0);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t buf = tcount % NBUF, tph = (tcount / NBUF) & 1;
-                if (mt == 0) TG_TRACE(tcount, 2);
-                if (DCE_TRACE && p.trace && mt == 0 && blockIdx.x == 0 && tcount < 60 && (threadIdx.x & 31) == 0) {
-                    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.trace[tcount * 16 + 15] = (long long)gt;
-                }
-                ptx::mbar_wait(&tempty[buf], tph ^ 1);
-                if (mt == 0) TG_TRACE(tcount, 3);
+            uint32_t it = 0;
+            if (my_tiles > 0) {
+                ptx::mbar_wait(&tempty[0], 1);                       // fresh barrier: passes
+                ptx::mbar_wait(&full[0], 0);
                 ptx::tc_fence_after_sync();
+            }
+            for (int tcount = 0; tcount < my_tiles; ++tcount) {
+                const uint32_t buf = tcount % NBUF;
+                if (mt == 0) TG_TRACE(tcount, 2);
                 const uint32_t d = tmem_base + buf * (MT * BN) + mt * BN;
                 for (int s = 0; s < p.stages; ++s, ++it) {
-                    const uint32_t slot = it % NSTAGE, ph = (it / NSTAGE) & 1;
-                    if (mt == 0 && s >= 1 && s <= 3) TG_TRACE(tcount, 7 + 2 * s);     // 9, 11, 13: before the wait
-                    ptx::mbar_wait(&full[slot], ph);
-                    if (mt == 0 && s >= 1 && s <= 3) TG_TRACE(tcount, 8 + 2 * s);     // 10, 12, 14: after
+                    const uint32_t slot = it % NSTAGE;
                     if (mt == 0 && s == 0) TG_TRACE(tcount, 4);
                     if (mt == 0 && s == p.stages - 1) TG_TRACE(tcount, 5);
-                    ptx::tc_fence_after_sync();
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + mt * Cfg::A_TILE;
                     const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
-                    if (ptx::elect_one()) {
 #pragma unroll
-                        for (int tap = 0; tap < TAPS; ++tap) {
-                            const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
 #pragma unroll
-                            for (int kk = 0; kk < KSA / 2; ++kk) {
-                                const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
-                                const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
-                                const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
-                                const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                                const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
-                                const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                                const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                        for (int kk = 0; kk < KSA / 2; ++kk) {
+                            const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
+                            const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
+                            const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
+                            const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                            const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
+                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                            if (leader) {
                                 ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
                                 ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
                                 ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
                             }
+                            // mid-stage: probe what the NEXT stage needs while MMAs of this one are still queued
+                            if (tap == (TAPS - 1) / 2 && kk == (KSA / 2 - 1) / 2 && it + 1 < total_stages) {
+                                if (s == p.stages - 1) {                       // next stage opens the next tile
+                                    const uint32_t nt = tcount + 1;
+                                    ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
+                                }
+                                ptx::mbar_wait(&full[(it + 1) % NSTAGE], ((it + 1) / NSTAGE) & 1);
+                                ptx::tc_fence_after_sync();
+                            }
                         }
+                    }
+                    if (leader) {
                         ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
                         if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
                     }
-                    __syncwarp();
                 }
             }
         }
