@@ -316,40 +316,41 @@ tapgemm_kernel(const TapGemmParams p) {
             ptx::mbar_wait_relaxed(&tfull[buf], tph);
             if (warp == 0) TG_TRACE(tcount, 7);
             ptx::tc_fence_after_sync();
-#pragma unroll 1
+            // per-M-tile row bookkeeping
+            int rows[MT]; bool valid[MT]; size_t out_off[MT]; bool zero_prev[MT];
+#pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-            const int row = 128 * (m0 + mt) + row_in_tile;
-            // per-mode row bookkeeping
-            bool valid = true; size_t out_off = 0; bool zero_prev = false;
-            if (p.dbg & 2) continue;
-            if (EPI == EPI_TAPE) {
-                const int t = row % p.rw;
-                valid = t < p.tv;
-                out_off = (size_t)(row + kGuard) * 16;
-                zero_prev = (row == 0);
-            } else if (EPI == EPI_POOL_TAPE) {
-                const int t = row % p.rw;
-                valid = (t >> 1) < (p.tv >> 1);
-                const int orow = row >> 1;
-                out_off = (size_t)(orow + kGuard) * 16;
-                zero_prev = (orow == 0);
-                if (orow >= p.out_rows_cap) out_off = (size_t)-1;
-            } else if (EPI == EPI_POOL_FC) {
-                const int w = row / p.rw, t = row % p.rw;
-                const int to = t >> 1;
-                valid = to < (p.tv >> 1);
-                out_off = (valid && w < p.out_rows_cap) ? (size_t)(to * (BN / 8)) * p.out_kch_stride + (size_t)(w + kGuard) * 16 : (size_t)-1;
-            } else if (EPI == EPI_FC_TAPE) {
-                out_off = (size_t)(row + kGuard) * 16;
+                const int row = 128 * (m0 + mt) + row_in_tile;
+                rows[mt] = row; valid[mt] = true; out_off[mt] = 0; zero_prev[mt] = false;
+                if (EPI == EPI_TAPE) {
+                    const int t = row % p.rw;
+                    valid[mt] = t < p.tv;
+                    out_off[mt] = (size_t)(row + kGuard) * 16;
+                    zero_prev[mt] = (row == 0);
+                } else if (EPI == EPI_POOL_TAPE) {
+                    const int t = row % p.rw;
+                    valid[mt] = (t >> 1) < (p.tv >> 1);
+                    const int orow = row >> 1;
+                    out_off[mt] = (size_t)(orow + kGuard) * 16;
+                    zero_prev[mt] = (orow == 0);
+                    if (orow >= p.out_rows_cap) out_off[mt] = (size_t)-1;
+                } else if (EPI == EPI_POOL_FC) {
+                    const int w = row / p.rw, t = row % p.rw;
+                    const int to = t >> 1;
+                    valid[mt] = to < (p.tv >> 1);
+                    out_off[mt] = (valid[mt] && w < p.out_rows_cap) ? (size_t)(to * (BN / 8)) * p.out_kch_stride + (size_t)(w + kGuard) * 16 : (size_t)-1;
+                } else if (EPI == EPI_FC_TAPE) {
+                    out_off[mt] = (size_t)(row + kGuard) * 16;
+                }
             }
+            constexpr int CPM = HALF / 32;                   // 32-column chunks per M-tile for this warp
+            constexpr int NCH = MT * CPM;
+            const uint32_t taddr0 = tmem_base + buf * (MT * BN) + h * HALF + ((uint32_t)(q * 32) << 16);
+            auto chunk_addr = [&](int ci) { return taddr0 + (ci / CPM) * BN + (ci % CPM) * 32; };
 
-            const uint32_t taddr = tmem_base + buf * (MT * BN) + mt * BN + h * HALF + ((uint32_t)(q * 32) << 16);
-
-#pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 32) {
-                uint32_t v[32];
-                ptx::tmem_ld32(taddr + c0, v);
-                ptx::tmem_ld_wait();
+            // one 32-column chunk: bias / ReLU / pool / guard -> bf16 hi/lo -> store
+            auto process = [&](const uint32_t (&v)[32], int ci) {
+                const int mt = ci / CPM, c0 = (ci % CPM) * 32;
                 float y[32];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -360,49 +361,65 @@ tapgemm_kernel(const TapGemmParams p) {
                     y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
                 }
                 if (EPI == EPI_FC_F32) {
-                    if (row < p.n_valid) {
-                        float* dst = p.out_f32 + (size_t)row * p.N + n0 + c0;
+                    if (rows[mt] < p.n_valid) {
+                        float* dst = p.out_f32 + (size_t)rows[mt] * p.N + n0 + c0;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
                     }
-                } else {
-                    if (EPI == EPI_POOL_TAPE || EPI == EPI_POOL_FC) {
-                        // MaxPool1d(2,2): rows (2i, 2i+1) are adjacent lanes (src/contact_cnn.py:24-25,42-43)
+                    return;
+                }
+                if (EPI == EPI_POOL_TAPE || EPI == EPI_POOL_FC) {
+                    // MaxPool1d(2,2): rows (2i, 2i+1) are adjacent lanes (src/contact_cnn.py:24-25,42-43)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
+                    for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
+                }
+                if (EPI == EPI_TAPE || EPI == EPI_POOL_TAPE) {
+                    if (!valid[mt]) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) y[i] = 0.f;                  // guard rows stay zero
                     }
-                    if (EPI == EPI_TAPE || EPI == EPI_POOL_TAPE) {
-                        if (!valid) {
+                }
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) y[i] = 0.f;              // guard rows stay zero
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 hi, lo;
+                    split8(y + qd * 8, hi, lo);
+                    const int kch = (n0 + c0) / 8 + qd;
+                    if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
+                        uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off[mt];
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
+                        if (EPI == EPI_TAPE && zero_prev[mt]) {
+                            *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
                         }
-                    }
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        uint4 hi, lo;
-                        split8(y + qd * 8, hi, lo);
-                        const int kch = (n0 + c0) / 8 + qd;
-                        if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
-                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off;
-                            *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
-                            if (EPI == EPI_TAPE && zero_prev) {
-                                *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
-                                *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
-                            }
-                        } else {
-                            // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
-                            if (out_off != (size_t)-1) {
-                                uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off + ((lane & 1) ? p.out_part_stride : 0);
-                                *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
-                                if (EPI == EPI_POOL_TAPE && zero_prev) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
-                            }
+                    } else {
+                        // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
+                        if (out_off[mt] != (size_t)-1) {
+                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off[mt] + ((lane & 1) ? p.out_part_stride : 0);
+                            *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
+                            if (EPI == EPI_POOL_TAPE && zero_prev[mt]) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
                         }
                     }
                 }
+            };
+
+            // software pipeline over the chunks: the TMEM load of chunk i+1 is in flight while chunk i is processed
+            if (!(p.dbg & 2)) {
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld32(chunk_addr(0), va);
+#pragma unroll
+                for (int ci = 0; ci < NCH; ci += 2) {
+                    ptx::tmem_ld_wait();
+                    if (ci + 1 < NCH) ptx::tmem_ld32(chunk_addr(ci + 1), vb);
+                    process(va, ci);
+                    if (ci + 1 < NCH) {
+                        ptx::tmem_ld_wait();
+                        if (ci + 2 < NCH) ptx::tmem_ld32(chunk_addr(ci + 2), va);
+                        process(vb, ci + 1);
+                    }
+                }
             }
-            }   // mt
             if (warp == 0) TG_TRACE(tcount, 8);
             ptx::tc_fence_before_sync();
             __syncwarp();
