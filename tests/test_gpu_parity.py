@@ -292,3 +292,24 @@ def test_entrypoint_script_on_gpu(dev, tmp_path):
     events = list(lcm_wire.read_events(str(tmp_path / "out.lcm")))
     assert len(events) == 3 * 451
     assert lcm_wire.decode_contact(events[-2][3])[2] == want[-1].tolist()
+
+
+def test_random_shapes_property(dev, params0):
+    """hypothesis over batch sizes, log lengths and window offsets (odd/even first rows: rows are
+    216 B, so only even rows are 16-byte aligned): classes and bits exact, logits within tolerance."""
+    from hypothesis import given, settings, strategies as st
+    eng = engine(dev, "bf16x3")
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(st.integers(1, 700), st.integers(0, 40), st.integers(0, 1000))
+    def check(n_windows, first, seed):
+        log = synth.make_sensor_log(first + n_windows + 149 + (seed % 3), seed=seed)
+        lg, cl, bi = eng.stream(log.to(dev), first, n_windows, want_logits=True)
+        wl, wc, wb = oracle.inference_stream(params0, log, first=first, count=n_windows, batch_size=256)
+        assert oracle.normwise_rel_err(lg.cpu().numpy(), wl.numpy()) <= TOL["bf16x3"] * 2
+        assert np.array_equal(cl.cpu().numpy(), wc.numpy()) and np.array_equal(bi.cpu().numpy(), wb.numpy())
+        x = oracle.extract_windows(log, first, min(n_windows, 64))
+        lo, c2, _ = eng.classify(x.to(dev))
+        assert np.array_equal(c2.cpu().numpy(), wc.numpy()[: x.shape[0]])
+
+    check()
