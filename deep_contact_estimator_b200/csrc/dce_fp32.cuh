@@ -310,15 +310,28 @@ fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3t, c
     float* ws = fc3_smem;                  // [512][16]
     float* hs = fc3_smem + 512 * 16;       // [16][516]
     const int tid = threadIdx.x, o = tid & 15, wl = tid >> 4;
-    for (int i = tid; i < 16 * 512 / 4; i += 256)                     // w3t is already k-major [512][16]
-        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w3t) + i);
+    {   // w3t is already k-major [512][16]; issue all 8 loads, then all 8 stores (one memory latency, not eight)
+        float4 wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(w3t) + tid + 256 * j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(ws)[tid + 256 * j] = wv[j];
+    }
     const float bias = __ldg(b3 + o);
     for (int64_t w0 = (int64_t)blockIdx.x * 16; w0 < n_windows; w0 += (int64_t)gridDim.x * 16) {
         __syncthreads();
-        for (int i = tid; i < 16 * 128; i += 256) {                       // 16 rows x 128 float4
-            const int r = i >> 7, c4 = i & 127;
-            const float4 v = (w0 + r < n_windows) ? __ldg(reinterpret_cast<const float4*>(h2 + (w0 + r) * 512) + c4) : make_float4(0, 0, 0, 0);
-            *reinterpret_cast<float4*>(hs + r * 516 + c4 * 4) = v;
+        {   // 16 rows x 128 float4: all loads first, then the stores
+            float4 hv8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = tid + 256 * j, r = i >> 7, c4 = i & 127;
+                hv8[j] = (w0 + r < n_windows) ? __ldg(reinterpret_cast<const float4*>(h2 + (w0 + r) * 512) + c4) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = tid + 256 * j, r = i >> 7, c4 = i & 127;
+                *reinterpret_cast<float4*>(hs + r * 516 + c4 * 4) = hv8[j];
+            }
         }
         __syncthreads();
         float acc[4] = {0.f, 0.f, 0.f, 0.f};                                // 4 partial sums: shorter dependency chains
