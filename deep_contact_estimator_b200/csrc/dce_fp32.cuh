@@ -310,6 +310,7 @@ fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3t, c
     float* ws = fc3_smem;                  // [512][16]
     float* hs = fc3_smem + 512 * 16;       // [16][516]
     const int tid = threadIdx.x, o = tid & 15, wl = tid >> 4;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {   // w3t is already k-major [512][16]; issue all 8 loads, then all 8 stores (one memory latency, not eight)
         float4 wv[8];
 #pragma unroll
@@ -318,6 +319,7 @@ fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3t, c
         for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(ws)[tid + 256 * j] = wv[j];
     }
     const float bias = __ldg(b3 + o);
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // h2 comes from the previous kernel (no-op without PDL)
     for (int64_t w0 = (int64_t)blockIdx.x * 16; w0 < n_windows; w0 += (int64_t)gridDim.x * 16) {
         __syncthreads();
         {   // 16 rows x 128 float4: all loads first, then the stores

@@ -169,11 +169,13 @@ tapgemm_kernel(const TapGemmParams p) {
         ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
     }
+    pdl_launch_dependents();                                    // the next kernel's prologue may overlap our tail
     if (warp == kMmaWarp) { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                 // everything the previous kernel wrote is visible from here on
 
     if (warp >= kProducerWarp0) {
         // ===== TMA producers (warp-uniform loops; one elected lane per warp issues) =====
@@ -513,6 +515,8 @@ ingest_kernel(const float* __restrict__ x, int64_t first, int n_windows, const f
 __global__ void __launch_bounds__(256)
 window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, float* __restrict__ mean, float* __restrict__ sdev,
                     int reciprocal) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = idx / 64, c = idx % 64;
     if (w >= n_windows || c >= 54) return;
@@ -594,7 +598,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    DCE_KL(ctx, name, kern<<<grid, tapgemm_threads(MT), Cfg::SMEM_BYTES, ctx.stream>>>(p));
+    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), Cfg::SMEM_BYTES, ctx.stream, p); (void)le_; });
     return DCE_OK;
 }
 

@@ -127,6 +127,7 @@ block1_kernel(const Block1Params p) {
         ptx::mbar_init(&raw_full[0], 1); ptx::mbar_init(&raw_full[1], 1);
         ptx::fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 12) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
     // zero the activation slabs once: kchunk 7 of slab0 (channels 56..63 do not exist) and the
     // never-written halo rows of slab1 must not hold NaN bit patterns
@@ -138,6 +139,7 @@ block1_kernel(const Block1Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // the X2 tape we overwrite may still be read by the previous step's conv3; the stream-mode stats come from the kernel before us
 
     if (warp < 4) {
         // ===== converters: fp32 rows -> slab0[buf] =====

@@ -43,7 +43,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         int rc;
         TapGemmParams p{};
         if (stream_mode)
-            DCE_KL(ctx, "tc_window_stats", window_stats_kernel<<<(m * 64 + 255) / 256, 256, 0, s>>>(src, first + c0, m, mean, sdev, fuse_block1_flag() ? 1 : 0));
+            DCE_KL(ctx, "tc_window_stats", { cudaError_t le_ = launch_pdl(window_stats_kernel, dim3((m * 64 + 255) / 256), dim3(256), 0, s, src, first + c0, m, mean, sdev, fuse_block1_flag() ? 1 : 0); (void)le_; });
         if (fuse_block1_flag()) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static DeviceOnce attr_once;
@@ -62,9 +62,9 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
             if (stream_mode)
-                DCE_KL(ctx, "tc_block1_stream", block1_kernel<true><<<grid, kB1Threads, kB1SmemBytes, s>>>(b));
+                DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
-                DCE_KL(ctx, "tc_block1", block1_kernel<false><<<grid, kB1Threads, kB1SmemBytes, s>>>(b));
+                DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1_kernel<false>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
         } else {
         // ---- ingest (a2/a3/a4): windows -> X0 tape
         const int iblocks = W.x0.m_tiles * 4;
@@ -151,8 +151,9 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32, 1>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
         // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
         const int g3 = (int)((m + 15) / 16 < sm_count * 2 ? (m + 15) / 16 : sm_count * 2);
-        DCE_KL(ctx, "fc3_argmax_bits", fp32::fc3_argmax_kernel<<<g3, 256, fp32::kFc3SmemBytes, s>>>(
-            h2, bp.w3, bp.b[6], m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr));
+        DCE_KL(ctx, "fc3_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::fc3_argmax_kernel, dim3(g3), dim3(256), fp32::kFc3SmemBytes, s,
+            (const float*)
+            h2, bp.w3, bp.b[6], (int64_t)m, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr, bits ? bits + c0 * 4 : nullptr); (void)le_; });
     }
     return DCE_OK;
 }
