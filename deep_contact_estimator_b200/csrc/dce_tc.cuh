@@ -75,7 +75,7 @@ struct Tape {
 };
 inline Tape make_tape(int64_t rows, int kch) {
     Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;   // even: MT = 2 tiles
-    t.cap = kGuard + t.m_tiles * 128 + 8; t.kch = kch;
+    t.cap = kGuard + t.m_tiles * 128 + 136; t.kch = kch;   // trailing guard: the fused kernels' 124-row tiles read up to 130 rows past a tile start
     t.kch_stride = (size_t)t.cap * 16; t.part_stride = t.kch_stride * kch; t.bytes = align_up(t.part_stride * 2, 256);
     return t;
 }
@@ -536,24 +536,26 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, f
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr LayerCfg kLayers[6] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
+constexpr int kNumPacked = 7;
+constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
-                                 {128, 1, 4, 64, 4, 2, 2048, 10}}; // fc.3
+                                 {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
+                                 {128, 3, 4, 4, 1, 0, 128, 6}};    // block2.2 again, in 48 KB blocks for the fused block2 kernel
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
-struct PackedLayout { size_t w[6]; size_t begin, end; };
+struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
 inline PackedLayout make_packed_layout(size_t base) {
     PackedLayout L; L.begin = base; size_t o = base;
-    for (int i = 0; i < 6; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }
+    for (int i = 0; i < kNumPacked; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }
     L.end = o;
     return L;
 }
 
 inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ctx& ctx) {
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < kNumPacked; ++i) {
         const LayerCfg& c = kLayers[i];
         const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);

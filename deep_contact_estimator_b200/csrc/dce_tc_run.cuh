@@ -2,6 +2,7 @@
 #pragma once
 #include "dce_tc.cuh"
 #include "dce_tc_block1.cuh"
+#include "dce_tc_block2.cuh"
 #include "dce_small.cuh"
 
 namespace dce {
@@ -9,6 +10,7 @@ namespace tc {
 
 // debug/ablation switch: 0 = one kernel per layer (ingest, conv1, conv2 as separate launches)
 inline int& fuse_block1_flag() { static int v = 1; return v; }
+inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
@@ -90,6 +92,23 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.out = x2; p.out_part_stride = W.x2.part_stride; p.out_kch_stride = W.x2.kch_stride; p.out_rows_cap = W.x2.m_tiles * 128;
         if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
         }
+        const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
+        if (fuse_block2_flag() && !tiny) {
+            // ---- fused conv3 + conv4 + pool + flatten (a7-a9): X2 -> X4, X3 stays in shared memory
+            static DeviceOnce b2_once;
+            if (b2_once.need()) {
+                cudaError_t e = cudaFuncSetAttribute(block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+            }
+            Block2Params b{};
+            b.x2 = x2; b.x2_part_stride = W.x2.part_stride; b.x2_kch_stride = W.x2.kch_stride; b.n_windows = m;
+            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[2]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[6]);
+            b.b3 = bp.b[2]; b.b4 = bp.b[3];
+            b.out = x4; b.out_part_stride = W.x4.part_stride; b.out_kch_stride = W.x4.kch_stride; b.out_rows_cap = W.x4.m_tiles * 128;
+            b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
+            const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
+            DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+        } else {
         p = TapGemmParams{};
         p.n_tiles = 1;
         // ---- conv3 (a7): X2 -> X3
@@ -100,7 +119,6 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.N = 128; p.rw = kRW2; p.tv = 75;
         p.dbg = tapgemm_dbg_flag();
         p.trace = (tapgemm_trace_layer() == 2) ? block1_trace_ptr() : nullptr;
-        const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
         if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
         rc = tiny ? launch_layer<128, 3, 4, 3, EPI_TAPE, 1, 2>(ctx, "tc_conv3", sm_count, p)
                   : launch_layer<128, 3, 4, 3, EPI_TAPE, 2, 2>(ctx, "tc_conv3", sm_count, p);
@@ -115,6 +133,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         rc = tiny ? launch_layer<128, 3, 2, 6, EPI_POOL_FC, 1>(ctx, "tc_conv4_pool", sm_count, p)
                   : launch_layer<128, 3, 2, 4, EPI_POOL_FC, 2>(ctx, "tc_conv4_pool", sm_count, p);
         if (rc != DCE_OK) return rc;
+        }
         if (m <= small::kMaxB) {
             // ---- latency mode (K3): fc.0 / fc.3 as split-N fp32 GEMVs over the fp32 weight images
             using namespace small;

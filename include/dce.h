@@ -158,6 +158,7 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  * Ablation / debugging switches (process-wide).  Keys:
  *   "block1_dbg"   bit mask of timing ablations inside the fused block1 kernel (results invalid);
  *   "block1_trace" 1: record a per-role clock64 timeline of CTA 0 (tools/trace_block1.py);
+ *   "fuse_block2"  1 (default): conv3 + conv4 + pool run as ONE kernel (X3 stays in shared memory); 0: two launches;
  *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
  *                  0: one kernel per layer (activations round-trip through HBM).
  * Returns DCE_EINVAL for an unknown key.

@@ -313,3 +313,21 @@ def test_random_shapes_property(dev, params0):
         assert np.array_equal(c2.cpu().numpy(), wc.numpy()[: x.shape[0]])
 
     check()
+
+
+def test_fused_and_layerwise_kernels_agree(dev, params0):
+    """The fused block kernels (default) and the one-kernel-per-layer path (dce_set_option) compute the
+    same function: identical classes, logits equal to rounding."""
+    eng = engine(dev, "bf16x3")
+    x = synth.make_windows(300, seed=77).to(dev)
+    ref_logits, ref_cls, _ = eng.classify(x)
+    try:
+        for key in (b"fuse_block1", b"fuse_block2"):
+            assert eng.lib.dce_set_option(key, 0) == 0
+            lo, cl, _ = eng.classify(x)
+            assert torch.equal(cl, ref_cls)
+            assert oracle.normwise_rel_err(lo.cpu().numpy(), ref_logits.cpu().numpy()) <= 1e-5
+            assert eng.lib.dce_set_option(key, 1) == 0
+        assert eng.lib.dce_set_option(b"no_such_option", 1) == -1
+    finally:
+        eng.lib.dce_set_option(b"fuse_block1", 1); eng.lib.dce_set_option(b"fuse_block2", 1)

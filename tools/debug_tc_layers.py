@@ -24,7 +24,7 @@ def align(v, a=256):
 def tape(rows, kch):
     m_tiles = (rows + 127) // 128
     m_tiles += m_tiles & 1
-    cap = GUARD + m_tiles * 128 + 8
+    cap = GUARD + m_tiles * 128 + 136
     return dict(rows=rows, m_tiles=m_tiles, cap=cap, kch=kch, bytes=align(cap * 16 * kch * 2))
 
 
@@ -59,6 +59,8 @@ def main():
     x = synth.make_windows(B, seed=1)
     eng = dce.ContactEngine(params, dev, "bf16x3")
     eng.lib.dce_set_option(b"fuse_block1", 0 if layerwise else 1)
+    fused2 = "--block2" in sys.argv
+    eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
     logits, cls, bits = eng.classify(x.to(dev))
     torch.cuda.synchronize()
     ws = eng._workspace
@@ -86,7 +88,8 @@ def main():
         print("x0 pad channels / guard rows:", x0[:, :, 54:].abs().max().item(), x0[:, 150:, :].abs().max().item())
         conv_tape("x1", a1, 152, 150, 64)
     conv_tape("x2", a2, 76, 75, 64)
-    conv_tape("x3", a3, 76, 75, 128)
+    if not fused2:
+        conv_tape("x3", a3, 76, 75, 128)
     x4 = decode(ws, W["x4"])                                  # [B][592*8], k' = t*128 + c
     report("x4", x4.reshape(B, 37, 128), a4.permute(0, 2, 1))
     report("h1", decode(ws, W["h1"]), f1)

@@ -20,7 +20,10 @@ for precision in ("bf16x3", "fp32"):
     _, cl, bi = eng.stream(log.to(dev)); torch.cuda.synchronize()
     _, wc, wb = oracle.inference_stream(params, log)
     assert np.array_equal(bi.cpu().numpy(), wb.numpy()), precision
-    eng.lib.dce_set_option(b"fuse_block1", 0)
-    lo, cl, bi = eng.classify(synth.make_windows(37, seed=37).to(dev)); torch.cuda.synchronize()
-    eng.lib.dce_set_option(b"fuse_block1", 1)
+    for key in (b"fuse_block1", b"fuse_block2"):
+        eng.lib.dce_set_option(key, 0)
+        x = synth.make_windows(37, seed=37)
+        lo, cl, bi = eng.classify(x.to(dev)); torch.cuda.synchronize()
+        assert np.array_equal(cl.cpu().numpy(), oracle.forward_torch(params, x).detach().numpy().argmax(1)), key
+        eng.lib.dce_set_option(key, 1)
 print("sanitize run ok")
