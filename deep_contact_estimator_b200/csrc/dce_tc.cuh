@@ -536,14 +536,15 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, f
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 7;
+constexpr int kNumPacked = 8;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
-                                 {128, 3, 4, 4, 1, 0, 128, 6}};    // block2.2 again, in 48 KB blocks for the fused block2 kernel
+                                 {128, 3, 4, 4, 1, 0, 128, 6},     // block2.2 again, in 48 KB blocks (unused; kept for ablations)
+                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };

@@ -102,10 +102,11 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             }
             Block2Params b{};
             b.x2 = x2; b.x2_part_stride = W.x2.part_stride; b.x2_kch_stride = W.x2.kch_stride; b.n_windows = m;
-            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[2]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[6]);
+            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[7]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[3]);
             b.b3 = bp.b[2]; b.b4 = bp.b[3];
             b.out = x4; b.out_part_stride = W.x4.part_stride; b.out_kch_stride = W.x4.kch_stride; b.out_rows_cap = W.x4.m_tiles * 128;
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
+            b.trace = (tapgemm_trace_layer() == 6) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
             DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
         } else {
