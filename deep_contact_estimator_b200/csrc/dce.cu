@@ -16,6 +16,7 @@
 #include "dce_fp32.cuh"
 #include "dce_tc.cuh"
 #include "dce_tc_run.cuh"
+#include "dce_latency.cuh"
 
 namespace {
 
@@ -32,6 +33,7 @@ struct Fp32Layout {
     size_t w1, w2, w3, w4;          // conv [3][cin][cout]
     size_t f1, f2, f3, f3t;         // fc [K][N], [K][N], [16][512], [512][16]
     size_t b[7];                    // biases in layer order
+    size_t w4q, f1s, f2s;           // latency kernel: per-CTA contiguous slices (dce_latency.cuh)
     size_t end;
 };
 
@@ -42,6 +44,7 @@ Fp32Layout make_fp32_layout(size_t base) {
     L.f1 = take((size_t)4736 * 2048);  L.f2 = take((size_t)2048 * 512);  L.f3 = take(16 * 512); L.f3t = take(16 * 512);
     const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
     for (int i = 0; i < 7; ++i) L.b[i] = take(bn[i]);
+    L.w4q = take(3 * 128 * 128);  L.f1s = take((size_t)4736 * 2048);  L.f2s = take((size_t)2048 * 512);
     L.end = o;
     return L;
 }
@@ -61,10 +64,11 @@ struct dce_weights {
 namespace {
 
 constexpr int64_t kChunkFp32 = 4096;   // windows per internal pass (bounds the workspace)
+inline int& latency_kernel_flag() { static int v = 1; return v; }   // dce_set_option("latency_kernel", 0): per-layer kernels for B <= 4
 
 struct Fp32Workspace { size_t act4, h1, h2, end; };
 Fp32Workspace fp32_workspace(int64_t n) {
-    Fp32Workspace W; size_t o = 0;
+    Fp32Workspace W; size_t o = 256;      // [0,256): the latency kernel's barrier counters (dce_latency.cuh)
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.act4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.h2 = take((size_t)n * 512 * 4);
     W.end = o; return W;
@@ -91,6 +95,10 @@ int pack_fp32(dce_weights* w, const float* const p[DCE_NUM_PARAMS], Ctx& ctx) {
     const int bn[7] = {64, 64, 128, 128, 2048, 512, 16};
     for (int i = 0; i < 7; ++i)
         DCE_CUDA(cudaMemcpyAsync(at_mut<float>(w, L.b[i]), p[bidx[i]], bn[i] * 4, cudaMemcpyDeviceToDevice, s));
+    // latency kernel slices, cut from the images above
+    DCE_KL(ctx, "pack_w4q", dce::lat::pack_w4q_kernel<<<(4 * 384 * 32 + 255) / 256, 256, 0, s>>>(at<float>(w, L.w4), at_mut<float>(w, L.w4q)));
+    DCE_KL(ctx, "pack_f1s", dce::lat::pack_f1s_kernel<<<(dce::lat::kSlices * 4736 * 4 + 255) / 256, 256, 0, s>>>(at<float>(w, L.f1), at_mut<float>(w, L.f1s)));
+    DCE_KL(ctx, "pack_f2s", dce::lat::pack_f2s_kernel<<<(dce::lat::kSlices * 2048 + 255) / 256, 256, 0, s>>>(at<float>(w, L.f2), at_mut<float>(w, L.f2s)));
     return DCE_OK;
 }
 
@@ -220,12 +228,17 @@ int dce_weights_adopt(dce_weights* w) { if (!w) return DCE_EINVAL; w->packed = t
 
 size_t dce_workspace_bytes(int64_t max_windows, int precision) {
     if (max_windows <= 0) return 256;
+    size_t need = 0;
     if (precision == DCE_PREC_FP32) {
         const int64_t n = max_windows < kChunkFp32 ? max_windows : kChunkFp32;
-        return fp32_workspace(n).end;
+        need = fp32_workspace(n).end;
+    } else if (precision == DCE_PREC_BF16X3) {
+        need = dce::tc::workspace_bytes(max_windows);
+    } else {
+        return 0;
     }
-    if (precision == DCE_PREC_BF16X3) return dce::tc::workspace_bytes(max_windows);
-    return 0;
+    const size_t lat = dce::lat::workspace_bytes();      // calls of <= 4 windows run the fused latency kernel
+    return need > lat ? need : lat;
 }
 
 }  // extern "C"
@@ -245,7 +258,18 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
     if (!src) return DCE_EINVAL;
     if ((uintptr_t)src % 16 || (logits && (uintptr_t)logits % 16) || (bits && (uintptr_t)bits % 4) || (cls && (uintptr_t)cls % 4))
         return DCE_EALIGN;
-    if (precision == DCE_PREC_FP32)
+    rc = DCE_EUNSUPPORTED;
+    if (n <= dce::lat::kMaxB && latency_kernel_flag()) {
+        // latency mode (K3): one cooperative fp32 kernel for the whole path, both precision modes
+        const Fp32Layout& L = w->f32;
+        dce::lat::Weights wt;
+        wt.w1 = at<float>(w, L.w1); wt.w2 = at<float>(w, L.w2); wt.w3 = at<float>(w, L.w3); wt.w4q = at<float>(w, L.w4q);
+        wt.f1s = at<float>(w, L.f1s); wt.f2s = at<float>(w, L.f2s); wt.f3t = at<float>(w, L.f3t);
+        for (int i = 0; i < 7; ++i) wt.b[i] = at<float>(w, L.b[i]);
+        rc = dce::lat::run(wt, w->sm_count, src, is_stream, first, (int)n, logits, cls, bits, (char*)ws, ctx);
+    }
+    if (rc != DCE_EUNSUPPORTED) { /* done (or failed) in the latency kernel */ }
+    else if (precision == DCE_PREC_FP32)
         rc = run_fp32(w, src, is_stream, first, n, logits, cls, bits, (char*)ws, ctx);
     else
     {
@@ -324,6 +348,8 @@ int dce_set_option(const char* key, int value) {
     if (!key) return DCE_EINVAL;
     if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
     if (!strcmp(key, "fuse_block2")) { dce::tc::fuse_block2_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "latency_kernel")) { latency_kernel_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "latency_coop")) { dce::lat::coop_flag() = value; return DCE_OK; }
     if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
     if (!strcmp(key, "tapgemm_dbg")) { dce::tc::tapgemm_dbg_flag() = value; return DCE_OK; }
     if (!strcmp(key, "trace_layer")) { dce::tc::tapgemm_trace_layer() = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3

@@ -1,0 +1,490 @@
+// Latency mode (K3, B <= 4): the WHOLE path — window ingest (+ z-score), four convolutions, two pools,
+// three Linear layers, argmax, contact bits — as ONE cooperative persistent kernel, fp32 on the CUDA cores.
+//   /root/reference/src/contact_cnn.py:60-66, utils/data_handler.py:55-57, src/inference_one_seq.py:26-27,59-62
+//
+// Why not the tensor-core kernels: one window is 39 MFLOP but 43 MB of weights.  A 128-row UMMA tile would
+// hold 150 (then 75) useful rows on ONE or two SMs while 146 idle, and six dependent launches cost more than
+// the arithmetic.  Here every SM takes a slice of every layer and the layers are separated by four grid
+// barriers instead of launch boundaries:
+//   A  conv1+ReLU+conv2+ReLU+pool   item = (window, pooled row): halo rows recomputed, nothing exchanged   -> P1
+//   B  conv3+ReLU+conv4+ReLU+pool   item = (window, pooled row, quarter of the 128 output channels)        -> A4 (fc.0 operand)
+//   C  fc.0+ReLU                    128 CTAs x 16 outputs: the CTA's 303 KB weight slice streams through a 5 x 32 KB ring -> H1
+//   D  fc.3+ReLU                    128 CTAs x 4 outputs (32 KB slice resident)                            -> H2
+//   E  fc.6 + argmax + bits         CTA b for window b
+// Every weight block is fetched with 1-D bulk TMA as early as shared memory allows (conv weights at kernel
+// start, the fc.0 ring and the fc.3 slice before the barrier that precedes them), and the fc.0 slice is
+// prefetched into L2 at kernel start, so a phase starts with its weights already on chip.  All sums run in
+// a fixed order: results are bit-reproducible call to call.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dce_common.cuh"
+#include "dce_tc_ptx.cuh"
+#include "dce_fp32.cuh"
+#include "dce_tc.cuh"
+
+namespace dce {
+namespace lat {
+
+constexpr int kMaxB = 4;
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSlices = 128;                 // fc.0: 16 outputs per CTA, fc.3: 4 outputs per CTA
+constexpr int kStageRows = 512;              // fc.0 k-rows per ring stage
+constexpr int kStages = 10;                  // 9 x 512 + 128 = 4736
+constexpr int kRing = 5;
+constexpr int kStageBytes = kStageRows * 64;
+constexpr int kFc1SliceFloats = 4736 * 16;
+constexpr int kFc2SliceFloats = 2048 * 4;
+constexpr int kW1Bytes = 3 * 54 * 64 * 4;    // 41472
+constexpr int kW2Bytes = 3 * 64 * 64 * 4;    // 49152
+constexpr int kW3Bytes = 3 * 64 * 128 * 4;   // 98304
+constexpr int kW4qBytes = 3 * 128 * 32 * 4;  // 49152: one quarter of the output channels
+constexpr int kF2Bytes = kFc2SliceFloats * 4;
+
+// shared-memory map (bytes).  Phases A/B: [W1 | W2] (later W4 quarter) | W3.  Phases C/D: ring | fc.3 slice.
+constexpr int oW1 = 0, oW2 = kW1Bytes, oW4 = 0, oW3 = kW1Bytes + kW2Bytes;      // W3 ends at 188928
+constexpr int oRing = 0, oF2 = kRing * kStageBytes;                            // 163840 .. 196608
+constexpr int oAct = oF2 + kF2Bytes;
+constexpr int kXinFloats = 384, kMidFloats = 512, kRedFloats = 2048, kStatFloats = 128, kLogitFloats = 16;
+constexpr int oBars = oAct + (kXinFloats + kMidFloats + kRedFloats + kStatFloats + kLogitFloats) * 4;
+constexpr int kNumBars = 4 + kRing;
+constexpr int kSmemBytes = oBars + 128;
+static_assert(oW3 + kW3Bytes <= oAct, "conv weights overlap the activation scratch");
+static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
+
+// caller workspace: [0,256) two barrier counters (must be zero before the first call; the kernel leaves
+// them zero), then P1, A4, H1, H2 (fp32)
+struct Workspace { size_t p1, a4, h1, h2, end; };
+inline Workspace make_workspace(int n) {
+    Workspace W; size_t o = 256;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    W.p1 = take((size_t)n * 75 * 64 * 4); W.a4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.h2 = take((size_t)n * 512 * 4);
+    W.end = o;
+    return W;
+}
+inline size_t workspace_bytes() { return make_workspace(kMaxB).end; }
+
+struct Params {
+    const float* x; int stream; long long first; int B;      // batch: [B][150][54]; stream: [T][54], windows first .. first+B
+    const float *w1, *w2, *w3, *w4q, *f1s, *f2s, *f3t;        // fp32 images (see pack kernels below)
+    const float *b1, *b2, *b3, *b4, *bf1, *bf2, *bf3;
+    float *p1, *a4, *h1, *h2;
+    unsigned* sync;
+    float* logits; int32_t* cls; uint8_t* bits;
+};
+
+// ---- K0 additions: contiguous per-CTA slices, so a slice is a handful of bulk copies -----------------
+// w4q[q][k = tap*128 + cin][32]  from wp4[tap][cin][cout]
+__global__ void pack_w4q_kernel(const float* __restrict__ wp4, float* __restrict__ w4q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * 384 * 32) return;
+    const int o = i & 31, k = (i >> 5) % 384, q = i / (384 * 32);
+    w4q[i] = wp4[k * 128 + q * 32 + o];
+}
+// f1s[slice][stage][j][row][4]: output n = slice*16 + j*4 + e, k' = stage*512 + row, from f1p[k'][n]
+__global__ void pack_f1s_kernel(const float* __restrict__ f1p, float* __restrict__ f1s) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    if (i >= (size_t)kSlices * 4736 * 4) return;
+    const int sl = (int)(i / (4736 * 4));
+    int r = (int)(i % (4736 * 4));
+    const int s = r / (kStageRows * 4);
+    r -= s * kStageRows * 4;
+    const int rows = s < kStages - 1 ? kStageRows : 4736 - (kStages - 1) * kStageRows;
+    const int j = r / rows, row = r % rows;
+    const int k = s * kStageRows + row;
+    reinterpret_cast<float4*>(f1s)[i] = *reinterpret_cast<const float4*>(f1p + (size_t)k * 2048 + sl * 16 + j * 4);
+}
+// f2s[slice][row][4] from f2p[row][n]
+__global__ void pack_f2s_kernel(const float* __restrict__ f2p, float* __restrict__ f2s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                 // float4 index
+    if (i >= kSlices * 2048) return;
+    const int sl = i / 2048, row = i % 2048;
+    reinterpret_cast<float4*>(f2s)[i] = *reinterpret_cast<const float4*>(f2p + (size_t)row * 512 + sl * 4);
+}
+
+// ---- device helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Partial sums of a k=3 convolution on R consecutive output rows for CT output channels.  The input is
+// channels-last, so output row r reads the contiguous span xflat[r*CIN .. r*CIN + 3*CIN) (SURVEY §8a note A):
+//   red[(ks*R + r)*CT + o] = sum over this thread's k of xflat[r*CIN + k] * w[k*CT + o]
+// thread = (o, ks); the k pairs are dealt round-robin to the KS = 512/CT k-slices.
+template <int CIN, int CT, int R>
+__device__ __forceinline__ void conv_partial(const float* __restrict__ xflat, const float* __restrict__ w, float* __restrict__ red) {
+    constexpr int KS = kThreads / CT;
+    constexpr int KP = 3 * CIN / 2;
+    static_assert(KS * R * CT <= kRedFloats, "reduction scratch too small");
+    static_assert(CIN % 2 == 0 && CT >= 32, "float2 loads / warp-uniform k-slice");
+    const int o = threadIdx.x % CT, ks = threadIdx.x / CT;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int kp = ks; kp < KP; kp += KS) {
+        const int k = 2 * kp;
+        const float w0 = w[k * CT + o], w1 = w[(k + 1) * CT + o];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float2 xv = *reinterpret_cast<const float2*>(xflat + r * CIN + k);
+            acc[r] = fmaf(xv.x, w0, acc[r]);
+            acc[r] = fmaf(xv.y, w1, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) red[(ks * R + r) * CT + o] = acc[r];
+}
+
+// per-channel mean and unbiased std of one 150-row window (utils/data_handler.py:55-56), two-pass:
+// stat[c] = mean, stat[64 + c] = std.  part: >= 486 floats of scratch.  Ends with a __syncthreads().
+__device__ __forceinline__ void window_stats(const float* __restrict__ xw, float* __restrict__ part, float* __restrict__ stat) {
+    const int tid = threadIdx.x, c = tid % 54, s = tid / 54;
+    const bool act = tid < 486;                      // 9 row-slices x 54 channels
+    float xv[17], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const int row = s + 9 * i;
+        const bool ok = act && row < 150;
+        xv[i] = ok ? __ldg(xw + row * 54 + c) : 0.f;
+        sum += xv[i];
+    }
+    if (act) part[s * 54 + c] = sum;
+    __syncthreads();
+    if (tid < 54) {
+        float m = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m += part[j * 54 + tid];
+        stat[tid] = m / 150.f;
+    }
+    __syncthreads();
+    const float m = act ? stat[c] : 0.f;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const int row = s + 9 * i;
+        if (act && row < 150) { const float d = xv[i] - m; v = fmaf(d, d, v); }
+    }
+    if (act) part[s * 54 + c] = v;
+    __syncthreads();
+    if (tid < 54) {
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) q += part[j * 54 + tid];
+        stat[64 + tid] = sqrtf(q / 149.f);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+latency_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* w1s = reinterpret_cast<float*>(smem + oW1);
+    float* w2s = reinterpret_cast<float*>(smem + oW2);
+    float* w3s = reinterpret_cast<float*>(smem + oW3);
+    float* w4s = reinterpret_cast<float*>(smem + oW4);
+    uint8_t* ring = smem + oRing;
+    const float4* f2v = reinterpret_cast<const float4*>(smem + oF2);
+    float* xin = reinterpret_cast<float*>(smem + oAct);
+    float* mid = xin + kXinFloats;
+    float* red = mid + kMidFloats;
+    float* stat = red + kRedFloats;
+    float* logit_s = stat + kStatFloats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBars);
+    uint64_t* bar_w12 = bars, *bar_w3 = bars + 1, *bar_w4 = bars + 2, *bar_f2 = bars + 3, *ring_full = bars + 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const bool fc_cta = cta < kSlices;
+    const int total_stages = p.B * kStages;
+
+    if (tid == 0) {
+        for (int i = 0; i < kNumBars; ++i) ptx::mbar_init(&bars[i], 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(bar_w12, kW1Bytes + kW2Bytes);
+        ptx::bulk_g2s(w1s, p.w1, kW1Bytes, bar_w12);
+        ptx::bulk_g2s(w2s, p.w2, kW2Bytes, bar_w12);
+        ptx::mbar_arrive_expect_tx(bar_w3, kW3Bytes);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ptx::bulk_g2s(w3s + i * 8192, p.w3 + i * 8192, 32768, bar_w3);
+    }
+    if (warp == 1 && fc_cta && lane < kStages) {      // pull this CTA's fc.0 slice HBM -> L2 while the convolutions run
+        const float* src = p.f1s + (size_t)cta * kFc1SliceFloats + (size_t)lane * kStageRows * 16;
+        const uint32_t bytes = lane < kStages - 1 ? kStageBytes : (4736 - (kStages - 1) * kStageRows) * 64;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    }
+
+    auto issue_stage = [&](int g) {                   // thread 0: stage g (= window g/10, k-rows (g%10)*512 ..) -> ring slot g%5
+        const int s = g % kStages, slot = g % kRing;
+        const uint32_t bytes = s < kStages - 1 ? kStageBytes : (4736 - (kStages - 1) * kStageRows) * 64;
+        ptx::mbar_arrive_expect_tx(&ring_full[slot], bytes);
+        ptx::bulk_g2s(ring + slot * kStageBytes, p.f1s + (size_t)cta * kFc1SliceFloats + (size_t)s * kStageRows * 16, bytes, &ring_full[slot]);
+    };
+
+    // ================= phase A: ingest (+ z-score) -> conv1 -> conv2 -> pool =================
+    {
+        const int nA = p.B * 75;
+        int stat_b = -1;
+        for (int it = cta; it < nA; it += G) {
+            const int b = it / 75, tp = it - b * 75;
+            const float* xw = p.stream ? p.x + (size_t)(p.first + b) * 54 : p.x + (size_t)b * 8100;
+            if (p.stream && b != stat_b) { window_stats(xw, red, stat); stat_b = b; }
+            for (int i = tid; i < 6 * 54; i += kThreads) {               // input rows 2tp-2 .. 2tp+3, zero outside the window
+                const int j = i / 54, c = i - j * 54, row = 2 * tp - 2 + j;
+                float v = 0.f;
+                if (row >= 0 && row < 150) {
+                    v = __ldg(xw + row * 54 + c);
+                    if (p.stream) v = (v - stat[c]) / stat[64 + c];
+                }
+                xin[i] = v;
+            }
+            __syncthreads();
+            ptx::mbar_wait(bar_w12, 0);
+            conv_partial<54, 64, 4>(xin, w1s, red);                      // conv1 rows 2tp-1 .. 2tp+2
+            __syncthreads();
+            if (tid < 256) {
+                const int r = tid >> 6, o = tid & 63, row = 2 * tp - 1 + r;
+                float s = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) s += red[(ks * 4 + r) * 64 + o];
+                s = tc::relu_nan(s + __ldg(p.b1 + o));
+                mid[r * 64 + o] = (row >= 0 && row < 150) ? s : 0.f;     // conv2's zero padding
+            }
+            __syncthreads();
+            conv_partial<64, 64, 2>(mid, w2s, red);                      // conv2 rows 2tp, 2tp+1
+            __syncthreads();
+            if (tid < 64) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) { s0 += red[(ks * 2) * 64 + tid]; s1 += red[(ks * 2 + 1) * 64 + tid]; }
+                const float bias = __ldg(p.b2 + tid);
+                p.p1[(size_t)(b * 75 + tp) * 64 + tid] = tc::max_nan(tc::relu_nan(s0 + bias), tc::relu_nan(s1 + bias));
+            }
+            __syncthreads();
+        }
+    }
+    const int q = cta & 3;
+    if (tid == 0) {                                   // [W1 | W2] is free now: fetch this CTA's quarter of conv4
+        ptx::mbar_wait(bar_w12, 0);
+        ptx::mbar_arrive_expect_tx(bar_w4, kW4qBytes);
+        ptx::bulk_g2s(w4s, p.w4q + (size_t)q * (kW4qBytes / 4), kW4qBytes / 2, bar_w4);
+        ptx::bulk_g2s(w4s + kW4qBytes / 8, p.w4q + (size_t)q * (kW4qBytes / 4) + kW4qBytes / 8, kW4qBytes / 2, bar_w4);
+    }
+    grid_sync(p.sync, (unsigned)G);
+
+    // ================= phase B: conv3 -> conv4 -> pool -> flatten (k' = t*128 + c) =================
+    {
+        const int nB = p.B * 37, grp = cta >> 2, NG = G >> 2;
+        for (int it = grp; it < nB; it += NG) {
+            const int b = it / 37, t = it - b * 37;
+            for (int i = tid; i < 6 * 64; i += kThreads) {                // P1 rows 2t-2 .. 2t+3, zero outside [0, 75)
+                const int j = i >> 6, c = i & 63, row = 2 * t - 2 + j;
+                xin[i] = (row >= 0 && row < 75) ? __ldcg(p.p1 + (size_t)(b * 75 + row) * 64 + c) : 0.f;
+            }
+            __syncthreads();
+            ptx::mbar_wait(bar_w3, 0);
+            conv_partial<64, 128, 4>(xin, w3s, red);                     // conv3 rows 2t-1 .. 2t+2, all 128 channels
+            __syncthreads();
+            {
+                const int r = tid >> 7, o = tid & 127, row = 2 * t - 1 + r;
+                float s = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) s += red[(ks * 4 + r) * 128 + o];
+                s = tc::relu_nan(s + __ldg(p.b3 + o));
+                mid[r * 128 + o] = (row >= 0 && row < 75) ? s : 0.f;      // conv4's zero padding
+            }
+            __syncthreads();
+            ptx::mbar_wait(bar_w4, 0);
+            conv_partial<128, 32, 2>(mid, w4s, red);                     // conv4 rows 2t, 2t+1, channels q*32 .. q*32+31
+            __syncthreads();
+            if (tid < 32) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) { s0 += red[(ks * 2) * 32 + tid]; s1 += red[(ks * 2 + 1) * 32 + tid]; }
+                const float bias = __ldg(p.b4 + q * 32 + tid);
+                p.a4[(size_t)b * 4736 + t * 128 + q * 32 + tid] = tc::max_nan(tc::relu_nan(s0 + bias), tc::relu_nan(s1 + bias));
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {                                   // conv weights are dead: start the fc.3 slice and the fc.0 ring
+        ptx::mbar_wait(bar_w3, 0);
+        ptx::mbar_wait(bar_w4, 0);
+        if (fc_cta) {
+            ptx::mbar_arrive_expect_tx(bar_f2, kF2Bytes);
+            ptx::bulk_g2s(smem + oF2, p.f2s + (size_t)cta * kFc2SliceFloats, kF2Bytes, bar_f2);
+            for (int g = 0; g < kRing && g < total_stages; ++g) issue_stage(g);
+        }
+    }
+    grid_sync(p.sync, 2u * (unsigned)G);
+
+    // ================= phase C: fc.0 + ReLU, outputs cta*16 .. cta*16+15 =================
+    if (fc_cta) {
+        int g = 0;
+        for (int b = 0; b < p.B; ++b) {
+            float xk[kStages];
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) {
+                const int k = s * kStageRows + tid;
+                xk[s] = (k < 4736) ? __ldcg(p.a4 + (size_t)b * 4736 + k) : 0.f;
+            }
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int s = 0; s < kStages; ++s, ++g) {
+                const int slot = g % kRing;
+                ptx::mbar_wait(&ring_full[slot], (uint32_t)((g / kRing) & 1));
+                constexpr int kLastRows = 4736 - (kStages - 1) * kStageRows;
+                const int rows = s < kStages - 1 ? kStageRows : kLastRows;
+                if (tid < rows) {
+                    const float4* st = reinterpret_cast<const float4*>(ring + slot * kStageBytes);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = st[j * rows + tid];
+                        acc[j * 4 + 0] = fmaf(xk[s], w.x, acc[j * 4 + 0]);
+                        acc[j * 4 + 1] = fmaf(xk[s], w.y, acc[j * 4 + 1]);
+                        acc[j * 4 + 2] = fmaf(xk[s], w.z, acc[j * 4 + 2]);
+                        acc[j * 4 + 3] = fmaf(xk[s], w.w, acc[j * 4 + 3]);
+                    }
+                }
+                __syncthreads();                                          // slot drained by every thread
+                if (tid == 0 && g + kRing < total_stages) issue_stage(g + kRing);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float v = warp_sum(acc[i]);
+                if (lane == 0) red[warp * 16 + i] = v;
+            }
+            __syncthreads();
+            if (tid < 16) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) s += red[w * 16 + tid];
+                p.h1[(size_t)b * 2048 + cta * 16 + tid] = tc::relu_nan(s + __ldg(p.bf1 + cta * 16 + tid));
+            }
+            __syncthreads();
+        }
+    }
+    grid_sync(p.sync, 3u * (unsigned)G);
+
+    // ================= phase D: fc.3 + ReLU, outputs cta*4 .. cta*4+3 =================
+    if (fc_cta) {
+        ptx::mbar_wait(bar_f2, 0);
+        for (int b = 0; b < p.B; ++b) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = i * kThreads + tid;
+                const float x = __ldcg(p.h1 + (size_t)b * 2048 + row);
+                const float4 w = f2v[row];
+                a0 = fmaf(x, w.x, a0); a1 = fmaf(x, w.y, a1); a2 = fmaf(x, w.z, a2); a3 = fmaf(x, w.w, a3);
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+            if (lane == 0) { red[warp * 4 + 0] = a0; red[warp * 4 + 1] = a1; red[warp * 4 + 2] = a2; red[warp * 4 + 3] = a3; }
+            __syncthreads();
+            if (tid < 4) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) s += red[w * 4 + tid];
+                p.h2[(size_t)b * 512 + cta * 4 + tid] = tc::relu_nan(s + __ldg(p.bf2 + cta * 4 + tid));
+            }
+            __syncthreads();
+        }
+    }
+    grid_sync(p.sync, 4u * (unsigned)G);
+
+    // ================= phase E: fc.6 + argmax + contact bits, CTA b for window b =================
+    if (cta < p.B) {
+        const int b = cta;
+        const float x = __ldcg(p.h2 + (size_t)b * 512 + tid);
+        float pr[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.f3t + (size_t)tid * 16) + j);
+            pr[j * 4 + 0] = x * w.x; pr[j * 4 + 1] = x * w.y; pr[j * 4 + 2] = x * w.z; pr[j * 4 + 3] = x * w.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float v = warp_sum(pr[i]);
+            if (lane == 0) red[warp * 16 + i] = v;
+        }
+        __syncthreads();
+        if (tid < 16) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += red[w * 16 + tid];
+            logit_s[tid] = s + __ldg(p.bf3 + tid);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = logit_s[j];
+            fp32::argmax_bits_store(y, (int64_t)b, p.logits, p.cls, p.bits);
+        }
+    }
+    // every CTA is past the last barrier's spin when it gets here: the last one out re-arms the counters
+    if (tid == 0) {
+        const unsigned old = atomicAdd(p.sync + 1, 1u);
+        if (old == (unsigned)G - 1u) { p.sync[0] = 0u; p.sync[1] = 0u; __threadfence(); }
+    }
+}
+
+struct Weights {                  // pointers into the packed buffer
+    const float *w1, *w2, *w3, *w4q, *f1s, *f2s, *f3t, *b[7];
+};
+
+inline int& coop_flag() { static int v = 1; return v; }
+
+// -> DCE_EUNSUPPORTED when the device cannot co-schedule the grid (the caller then uses the per-layer kernels)
+inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mode, int64_t first, int n,
+               float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+    const int grid = sm_count / 4 * 4;
+    if (grid < kSlices || n < 1 || n > kMaxB) return DCE_EUNSUPPORTED;
+    static DeviceOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+    }
+    const Workspace W = make_workspace(n);
+    Params p{};
+    p.x = src; p.stream = stream_mode ? 1 : 0; p.first = first; p.B = n;
+    p.w1 = wt.w1; p.w2 = wt.w2; p.w3 = wt.w3; p.w4q = wt.w4q; p.f1s = wt.f1s; p.f2s = wt.f2s; p.f3t = wt.f3t;
+    p.b1 = wt.b[0]; p.b2 = wt.b[1]; p.b3 = wt.b[2]; p.b4 = wt.b[3]; p.bf1 = wt.b[4]; p.bf2 = wt.b[5]; p.bf3 = wt.b[6];
+    p.p1 = reinterpret_cast<float*>(ws + W.p1); p.a4 = reinterpret_cast<float*>(ws + W.a4);
+    p.h1 = reinterpret_cast<float*>(ws + W.h1); p.h2 = reinterpret_cast<float*>(ws + W.h2);
+    p.sync = reinterpret_cast<unsigned*>(ws);
+    p.logits = logits; p.cls = cls; p.bits = bits;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = ctx.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;        // the launch fails instead of deadlocking if the grid cannot be co-resident
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = coop_flag() ? 1 : 0;
+    DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel, p); (void)le_; });
+    return DCE_OK;
+}
+
+}  // namespace lat
+}  // namespace dce

@@ -571,7 +571,7 @@ struct Workspace {
     size_t o_x0, o_x1, o_x2, o_x3, o_x4, o_h1, o_h2, o_mean, o_sdev, end;
 };
 inline Workspace make_workspace(int64_t n) {
-    Workspace W; size_t o = 0;
+    Workspace W; size_t o = 256;          // [0,256): the latency kernel's barrier counters (dce_latency.cuh)
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.x0 = make_tape(n * kRW1, 8);   W.o_x0 = take(W.x0.bytes);
     W.x1 = make_tape(n * kRW1, 8);   W.o_x1 = take(W.x1.bytes);
