@@ -17,6 +17,7 @@ One JSON line on stdout (rank 0):
                host class/bits out, H2D + D2H inside the timed region
   roofline     dominant kernel: algorithmic FLOPs / its CUDA-event duration vs measured bf16 peak
   cpu_baseline the oracle (torch CPU restatement of the reference forward) on this box's host cores
+  latency_b1   BASELINE.json's second headline: p50 per-window microseconds at batch 1 (graph replay)
 --impl reference times that CPU path alone, same metric/config.
 """
 from __future__ import annotations
@@ -119,6 +120,64 @@ def cpu_forward_baseline(batch: int, budget_s: float = 20.0, max_runs: int = 5):
             "ms_per_batch": med * 1e3}, y
 
 
+def gpu_latency_b1(eng, dev, calls: int = 500):
+    """BASELINE.json's second headline: p50 per-window microseconds at batch 1 (latency mode, configs[4]).
+    A call = ContactEngine.latency_runner().step(): the new 150x54 window lies in pinned host memory, the fused
+    latency kernel (one CUDA-graph launch) reads it in place over PCIe and writes class + contact bits back to
+    pinned host memory.
+      host_us   wall clock of step() (graph launch -> results visible on the host)
+      gpu_us    CUDA events around one graph launch on an idle stream (includes launch latency)
+      gpu_us_back_to_back   `calls` launches queued without waiting / calls: the device time one step occupies"""
+    import numpy as np
+    import torch
+    from deep_contact_estimator_b200 import synth
+    run = eng.latency_runner(1)
+    run.x_host.copy_(synth.make_windows(1, seed=6))
+    for _ in range(20):
+        run.step()
+    host, gpu = [], []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        run.step()
+        host.append((time.perf_counter() - t0) * 1e6)
+    for _ in range(calls):
+        a.record(run.stream); run.enqueue(); b.record(run.stream)
+        b.synchronize()
+        gpu.append(a.elapsed_time(b) * 1e3)
+    a.record(run.stream)
+    for _ in range(calls):
+        run.enqueue()
+    b.record(run.stream)
+    b.synchronize()
+    b2b = a.elapsed_time(b) * 1e3 / calls
+    return {"gpu_us_p50": float(np.percentile(gpu, 50)), "gpu_us_p99": float(np.percentile(gpu, 99)),
+            "gpu_us_back_to_back": b2b,
+            "host_us_p50": float(np.percentile(host, 50)), "host_us_p99": float(np.percentile(host, 99)),
+            "calls": calls, "launches_per_call": run.launches, "bits": run.bits_host.tolist(),
+            "what": "batch=1 through ContactEngine.latency_runner().step(): one graph launch of the fused latency kernel, which reads the "
+                    "window (32.4 KB) from pinned host memory and writes class + contact bits to pinned host memory"}
+
+
+def cpu_latency_b1(params, calls: int = 100):
+    """The reference's forward at batch 1 on the host cores (oracle port), p50 microseconds per window."""
+    import numpy as np
+    import torch
+    from deep_contact_estimator_b200 import synth
+    from oracle import contact_oracle as oracle
+    x = synth.make_windows(1, seed=5)
+    t = []
+    with torch.no_grad():
+        for i in range(calls + 5):
+            t0 = time.perf_counter()
+            logits = oracle.forward_torch(params, x)
+            oracle.decimal2binary(oracle.argmax_class(logits))
+            if i >= 5:
+                t.append((time.perf_counter() - t0) * 1e6)
+    return {"host_us_p50": float(np.percentile(t, 50)), "host_us_p99": float(np.percentile(t, 99)), "calls": calls,
+            "what": "batch=1 forward + argmax + bits through the oracle port (reference ops) on the host cores"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path (the
     oracle port: /root/reference is Python and cannot travel to the GPU box)."""
@@ -153,6 +212,7 @@ def run_reference_arm(args):
                          "sample": f"{args.steps} steps x {batch} windows through oracle.forward_torch (reference ops on CPU)"},
         "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "latency_b1": cpu_latency_b1(params),
     }
     print(json.dumps(line), flush=True)
 
@@ -290,6 +350,7 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
 
+    latency = gpu_latency_b1(eng, dev)
     peaks, peak_src = load_peaks()
     dom = max(per_kernel_ms, key=per_kernel_ms.get) if per_kernel_ms else None
     roofline = None
@@ -335,7 +396,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * 32400, "d2h_bytes_per_step": B * 8,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "api": "ContactEngine.classify_host (pinned host windows -> host cls+bits)"},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "latency_b1": latency,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -6,13 +6,13 @@ the ``contact_cnn`` module surface, ``contact_dataset``, and the
 hand-written sm_100a kernels behind the C ABI in ``include/dce.h``.
 """
 from .synth import WINDOW, CHANNELS, CLASSES, PARAM_NAMES, PARAM_SHAPES
-from .engine import ContactEngine, default_precision
+from .engine import ContactEngine, LatencyRunner, default_precision
 from .contact_cnn import contact_cnn
 from .data_handler import contact_dataset
 from .inference import inference, inference_and_compute_acc, compute_accuracy, decimal2binary
 
 __all__ = [
-    "contact_cnn", "contact_dataset", "ContactEngine", "inference", "inference_and_compute_acc",
+    "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "inference", "inference_and_compute_acc",
     "compute_accuracy", "decimal2binary", "default_precision",
     "WINDOW", "CHANNELS", "CLASSES", "PARAM_NAMES", "PARAM_SHAPES",
 ]

@@ -350,6 +350,7 @@ int dce_set_option(const char* key, int value) {
     if (!strcmp(key, "fuse_block2")) { dce::tc::fuse_block2_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { latency_kernel_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { dce::lat::coop_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "latency_tma_in")) { dce::lat::tma_in_flag() = value; return DCE_OK; }
     if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
     if (!strcmp(key, "tapgemm_dbg")) { dce::tc::tapgemm_dbg_flag() = value; return DCE_OK; }
     if (!strcmp(key, "trace_layer")) { dce::tc::tapgemm_trace_layer() = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3

@@ -4,13 +4,13 @@
 //
 // Why not the tensor-core kernels: one window is 39 MFLOP but 43 MB of weights.  A 128-row UMMA tile would
 // hold 150 (then 75) useful rows on ONE or two SMs while 146 idle, and six dependent launches cost more than
-// the arithmetic.  Here every SM takes a slice of every layer and the layers are separated by four grid
+// the arithmetic.  Here every SM takes a slice of every layer and the layers are separated by three grid
 // barriers instead of launch boundaries:
 //   A  conv1+ReLU+conv2+ReLU+pool   item = (window, pooled row): halo rows recomputed, nothing exchanged   -> P1
 //   B  conv3+ReLU+conv4+ReLU+pool   item = (window, pooled row, quarter of the 128 output channels)        -> A4 (fc.0 operand)
 //   C  fc.0+ReLU                    128 CTAs x 16 outputs: the CTA's 303 KB weight slice streams through a 5 x 32 KB ring -> H1
-//   D  fc.3+ReLU                    128 CTAs x 4 outputs (32 KB slice resident)                            -> H2
-//   E  fc.6 + argmax + bits         CTA b for window b
+//   D  fc.3+ReLU, fc.6              128 CTAs x 4 outputs (32 KB slice resident), each adds its share of the 16 logits;
+//      + argmax + bits              the LAST CTA to finish (atomic ticket, no barrier) sums the 128 shares in a fixed order
 // Every weight block is fetched with 1-D bulk TMA as early as shared memory allows (conv weights at kernel
 // start, the fc.0 ring and the fc.3 slice before the barrier that precedes them), and the fc.0 slice is
 // prefetched into L2 at kernel start, so a phase starts with its weights already on chip.  All sums run in
@@ -48,28 +48,28 @@ constexpr int oRing = 0, oF2 = kRing * kStageBytes;                            /
 constexpr int oAct = oF2 + kF2Bytes;
 constexpr int kXinFloats = 384, kMidFloats = 512, kRedFloats = 2048, kStatFloats = 128, kLogitFloats = 16;
 constexpr int oBars = oAct + (kXinFloats + kMidFloats + kRedFloats + kStatFloats + kLogitFloats) * 4;
-constexpr int kNumBars = 4 + kRing;
+constexpr int kNumBars = 6 + kRing;
 constexpr int kSmemBytes = oBars + 128;
 static_assert(oW3 + kW3Bytes <= oAct, "conv weights overlap the activation scratch");
 static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
 
-// caller workspace: [0,256) two barrier counters (must be zero before the first call; the kernel leaves
-// them zero), then P1, A4, H1, H2 (fp32)
-struct Workspace { size_t p1, a4, h1, h2, end; };
+// caller workspace: [0,256) barrier / exit / ticket counters (must be zero before the first call; the kernel
+// leaves them zero) and a small clock64 trace, then P1, A4, H1 and the per-CTA logit shares (fp32)
+struct Workspace { size_t p1, a4, h1, part, end; };
 inline Workspace make_workspace(int n) {
     Workspace W; size_t o = 256;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    W.p1 = take((size_t)n * 75 * 64 * 4); W.a4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.h2 = take((size_t)n * 512 * 4);
+    W.p1 = take((size_t)n * 75 * 64 * 4); W.a4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.part = take((size_t)n * kSlices * 16 * 4);
     W.end = o;
     return W;
 }
 inline size_t workspace_bytes() { return make_workspace(kMaxB).end; }
 
 struct Params {
-    const float* x; int stream; long long first; int B;      // batch: [B][150][54]; stream: [T][54], windows first .. first+B
+    const float* x; int stream; int tma_in; long long first; int B;      // batch: [B][150][54]; stream: [T][54], windows first .. first+B
     const float *w1, *w2, *w3, *w4q, *f1s, *f2s, *f3t;        // fp32 images (see pack kernels below)
     const float *b1, *b2, *b3, *b4, *bf1, *bf2, *bf3;
-    float *p1, *a4, *h1, *h2;
+    float *p1, *a4, *h1, *part;
     unsigned* sync;
     float* logits; int32_t* cls; uint8_t* bits;
 };
@@ -104,15 +104,18 @@ __global__ void pack_f2s_kernel(const float* __restrict__ f2p, float* __restrict
 }
 
 // ---- device helpers ----------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned target) {
+// k-th grid barrier of the launch (k = 1, 2, ...): sync[0] counts arrivals, everyone polls it.  (Measured
+// alternative: the last arriver — found with a value-returning atom.acq_rel — publishes a separate flag word the
+// others poll; that was 0.4 us per barrier SLOWER than this fire-and-forget red + poll.)
+__device__ __forceinline__ void grid_sync(unsigned* sync, unsigned k, unsigned G) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
         unsigned v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while (v < target);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+        } while (v < k * G);
         __threadfence();
     }
     __syncthreads();
@@ -193,6 +196,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// clock64 timeline of the first and the last CTA, in the workspace header behind the two counters
+// (bytes 64.. : [which CTA 0/1][event 0..11] u64) — read by tools/debug_latency.py
+#define LAT_TRACE(ev) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+    reinterpret_cast<long long*>(p.sync)[8 + (blockIdx.x ? 12 : 0) + (ev)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kThreads, 1)
 latency_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -208,22 +216,42 @@ latency_kernel(const Params p) {
     float* stat = red + kRedFloats;
     float* logit_s = stat + kStatFloats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBars);
-    uint64_t* bar_w12 = bars, *bar_w3 = bars + 1, *bar_w4 = bars + 2, *bar_f2 = bars + 3, *ring_full = bars + 4;
+    uint64_t* bar_w1 = bars, *bar_w2 = bars + 1, *bar_w3 = bars + 2, *bar_w4 = bars + 3, *bar_f2 = bars + 4, *ring_full = bars + 5;
+    uint64_t* bar_x = bars + 5 + kRing;
+    int* last_flag = reinterpret_cast<int*>(bars + 12);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const bool fc_cta = cta < kSlices;
     const int total_stages = p.B * kStages;
+    const int nA = p.B * 75;
+    const bool a_cta = cta < nA;                      // has phase-A items: needs conv1 / conv2 weights
+    const float w3r = (fc_cta && tid < 64) ? __ldg(p.f3t + cta * 64 + tid) : 0.f;   // fc.6 weights of h2[cta*4 .. cta*4+3]
 
     if (tid == 0) {
         for (int i = 0; i < kNumBars; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_barrier_init();
     }
     __syncthreads();
+    LAT_TRACE(0);
+    // batch mode: the 6 input rows of an item are one contiguous, 16-byte aligned span of x (rows are 216 B, the
+    // span starts on an even row): ONE bulk copy straight into xin — x may be pinned HOST memory (LatencyRunner),
+    // where one large read beats 324 scalar loads over PCIe.  Rows outside the window are zero-filled by hand.
+    const bool tma_in = !p.stream && p.tma_in;
+    auto issue_x = [&](int it) {                      // thread 0
+        const int b = it / 75, tp = it - b * 75;
+        const int lo = (2 * tp - 2 > 0) ? 2 * tp - 2 : 0, hi = (2 * tp + 4 < 150) ? 2 * tp + 4 : 150;
+        ptx::mbar_arrive_expect_tx(bar_x, (uint32_t)(hi - lo) * 216u);
+        ptx::bulk_g2s(xin + (lo - (2 * tp - 2)) * 54, p.x + (size_t)b * 8100 + lo * 54, (uint32_t)(hi - lo) * 216u, bar_x);
+    };
     if (tid == 0) {
-        ptx::mbar_arrive_expect_tx(bar_w12, kW1Bytes + kW2Bytes);
-        ptx::bulk_g2s(w1s, p.w1, kW1Bytes, bar_w12);
-        ptx::bulk_g2s(w2s, p.w2, kW2Bytes, bar_w12);
+        if (a_cta && tma_in) issue_x(cta);
+        if (a_cta) {
+            ptx::mbar_arrive_expect_tx(bar_w1, kW1Bytes);
+            ptx::bulk_g2s(w1s, p.w1, kW1Bytes, bar_w1);
+            ptx::mbar_arrive_expect_tx(bar_w2, kW2Bytes);
+            ptx::bulk_g2s(w2s, p.w2, kW2Bytes, bar_w2);
+        }
         ptx::mbar_arrive_expect_tx(bar_w3, kW3Bytes);
 #pragma unroll
         for (int i = 0; i < 3; ++i) ptx::bulk_g2s(w3s + i * 8192, p.w3 + i * 8192, 32768, bar_w3);
@@ -243,23 +271,33 @@ latency_kernel(const Params p) {
 
     // ================= phase A: ingest (+ z-score) -> conv1 -> conv2 -> pool =================
     {
-        const int nA = p.B * 75;
         int stat_b = -1;
+        uint32_t xphase = 0;
         for (int it = cta; it < nA; it += G) {
             const int b = it / 75, tp = it - b * 75;
             const float* xw = p.stream ? p.x + (size_t)(p.first + b) * 54 : p.x + (size_t)b * 8100;
             if (p.stream && b != stat_b) { window_stats(xw, red, stat); stat_b = b; }
-            for (int i = tid; i < 6 * 54; i += kThreads) {               // input rows 2tp-2 .. 2tp+3, zero outside the window
-                const int j = i / 54, c = i - j * 54, row = 2 * tp - 2 + j;
-                float v = 0.f;
-                if (row >= 0 && row < 150) {
-                    v = __ldg(xw + row * 54 + c);
-                    if (p.stream) v = (v - stat[c]) / stat[64 + c];
+            if (tma_in) {
+                if (it != cta && tid == 0) issue_x(it);                  // (the first item's copy was issued in the prologue)
+                for (int i = tid; i < 6 * 54; i += kThreads) {
+                    const int row = 2 * tp - 2 + i / 54;
+                    if (row < 0 || row >= 150) xin[i] = 0.f;
                 }
-                xin[i] = v;
+                ptx::mbar_wait(bar_x, xphase);
+                xphase ^= 1u;
+            } else {
+                for (int i = tid; i < 6 * 54; i += kThreads) {           // input rows 2tp-2 .. 2tp+3, zero outside the window
+                    const int j = i / 54, c = i - j * 54, row = 2 * tp - 2 + j;
+                    float v = 0.f;
+                    if (row >= 0 && row < 150) {
+                        v = __ldg(xw + row * 54 + c);
+                        if (p.stream) v = (v - stat[c]) / stat[64 + c];
+                    }
+                    xin[i] = v;
+                }
             }
             __syncthreads();
-            ptx::mbar_wait(bar_w12, 0);
+            ptx::mbar_wait(bar_w1, 0);
             conv_partial<54, 64, 4>(xin, w1s, red);                      // conv1 rows 2tp-1 .. 2tp+2
             __syncthreads();
             if (tid < 256) {
@@ -271,6 +309,7 @@ latency_kernel(const Params p) {
                 mid[r * 64 + o] = (row >= 0 && row < 150) ? s : 0.f;     // conv2's zero padding
             }
             __syncthreads();
+            ptx::mbar_wait(bar_w2, 0);
             conv_partial<64, 64, 2>(mid, w2s, red);                      // conv2 rows 2tp, 2tp+1
             __syncthreads();
             if (tid < 64) {
@@ -283,14 +322,16 @@ latency_kernel(const Params p) {
             __syncthreads();
         }
     }
+    LAT_TRACE(1);
     const int q = cta & 3;
     if (tid == 0) {                                   // [W1 | W2] is free now: fetch this CTA's quarter of conv4
-        ptx::mbar_wait(bar_w12, 0);
+        if (a_cta) { ptx::mbar_wait(bar_w1, 0); ptx::mbar_wait(bar_w2, 0); }
         ptx::mbar_arrive_expect_tx(bar_w4, kW4qBytes);
         ptx::bulk_g2s(w4s, p.w4q + (size_t)q * (kW4qBytes / 4), kW4qBytes / 2, bar_w4);
         ptx::bulk_g2s(w4s + kW4qBytes / 8, p.w4q + (size_t)q * (kW4qBytes / 4) + kW4qBytes / 8, kW4qBytes / 2, bar_w4);
     }
-    grid_sync(p.sync, (unsigned)G);
+    grid_sync(p.sync, 1u, (unsigned)G);
+    LAT_TRACE(2);
 
     // ================= phase B: conv3 -> conv4 -> pool -> flatten (k' = t*128 + c) =================
     {
@@ -327,6 +368,7 @@ latency_kernel(const Params p) {
             __syncthreads();
         }
     }
+    LAT_TRACE(3);
     if (tid == 0) {                                   // conv weights are dead: start the fc.3 slice and the fc.0 ring
         ptx::mbar_wait(bar_w3, 0);
         ptx::mbar_wait(bar_w4, 0);
@@ -336,7 +378,8 @@ latency_kernel(const Params p) {
             for (int g = 0; g < kRing && g < total_stages; ++g) issue_stage(g);
         }
     }
-    grid_sync(p.sync, 2u * (unsigned)G);
+    grid_sync(p.sync, 2u, (unsigned)G);
+    LAT_TRACE(4);
 
     // ================= phase C: fc.0 + ReLU, outputs cta*16 .. cta*16+15 =================
     if (fc_cta) {
@@ -386,10 +429,15 @@ latency_kernel(const Params p) {
             __syncthreads();
         }
     }
-    grid_sync(p.sync, 3u * (unsigned)G);
+    LAT_TRACE(5);
+    grid_sync(p.sync, 3u, (unsigned)G);
+    LAT_TRACE(6);
 
-    // ================= phase D: fc.3 + ReLU, outputs cta*4 .. cta*4+3 =================
+    // ================= phase D: fc.3 + ReLU (outputs cta*4 .. cta*4+3) and this CTA's share of fc.6 =================
     if (fc_cta) {
+        float* w3sl = stat;                            // [4][16] fc.6 weights of this CTA's four fc.3 outputs
+        float* h2s = stat + 64;                        // [B][4]
+        if (tid < 64) w3sl[tid] = w3r;
         ptx::mbar_wait(bar_f2, 0);
         for (int b = 0; b < p.B; ++b) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -407,47 +455,56 @@ latency_kernel(const Params p) {
                 float s = 0.f;
 #pragma unroll
                 for (int w = 0; w < kWarps; ++w) s += red[w * 4 + tid];
-                p.h2[(size_t)b * 512 + cta * 4 + tid] = tc::relu_nan(s + __ldg(p.bf2 + cta * 4 + tid));
+                h2s[b * 4 + tid] = tc::relu_nan(s + __ldg(p.bf2 + cta * 4 + tid));
             }
             __syncthreads();
         }
-    }
-    grid_sync(p.sync, 4u * (unsigned)G);
-
-    // ================= phase E: fc.6 + argmax + contact bits, CTA b for window b =================
-    if (cta < p.B) {
-        const int b = cta;
-        const float x = __ldcg(p.h2 + (size_t)b * 512 + tid);
-        float pr[16];
+        if (tid < 16 * p.B) {                          // share[b][cta][o] = sum_e h2[cta*4+e] * W3[o][cta*4+e]
+            const int b = tid >> 4, o = tid & 15;
+            float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(p.f3t + (size_t)tid * 16) + j);
-            pr[j * 4 + 0] = x * w.x; pr[j * 4 + 1] = x * w.y; pr[j * 4 + 2] = x * w.z; pr[j * 4 + 3] = x * w.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float v = warp_sum(pr[i]);
-            if (lane == 0) red[warp * 16 + i] = v;
+            for (int e = 0; e < 4; ++e) v = fmaf(h2s[b * 4 + e], w3sl[e * 16 + o], v);
+            p.part[((size_t)b * kSlices + cta) * 16 + o] = v;
+            __threadfence();
         }
         __syncthreads();
-        if (tid < 16) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += red[w * 16 + tid];
-            logit_s[tid] = s + __ldg(p.bf3 + tid);
-        }
+        LAT_TRACE(7);
+        // ============= phase E: the last CTA to take a ticket sums the shares (fixed order), argmax, contact bits =============
+        if (tid == 0) *last_flag = (atomicAdd(p.sync + 2, 1u) == (unsigned)kSlices - 1u) ? 1 : 0;
         __syncthreads();
-        if (tid == 0) {
-            float y[16];
+        if (*last_flag) {
+            __threadfence();
+            for (int b = 0; b < p.B; ++b) {
+                const int o = tid & 15, grp = tid >> 4;                       // 32 groups of 4 CTAs
+                float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = logit_s[j];
-            fp32::argmax_bits_store(y, (int64_t)b, p.logits, p.cls, p.bits);
+                for (int i = 0; i < 4; ++i) s += __ldcg(p.part + ((size_t)b * kSlices + grp * 4 + i) * 16 + o);
+                red[grp * 16 + o] = s;
+                __syncthreads();
+                if (tid < 16) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int g2 = 0; g2 < 32; ++g2) t += red[g2 * 16 + tid];
+                    logit_s[tid] = t + __ldg(p.bf3 + tid);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = logit_s[j];
+                    fp32::argmax_bits_store(y, (int64_t)b, p.logits, p.cls, p.bits);
+                }
+                __syncthreads();
+            }
+            if (tid == 0) p.sync[2] = 0u;
+            LAT_TRACE(8);
         }
     }
+    LAT_TRACE(9);
     // every CTA is past the last barrier's spin when it gets here: the last one out re-arms the counters
     if (tid == 0) {
         const unsigned old = atomicAdd(p.sync + 1, 1u);
-        if (old == (unsigned)G - 1u) { p.sync[0] = 0u; p.sync[1] = 0u; __threadfence(); }
+        if (old == (unsigned)G - 1u) { p.sync[0] = 0u; p.sync[1] = 0u; p.sync[3] = 0u; __threadfence(); }
     }
 }
 
@@ -456,6 +513,7 @@ struct Weights {                  // pointers into the packed buffer
 };
 
 inline int& coop_flag() { static int v = 1; return v; }
+inline int& tma_in_flag() { static int v = 1; return v; }
 
 // -> DCE_EUNSUPPORTED when the device cannot co-schedule the grid (the caller then uses the per-layer kernels)
 inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mode, int64_t first, int n,
@@ -469,11 +527,11 @@ inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mo
     }
     const Workspace W = make_workspace(n);
     Params p{};
-    p.x = src; p.stream = stream_mode ? 1 : 0; p.first = first; p.B = n;
+    p.x = src; p.stream = stream_mode ? 1 : 0; p.tma_in = tma_in_flag(); p.first = first; p.B = n;
     p.w1 = wt.w1; p.w2 = wt.w2; p.w3 = wt.w3; p.w4q = wt.w4q; p.f1s = wt.f1s; p.f2s = wt.f2s; p.f3t = wt.f3t;
     p.b1 = wt.b[0]; p.b2 = wt.b[1]; p.b3 = wt.b[2]; p.b4 = wt.b[3]; p.bf1 = wt.b[4]; p.bf2 = wt.b[5]; p.bf3 = wt.b[6];
     p.p1 = reinterpret_cast<float*>(ws + W.p1); p.a4 = reinterpret_cast<float*>(ws + W.a4);
-    p.h1 = reinterpret_cast<float*>(ws + W.h1); p.h2 = reinterpret_cast<float*>(ws + W.h2);
+    p.h1 = reinterpret_cast<float*>(ws + W.h1); p.part = reinterpret_cast<float*>(ws + W.part);
     p.sync = reinterpret_cast<unsigned*>(ws);
     p.logits = logits; p.cls = cls; p.bits = bits;
     cudaLaunchConfig_t cfg{};

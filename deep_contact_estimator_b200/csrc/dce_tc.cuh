@@ -511,24 +511,97 @@ ingest_kernel(const float* __restrict__ x, int64_t first, int n_windows, const f
     }
 }
 
-// per-window, per-channel mean and unbiased std, two-pass in fp32 (utils/data_handler.py:55-56)
-__global__ void __launch_bounds__(256)
-window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, float* __restrict__ mean, float* __restrict__ sdev,
-                    int reciprocal) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = idx / 64, c = idx % 64;
-    if (w >= n_windows || c >= 54) return;
-    const float* src = x + (size_t)(first + w) * 54 + c;
+// per-window, per-channel mean and unbiased std in fp32 (utils/data_handler.py:55-56).
+// A CTA owns 32 consecutive windows = 181 log rows, read ONCE into shared memory as y = x - pivot (the tile's
+// middle row, per channel: removes the channel offset, so the sums below carry no cancellation from it), then
+// per-channel prefix sums of y and y^2 along time give every window's two sums as a difference of two prefixes:
+//     mean = pivot + sum/150,   var = (sumsq - sum * sum/150) / 149
+// instead of 300 strided loads per (window, channel) (the first version of this kernel was LSU-bound, 21 us per
+// 4096 windows).  A tile holding a non-finite value (a NaN would poison every later prefix) takes the direct
+// two-pass route, window by window, so NaN / inf stay confined to the windows that contain them.
+constexpr int kStatWT = 32;
+constexpr int kStatRows = kStatWT + 149;
+constexpr int kStatSmemBytes = 2 * kStatRows * 54 * 4;
+
+__device__ __forceinline__ void window_stats_direct(const float* __restrict__ src, float& mu, float& sd) {
     float s = 0.f;
     for (int t = 0; t < 150; ++t) s += __ldg(src + (size_t)t * 54);
-    const float mu = s / 150.f;
+    mu = s / 150.f;
     float v = 0.f;
     for (int t = 0; t < 150; ++t) { const float d = __ldg(src + (size_t)t * 54) - mu; v = fmaf(d, d, v); }
-    mean[(size_t)w * 64 + c] = mu;
-    const float sd = sqrtf(v / 149.f);
-    sdev[(size_t)w * 64 + c] = reciprocal ? 1.f / sd : sd;     // std == 0 -> inf -> (x - mean) * inf = NaN, as 0/0 in the reference
+    sd = sqrtf(v / 149.f);
+}
+
+// Tiles are aligned to ABSOLUTE window indices (tile j = windows 32j .. 32j+31 of the log, pivot = log row 32j+90,
+// scan from log row 32j) so a window's statistics — and with them its logits — do not depend on which sub-range
+// of the log a call asks for: dce_stream(first, n) equals the matching slice of a whole-log call bit for bit.
+__global__ void __launch_bounds__(256)
+window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, int64_t total_rows,
+                    float* __restrict__ mean, float* __restrict__ sdev, int reciprocal) {
+    extern __shared__ __align__(16) float st_smem[];
+    float* S = st_smem;
+    float* Q = st_smem + kStatRows * 54;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t row0 = (first / kStatWT + blockIdx.x) * kStatWT;            // first log row (= first window) of this tile
+    const int R = (total_rows - row0 < kStatRows) ? (int)(total_rows - row0) : kStatRows;
+    const int wlo = (first > row0) ? (int)(first - row0) : 0;                   // windows [wlo, whi) of the tile are wanted
+    const int whi = (first + n_windows - row0 < kStatWT) ? (int)(first + n_windows - row0) : kStatWT;
+    const float* src = x + (size_t)row0 * 54;
+    constexpr int rp = 90;                                                      // pivot row: a wanted window exists, so R >= 150
+    int bad = 0;
+    for (int i = threadIdx.x; i < R * 54; i += 256) {
+        const float y = __ldg(src + i) - __ldg(src + rp * 54 + i % 54);
+        bad |= !(fabsf(y) <= 3.0e38f);                 // NaN or inf (also a finite overflow of the difference)
+        S[i] = y; Q[i] = y * y;
+    }
+    bad = __syncthreads_or(bad);
+    if (bad) {
+        for (int i = wlo * 54 + threadIdx.x; i < whi * 54; i += 256) {
+            const int w = i / 54, c = i % 54;
+            float mu, sd;
+            window_stats_direct(src + (size_t)w * 54 + c, mu, sd);
+            const size_t o = (size_t)(row0 + w - first) * 64 + c;
+            mean[o] = mu;
+            sdev[o] = reciprocal ? 1.f / sd : sd;
+        }
+        return;
+    }
+    // inclusive scan along time, per channel: 4 row segments per channel, then the segment offsets
+    const int c = threadIdx.x % 54, seg = threadIdx.x / 54;          // threads 216..255 idle here
+    const int seg_rows = (R + 3) / 4;
+    const int r0 = seg * seg_rows, r1 = (r0 + seg_rows < R) ? r0 + seg_rows : R;
+    if (seg < 4) {
+        float s = 0.f, q = 0.f;
+        for (int r = r0; r < r1; ++r) { s += S[r * 54 + c]; S[r * 54 + c] = s; q += Q[r * 54 + c]; Q[r * 54 + c] = q; }
+    }
+    __syncthreads();
+    float so = 0.f, qo = 0.f;
+    if (seg < 4)
+        for (int j = 0; j < seg; ++j) {
+            const int e = (((j + 1) * seg_rows < R) ? (j + 1) * seg_rows : R) - 1;
+            so += S[e * 54 + c]; qo += Q[e * 54 + c];
+        }
+    __syncthreads();
+    if (seg > 0 && seg < 4)
+        for (int r = r0; r < r1; ++r) { S[r * 54 + c] += so; Q[r * 54 + c] += qo; }
+    __syncthreads();
+    for (int i = wlo * 54 + threadIdx.x; i < whi * 54; i += 256) {
+        const int w = i / 54, cc = i % 54;
+        float s = S[(w + 149) * 54 + cc], q = Q[(w + 149) * 54 + cc];
+        if (w > 0) { s -= S[(w - 1) * 54 + cc]; q -= Q[(w - 1) * 54 + cc]; }
+        const float my = s / 150.f;
+        const float ss = q - s * my;                   // sum of squared deviations
+        float mu = __ldg(src + rp * 54 + cc) + my;
+        float sd = sqrtf(((ss < 0.f) ? 0.f : ss) / 149.f);
+        // the window sits far from the pivot compared with its spread (or is constant): the difference above has
+        // lost >10 bits, so take the direct two-pass route for this (window, channel) — rare, and it keeps a
+        // constant channel exactly at std = 0 -> NaN, as in the reference
+        if (ss < 1e-3f * q) window_stats_direct(src + (size_t)w * 54 + cc, mu, sd);
+        const size_t o = (size_t)(row0 + w - first) * 64 + cc;
+        mean[o] = mu;
+        sdev[o] = reciprocal ? 1.f / sd : sd;          // std == 0 -> inf -> (x - mean) * inf = NaN, as 0/0 in the reference
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -44,8 +44,16 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
 
         int rc;
         TapGemmParams p{};
-        if (stream_mode)
-            DCE_KL(ctx, "tc_window_stats", { cudaError_t le_ = launch_pdl(window_stats_kernel, dim3((m * 64 + 255) / 256), dim3(256), 0, s, src, first + c0, m, mean, sdev, fuse_block1_flag() ? 1 : 0); (void)le_; });
+        if (stream_mode) {
+            static DeviceOnce st_once;
+            if (st_once.need()) {
+                cudaError_t e = cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatSmemBytes);
+                if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+            }
+            const int64_t fa = first + c0;
+            const int tiles = (int)((fa + m - 1) / kStatWT - fa / kStatWT + 1);       // tiles are aligned to absolute window indices
+            DCE_KL(ctx, "tc_window_stats", { cudaError_t le_ = launch_pdl(window_stats_kernel, dim3(tiles), dim3(256), kStatSmemBytes, s, src, fa, m, total_rows, mean, sdev, fuse_block1_flag() ? 1 : 0); (void)le_; });
+        }
         if (fuse_block1_flag()) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static DeviceOnce attr_once;

@@ -255,6 +255,11 @@ class ContactEngine:
         self.last_launches = self.lib.dce_last_launch_count()
         return logits, cls, bits
 
+    # -- K3: control-loop runner -------------------------------------------------
+    def latency_runner(self, n: int = 1, want_logits: bool = False) -> "LatencyRunner":
+        """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
+        return LatencyRunner(self, n, want_logits)
+
     # -- small helpers on the same ABI ------------------------------------------
     def decimal2binary(self, x: torch.Tensor) -> torch.Tensor:
         flat = x.reshape(-1).to(torch.int64).contiguous()
@@ -279,3 +284,61 @@ class ContactEngine:
                                               ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_accuracy_counts")
         return counts
+
+
+class LatencyRunner:
+    """The 1 kHz control-loop call (BASELINE configs[4]).  The newest window(s) sit in PINNED host memory and the
+    fused latency kernel reads them in place over PCIe (zero-copy: 32.4 KB per window, once) and writes class,
+    contact bits (and logits) straight back into pinned host memory — no copy-engine hops on either side, which
+    cost more than the kernel itself at this size.  The launch is captured ONCE in a CUDA graph, so a step is one
+    graph launch and one stream synchronise.
+
+        run = engine.latency_runner()
+        run.x_host[0] = newest_window          # (150, 54) float32, z-scored (utils/data_handler.py:55-56)
+        cls, bits = run.step()                 # pinned host tensors, valid until the next step()
+
+    Replaces one iteration of the reference loop at its default batch_size 1
+    (/root/reference/src/inference_one_seq.py:23-28, config/inference_one_seq_params.yaml:10).
+    """
+
+    def __init__(self, eng: ContactEngine, n: int = 1, want_logits: bool = False):
+        if not 1 <= n <= 4:
+            raise ValueError("the latency path takes 1..4 windows per step")
+        self.eng, self.n = eng, n
+        dev = eng.device
+        self.x_host = torch.zeros((n, WINDOW, CHANNELS), dtype=torch.float32).pin_memory()
+        self.cls_host = torch.zeros((n,), dtype=torch.int32).pin_memory()
+        self.bits_host = torch.zeros((n, 4), dtype=torch.uint8).pin_memory()
+        self.logits_host = torch.zeros((n, CLASSES), dtype=torch.float32).pin_memory() if want_logits else None
+        self.stream = torch.cuda.Stream(dev)
+        ws = eng._ws(n)
+        P = ContactEngine._p
+
+        def launch():
+            # pinned host pointers are device-accessible under unified addressing: the kernel dereferences them directly
+            rc = eng.lib.dce_forward(eng._handle, P(self.x_host), n, P(self.logits_host), P(self.cls_host), P(self.bits_host),
+                                     P(ws), ws.numel(), _lib.PRECISIONS[eng.precision], ctypes.c_void_p(self.stream.cuda_stream))
+            _lib.check(rc, "dce_forward")
+
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            for _ in range(2):                                   # kernel attributes set before the capture
+                launch()
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                launch()
+        self.launches = eng.lib.dce_last_launch_count()
+        self._ws = ws
+
+    def enqueue(self):
+        """Launch one step without waiting (``self.stream``)."""
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+
+    def step(self, window: Optional[torch.Tensor] = None):
+        """Classify ``self.x_host`` (or ``window``, copied into it first); returns host ``(cls, bits)``."""
+        if window is not None:
+            self.x_host.copy_(window.reshape(self.x_host.shape))
+        self.enqueue()
+        self.stream.synchronize()
+        return self.cls_host, self.bits_host

@@ -331,3 +331,84 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
         assert eng.lib.dce_set_option(b"no_such_option", 1) == -1
     finally:
         eng.lib.dce_set_option(b"fuse_block1", 1); eng.lib.dce_set_option(b"fuse_block2", 1)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_latency_kernel_batch_and_stream(dev, params0, precision):
+    """B <= 4 runs the single cooperative kernel (dce_latency.cuh): one launch, parity with the oracle in
+    batch and stream mode, bit-identical call after call (its grid-barrier counters re-arm themselves), and
+    equal to the per-layer kernels it replaces."""
+    eng = engine(dev, precision)
+    log = synth.make_sensor_log(150 + 9, seed=31)
+    logd = log.to(dev)
+    wl, wc, wb = oracle.inference_stream(params0, log)
+    for B in (1, 2, 3, 4):
+        x = synth.make_windows(B, seed=40 + B)
+        want = oracle_logits(params0, x)
+        outs = [eng.classify(x.to(dev)) for _ in range(4)]
+        assert eng.last_launches == 1
+        torch.cuda.synchronize()
+        lg, cl, bi = outs[0]
+        assert oracle.normwise_rel_err(lg.cpu().numpy(), want) <= 1e-5
+        assert np.array_equal(cl.cpu().numpy(), want.argmax(1))
+        assert np.array_equal(bi.cpu().numpy(), oracle.decimal2binary_numpy(want.argmax(1)))
+        for lg2, cl2, bi2 in outs[1:]:
+            assert torch.equal(lg2, lg) and torch.equal(cl2, cl) and torch.equal(bi2, bi)
+        for first in (0, 5):
+            ls, cs, bs = eng.stream(logd, first, B, want_logits=True)
+            assert oracle.normwise_rel_err(ls.cpu().numpy(), wl.numpy()[first:first + B]) <= 1e-5
+            assert np.array_equal(bs.cpu().numpy(), wb.numpy()[first:first + B])
+        try:
+            assert eng.lib.dce_set_option(b"latency_kernel", 0) == 0
+            lo, co, _ = eng.classify(x.to(dev))
+            assert eng.last_launches > 1
+            assert torch.equal(co, cl) and oracle.normwise_rel_err(lo.cpu().numpy(), lg.cpu().numpy()) <= TOL[precision]
+        finally:
+            eng.lib.dce_set_option(b"latency_kernel", 1)
+    # a bigger batch in between reuses the same workspace (tapes over the latency buffers): the header with the
+    # barrier counters must survive it
+    eng.classify(synth.make_windows(300, seed=3).to(dev))
+    lg3, _, _ = eng.classify(synth.make_windows(1, seed=41).to(dev))
+    assert torch.equal(lg3, eng.classify(synth.make_windows(1, seed=41).to(dev))[0])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_stream_statistics_offsets_and_nonfinite(dev, params0, precision):
+    """The windowed z-score statistics (prefix sums around a per-tile pivot): large channel offsets must not
+    cost accuracy, and a NaN / inf sample must poison exactly the windows that contain it."""
+    eng = engine(dev, precision)
+    log = synth.make_sensor_log(700, seed=17)
+    log[:, ::5] += 40.0                            # joint-angle-like offsets, 400x the smallest channel std
+    log[:, 1::7] -= 25.0
+    wl, wc, wb = oracle.inference_stream(params0, log, batch_size=128)
+    lg, cl, bi = eng.stream(log.to(dev), want_logits=True)
+    # the reference's own fp32 mean loses ~2e-5 sigma at these offsets: compare at the north-star bar
+    assert oracle.normwise_rel_err(lg.cpu().numpy(), wl.numpy()) <= NORTH_STAR_TOL
+    assert (cl.cpu().numpy() == wc.numpy()).mean() >= 0.995
+    bad = synth.make_sensor_log(700, seed=18)
+    bad[333, 7] = float("nan")
+    bad[500, 20] = float("inf")
+    wl, wc, wb = oracle.inference_stream(params0, bad, batch_size=128)
+    lg, cl, bi = eng.stream(bad.to(dev), want_logits=True)
+    nan_rows = torch.isnan(wl).any(1)
+    assert int(nan_rows.sum()) == 150 + 150        # windows 184..333 and 351..500
+    assert torch.equal(torch.isnan(lg.cpu()).any(1), nan_rows)
+    ok = ~nan_rows
+    assert oracle.normwise_rel_err(lg.cpu().numpy()[ok], wl.numpy()[ok]) <= TOL[precision] * 2
+    assert np.array_equal(cl.cpu().numpy(), wc.numpy()) and np.array_equal(bi.cpu().numpy(), wb.numpy())
+
+
+def test_latency_runner_control_loop(dev, params0):
+    """LatencyRunner: H2D + fused kernel + D2H in one CUDA graph; a sliding window fed row by row gives the
+    same contact bits as the reference loop at batch_size 1."""
+    eng = engine(dev, "bf16x3")
+    log = synth.make_sensor_log(150 + 12, seed=9)
+    _, wc, wb = oracle.inference_stream(params0, log)
+    run = eng.latency_runner(1, want_logits=True)
+    assert run.launches == 1
+    for i in range(12):
+        w = log[i:i + 150]
+        cls, bits = run.step((w - w.mean(0)) / w.std(0))          # utils/data_handler.py:55-56 on the host
+        assert int(cls[0]) == int(wc[i]) and bits[0].tolist() == wb[i].tolist()
+    with pytest.raises(ValueError):
+        eng.latency_runner(5)

@@ -44,37 +44,32 @@ def stream(args, dev, eng):
 
 
 def latency(args, dev, eng):
-    x = synth.make_windows(1, seed=5).to(dev)
-    want = oracle.forward_torch(synth.make_params(0), x.cpu()).numpy()
-    s = torch.cuda.Stream(dev)
-    with torch.cuda.stream(s):
-        for _ in range(3):
-            eng.classify(x)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
-            logits, cls, bits = eng.classify(x)
-    torch.cuda.synchronize()
-    g.replay(); torch.cuda.synchronize()
-    err = oracle.normwise_rel_err(logits.cpu().numpy(), want)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.calls)]
-    host = []
-    xh = synth.make_windows(1, seed=5).pin_memory()
-    for a, b in ev:
+    x1 = synth.make_windows(1, seed=5)
+    want = oracle.forward_torch(synth.make_params(0), x1).numpy()
+    run = eng.latency_runner(1, want_logits=True)
+    run.x_host.copy_(x1)
+    for _ in range(20):
+        run.step()
+    err = oracle.normwise_rel_err(run.logits_host.numpy(), want)
+    host, gpu = [], []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.calls):
         t0 = time.perf_counter()
-        a.record()
-        x.copy_(xh, non_blocking=True)            # the new window arrives from the host (32.4 KB)
-        g.replay()
-        b.record()
-        b.synchronize()
-        _ = bits.cpu()                             # 4 contact bits back to the control loop
+        run.step()                                 # one graph launch (kernel reads/writes pinned host memory), then stream sync
         host.append((time.perf_counter() - t0) * 1e6)
-    dev_us = np.array([a.elapsed_time(b) * 1e3 for a, b in ev])
-    host = np.array(host)
+    for _ in range(args.calls):
+        a.record(run.stream); run.enqueue(); b.record(run.stream); b.synchronize()
+        gpu.append(a.elapsed_time(b) * 1e3)
+    a.record(run.stream)
+    for _ in range(args.calls):
+        run.enqueue()
+    b.record(run.stream); b.synchronize()
     print(json.dumps({"config": "latency", "batch": 1, "calls": args.calls, "precision": eng.precision,
-                      "gpu_us_p50": float(np.percentile(dev_us, 50)), "gpu_us_p99": float(np.percentile(dev_us, 99)),
+                      "gpu_us_p50": float(np.percentile(gpu, 50)), "gpu_us_p99": float(np.percentile(gpu, 99)),
+                      "gpu_us_back_to_back": a.elapsed_time(b) * 1e3 / args.calls,
                       "host_us_p50": float(np.percentile(host, 50)), "host_us_p99": float(np.percentile(host, 99)),
-                      "launches_per_call": eng.last_launches, "normwise_err": err,
-                      "bits": bits.cpu().numpy().tolist()}))
+                      "launches_per_call": run.launches, "normwise_err": err,
+                      "bits": run.bits_host.numpy().tolist()}))
 
 
 def main():

@@ -36,7 +36,7 @@ def ws_views(eng, n):
     ws = eng._workspace
     al = lambda v: (v + 255) // 256 * 256
     o = 256; out = []
-    for cnt in (n * 75 * 64, n * 4736, n * 2048, n * 512):
+    for cnt in (n * 75 * 64, n * 4736, n * 2048):
         out.append(ws[o:o + cnt * 4].view(torch.float32).cpu().numpy()); o = al(o + cnt * 4)
     return out
 
@@ -60,7 +60,7 @@ for precision in ("bf16x3", "fp32"):
         if not good:
             ok = False
             got = ws_views(eng, B)
-            for name, g, w in zip(("p1", "a4", "h1", "h2"), got, want[:4]):
+            for name, g, w in zip(("p1", "a4", "h1"), got, want[:3]):
                 print(f"    {name}: rel err {rel(g, w.reshape(-1)):.3e}  nan {int(np.isnan(g).sum())}")
             print("    sync counters", eng._workspace[:8].view(torch.int32).cpu().numpy())
     log = synth.make_sensor_log(150 + 7, seed=2)
@@ -99,4 +99,15 @@ for label, opts in (("fused coop", {b"latency_kernel": 1, b"latency_coop": 1}), 
         print(f"{label}: FAILED {type(e).__name__}: {e}", flush=True)
         ok = False
 eng.lib.dce_set_option(b"latency_kernel", 1); eng.lib.dce_set_option(b"latency_coop", 1)
+# phase timeline (clock64 of the first and last CTA, written behind the barrier counters)
+NAMES = ["start", "A done", "bar1", "B done", "bar2", "C done", "bar3", "D done", "E done (last CTA only)", "exit"]
+for mode in ("batch", "stream"):
+    logd = synth.make_sensor_log(151, seed=2).to(dev)
+    for _ in range(5):
+        eng.classify(x) if mode == "batch" else eng.stream(logd, 0, 1)
+    torch.cuda.synchronize()
+    tr = eng._workspace[64:64 + 24 * 8].view(torch.int64).cpu().numpy().reshape(2, 12)
+    for which, row in zip(("cta 0", "last cta"), tr):
+        d = (row[1:10] - row[0]) / 1.965e3
+        print(f"trace[{mode}] {which} (us since start): " + "  ".join(f"{n} {v:.2f}" for n, v in zip(NAMES[1:], d)), flush=True)
 print("debug_latency", "OK" if ok else "FAILED")
