@@ -44,6 +44,11 @@ LAYER_FLOP = {                        # per window, BASELINE.md §3
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def workload_name(batch: int) -> str:
+    return (f"batch={batch} synthetic z-scored 150x54 fp32 windows per GPU -> 16 logits + class + 4 contact bits "
+            f"(BASELINE configs[1])")
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -206,7 +211,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "contact windows/sec at batch=4096", "value": v, "unit": "windows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={batch} synthetic z-scored 150x54 fp32 windows, contact_cnn forward + argmax + bits",
+        "config": {"workload": workload_name(batch), "precision": "fp32 (ATen CPU kernels)",
+                   "weights": "seeded random init (synth.make_params(0))",
                    "host": f"{cores} CPU threads, torch {torch.__version__}"},
         "cpu_baseline": {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} steps x {batch} windows through oracle.forward_torch (reference ops on CPU)"},
@@ -387,8 +393,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3_f32acc" if precision == "bf16x3" else "f32", "data": "synthetic",
-        "config": {"workload": f"batch={B} synthetic z-scored 150x54 fp32 windows per GPU -> 16 logits + class + 4 contact bits "
-                               f"(BASELINE configs[1])",
+        "config": {"workload": workload_name(B),
                    "precision": precision, "weights": "seeded random init (synth.make_params(0))",
                    "l2": f"inputs rotate over {NBUF} resident batches of {B * 32400 / 1e6:.1f} MB each (> 126 MB L2 in total)",
                    "parallelism": f"window-range shards x{world}, one-time NCCL weight broadcast"

@@ -92,7 +92,10 @@ DCE_API int    dce_weights_adopt(dce_weights *w);
 
 /* Scratch the caller must provide to dce_forward / dce_stream for up to
  * `max_windows` windows per call (the library chunks internally, so this
- * saturates at a fixed size). 256-byte aligned device memory. */
+ * saturates at a fixed size). 256-byte aligned device memory, ZERO-FILLED
+ * ONCE after allocation (cudaMemset): its first 256 bytes hold the grid-barrier
+ * counters of the latency kernel, which every call leaves at zero, and tape
+ * padding rows must start finite.  One workspace serves one call at a time. */
 DCE_API size_t dce_workspace_bytes(int64_t max_windows, int precision);
 
 /*
@@ -104,6 +107,10 @@ DCE_API size_t dce_workspace_bytes(int64_t max_windows, int precision);
  *   logits_dev  [B][16] fp32 or NULL
  *   cls_dev     [B] int32 class 0..15 or NULL (first maximal index; NaN wins)
  *   bits_dev    [B][4] uint8 contact bits, MSB first = leg 0 (RF), or NULL
+ * Latency mode: a call with B <= 4 is ONE cooperative fp32 kernel (the reference's
+ * default batch_size 1 loop, config/inference_one_seq_params.yaml:10); for such
+ * calls x_dev and the outputs may also be pinned HOST memory (cudaHostAlloc),
+ * which the kernel reads and writes in place over PCIe.
  */
 DCE_API int dce_forward(const dce_weights *w, const float *x_dev, int64_t B,
                 float *logits_dev, int32_t *cls_dev, uint8_t *bits_dev,
@@ -161,6 +168,9 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *   "fuse_block2"  1 (default): conv3 + conv4 + pool run as ONE kernel (X3 stays in shared memory); 0: two launches;
  *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
  *                  0: one kernel per layer (activations round-trip through HBM).
+ *   "latency_kernel" 1 (default): calls of <= 4 windows run the single cooperative latency kernel;
+ *                  0: the per-layer kernels (tensor-core convolutions + fp32 GEMV Linear layers);
+ *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel.
  * Returns DCE_EINVAL for an unknown key.
  */
 DCE_API int dce_set_option(const char *key, int value);
