@@ -56,6 +56,7 @@ _SIGNATURES = {
     "dce_debug_read_trace": (c_int, [c_void_p, c_int]),
     "dce_decimal2binary": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dce_accuracy_counts": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dce_ingest_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 

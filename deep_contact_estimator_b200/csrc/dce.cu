@@ -348,6 +348,7 @@ int dce_set_option(const char* key, int value) {
     if (!key) return DCE_EINVAL;
     if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
     if (!strcmp(key, "fuse_block2")) { dce::tc::fuse_block2_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "fuse_fc3")) { dce::tc::fuse_fc3_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { latency_kernel_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { dce::lat::coop_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_tma_in")) { dce::lat::tma_in_flag() = value; return DCE_OK; }
@@ -377,6 +378,20 @@ int dce_decimal2binary(const int64_t* cls_dev, int64_t n, uint8_t* bits_dev, voi
     Ctx ctx; ctx.stream = (cudaStream_t)stream;
     ctx.begin("decimal2binary");
     dce::fp32::decimal2binary_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(cls_dev, n, bits_dev);
+    const bool ok = ctx.end();
+    g_launches = ctx.launches;
+    return ok ? DCE_OK : cuda_fail(ctx.err);
+}
+
+int dce_ingest_f64(const double* src_dev, float* dst_dev, int64_t n, void* stream) {
+    if (n < 0) return DCE_EINVAL;
+    if (n == 0) return DCE_OK;
+    if (!src_dev || !dst_dev) return DCE_EINVAL;
+    if ((uintptr_t)src_dev % 16 || (uintptr_t)dst_dev % 8) return DCE_EALIGN;
+    int64_t blocks = (n / 2 + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    ctx.begin("ingest_f64");
+    dce::fp32::ingest_f64_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(src_dev, dst_dev, n);
     const bool ok = ctx.end();
     g_launches = ctx.launches;
     return ok ? DCE_OK : cuda_fail(ctx.err);

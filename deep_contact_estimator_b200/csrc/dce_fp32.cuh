@@ -357,6 +357,34 @@ fc3_argmax_kernel(const float* __restrict__ h2, const float* __restrict__ w3t, c
 }
 constexpr int kFc3SmemBytes = (512 * 16 + 16 * 516) * 4;
 
+// fc.6 folded into fc.3's epilogue (tc::EPI_FC_LOGITS): every window's 16 logits arrive as `nparts` shares
+// part[s][w][16]; add them in a fixed order (+ bias), argmax, contact bits.  One thread per window.
+__global__ void __launch_bounds__(128)
+logit_shares_argmax_kernel(const float* __restrict__ part, const float* __restrict__ b3, int64_t n_windows, int nparts,
+                           float* __restrict__ logits, int32_t* __restrict__ cls, uint8_t* __restrict__ bits) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __ldg(b3 + j);
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // the shares come from the previous kernel
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = 0.f;
+    for (int sidx = 0; sidx < nparts; ++sidx) {
+        const float4* src = reinterpret_cast<const float4*>(part + ((size_t)sidx * n_windows + w) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldcg(src + j);
+            s[4 * j] += v.x; s[4 * j + 1] += v.y; s[4 * j + 2] += v.z; s[4 * j + 3] += v.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] += s[j];
+    argmax_bits_store(y, w, logits, cls, bits);
+}
+
 // ---------------------------------------------------------------------------
 // decimal2binary on labels; accuracy counters
 // ---------------------------------------------------------------------------
@@ -365,6 +393,20 @@ __global__ void decimal2binary_kernel(const int64_t* __restrict__ cls, int64_t n
     if (i >= n) return;
     const int64_t v = cls[i];
     *reinterpret_cast<uchar4*>(bits + i * 4) = make_uchar4((v & 8) != 0, (v & 4) != 0, (v & 2) != 0, (v & 1) != 0);
+}
+
+// float64 log on disk (utils/mat2numpy.py:73,80 saves float64 .npy) -> the fp32 device stream, round-to-nearest
+// exactly as `torch.FloatTensor(np.load(...))` (utils/data_handler.py:21-26) does on the host
+__global__ void ingest_f64_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            const double2 v = *reinterpret_cast<const double2*>(src + i);
+            *reinterpret_cast<float2*>(dst + i) = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+        } else {
+            dst[i] = __double2float_rn(src[i]);
+        }
+    }
 }
 
 __global__ void accuracy_counts_kernel(const int32_t* __restrict__ cls, const int64_t* __restrict__ labels, int64_t n,

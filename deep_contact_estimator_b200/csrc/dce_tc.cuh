@@ -47,7 +47,7 @@ constexpr int kSlabRows = 130;       // 1 + 128 + 1
 constexpr int kSlabBytes = kSlabRows * 16;
 constexpr int64_t kChunk = 4096;     // windows per internal pass
 
-enum Epi { EPI_TAPE = 0, EPI_POOL_TAPE = 1, EPI_POOL_FC = 2, EPI_FC_TAPE = 3, EPI_FC_F32 = 4 };
+enum Epi { EPI_TAPE = 0, EPI_POOL_TAPE = 1, EPI_POOL_FC = 2, EPI_FC_TAPE = 3, EPI_FC_F32 = 4, EPI_FC_LOGITS = 5 };
 
 struct TapGemmParams {
     const uint8_t* a_tape;       // part 0 (hi); lo at + a_part_stride
@@ -60,7 +60,8 @@ struct TapGemmParams {
     uint8_t* out;                // tape outputs: part 0
     size_t out_part_stride, out_kch_stride;
     int out_rows_cap;            // rows the output tape can hold (excluding guards)
-    float* out_f32;              // EPI_FC_F32: [n_valid][N]
+    float* out_f32;              // EPI_FC_F32: [n_valid][N];  EPI_FC_LOGITS: logit shares [2 * n_tiles][n_valid][16]
+    const float* w3t;            // EPI_FC_LOGITS: the NEXT Linear layer's weight, k-major [N][16] (fc.6)
     int N;                       // total output features
     int rw, tv;                  // rows per window / valid rows per window of the INPUT tape (conv modes)
     int n_valid;                 // EPI_FC_F32: valid rows
@@ -159,6 +160,8 @@ tapgemm_kernel(const TapGemmParams p) {
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     float* s_bias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::WRES_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
+    float4* s_w3 = reinterpret_cast<float4*>(s_bias + kEpiWarps * (BN / 2));    // EPI_FC_LOGITS: [BN columns][16] fc.6 weights of this n-tile
+    static_assert(EPI != EPI_FC_LOGITS || MT == 1, "the logit-share epilogue keeps one row per thread");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
@@ -310,6 +313,12 @@ tapgemm_kernel(const TapGemmParams p) {
             if (n != last_n) {                               // stage this warp's bias slice (warp-private copy)
                 __syncwarp();
                 for (int i = lane; i < HALF; i += 32) my_bias[i] = __ldg(p.bias + n0 + i);
+                if (EPI == EPI_FC_LOGITS) {
+                    // fc.6 rows n0 .. n0+HALF-1: the four warps of this column half write identical values, each
+                    // warp reads back only after its own writes
+                    const float4* src = reinterpret_cast<const float4*>(p.w3t) + (size_t)n0 * 4;
+                    for (int i = lane; i < HALF * 4; i += 32) s_w3[h * HALF * 4 + i] = __ldg(src + i);
+                }
                 __syncwarp();
                 last_n = n;
             }
@@ -350,6 +359,9 @@ tapgemm_kernel(const TapGemmParams p) {
             const uint32_t taddr0 = tmem_base + buf * (MT * BN) + h * HALF + ((uint32_t)(q * 32) << 16);
             auto chunk_addr = [&](int ci) { return taddr0 + (ci / CPM) * BN + (ci % CPM) * 32; };
 
+            float lg[16];                                    // EPI_FC_LOGITS: this thread's share of its row's 16 logits
+#pragma unroll
+            for (int o = 0; o < 16; ++o) lg[o] = 0.f;
             // one 32-column chunk: bias / ReLU / pool / guard -> bf16 hi/lo -> store
             auto process = [&](const uint32_t (&v)[32], int ci) {
                 const int mt = ci / CPM, c0 = (ci % CPM) * 32;
@@ -361,6 +373,22 @@ tapgemm_kernel(const TapGemmParams p) {
                     y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
                     y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
                     y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
+                }
+                if (EPI == EPI_FC_LOGITS) {
+                    // fc.6 folded into fc.3's epilogue: H2 never leaves the registers (smem reads are warp broadcasts)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float4* wr = s_w3 + (h * HALF + c0 + i) * 4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 w = wr[j];
+                            lg[4 * j + 0] = fmaf(y[i], w.x, lg[4 * j + 0]);
+                            lg[4 * j + 1] = fmaf(y[i], w.y, lg[4 * j + 1]);
+                            lg[4 * j + 2] = fmaf(y[i], w.z, lg[4 * j + 2]);
+                            lg[4 * j + 3] = fmaf(y[i], w.w, lg[4 * j + 3]);
+                        }
+                    }
+                    return;
                 }
                 if (EPI == EPI_FC_F32) {
                     if (rows[mt] < p.n_valid) {
@@ -421,6 +449,11 @@ tapgemm_kernel(const TapGemmParams p) {
                         process(vb, ci + 1);
                     }
                 }
+            }
+            if (EPI == EPI_FC_LOGITS && !(p.dbg & 2) && rows[0] < p.n_valid) {
+                float4* dst = reinterpret_cast<float4*>(p.out_f32 + ((size_t)(n * 2 + h) * p.n_valid + rows[0]) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(lg[4 * j], lg[4 * j + 1], lg[4 * j + 2], lg[4 * j + 3]);
             }
             if (warp == 0) TG_TRACE(tcount, 8);
             ptx::tc_fence_before_sync();
@@ -667,14 +700,16 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST>;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
+    constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
+    static_assert(kSmem <= 232448, "exceeds 227 KB");
     static DeviceOnce attr_once;
     if (attr_once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), Cfg::SMEM_BYTES, ctx.stream, p); (void)le_; });
+    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
     return DCE_OK;
 }
 

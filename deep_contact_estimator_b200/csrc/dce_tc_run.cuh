@@ -11,6 +11,7 @@ namespace tc {
 // debug/ablation switch: 0 = one kernel per layer (ingest, conv1, conv2 as separate launches)
 inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& fuse_block2_flag() { static int v = 1; return v; }
+inline int& fuse_fc3_flag() { static int v = 1; return v; }
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
@@ -176,6 +177,15 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.h1.m_tiles; p.n_tiles = kLayers[5].n_tiles; p.stages = kLayers[5].stages;
         p.out = nullptr; p.out_f32 = h2; p.N = 512; p.n_valid = m;
         p.trace = (tapgemm_trace_layer() == 5) ? block1_trace_ptr() : nullptr;
+        if (fuse_fc3_flag()) {
+            // ---- fc.3 + ReLU with fc.6 folded into the epilogue (a11, a12): H2 stays in registers; 8 logit shares per window
+            p.w3t = bp.w3;
+            if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p)) != DCE_OK) return rc;
+            DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,
+                (const float*)h2, bp.b[6], (int64_t)m, 2 * kLayers[5].n_tiles, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,
+                bits ? bits + c0 * 4 : nullptr); (void)le_; });
+            continue;
+        }
         if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_F32, 1>(ctx, "tc_fc2", sm_count, p)) != DCE_OK) return rc;
         // ---- fc.6 + argmax + bits (a12-a14), fp32 CUDA cores (16 K FLOP per window)
         const int g3 = (int)((m + 15) / 16 < sm_count * 2 ? (m + 15) / 16 : sm_count * 2);

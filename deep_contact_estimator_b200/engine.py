@@ -255,6 +255,57 @@ class ContactEngine:
         self.last_launches = self.lib.dce_last_launch_count()
         return logits, cls, bits
 
+    def stream_host(self, log_host: torch.Tensor, chunk_rows: int = 1 << 18, out_bits_host: Optional[torch.Tensor] = None,
+                    out_cls_host: Optional[torch.Tensor] = None):
+        """Whole-log inference from a HOST log (``(T,54)`` float32, pinned for full speed): the log is uploaded in
+        chunks on a side stream while ``dce_stream`` classifies the windows whose rows have already arrived, so
+        the 216 B/step upload hides behind the kernels.  Returns host ``(cls (N,) int32, bits (N,4) uint8)`` after
+        the device->host read has completed; results are bit-identical to ``stream()`` on the resident log
+        (calls end on the 32-window tile boundaries of the statistics kernel)."""
+        if log_host.dim() != 2 or log_host.shape[1] != CHANNELS or log_host.dtype != torch.float32 or log_host.is_cuda:
+            raise ValueError(f"expected a host (T,{CHANNELS}) float32 log")
+        T = log_host.shape[0]
+        n = max(T - WINDOW + 1, 0)
+        if out_bits_host is None:
+            out_bits_host = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+        if out_cls_host is None:
+            out_cls_host = torch.empty((n,), dtype=torch.int32).pin_memory()
+        if n == 0:
+            return out_cls_host, out_bits_host
+        with torch.cuda.device(self.device):
+            compute = torch.cuda.current_stream(self.device)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            copy = self._copy_stream
+            copy.wait_stream(compute)
+            log_dev = torch.empty((T, CHANNELS), dtype=torch.float32, device=self.device)
+            log_dev.record_stream(copy)
+            cls = torch.empty((n,), dtype=torch.int32, device=self.device)
+            bits = torch.empty((n, 4), dtype=torch.uint8, device=self.device)
+            ws = self._ws(n)
+            launches, done = 0, 0
+            for r0 in range(0, T, chunk_rows):
+                r1 = min(T, r0 + chunk_rows)
+                with torch.cuda.stream(copy):
+                    log_dev[r0:r1].copy_(log_host[r0:r1], non_blocking=True)
+                    ready = torch.cuda.Event(); ready.record(copy)
+                # windows whose statistics tile (32 windows, 181 rows) lies inside the rows uploaded so far
+                hi = n if r1 == T else min(n, max(done, ((r1 - 181) // 32 + 1) * 32 if r1 >= 181 else 0))
+                if hi > done:
+                    compute.wait_event(ready)
+                    rc = self.lib.dce_stream(self._handle, self._p(log_dev), T, done, hi - done, None,
+                                             ctypes.c_void_p(cls[done:].data_ptr()), ctypes.c_void_p(bits[done:].data_ptr()),
+                                             self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
+                                             ctypes.c_void_p(compute.cuda_stream))
+                    _lib.check(rc, "dce_stream")
+                    launches += self.lib.dce_last_launch_count()
+                    done = hi
+            out_bits_host.copy_(bits, non_blocking=True)
+            out_cls_host.copy_(cls, non_blocking=True)
+            compute.synchronize()
+        self.last_launches = launches
+        return out_cls_host, out_bits_host
+
     # -- K3: control-loop runner -------------------------------------------------
     def latency_runner(self, n: int = 1, want_logits: bool = False) -> "LatencyRunner":
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
@@ -311,7 +362,8 @@ class LatencyRunner:
         self.bits_host = torch.zeros((n, 4), dtype=torch.uint8).pin_memory()
         self.logits_host = torch.zeros((n, CLASSES), dtype=torch.float32).pin_memory() if want_logits else None
         self.stream = torch.cuda.Stream(dev)
-        ws = eng._ws(n)
+        # its own zero-filled workspace: the engine's may be in use by (or regrown for) other calls on other streams
+        ws = torch.zeros(eng.lib.dce_workspace_bytes(n, _lib.PRECISIONS[eng.precision]), dtype=torch.uint8, device=dev)
         P = ContactEngine._p
 
         def launch():

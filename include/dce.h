@@ -153,6 +153,14 @@ DCE_API int dce_stream_profile(const dce_weights *w, const float *data_dev, int6
 DCE_API int dce_decimal2binary(const int64_t *cls_dev, int64_t n, uint8_t *bits_dev, void *stream);
 
 /*
+ * Device-side ingest of the on-disk log format: `np.load(data_path)` is float64 (utils/mat2numpy.py:73,80 save
+ * float64 .npy) and `contact_dataset.__init__` converts it to float32 on the host before the upload
+ * (utils/data_handler.py:21-27).  Here the float64 rows are uploaded in chunks and converted on the device,
+ * round-to-nearest as the host cast:  dst_dev[i] = (float)src_dev[i], i < n.  src 16-byte, dst 8-byte aligned.
+ */
+DCE_API int dce_ingest_f64(const double *src_dev, float *dst_dev, int64_t n, void *stream);
+
+/*
  * Fused accuracy counters of `inference_and_compute_acc` / `compute_accuracy`
  * (src/inference_one_seq.py:33-57, src/test.py:72-107): given predicted
  * classes and labels, accumulate counts_dev[0] += #(pred == label),
@@ -166,6 +174,8 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *   "block1_dbg"   bit mask of timing ablations inside the fused block1 kernel (results invalid);
  *   "block1_trace" 1: record a per-role clock64 timeline of CTA 0 (tools/trace_block1.py);
  *   "fuse_block2"  1 (default): conv3 + conv4 + pool run as ONE kernel (X3 stays in shared memory); 0: two launches;
+ *   "fuse_fc3"     1 (default): fc.6 is folded into fc.3's epilogue (logit shares + a small reduce/argmax kernel);
+ *                  0: fc.3 writes H2, a separate kernel does fc.6 + argmax + bits;
  *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
  *                  0: one kernel per layer (activations round-trip through HBM).
  *   "latency_kernel" 1 (default): calls of <= 4 windows run the single cooperative latency kernel;

@@ -322,7 +322,7 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
     x = synth.make_windows(300, seed=77).to(dev)
     ref_logits, ref_cls, _ = eng.classify(x)
     try:
-        for key in (b"fuse_block1", b"fuse_block2"):
+        for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3"):
             assert eng.lib.dce_set_option(key, 0) == 0
             lo, cl, _ = eng.classify(x)
             assert torch.equal(cl, ref_cls)
@@ -330,7 +330,7 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
             assert eng.lib.dce_set_option(key, 1) == 0
         assert eng.lib.dce_set_option(b"no_such_option", 1) == -1
     finally:
-        eng.lib.dce_set_option(b"fuse_block1", 1); eng.lib.dce_set_option(b"fuse_block2", 1)
+        eng.lib.dce_set_option(b"fuse_block1", 1); eng.lib.dce_set_option(b"fuse_block2", 1); eng.lib.dce_set_option(b"fuse_fc3", 1)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -412,3 +412,24 @@ def test_latency_runner_control_loop(dev, params0):
         assert int(cls[0]) == int(wc[i]) and bits[0].tolist() == wb[i].tolist()
     with pytest.raises(ValueError):
         eng.latency_runner(5)
+
+
+def test_device_ingest_and_stream_host(dev, params0):
+    """§8(f) row 2: float64 .npy log -> fp32 device stream converted on the device (same bits as the host cast);
+    stream_host (chunked upload overlapped with the kernels) == stream() on the resident log, bit for bit."""
+    from deep_contact_estimator_b200.data_handler import ingest_log
+    log64 = synth.make_sensor_log(5000, seed=12).double() * 1.000000123 + 1e-9      # not representable in fp32
+    got = ingest_log(log64.numpy(), dev, chunk_rows=777)
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), log64.float())
+    got32 = ingest_log(log64.float().numpy(), dev, chunk_rows=4096)
+    assert torch.equal(got32.cpu(), log64.float())
+    ds = dce.contact_dataset(data=log64.numpy(), label=synth.make_labels(5000, seed=3).numpy(), device=dev)
+    assert ds.data.is_cuda and torch.equal(ds.data.cpu(), log64.float())
+    eng = engine(dev, "bf16x3")
+    log = log64.float()
+    _, cl, bi = eng.stream(log.to(dev))
+    for chunk in (700, 1 << 18):
+        hc, hb = eng.stream_host(log.pin_memory(), chunk_rows=chunk)
+        assert torch.equal(hc, cl.cpu()) and torch.equal(hb, bi.cpu())
+    _, wc, wb = oracle.inference_stream(params0, log[:600])
+    assert np.array_equal(hb.numpy()[:451], wb.numpy())
