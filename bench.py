@@ -385,7 +385,7 @@ def main():
         }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (the other ranks' processes share the host cores)
         cpu, _ = cpu_forward_baseline(B)
 
     line = {

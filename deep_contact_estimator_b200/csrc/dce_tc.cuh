@@ -314,10 +314,12 @@ tapgemm_kernel(const TapGemmParams p) {
                 __syncwarp();
                 for (int i = lane; i < HALF; i += 32) my_bias[i] = __ldg(p.bias + n0 + i);
                 if (EPI == EPI_FC_LOGITS) {
-                    // fc.6 rows n0 .. n0+HALF-1: the four warps of this column half write identical values, each
-                    // warp reads back only after its own writes
-                    const float4* src = reinterpret_cast<const float4*>(p.w3t) + (size_t)n0 * 4;
-                    for (int i = lane; i < HALF * 4; i += 32) s_w3[h * HALF * 4 + i] = __ldg(src + i);
+                    // fc.6 rows n*BN .. n*BN+BN-1, staged once by the eight epilogue warps together (they walk the same
+                    // tile sequence, so they meet at this named barrier the same number of times)
+                    asm volatile("bar.sync 2, 256;" ::: "memory");       // everyone is done with the previous n-tile's rows
+                    const float4* src = reinterpret_cast<const float4*>(p.w3t) + (size_t)n * BN * 4;
+                    for (int i = warp * 32 + lane; i < BN * 4; i += kEpiWarps * 32) s_w3[i] = __ldg(src + i);
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
                 }
                 __syncwarp();
                 last_n = n;
