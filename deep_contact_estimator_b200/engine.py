@@ -283,23 +283,21 @@ class ContactEngine:
             cls = torch.empty((n,), dtype=torch.int32, device=self.device)
             bits = torch.empty((n, 4), dtype=torch.uint8, device=self.device)
             ws = self._ws(n)
-            launches, done = 0, 0
-            for r0 in range(0, T, chunk_rows):
-                r1 = min(T, r0 + chunk_rows)
+            from .sharding import upload_schedule
+            launches, up = 0, 0
+            for rows_up, first, end in upload_schedule(T, chunk_rows):
                 with torch.cuda.stream(copy):
-                    log_dev[r0:r1].copy_(log_host[r0:r1], non_blocking=True)
+                    for r0 in range(up, rows_up, chunk_rows):
+                        log_dev[r0:min(rows_up, r0 + chunk_rows)].copy_(log_host[r0:min(rows_up, r0 + chunk_rows)], non_blocking=True)
                     ready = torch.cuda.Event(); ready.record(copy)
-                # windows whose statistics tile (32 windows, 181 rows) lies inside the rows uploaded so far
-                hi = n if r1 == T else min(n, max(done, ((r1 - 181) // 32 + 1) * 32 if r1 >= 181 else 0))
-                if hi > done:
-                    compute.wait_event(ready)
-                    rc = self.lib.dce_stream(self._handle, self._p(log_dev), T, done, hi - done, None,
-                                             ctypes.c_void_p(cls[done:].data_ptr()), ctypes.c_void_p(bits[done:].data_ptr()),
-                                             self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
-                                             ctypes.c_void_p(compute.cuda_stream))
-                    _lib.check(rc, "dce_stream")
-                    launches += self.lib.dce_last_launch_count()
-                    done = hi
+                up = rows_up
+                compute.wait_event(ready)             # windows [first, end): their rows (and statistics tiles) have arrived
+                rc = self.lib.dce_stream(self._handle, self._p(log_dev), T, first, end - first, None,
+                                         ctypes.c_void_p(cls[first:].data_ptr()), ctypes.c_void_p(bits[first:].data_ptr()),
+                                         self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
+                                         ctypes.c_void_p(compute.cuda_stream))
+                _lib.check(rc, "dce_stream")
+                launches += self.lib.dce_last_launch_count()
             out_bits_host.copy_(bits, non_blocking=True)
             out_cls_host.copy_(cls, non_blocking=True)
             compute.synchronize()

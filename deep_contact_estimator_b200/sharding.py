@@ -32,6 +32,27 @@ def rows_for_windows(start: int, end: int, window: int = WINDOW) -> Tuple[int, i
     return (start, start) if end <= start else (start, end + window - 1)
 
 
+def upload_schedule(total_rows: int, chunk_rows: int, window: int = WINDOW, tile: int = 32) -> List[Tuple[int, int, int]]:
+    """Schedule of ``ContactEngine.stream_host``: the log is uploaded in chunks of ``chunk_rows`` rows and, after
+    each chunk, the windows whose rows have all arrived are classified.  Returns ``(rows_uploaded, first, end)``
+    per call: windows ``[first, end)`` run once rows ``[0, rows_uploaded)`` are on the device.  Every call but the
+    last ends on a multiple of ``tile`` whose whole statistics tile (``tile + window - 1`` rows from its first
+    window) has been uploaded, so chunked and one-shot results are bit-identical (csrc/dce_tc.cuh,
+    ``window_stats_kernel``)."""
+    if total_rows < 0 or chunk_rows <= 0:
+        raise ValueError("bad total_rows / chunk_rows")
+    n = max(total_rows - window + 1, 0)
+    span = tile + window - 1
+    out, done = [], 0
+    for r0 in range(0, total_rows, chunk_rows):
+        r1 = min(total_rows, r0 + chunk_rows)
+        hi = n if r1 == total_rows else min(n, max(done, ((r1 - span) // tile + 1) * tile if r1 >= span else 0))
+        if hi > done:
+            out.append((r1, done, hi))
+            done = hi
+    return out
+
+
 def all_gather_bits(bits: torch.Tensor, n_windows: int, group=None) -> torch.Tensor:
     """Assemble the full ``(N,4)`` uint8 result from per-rank shards (ragged
     shards are padded to the largest one for the collective)."""

@@ -124,3 +124,21 @@ def test_two_rank_sharded_inference_equals_single(tmp_path):
     log = synth.make_sensor_log(150 + 36, seed=2)
     _, _, want = oracle.inference_stream(synth.make_params(0), log, batch_size=8)
     assert torch.equal(full, want)
+
+
+def test_upload_schedule_covers_every_window_once_on_tile_boundaries():
+    """ContactEngine.stream_host's chunk schedule: every window exactly once, in order, only after its rows (and,
+    except for the last call, its whole 32-window statistics tile) have been uploaded."""
+    from deep_contact_estimator_b200 import sharding
+    for T, chunk in ((1_000_003, 1 << 18), (5000, 700), (149, 64), (150, 64), (181, 10), (400, 1), (10_000, 10_000), (0, 5)):
+        sched = sharding.upload_schedule(T, chunk)
+        n = max(T - 149, 0)
+        pos = 0
+        for k, (rows_up, first, end) in enumerate(sched):
+            assert first == pos and end > first and rows_up <= T and end - 1 + 150 <= rows_up
+            if k < len(sched) - 1:
+                assert end % 32 == 0 and (end - 32) + 181 <= rows_up
+            pos = end
+        assert pos == n and (not sched or sched[-1][0] == T)
+    with pytest.raises(ValueError):
+        sharding.upload_schedule(10, 0)

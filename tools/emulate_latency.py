@@ -76,12 +76,19 @@ def run(x, stream=False, first=0, B=1):
         lg[b] = h2[b].astype(np.float64) @ f3t.astype(np.float64) + P["fc.6.bias"]
     return lg
 
-x = synth.make_windows(2, seed=1)
-want = oracle.forward_torch(params, x).detach().numpy()
-got = run(x.numpy(), B=2)
-print("batch  err", oracle.normwise_rel_err(got, want))
-log = synth.make_sensor_log(152, seed=2)
-got = run(log.numpy(), stream=True, first=1, B=2)
-ds = torch.stack([(log[i:i + 150] - log[i:i + 150].mean(0)) / log[i:i + 150].std(0) for i in (1, 2)])
-want = oracle.forward_torch(params, ds).detach().numpy()
-print("stream err", oracle.normwise_rel_err(got, want))
+def check(batch: int = 2):
+    """-> (batch-mode error, stream-mode error), norm-wise relative to the oracle"""
+    x = synth.make_windows(batch, seed=1)
+    want = oracle.forward_torch(params, x).detach().numpy()
+    e_batch = oracle.normwise_rel_err(run(x.numpy(), B=batch), want)
+    log = synth.make_sensor_log(150 + batch, seed=2)
+    got = run(log.numpy(), stream=True, first=1, B=batch)
+    ds = torch.stack([(log[i:i + 150] - log[i:i + 150].mean(0)) / log[i:i + 150].std(0) for i in range(1, 1 + batch)])
+    e_stream = oracle.normwise_rel_err(got, oracle.forward_torch(params, ds).detach().numpy())
+    return e_batch, e_stream
+
+
+if __name__ == "__main__":
+    eb, es = check()
+    print("batch  err", eb)
+    print("stream err", es)
