@@ -107,11 +107,16 @@ __global__ void pack_f2s_kernel(const float* __restrict__ f2p, float* __restrict
 // k-th grid barrier of the launch (k = 1, 2, ...): sync[0] counts arrivals, everyone polls it.  (Measured
 // alternative: the last arriver — found with a value-returning atom.acq_rel — publishes a separate flag word the
 // others poll; that was 0.4 us per barrier SLOWER than this fire-and-forget red + poll.)
-__device__ __forceinline__ void grid_sync(unsigned* sync, unsigned k, unsigned G) {
+// `after_arrive` runs in thread 0 between its arrival and its wait: the place to issue the NEXT phase's weight
+// prefetch.  Issued before the arrival, the bulk copies (up to 192 KB per CTA) sat in front of the fence and the
+// arrival in the memory system and made this barrier 1.5 us longer than the others.
+template <class F>
+__device__ __forceinline__ void grid_sync(unsigned* sync, unsigned k, unsigned G, F after_arrive) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
+        after_arrive();
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
@@ -324,13 +329,12 @@ latency_kernel(const Params p) {
     }
     LAT_TRACE(1);
     const int q = cta & 3;
-    if (tid == 0) {                                   // [W1 | W2] is free now: fetch this CTA's quarter of conv4
+    grid_sync(p.sync, 1u, (unsigned)G, [&]() {        // [W1 | W2] is free now: fetch this CTA's quarter of conv4
         if (a_cta) { ptx::mbar_wait(bar_w1, 0); ptx::mbar_wait(bar_w2, 0); }
         ptx::mbar_arrive_expect_tx(bar_w4, kW4qBytes);
         ptx::bulk_g2s(w4s, p.w4q + (size_t)q * (kW4qBytes / 4), kW4qBytes / 2, bar_w4);
         ptx::bulk_g2s(w4s + kW4qBytes / 8, p.w4q + (size_t)q * (kW4qBytes / 4) + kW4qBytes / 8, kW4qBytes / 2, bar_w4);
-    }
-    grid_sync(p.sync, 1u, (unsigned)G);
+    });
     LAT_TRACE(2);
 
     // ================= phase B: conv3 -> conv4 -> pool -> flatten (k' = t*128 + c) =================
@@ -369,16 +373,15 @@ latency_kernel(const Params p) {
         }
     }
     LAT_TRACE(3);
-    if (tid == 0) {                                   // conv weights are dead: start the fc.3 slice and the fc.0 ring
+    grid_sync(p.sync, 2u, (unsigned)G, [&]() {        // conv weights are dead: start the fc.0 ring and the fc.3 slice
         ptx::mbar_wait(bar_w3, 0);
         ptx::mbar_wait(bar_w4, 0);
         if (fc_cta) {
+            for (int g = 0; g < kRing && g < total_stages; ++g) issue_stage(g);
             ptx::mbar_arrive_expect_tx(bar_f2, kF2Bytes);
             ptx::bulk_g2s(smem + oF2, p.f2s + (size_t)cta * kFc2SliceFloats, kF2Bytes, bar_f2);
-            for (int g = 0; g < kRing && g < total_stages; ++g) issue_stage(g);
         }
-    }
-    grid_sync(p.sync, 2u, (unsigned)G);
+    });
     LAT_TRACE(4);
 
     // ================= phase C: fc.0 + ReLU, outputs cta*16 .. cta*16+15 =================
@@ -430,7 +433,7 @@ latency_kernel(const Params p) {
         }
     }
     LAT_TRACE(5);
-    grid_sync(p.sync, 3u, (unsigned)G);
+    grid_sync(p.sync, 3u, (unsigned)G, []() {});
     LAT_TRACE(6);
 
     // ================= phase D: fc.3 + ReLU (outputs cta*4 .. cta*4+3) and this CTA's share of fc.6 =================

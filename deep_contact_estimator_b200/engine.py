@@ -305,9 +305,9 @@ class ContactEngine:
         return out_cls_host, out_bits_host
 
     # -- K3: control-loop runner -------------------------------------------------
-    def latency_runner(self, n: int = 1, want_logits: bool = False) -> "LatencyRunner":
+    def latency_runner(self, n: int = 1, want_logits: bool = False, use_graph: bool = False) -> "LatencyRunner":
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
-        return LatencyRunner(self, n, want_logits)
+        return LatencyRunner(self, n, want_logits, use_graph)
 
     # -- small helpers on the same ABI ------------------------------------------
     def decimal2binary(self, x: torch.Tensor) -> torch.Tensor:
@@ -339,8 +339,9 @@ class LatencyRunner:
     """The 1 kHz control-loop call (BASELINE configs[4]).  The newest window(s) sit in PINNED host memory and the
     fused latency kernel reads them in place over PCIe (zero-copy: 32.4 KB per window, once) and writes class,
     contact bits (and logits) straight back into pinned host memory — no copy-engine hops on either side, which
-    cost more than the kernel itself at this size.  The launch is captured ONCE in a CUDA graph, so a step is one
-    graph launch and one stream synchronise.
+    cost more than the kernel itself at this size.  A step is one ``dce_forward`` call (a single kernel launch) and
+    one stream synchronise; ``use_graph=True`` replays a captured CUDA graph instead (measured 4 us slower per step
+    from Python, `tools/latency_diag.py`, but it is the form a larger captured control loop would embed).
 
         run = engine.latency_runner()
         run.x_host[0] = newest_window          # (150, 54) float32, z-scored (utils/data_handler.py:55-56)
@@ -350,10 +351,10 @@ class LatencyRunner:
     (/root/reference/src/inference_one_seq.py:23-28, config/inference_one_seq_params.yaml:10).
     """
 
-    def __init__(self, eng: ContactEngine, n: int = 1, want_logits: bool = False):
+    def __init__(self, eng: ContactEngine, n: int = 1, want_logits: bool = False, use_graph: bool = False):
         if not 1 <= n <= 4:
             raise ValueError("the latency path takes 1..4 windows per step")
-        self.eng, self.n = eng, n
+        self.eng, self.n, self.use_graph = eng, n, use_graph
         dev = eng.device
         self.x_host = torch.zeros((n, WINDOW, CHANNELS), dtype=torch.float32).pin_memory()
         self.cls_host = torch.zeros((n,), dtype=torch.int32).pin_memory()
@@ -370,20 +371,26 @@ class LatencyRunner:
                                      P(ws), ws.numel(), _lib.PRECISIONS[eng.precision], ctypes.c_void_p(self.stream.cuda_stream))
             _lib.check(rc, "dce_forward")
 
+        self._launch = launch
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
             for _ in range(2):                                   # kernel attributes set before the capture
                 launch()
             self.stream.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                launch()
-        self.launches = eng.lib.dce_last_launch_count()
+            self.launches = eng.lib.dce_last_launch_count()
+            self.graph = None
+            if use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    launch()
         self._ws = ws
 
     def enqueue(self):
         """Launch one step without waiting (``self.stream``)."""
-        with torch.cuda.stream(self.stream):
-            self.graph.replay()
+        if self.graph is None:
+            self._launch()                                       # enqueues on self.stream (passed to the C ABI)
+        else:
+            with torch.cuda.stream(self.stream):
+                self.graph.replay()
 
     def step(self, window: Optional[torch.Tensor] = None):
         """Classify ``self.x_host`` (or ``window``, copied into it first); returns host ``(cls, bits)``."""

@@ -404,12 +404,13 @@ def test_latency_runner_control_loop(dev, params0):
     eng = engine(dev, "bf16x3")
     log = synth.make_sensor_log(150 + 12, seed=9)
     _, wc, wb = oracle.inference_stream(params0, log)
-    run = eng.latency_runner(1, want_logits=True)
-    assert run.launches == 1
-    for i in range(12):
-        w = log[i:i + 150]
-        cls, bits = run.step((w - w.mean(0)) / w.std(0))          # utils/data_handler.py:55-56 on the host
-        assert int(cls[0]) == int(wc[i]) and bits[0].tolist() == wb[i].tolist()
+    for use_graph in (False, True):
+        run = eng.latency_runner(1, want_logits=True, use_graph=use_graph)
+        assert run.launches == 1
+        for i in range(12):
+            w = log[i:i + 150]
+            cls, bits = run.step((w - w.mean(0)) / w.std(0))      # utils/data_handler.py:55-56 on the host
+            assert int(cls[0]) == int(wc[i]) and bits[0].tolist() == wb[i].tolist()
     with pytest.raises(ValueError):
         eng.latency_runner(5)
 
