@@ -10,9 +10,10 @@ from .engine import ContactEngine, LatencyRunner, default_precision
 from .contact_cnn import contact_cnn
 from .data_handler import contact_dataset
 from .inference import inference, inference_and_compute_acc, compute_accuracy, decimal2binary
+from .realtime import RealtimeContactEstimator
 
 __all__ = [
-    "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "inference", "inference_and_compute_acc",
+    "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "RealtimeContactEstimator", "inference", "inference_and_compute_acc",
     "compute_accuracy", "decimal2binary", "default_precision",
     "WINDOW", "CHANNELS", "CLASSES", "PARAM_NAMES", "PARAM_SHAPES",
 ]

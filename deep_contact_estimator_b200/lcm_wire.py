@@ -4,7 +4,7 @@
 to an `lcm.EventLog`.  liblcm is not installed in this image, so this module provides the few
 pieces that function needs, written from the IDL (/root/reference/lcm_types/*.lcm):
 
-  * encoders for `contact_t`, `leg_control_data_lcmt`, `microstrain_lcmt`: 8-byte big-endian type
+  * encoders / decoders for `contact_t`, `leg_control_data_lcmt`, `microstrain_lcmt`: 8-byte big-endian type
     fingerprint, then the fields in declaration order, big-endian (the LCM marshalling rules);
   * `EventLog`: the LCM log-file container (sync word 0xEDA1DA01, event number, timestamp in
     microseconds, channel length, payload length, channel, payload — all big-endian).
@@ -59,6 +59,23 @@ def encode_microstrain(quat, rpy, omega, acc, good_packets: int = 0, bad_packets
     return (_FP_IMU + struct.pack(">4f", *[float(a) for a in quat[:4]]) + struct.pack(">3f", *[float(a) for a in rpy[:3]])
             + struct.pack(">3f", *[float(a) for a in omega[:3]]) + struct.pack(">3f", *[float(a) for a in acc[:3]])
             + struct.pack(">qq", int(good_packets), int(bad_packets)))
+
+
+def decode_leg_control_data(data: bytes):
+    """-> (q, qd, p, v, tau_est), five tuples of 12 floats"""
+    if data[:8] != _FP_LEG or len(data) < 8 + 5 * 48:
+        raise ValueError("not a leg_control_data_lcmt")
+    return tuple(struct.unpack(">12f", data[8 + 48 * i: 8 + 48 * (i + 1)]) for i in range(5))
+
+
+def decode_microstrain(data: bytes):
+    """-> (quat[4], rpy[3], omega[3], acc[3], good_packets, bad_packets)"""
+    if data[:8] != _FP_IMU or len(data) < 8 + 52 + 16:
+        raise ValueError("not a microstrain_lcmt")
+    quat = struct.unpack(">4f", data[8:24])
+    rpy, omega, acc = (struct.unpack(">3f", data[24 + 12 * i: 36 + 12 * i]) for i in range(3))
+    good, bad = struct.unpack(">qq", data[60:76])
+    return quat, rpy, omega, acc, good, bad
 
 
 class EventLog:

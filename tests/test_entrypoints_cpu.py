@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import scipy.io as sio
 import torch
 import yaml
@@ -67,3 +68,61 @@ def test_test_script(tmp_path):
     assert abs(acc - float((cls.numpy() == gt).mean())) < 1e-12
     assert np.allclose(per_leg, (bits.numpy() == oracle.decimal2binary_numpy(gt)).mean(axis=0))
     assert m["confusion_mat"]["total"].sum() == 4 * 51
+
+
+def test_lcm_decoders_invert_the_reference_encoders(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lcm_bytes.npz"))
+    q, qd, p, v, tau = lcm_wire.decode_leg_control_data(g["leg"].tobytes())
+    for got, key in ((q, "leg_q"), (qd, "leg_qd"), (p, "leg_p"), (v, "leg_v"), (tau, "leg_tau_est")):
+        assert np.array_equal(np.asarray(got, dtype=np.float32), g[key])
+    quat, rpy, omega, acc, good, bad = lcm_wire.decode_microstrain(g["imu"].tobytes())
+    for got, key in ((quat, "imu_quat"), (rpy, "imu_rpy"), (omega, "imu_omega"), (acc, "imu_acc")):
+        assert np.array_equal(np.asarray(got, dtype=np.float32), g[key])
+    assert (good, bad) == (7, 2)
+    with pytest.raises(ValueError):
+        lcm_wire.decode_microstrain(g["leg"].tobytes())
+    with pytest.raises(ValueError):
+        lcm_wire.decode_leg_control_data(g["contact"].tobytes())
+
+
+class _OracleRunner:
+    """CPU stand-in for LatencyRunner (x_host + step()), classifying with the oracle."""
+
+    def __init__(self, params):
+        self.params = params
+        self.x_host = torch.zeros((1, 150, 54), dtype=torch.float32)
+
+    def step(self):
+        logits = oracle.forward_torch(self.params, self.x_host)
+        cls = oracle.argmax_class(logits)
+        return cls.to(torch.int32), oracle.decimal2binary(cls)
+
+
+def test_realtime_estimator_ring_and_messages_match_the_reference_loop():
+    """RealtimeContactEstimator: rows arrive as leg_control_data + microstrain messages, the
+    150-row ring and z-score reproduce contact_dataset.__getitem__, and contact_t messages carry the same bits
+    as the reference loop at batch_size 1 over the same log."""
+    from deep_contact_estimator_b200.realtime import RealtimeContactEstimator
+    params = synth.make_params(0)
+    T = 150 + 160                                  # wraps the ring once
+    log = synth.make_sensor_log(T, seed=4)
+    _, wc, wb = oracle.inference_stream(params, log)
+    est = RealtimeContactEstimator(runner=_OracleRunner(params))
+    outs = []
+    for t in range(T):
+        r = log[t]
+        leg = lcm_wire.encode_leg_control_data(r[0:12], r[12:24], r[30:42], r[42:54], np.zeros(12))   # q, qd, p, v
+        imu = lcm_wire.encode_microstrain([1, 0, 0, 0], [0, 0, 0], r[27:30], r[24:27])                # omega, acc
+        msg = est.push_messages(leg, imu, timestamp=t * 1e-3)
+        assert (msg is None) == (t < 149)
+        if msg is not None:
+            outs.append(lcm_wire.decode_contact(msg))
+    assert len(outs) == T - 149
+    assert [o[2] for o in outs] == wb.tolist()
+    assert outs[0][0] == 4 and abs(outs[5][1] - (149 + 5) * 1e-3) < 1e-12
+    # push_row gives class + bits
+    est2 = RealtimeContactEstimator(runner=_OracleRunner(params))
+    res = [est2.push_row(log[t]) for t in range(151)]
+    assert res[148] is None and res[149] == (int(wc[0]), tuple(wb[0].tolist())) and res[150][0] == int(wc[1])
+    with pytest.raises(ValueError):
+        RealtimeContactEstimator()

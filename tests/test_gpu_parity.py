@@ -434,3 +434,14 @@ def test_device_ingest_and_stream_host(dev, params0):
         assert torch.equal(hc, cl.cpu()) and torch.equal(hb, bi.cpu())
     _, wc, wb = oracle.inference_stream(params0, log[:600])
     assert np.array_equal(hb.numpy()[:451], wb.numpy())
+
+
+def test_realtime_estimator_on_gpu(dev, params0):
+    """RealtimeContactEstimator over the real LatencyRunner: contact bits per tick == the reference loop's."""
+    from deep_contact_estimator_b200.realtime import RealtimeContactEstimator
+    log = synth.make_sensor_log(150 + 20, seed=4)
+    _, wc, wb = oracle.inference_stream(params0, log)
+    est = RealtimeContactEstimator(engine=engine(dev, "bf16x3"))
+    got = [est.push_row(log[t]) for t in range(log.shape[0])]
+    assert all(g is None for g in got[:149])
+    assert [g[0] for g in got[149:]] == wc.tolist() and [list(g[1]) for g in got[149:]] == wb.tolist()
