@@ -38,7 +38,7 @@ extern "C" {
 #define DCE_API
 #endif
 
-/* model geometry — src/contact_cnn.py:10-58, config/*.yaml window_size */
+/* model geometry — src/contact_cnn.py:10-58, window_size in the config yaml files */
 #define DCE_WINDOW   150
 #define DCE_CHANNELS 54
 #define DCE_CLASSES  16

@@ -64,3 +64,26 @@ def test_no_cpu_fallback_on_missing_library(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no fallback"):
         _lib.load()
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """include/dce.h compiles as C99 (no C++ or torch types at the boundary) and a C program links against the
+    library: examples/realtime_step.c is the control-loop caller a C/C++ front end would write."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    cuda_lib = "/usr/local/cuda/lib64"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    exe = str(tmp_path / "realtime_step")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-I", cuda_inc,
+           os.path.join(root, "examples", "realtime_step.c"), "-L", os.path.dirname(_lib.LIB_PATH), "-ldce_b200",
+           "-L", cuda_lib, "-lcudart", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-Wl,-rpath," + cuda_lib, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and "version 100" in run.stdout and "invalid argument" in run.stdout
