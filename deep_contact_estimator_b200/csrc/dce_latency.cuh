@@ -12,9 +12,9 @@
 //   D  fc.3+ReLU, fc.6              128 CTAs x 4 outputs (32 KB slice resident), each adds its share of the 16 logits;
 //      + argmax + bits              the LAST CTA to finish (atomic ticket, no barrier) sums the 128 shares in a fixed order
 // Every weight block is fetched with 1-D bulk TMA as early as shared memory allows (conv weights at kernel
-// start, the fc.0 ring and the fc.3 slice before the barrier that precedes them), and the fc.0 slice is
-// prefetched into L2 at kernel start, so a phase starts with its weights already on chip.  All sums run in
-// a fixed order: results are bit-reproducible call to call.
+// start; the conv4 quarter, the fc.0 ring and the fc.3 slice while the CTA waits in the barrier that precedes
+// their phase), and the fc.0 slice is prefetched into L2 at kernel start, so a phase starts with its weights
+// already on chip.  All sums run in a fixed order: results are bit-reproducible call to call.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
