@@ -32,6 +32,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include "dce_common.cuh"
 #include "dce_tc_ptx.cuh"
@@ -67,6 +69,7 @@ struct TapGemmParams {
     int n_valid;                 // EPI_FC_F32: valid rows
     long long* trace;            // optional clock64 timeline of CTA 0: [tile][8] (tools/trace_tapgemm.py)
     int dbg;                     // timing ablations (results invalid): 1 = every tile loads the A slabs of tile 0; 2 = skip epilogue stores
+    const float* acc_scale;      // F8 kernels: one float, 1 / (the layer's power-of-two weight scale), applied to the accumulator
 };
 
 struct Tape {
@@ -97,6 +100,40 @@ __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// ---- fp16 main + e4m3 corrections (experimental FC operand format, option "fc_f16f8") ----------------
+//     x * w ~= f16(x) * f16(w sw) + e4m3((x - f16(x)) 2^12) * e4m3(w sw 2^3) + e4m3(x 2^1) * e4m3((w sw - f16(w sw)) 2^14)
+// sw = the layer's power-of-two weight scale (max |w sw| in [1, 2)).  Both correction products carry 2^15 and
+// are accumulated first; the first fp16 MMA rescales the accumulator by 2^-15 (scale-input-d).  fp8 MMAs take
+// K = 32 per instruction, so a K-step costs 2 + 2 MMA slots per 32 elements instead of 6
+// (tools/emulate_split_precision.py: 6e-6 norm-wise on the logits; tools/microbench/umma_f16f8.cu).
+constexpr int kF8ExL = 12, kF8EwH = 3, kF8ExH = 1, kF8EwL = 14, kF8ScaleD = 15;
+static_assert(kF8ExL + kF8EwH == kF8ScaleD && kF8ExH + kF8EwL == kF8ScaleD, "both correction products carry the same scale");
+
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float d;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+// 16 consecutive K elements of one row -> two 16-byte fp16 chunks + one 16-byte chunk of each e4m3 image.
+// Activations saturate at the largest finite fp16 (65504); NaN propagates through all three images.
+__device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
+    uint32_t h[8], l[4], g[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float a = min_nan(y[2 * i], 65504.f), b = min_nan(y[2 * i + 1], 65504.f);
+        const __half2 hb = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hb);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2((a - hf.x) * (float)(1 << kF8ExL), (b - hf.y) * (float)(1 << kF8ExL)), __NV_SATFINITE, __NV_E4M3);
+        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a * (float)(1 << kF8ExH), b * (float)(1 << kF8ExH)), __NV_SATFINITE, __NV_E4M3);
+        if (i & 1) { l[i >> 1] |= lo << 16; g[i >> 1] |= hi << 16; } else { l[i >> 1] = lo; g[i >> 1] = hi; }
+    }
+    f16a = make_uint4(h[0], h[1], h[2], h[3]);
+    f16b = make_uint4(h[4], h[5], h[6], h[7]);
+    lo8 = make_uint4(l[0], l[1], l[2], l[3]);
+    hi8 = make_uint4(g[0], g[1], g[2], g[3]);
+}
+
 // NaN-propagating max (FMNMX.NAN): torch's ReLU and MaxPool1d both propagate NaN.
 __device__ __forceinline__ float max_nan(float a, float b) {
     float d;
@@ -145,9 +182,14 @@ struct TapGemmCfg {
 #endif
 #define TG_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
+// F8 = 1 (Linear layers only): operands in the fp16 + e4m3 format (split16_f16f8).  A tile's K loop is two sweeps
+// of p.stages / 2 stages each, 64 K-elements per stage and the same bytes per stage as the bf16x3 layout: sweep 1
+// streams the e4m3 images (A: [lo8 | hi8], B: [w8 | wl8]) and issues the correction MMAs, sweep 2 streams the
+// fp16 images and issues the main MMAs, the first of them with scale-input-d.
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0>
 __global__ void __launch_bounds__(tapgemm_threads(MT), 1)
 tapgemm_kernel(const TapGemmParams p) {
+    static_assert(!F8 || (TAPS == 1 && KSA == 4 && WST == 0 && (EPI == EPI_FC_TAPE || EPI == EPI_FC_LOGITS)), "F8: Linear layers, 64 K-elements per stage");
     constexpr int kProducerWarp0 = kEpiWarps + MT;
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     constexpr int NBUF = Cfg::NBUF;
@@ -220,9 +262,19 @@ tapgemm_kernel(const TapGemmParams p) {
                             const int c = c0 + pw;
                             if (c < NA) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
-                                ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
-                                              a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
-                                              kSlabBytes, &full[slot]);
+                                if (F8) {
+                                    // sweep 1: 16-element chunk s*4 + j of e4m3 image `part` (lo8 | hi8; an image has K/16 =
+                                    // 2 * stages chunks, both live in tape part 1); sweep 2: 8-element fp16 chunk, tape part 0
+                                    const int half = p.stages >> 1;
+                                    const size_t src_off = (s < half) ? p.a_part_stride + (size_t)(part * 2 * p.stages + s * KSA + j) * p.a_kch_stride
+                                                                      : (size_t)((s - half) * 2 * KSA + part * KSA + j) * p.a_kch_stride;
+                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                                  a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot]);
+                                } else {
+                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                                  a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                                  kSlabBytes, &full[slot]);
+                                }
                             } else if (c == NA && !WST) {
                                 ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
                             }
@@ -262,6 +314,48 @@ tapgemm_kernel(const TapGemmParams p) {
                     if (mt == 0 && s == p.stages - 1) TG_TRACE(tcount, 5);
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + mt * Cfg::A_TILE;
                     const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
+                    if (F8) {
+                        constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, BN), id16 = ptx::make_idesc_f16_f32(128, BN);
+                        const int half = p.stages >> 1;
+                        const uint32_t ac = a0 + 16;                       // Linear layers read the centre row of a slab
+                        auto probe_next = [&]() {                          // as below: probe the next stage mid-stage
+                            if (it + 1 < total_stages) {
+                                if (s == p.stages - 1) {
+                                    const uint32_t nt = tcount + 1;
+                                    ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
+                                }
+                                ptx::mbar_wait(&full[(it + 1) % NSTAGE], ((it + 1) / NSTAGE) & 1);
+                                ptx::tc_fence_after_sync();
+                            }
+                        };
+                        if (s < half) {
+                            // corrections: (x - f16 x) 2^12 * w 2^3  and  x 2^1 * (w - f16 w) 2^14, K = 32 per MMA
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const uint64_t da_l = ptx::make_smem_desc(ac + 2 * kk * kSlabBytes, kSlabBytes, 128);
+                                const uint64_t da_h = ptx::make_smem_desc(ac + Cfg::A_PART + 2 * kk * kSlabBytes, kSlabBytes, 128);
+                                const uint64_t db_h = ptx::make_smem_desc(b0 + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
+                                const uint64_t db_l = ptx::make_smem_desc(b0 + Cfg::B_PART + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
+                                if (leader) {
+                                    ptx::umma_e4m3_ss(d, da_l, db_h, id8, (s == 0 && kk == 0) ? 0u : 1u);
+                                    ptx::umma_e4m3_ss(d, da_h, db_l, id8, 1u);
+                                }
+                                if (kk == 0) probe_next();
+                            }
+                        } else {
+                            // main products: the stage holds 8 consecutive fp16 chunks of A (both "parts") and of B
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t da = ptx::make_smem_desc(ac + 2 * kk * kSlabBytes, kSlabBytes, 128);
+                                const uint64_t db = ptx::make_smem_desc(b0 + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
+                                if (leader) {
+                                    if (s == half && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
+                                    else ptx::umma_bf16_ss(d, da, db, id16, 1u);          // kind::f16; the operand format is in the idesc
+                                }
+                                if (kk == 1) probe_next();
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
                         const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
@@ -290,6 +384,7 @@ tapgemm_kernel(const TapGemmParams p) {
                             }
                         }
                     }
+                    }
                     if (leader) {
                         ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
                         if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
@@ -304,6 +399,7 @@ tapgemm_kernel(const TapGemmParams p) {
         const int q = warp & 3, h = warp >> 2;
         const int row_in_tile = q * 32 + lane;
         float* my_bias = s_bias + warp * HALF;               // warp-private copy of this warp's bias slice
+        const float acc_scale = F8 ? __ldg(p.acc_scale) : 1.f;   // F8: the weights were packed times a power of two
         uint32_t tcount = 0;
         int last_n = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -371,6 +467,13 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c0 + i);     // smem broadcast
+                    if (F8) {
+                        y[i] = relu_nan(fmaf(__uint_as_float(v[i]), acc_scale, b4.x));
+                        y[i + 1] = relu_nan(fmaf(__uint_as_float(v[i + 1]), acc_scale, b4.y));
+                        y[i + 2] = relu_nan(fmaf(__uint_as_float(v[i + 2]), acc_scale, b4.z));
+                        y[i + 3] = relu_nan(fmaf(__uint_as_float(v[i + 3]), acc_scale, b4.w));
+                        continue;
+                    }
                     y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
                     y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
                     y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
@@ -398,6 +501,23 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                    }
+                    return;
+                }
+                if (F8 && EPI == EPI_FC_TAPE) {
+                    // next layer's operand in the fp16 + e4m3 format: fp16 chunks in tape part 0, the two e4m3 images
+                    // (N / 16 chunks each: lo8, then hi8) in tape part 1
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 fa, fb, lo8, hi8;
+                        split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                        const int k16 = (n0 + c0) / 16 + hh;
+                        uint8_t* d16 = p.out + (size_t)(2 * k16) * p.out_kch_stride + out_off[mt];
+                        *reinterpret_cast<uint4*>(d16) = fa;
+                        *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
+                        uint8_t* d8 = p.out + p.out_part_stride + (size_t)k16 * p.out_kch_stride + out_off[mt];
+                        *reinterpret_cast<uint4*>(d8) = lo8;
+                        *reinterpret_cast<uint4*>(d8 + (size_t)(p.N / 16) * p.out_kch_stride) = hi8;
                     }
                     return;
                 }
@@ -499,6 +619,58 @@ __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__
         const size_t within = ((((size_t)tap * KSA + j) * BN + nn) * 8 + e) * 2;
         *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
         *reinterpret_cast<__nv_bfloat16*>(out + blk + per_part * 2 + within) = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0, fp16 + e4m3 format (option "fc_f16f8"; Linear layers): per n-tile, `stages` blocks of 8 * BN * 16 bytes in
+// the order the F8 kernel streams them: stages/2 correction blocks [w8 | wl8] (4 chunks of 16 e4m3 each) covering
+// 64 K-elements apiece, then stages/2 main blocks (8 chunks of 8 fp16).  Weights are multiplied by the layer's
+// power-of-two scale sw first (max |w sw| in [1, 2)), so small weights stay clear of the fp16 subnormals.
+// kind 3: fc.0 (K index k' = t*128 + c), kind 4: fc.3.
+// ---------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ W, size_t n, unsigned int* __restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(W[i]);
+        if (a <= 3.0e38f) m = fmaxf(m, a);                     // NaN / inf weights do not set the scale
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));      // non-negative floats order like their bits
+}
+// scale[0] = sw = 2^-floor(log2 max|w|), scale[1] = 1 / sw; scale[2] holds the absmax bits on entry
+__global__ void weight_scale_kernel(float* __restrict__ scale) {
+    const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]);
+    int e = 1;
+    if (m > 0.f) frexpf(m, &e);                                // m = f * 2^e, f in [0.5, 1)  ->  floor(log2 m) = e - 1
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    scale[0] = ldexpf(1.f, 1 - e);
+    scale[1] = ldexpf(1.f, e - 1);
+}
+__global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
+                                    int BN, int kind, int K, const float* __restrict__ scale) {
+    const float sw = scale[0];
+    const size_t total = (size_t)n_tiles * BN * K;
+    const size_t blk_bytes = (size_t)8 * BN * 16;
+    const int half = stages / 2;                               // K == 64 * half
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % K);
+        const int n = (int)(idx / K);
+        const int nt = n / BN, nn = n % BN;
+        float v;
+        if (kind == 3) { const int t = k / 128, ch = k % 128; v = W[(size_t)n * 4736 + ch * 37 + t]; }
+        else v = W[(size_t)n * K + k];
+        v *= sw;
+        const __half h = __float2half_rn(v);
+        const float r = v - __half2float(h);
+        const int s = k / 64, kr = k % 64;
+        uint8_t* corr = out + ((size_t)nt * stages + s) * blk_bytes;
+        uint8_t* mainb = out + ((size_t)nt * stages + half + s) * blk_bytes;
+        *reinterpret_cast<__half*>(mainb + (((size_t)(kr / 8) * BN + nn) * 8 + kr % 8) * 2) = h;
+        const size_t o8 = ((size_t)(kr / 16) * BN + nn) * 16 + kr % 16;
+        corr[o8] = (uint8_t)__nv_cvt_float_to_fp8(v * (float)(1 << kF8EwH), __NV_SATFINITE, __NV_E4M3);
+        corr[blk_bytes / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
     }
 }
 
@@ -644,7 +816,7 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 8;
+constexpr int kNumPacked = 10;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
@@ -652,13 +824,16 @@ constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // b
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
                                  {128, 3, 4, 4, 1, 0, 128, 6},     // block2.2 again, in 48 KB blocks (unused; kept for ablations)
-                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+                                 {256, 1, 4, 148, 8, 3, 4736, 8},  // fc.0 in the fp16 + e4m3 format (option "fc_f16f8")
+                                 {128, 1, 4, 64, 4, 4, 2048, 10}}; // fc.3 in the fp16 + e4m3 format
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
-struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
+struct PackedLayout { size_t w[kNumPacked]; size_t scales; size_t begin, end; };   // scales: [kNumPacked][4] floats {sw, 1/sw, absmax bits, -}
 inline PackedLayout make_packed_layout(size_t base) {
     PackedLayout L; L.begin = base; size_t o = base;
     for (int i = 0; i < kNumPacked; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }
+    L.scales = o; o = align_up(o + kNumPacked * 16, 256);
     L.end = o;
     return L;
 }
@@ -668,6 +843,17 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
         const LayerCfg& c = kLayers[i];
         const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        if (c.kind >= 3) {                                     // fp16 + e4m3 format: scale from max |w|, then the images
+            float* sc = reinterpret_cast<float*>(buf + L.scales) + i * 4;
+            const size_t nw = (size_t)c.n_tiles * c.BN * c.cin;
+            cudaError_t e = cudaMemsetAsync(sc, 0, 16, ctx.stream);
+            if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+            DCE_KL(ctx, "tc_absmax", absmax_kernel<<<1024, 256, 0, ctx.stream>>>(params[c.src], nw, reinterpret_cast<unsigned int*>(sc) + 2));
+            DCE_KL(ctx, "tc_weight_scale", weight_scale_kernel<<<1, 1, 0, ctx.stream>>>(sc));
+            DCE_KL(ctx, "tc_pack_b_f16f8", pack_b_f16f8_kernel<<<4096, 256, 0, ctx.stream>>>(
+                params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.kind, c.cin, sc));
+            continue;
+        }
         DCE_KL(ctx, "tc_pack_b", pack_b_kernel<<<blocks, 256, 0, ctx.stream>>>(
             params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin));
     }
@@ -697,11 +883,12 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, F8>;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
+    if (F8 && ((p.stages & 1) || !p.acc_scale)) return DCE_EINVAL;
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
     static_assert(kSmem <= 232448, "exceeds 227 KB");
     static DeviceOnce attr_once;

@@ -38,6 +38,8 @@ struct Block2Params {
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
+// F8OUT: write the fc.0 operand in the fp16 + e4m3 format (dce_tc.cuh: split16_f16f8) instead of bf16 hi/lo.
+template <bool F8OUT>
 __global__ void __launch_bounds__(kB2Threads, 1)
 block2_kernel(const Block2Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -264,7 +266,26 @@ block2_kernel(const Block2Params p) {
                 }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
-                if (store) {
+                if (F8OUT) {
+                    // k' = to*128 + channel.  Even lane: the four fp16 chunks (tape part 0, chunk to*16 + channel/8);
+                    // odd lane: the e4m3 images (tape part 1: lo8 chunks [0, 296), hi8 chunks [296, 592), chunk to*8 + channel/16)
+                    if (store) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint4 fa, fb, lo8, hi8;
+                            split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                            if (lane & 1) {
+                                uint8_t* d8 = p.out + p.out_part_stride + (size_t)(to * 8 + h * 4 + c * 2 + hh) * p.out_kch_stride + (size_t)(w + kGuard) * 16;
+                                *reinterpret_cast<uint4*>(d8) = lo8;
+                                *reinterpret_cast<uint4*>(d8 + (size_t)(37 * 8) * p.out_kch_stride) = hi8;
+                            } else {
+                                uint8_t* d16 = p.out + (size_t)(to * 16 + h * 8 + c * 4 + hh * 2) * p.out_kch_stride + (size_t)(w + kGuard) * 16;
+                                *reinterpret_cast<uint4*>(d16) = fa;
+                                *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
+                            }
+                        }
+                    }
+                } else if (store) {
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) {
                         uint4 hi, lo;

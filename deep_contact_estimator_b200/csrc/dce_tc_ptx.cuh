@@ -107,6 +107,33 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- fp16 main + e4m3 corrections (experimental FC mode, dce_tc_f16f8.cuh) -----------------------
+// kind::f16 with fp16 operands, and kind::f8f6f4 with e4m3 operands (K = 32 per instruction: two 16-byte
+// K chunks of 16 elements, same descriptors as above).  Both accumulate in fp32 in the same TMEM columns.
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // A = B = F16 (format 0)
+}
+__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // A = B = E4M3 (format 0 of kind::f8f6f4)
+}
+__device__ __forceinline__ void umma_e4m3_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A * B + D * 2^-S (scale-input-d, kind::f16 only): brings an accumulator that holds the e4m3 correction
+// products at scale 2^S down to the scale of the fp16 main products.
+template <int S>
+__device__ __forceinline__ void umma_f16_ss_scale_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    static_assert(S >= 0 && S <= 15, "scale-input-d is a 4-bit immediate");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.b32 p, %3, %3;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(S) : "memory");
+}
 // mbarrier arrives when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

@@ -12,6 +12,7 @@ namespace tc {
 inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& fuse_fc3_flag() { static int v = 1; return v; }
+inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
@@ -102,11 +103,14 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
         }
         const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
+        const bool f8 = fc_f16f8_flag() && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
+        const float* scales = reinterpret_cast<const float*>(buf + L.scales);
         if (fuse_block2_flag() && !tiny) {
             // ---- fused conv3 + conv4 + pool + flatten (a7-a9): X2 -> X4, X3 stays in shared memory
             static DeviceOnce b2_once;
             if (b2_once.need()) {
-                cudaError_t e = cudaFuncSetAttribute(block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                cudaError_t e = cudaFuncSetAttribute(block2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
             Block2Params b{};
@@ -117,7 +121,10 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
             b.trace = (tapgemm_trace_layer() == 6) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+            if (f8)
+                DCE_KL(ctx, "tc_block2_f8out", { cudaError_t le_ = launch_pdl(block2_kernel<true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+            else
+                DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel<false>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
         } else {
         p = TapGemmParams{};
         p.n_tiles = 1;
@@ -170,7 +177,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.N = 2048; p.rw = 1; p.tv = 1;
         p.dbg = tapgemm_dbg_flag();
         p.trace = (tapgemm_trace_layer() == 4) ? block1_trace_ptr() : nullptr;
-        if ((rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p)) != DCE_OK) return rc;
+        if (f8) {
+            p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[8]); p.acc_scale = scales + 8 * 4 + 1;
+            rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1_f16f8", sm_count, p);
+        } else {
+            rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
+        }
+        if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
         p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[5]); p.bias = bp.b[5];
@@ -180,7 +193,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         if (fuse_fc3_flag()) {
             // ---- fc.3 + ReLU with fc.6 folded into the epilogue (a11, a12): H2 stays in registers; 8 logit shares per window
             p.w3t = bp.w3;
-            if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p)) != DCE_OK) return rc;
+            if (f8) {
+                p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[9]); p.acc_scale = scales + 9 * 4 + 1;
+                rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1>(ctx, "tc_fc2_fc3_f16f8", sm_count, p);
+            } else {
+                rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
+            }
+            if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,
                 (const float*)h2, bp.b[6], (int64_t)m, 2 * kLayers[5].n_tiles, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,
                 bits ? bits + c0 * 4 : nullptr); (void)le_; });

@@ -445,3 +445,22 @@ def test_realtime_estimator_on_gpu(dev, params0):
     got = [est.push_row(log[t]) for t in range(log.shape[0])]
     assert all(g is None for g in got[:149])
     assert [g[0] for g in got[149:]] == wc.tolist() and [list(g[1]) for g in got[149:]] == wb.tolist()
+
+
+@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
+                    reason="fp16 + e4m3 FC mode (option fc_f16f8) has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
+@pytest.mark.parametrize("scale", [1.0, 50.0])
+def test_experimental_fc_f16f8_matches_oracle(dev, scale):
+    """fc.0 / fc.3 with fp16 main products + e4m3 corrections (two MMA-slot equivalents instead of three): same
+    bar as bf16x3.  Off by default; the option is restored whatever happens."""
+    eng = engine(dev, "bf16x3", 0, scale)
+    x = synth.make_windows(300, seed=77)
+    want = oracle_logits(synth.make_params(0, logit_scale=scale), x)
+    try:
+        assert eng.lib.dce_set_option(b"fc_f16f8", 1) == 0
+        logits, cls, bits = eng.classify(x.to(dev))
+        torch.cuda.synchronize()
+    finally:
+        eng.lib.dce_set_option(b"fc_f16f8", 0)
+    assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL["bf16x3"]
+    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))

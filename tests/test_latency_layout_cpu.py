@@ -12,3 +12,15 @@ def test_latency_kernel_layouts_match_oracle():
     spec.loader.exec_module(mod)
     e_batch, e_stream = mod.check(batch=1)
     assert e_batch <= 1e-6 and e_stream <= 1e-6
+
+
+def test_f16f8_fc_layouts_match_float64():
+    """Experimental fp16 + e4m3 FC mode (option "fc_f16f8", off by default): weight images, both tape writers and the
+    F8 producer / issuer addressing of tapgemm_kernel, restated in numpy by tools/emulate_f16f8.py.  The bound is the
+    arithmetic's own error for this data (plain-matrix fp16 + e4m3: 1.2e-5; fp16 alone: 3e-4)."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "emulate_f16f8.py")
+    spec = importlib.util.spec_from_file_location("emulate_f16f8", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    e_fc0, e_fc3 = mod.check(rows=3)
+    assert e_fc0 <= 3e-5 and e_fc3 <= 3e-5

@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""CPU emulation of the index arithmetic of the experimental fp16 + e4m3 FC mode (option "fc_f16f8"):
+    pack_b_f16f8_kernel, split16_f16f8, the two tape writers (tapgemm EPI_FC_TAPE with F8, block2_kernel<true>),
+    and the F8 producer / issuer of tapgemm_kernel (csrc/dce_tc.cuh, dce_tc_block2.cuh)
+restated in numpy: bulk copies land in a byte array shaped like a ring stage, every MMA gathers its operands
+through the (start, LBO, SBO = 128) descriptor it would be issued with, corrections accumulate at 2^15 and the
+first fp16 MMA applies scale-input-d.  Checked against float64 x @ W^T.  No GPU: this pins the layout formulas and
+the operand pairing, not the synchronisation.       python tools/emulate_f16f8.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+GUARD, SLAB = 8, 130 * 16
+EXL, EWH, EXH, EWL, SCALE_D = 12, 3, 1, 14, 15
+
+
+def e4m3(v):
+    """float array -> e4m3 bytes (round to nearest even, saturating, as cvt.rn.satfinite.e4m3x2.f32)."""
+    t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).clamp(-448.0, 448.0)
+    return t.to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+
+
+def e4m3_to_f(b):
+    return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).float().numpy()
+
+
+def make_tape(rows, kch):
+    m_tiles = (rows + 127) // 128
+    m_tiles += m_tiles & 1
+    cap = GUARD + m_tiles * 128 + 136
+    return dict(rows=rows, m_tiles=m_tiles, cap=cap, kch=kch, kch_stride=cap * 16, part_stride=cap * 16 * kch,
+                buf=np.zeros(2 * cap * 16 * kch, np.uint8))
+
+
+def weight_scale(W):
+    m, e = np.frexp(np.float32(np.abs(W).max()))               # weight_scale_kernel
+    return np.float32(np.ldexp(1.0, 1 - int(e))), np.float32(np.ldexp(1.0, int(e) - 1))
+
+
+def pack_b_f16f8(W, n_tiles, stages, BN, kind, K, sw):
+    """pack_b_f16f8_kernel, vectorised over idx."""
+    out = np.zeros(n_tiles * stages * 8 * BN * 16, np.uint8)
+    blk, half = 8 * BN * 16, stages // 2
+    idx = np.arange(n_tiles * BN * K, dtype=np.int64)
+    k, n = idx % K, idx // K
+    nt, nn = n // BN, n % BN
+    if kind == 3:
+        v = W.reshape(-1)[n * 4736 + (k % 128) * 37 + k // 128]
+    else:
+        v = W.reshape(-1)[n * K + k]
+    v = (v * sw).astype(np.float32)
+    h = v.astype(np.float16)
+    r = v - h.astype(np.float32)
+    s, kr = k // 64, k % 64
+    corr = (nt * stages + s) * blk
+    mainb = (nt * stages + half + s) * blk
+    o16 = mainb + (((kr // 8) * BN + nn) * 8 + kr % 8) * 2
+    hb = h.view(np.uint16)
+    out[o16] = (hb & 0xFF).astype(np.uint8)
+    out[o16 + 1] = (hb >> 8).astype(np.uint8)
+    o8 = ((kr // 16) * BN + nn) * 16 + kr % 16
+    out[corr + o8] = e4m3(v * 2.0 ** EWH)
+    out[corr + blk // 2 + o8] = e4m3(r * 2.0 ** EWL)
+    return out
+
+
+def split16(y):
+    """split16_f16f8 on [..., 16] -> (fp16 bytes [..., 32], lo8 [..., 16], hi8 [..., 16])."""
+    a = np.minimum(y.astype(np.float32), np.float32(65504.0))
+    h = a.astype(np.float16)
+    lo = e4m3((a - h.astype(np.float32)) * 2.0 ** EXL)
+    hi = e4m3(a * 2.0 ** EXH)
+    return h.view(np.uint8).reshape(*y.shape[:-1], 32), lo.reshape(y.shape), hi.reshape(y.shape)
+
+
+def write_fc_tape(tape, y, N):
+    """tapgemm epilogue, EPI_FC_TAPE with F8: row = window, thread chunks of 32 columns -> 2 x 16."""
+    for row in range(y.shape[0]):
+        off = (row + GUARD) * 16
+        for k16 in range(N // 16):
+            f, lo, hi = split16(y[row, 16 * k16: 16 * k16 + 16])
+            d16 = (2 * k16) * tape["kch_stride"] + off
+            tape["buf"][d16: d16 + 16] = f[:16]
+            tape["buf"][d16 + tape["kch_stride"]: d16 + tape["kch_stride"] + 16] = f[16:]
+            d8 = tape["part_stride"] + k16 * tape["kch_stride"] + off
+            tape["buf"][d8: d8 + 16] = lo
+            d8h = d8 + (N // 16) * tape["kch_stride"]
+            tape["buf"][d8h: d8h + 16] = hi
+
+
+def write_block2_tape(tape, y4):
+    """block2_kernel<true> epi2: y4[w][to][128 channels] (pooled); thread = (h, c) 32-channel group, hh = 16-channel half."""
+    for w in range(y4.shape[0]):
+        for to in range(37):
+            for h in range(2):
+                for c in range(2):
+                    for hh in range(2):
+                        ch0 = h * 64 + c * 32 + hh * 16
+                        f, lo, hi = split16(y4[w, to, ch0: ch0 + 16])
+                        d8 = tape["part_stride"] + (to * 8 + h * 4 + c * 2 + hh) * tape["kch_stride"] + (w + GUARD) * 16
+                        tape["buf"][d8: d8 + 16] = lo                                  # odd lane
+                        d8h = d8 + (37 * 8) * tape["kch_stride"]
+                        tape["buf"][d8h: d8h + 16] = hi
+                        d16 = (to * 16 + h * 8 + c * 4 + hh * 2) * tape["kch_stride"] + (w + GUARD) * 16
+                        tape["buf"][d16: d16 + 16] = f[:16]                             # even lane
+                        tape["buf"][d16 + tape["kch_stride"]: d16 + tape["kch_stride"] + 16] = f[16:]
+
+
+def gather(smem, start, lbo, rows, elem_bytes):
+    """Operand of one MMA through its SWIZZLE_NONE K-major descriptor: two 16-byte K chunks, SBO = 128 (row pitch 16)."""
+    out = []
+    for kc in range(2):
+        raw = np.stack([smem[start + kc * lbo + r * 16: start + kc * lbo + r * 16 + 16] for r in range(rows)])
+        out.append(raw.view(np.float16).astype(np.float64) if elem_bytes == 2 else e4m3_to_f(raw).astype(np.float64))
+    return np.concatenate(out, axis=1)                          # [rows][K of the MMA]
+
+
+def tile(tape, wpk, m, n, stages, BN, MT):
+    """One CTA tile of tapgemm_kernel<BN, 1, 4, *, *, MT, 0, F8 = 1>: returns the MT accumulators [MT][128][BN]."""
+    KSA = 4
+    A_PART, A_TILE, B_TAPCH = KSA * SLAB, 2 * KSA * SLAB, BN * 16
+    A_BYTES, B_PART = MT * A_TILE, KSA * B_TAPCH
+    B_BYTES = 2 * B_PART
+    half = stages // 2
+    D = np.zeros((MT, 128, BN))
+    a_row = (128 * m + GUARD - 1) * 16
+    for s in range(stages):
+        st = np.zeros(A_BYTES + B_BYTES, np.uint8)
+        for c in range(MT * 2 * KSA):                           # producer: A slabs
+            mt, part, j = c // (2 * KSA), (c // KSA) & 1, c % KSA
+            if s < half:
+                src_off = tape["part_stride"] + (part * 2 * stages + s * KSA + j) * tape["kch_stride"]
+            else:
+                src_off = ((s - half) * 2 * KSA + part * KSA + j) * tape["kch_stride"]
+            src = a_row + mt * 2048 + src_off
+            dst = mt * A_TILE + part * A_PART + j * SLAB
+            st[dst: dst + SLAB] = tape["buf"][src: src + SLAB]
+        wsrc = (n * stages + s) * B_BYTES                       # producer: the B block
+        st[A_BYTES: A_BYTES + B_BYTES] = wpk[wsrc: wsrc + B_BYTES]
+        for mt in range(MT):                                    # issuers
+            a0, b0 = mt * A_TILE, A_BYTES
+            ac = a0 + 16
+            if s < half:
+                for kk in range(2):
+                    a_l = gather(st, ac + 2 * kk * SLAB, SLAB, 128, 1)
+                    a_h = gather(st, ac + A_PART + 2 * kk * SLAB, SLAB, 128, 1)
+                    b_h = gather(st, b0 + 2 * kk * B_TAPCH, B_TAPCH, BN, 1)
+                    b_l = gather(st, b0 + B_PART + 2 * kk * B_TAPCH, B_TAPCH, BN, 1)
+                    if s == 0 and kk == 0:
+                        D[mt] = 0.0
+                    D[mt] += a_l @ b_h.T
+                    D[mt] += a_h @ b_l.T
+            else:
+                for kk in range(4):
+                    a = gather(st, ac + 2 * kk * SLAB, SLAB, 128, 2)
+                    b = gather(st, b0 + 2 * kk * B_TAPCH, B_TAPCH, BN, 2)
+                    if s == half and kk == 0:
+                        D[mt] *= 2.0 ** -SCALE_D
+                    D[mt] += a @ b.T
+    return D
+
+
+def check(rows=5, seed=0):
+    """Returns the norm-wise errors of (fc.0 fed by the block2 writer, fc.3 fed by fc.0's writer)."""
+    from deep_contact_estimator_b200 import synth
+    P = {k: v.numpy() for k, v in synth.make_params(seed).items()}
+    rng = np.random.default_rng(seed + 1)
+    relu = lambda v: np.maximum(v, 0.0)
+    # ---- fc.0: X4 written by block2_kernel<true>, K order k' = t*128 + c (flatten c*37 + t of src/contact_cnn.py:64)
+    y4 = relu(rng.standard_normal((rows, 37, 128))).astype(np.float32)          # pooled conv4 output [w][t][c]
+    x4 = make_tape(rows, 592)
+    write_block2_tape(x4, y4)
+    W0 = P["fc.0.weight"]
+    sw0, inv0 = weight_scale(W0)
+    wp0 = pack_b_f16f8(W0, 8, 148, 256, 3, 4736, sw0)
+    want0 = y4.transpose(0, 2, 1).reshape(rows, -1).astype(np.float64) @ W0.astype(np.float64).T      # reference flatten
+    errs = []
+    h1_full = relu(want0 + P["fc.0.bias"]).astype(np.float32)
+    for n in (0, 7):
+        D = tile(x4, wp0, 0, n, 148, 256, 2)
+        got = D[0][:rows] * float(inv0)
+        ref = want0[:, n * 256:(n + 1) * 256]
+        errs.append(np.abs(got - ref).max() / np.abs(ref).max())
+        assert np.abs(D[1]).max() == 0.0                       # the second M-tile holds only padding rows here
+    # ---- fc.3: H1 written by fc.0's epilogue
+    h1 = make_tape(rows, 256)
+    write_fc_tape(h1, h1_full, 2048)
+    W1 = P["fc.3.weight"]
+    sw1, inv1 = weight_scale(W1)
+    wp1 = pack_b_f16f8(W1, 4, 64, 128, 4, 2048, sw1)
+    want1 = h1_full.astype(np.float64) @ W1.astype(np.float64).T
+    e3 = []
+    for n in range(4):
+        D = tile(h1, wp1, 0, n, 64, 128, 1)
+        got = D[0][:rows] * float(inv1)
+        ref = want1[:, n * 128:(n + 1) * 128]
+        e3.append(np.abs(got - ref).max() / np.abs(ref).max())
+    return max(errs), max(e3)
+
+
+if __name__ == "__main__":
+    e0, e3 = check()
+    print(f"fc.0 (block2 writer -> F8 tile): {e0:.2e}   fc.3 (fc.0 writer -> F8 tile): {e3:.2e}")

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""First GPU run of the experimental fp16 + e4m3 FC mode (dce_set_option("fc_f16f8", 1)):
+parity against the oracle on 512 windows, then an A/B of the batch-4096 step with per-kernel times.
+Run it under a timeout — the mode has not been on a GPU yet:
+    timeout 120 python tools/try_f16f8.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import deep_contact_estimator_b200 as dce          # noqa: E402
+from deep_contact_estimator_b200 import synth      # noqa: E402
+from oracle import contact_oracle as oracle        # noqa: E402
+
+dev = torch.device("cuda", 0)
+for scale in (1.0, 50.0):
+    params = synth.make_params(0, logit_scale=scale)
+    eng = dce.ContactEngine(params, dev, "bf16x3")
+    x = synth.make_windows(512, seed=1)
+    with torch.no_grad():
+        want = oracle.forward_torch(params, x)
+    for on in (0, 1):
+        assert eng.lib.dce_set_option(b"fc_f16f8", on) == 0
+        logits, cls, bits = eng.classify(x.to(dev))
+        torch.cuda.synchronize()
+        err = oracle.normwise_rel_err(logits.cpu().numpy(), want.numpy())
+        same = bool((cls.cpu().long() == oracle.argmax_class(want)).all())
+        print(f"logit scale {scale:4.0f}  fc_f16f8={on}: normwise err {err:.2e}, classes exact {same}, {eng.last_launches} launches", flush=True)
+    eng.lib.dce_set_option(b"fc_f16f8", 0)
+
+eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
+xs = [synth.make_windows(4096, seed=5 + i).to(dev) for i in range(4)]
+
+
+def step_us(n=60):
+    for i in range(5):
+        eng.classify(xs[i % 4])
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n):
+        eng.classify(xs[i % 4])
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / n
+
+
+res = {}
+for on in (0, 1, 0, 1):
+    eng.lib.dce_set_option(b"fc_f16f8", on)
+    res.setdefault(on, []).append(round(step_us(), 1))
+    prof = {}
+    for i in range(10):
+        for name, ms in eng.profile_forward(xs[i % 4]):
+            prof[name] = prof.get(name, 0) + ms * 100
+    print(f"fc_f16f8={on}: step {res[on][-1]} us | per-kernel us:", {k: round(v, 1) for k, v in prof.items()}, flush=True)
+eng.lib.dce_set_option(b"fc_f16f8", 0)
