@@ -44,6 +44,14 @@ class contact_cnn(nn.Module):
         self._engine: Optional[ContactEngine] = None
         self._engine_key = None
 
+    def __getstate__(self):
+        # copy.deepcopy / pickling of the whole module: the engine wraps a device handle of THIS process and is
+        # rebuilt lazily from the parameters, so it is never part of the module's state
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_key"] = None
+        return state
+
     # -- stock path (training, CPU) ------------------------------------------
     def _forward_torch(self, x: torch.Tensor) -> torch.Tensor:
         x = x.permute(0, 2, 1)

@@ -186,15 +186,29 @@ class ContactEngine:
         Copies chunk by chunk on a side stream so the host->device transfer of
         chunk i+1 overlaps the kernels of chunk i; returns host ``(cls, bits)``
         after the device->host read of the results has completed."""
+        if (x_host.dim() != 3 or tuple(x_host.shape[1:]) != (WINDOW, CHANNELS) or x_host.dtype != torch.float32
+                or x_host.is_cuda):
+            raise ValueError(f"expected a host (B,{WINDOW},{CHANNELS}) float32 tensor, got {tuple(x_host.shape)} "
+                             f"{x_host.dtype} on {x_host.device}")
+        if chunk < 1:
+            raise ValueError("chunk must be positive")
         n = x_host.shape[0]
         if out_bits_host is None:
-            out_bits_host = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+            out_bits_host = torch.empty((n, 4), dtype=torch.uint8)
+            out_bits_host = out_bits_host.pin_memory() if n else out_bits_host
         if out_cls_host is None:
-            out_cls_host = torch.empty((n,), dtype=torch.int32).pin_memory()
+            out_cls_host = torch.empty((n,), dtype=torch.int32)
+            out_cls_host = out_cls_host.pin_memory() if n else out_cls_host
+        if tuple(out_bits_host.shape) != (n, 4) or out_bits_host.dtype != torch.uint8 or \
+                tuple(out_cls_host.shape) != (n,) or out_cls_host.dtype != torch.int32:
+            raise ValueError("out_bits_host must be (B,4) uint8 and out_cls_host (B,) int32")
+        if n == 0:
+            return out_cls_host, out_bits_host
         with torch.cuda.device(self.device):
             compute = torch.cuda.current_stream(self.device)
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
+            if getattr(self, "_stage", None) is None:
                 self._stage = [torch.empty((chunk, WINDOW, CHANNELS), dtype=torch.float32, device=self.device) for _ in range(2)]
                 self._stage_free = [torch.cuda.Event() for _ in range(2)]
             if self._stage[0].shape[0] != chunk:

@@ -436,6 +436,31 @@ def test_device_ingest_and_stream_host(dev, params0):
     assert np.array_equal(hb.numpy()[:451], wb.numpy())
 
 
+def test_classify_host_matches_classify(dev, params0):
+    """The host-buffer entry point bench.py's `e2e` times (pinned host windows -> chunked upload overlapped with the
+    kernels -> host classes + bits) returns exactly what classify() returns for the same windows, also on an engine
+    whose side stream was created by stream_host() first, with a ragged last chunk and caller-provided outputs."""
+    eng = engine(dev, "bf16x3")
+    eng.stream_host(synth.make_sensor_log(400, seed=5).pin_memory())
+    x = synth.make_windows(2500, seed=31)
+    _, cl, bi = eng.classify(x.to(dev), want_logits=False)
+    hc, hb = eng.classify_host(x.pin_memory(), chunk=1024)
+    assert torch.equal(hc, cl.cpu()) and torch.equal(hb, bi.cpu()) and eng.last_launches > 0
+    out_b, out_c = torch.empty((2500, 4), dtype=torch.uint8).pin_memory(), torch.empty((2500,), dtype=torch.int32).pin_memory()
+    hc2, hb2 = eng.classify_host(x, out_b, out_c, chunk=700)                 # pageable input works too
+    assert hc2 is out_c and hb2 is out_b and torch.equal(out_c, cl.cpu()) and torch.equal(out_b, bi.cpu())
+    want = oracle_logits(params0, x[:64]).argmax(1)
+    assert np.array_equal(hc.numpy()[:64], want)
+    e_c, e_b = eng.classify_host(torch.empty(0, 150, 54))
+    assert e_c.shape == (0,) and e_b.shape == (0, 4)
+    with pytest.raises(ValueError):
+        eng.classify_host(x.to(dev))
+    with pytest.raises(ValueError):
+        eng.classify_host(x[:, :149])
+    with pytest.raises(ValueError):
+        eng.classify_host(x, torch.empty((3, 4), dtype=torch.uint8))
+
+
 def test_realtime_estimator_on_gpu(dev, params0):
     """RealtimeContactEstimator over the real LatencyRunner: contact bits per tick == the reference loop's."""
     from deep_contact_estimator_b200.realtime import RealtimeContactEstimator

@@ -142,3 +142,15 @@ def test_upload_schedule_covers_every_window_once_on_tile_boundaries():
         assert pos == n and (not sched or sched[-1][0] == T)
     with pytest.raises(ValueError):
         sharding.upload_schedule(10, 0)
+
+
+def test_module_copies_and_pickles_without_its_engine():
+    """copy.deepcopy / pickle of the module never carries the device handle (it is rebuilt from the parameters)."""
+    import copy
+    import pickle
+    m = dce.contact_cnn().eval()
+    m._engine, m._engine_key = object(), ("cuda:0",)          # stand-ins for a live engine
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._engine is None and clone._engine_key is None
+        assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
+    assert m._engine is not None
