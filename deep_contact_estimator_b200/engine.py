@@ -281,9 +281,11 @@ class ContactEngine:
         T = log_host.shape[0]
         n = max(T - WINDOW + 1, 0)
         if out_bits_host is None:
-            out_bits_host = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+            out_bits_host = torch.empty((n, 4), dtype=torch.uint8)
+            out_bits_host = out_bits_host.pin_memory() if n else out_bits_host
         if out_cls_host is None:
-            out_cls_host = torch.empty((n,), dtype=torch.int32).pin_memory()
+            out_cls_host = torch.empty((n,), dtype=torch.int32)
+            out_cls_host = out_cls_host.pin_memory() if n else out_cls_host
         if n == 0:
             return out_cls_host, out_bits_host
         with torch.cuda.device(self.device):
