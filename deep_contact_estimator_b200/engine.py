@@ -181,11 +181,16 @@ class ContactEngine:
 
     # -- host-buffer entry point (what a user with numpy / pinned data calls) ----
     def classify_host(self, x_host: torch.Tensor, out_bits_host: Optional[torch.Tensor] = None,
-                      out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024):
+                      out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024, zero_copy: bool = False):
         """``x_host``: ``(B,150,54)`` fp32 on the HOST (pinned for full speed).
         Copies chunk by chunk on a side stream so the host->device transfer of
         chunk i+1 overlaps the kernels of chunk i; returns host ``(cls, bits)``
-        after the device->host read of the results has completed."""
+        after the device->host read of the results has completed.
+
+        ``zero_copy=True`` (pinned ``x_host`` and pinned outputs only; not yet measured at this size): no
+        staging copy at all — one ``dce_forward`` over the whole batch whose first kernel's bulk-TMA loader reads
+        the windows in place over PCIe, and whose last kernel writes classes and bits straight into the pinned
+        outputs, as ``LatencyRunner`` does for one window."""
         if (x_host.dim() != 3 or tuple(x_host.shape[1:]) != (WINDOW, CHANNELS) or x_host.dtype != torch.float32
                 or x_host.is_cuda):
             raise ValueError(f"expected a host (B,{WINDOW},{CHANNELS}) float32 tensor, got {tuple(x_host.shape)} "
@@ -203,6 +208,20 @@ class ContactEngine:
                 tuple(out_cls_host.shape) != (n,) or out_cls_host.dtype != torch.int32:
             raise ValueError("out_bits_host must be (B,4) uint8 and out_cls_host (B,) int32")
         if n == 0:
+            return out_cls_host, out_bits_host
+        if zero_copy:
+            if not (x_host.is_pinned() and out_bits_host.is_pinned() and out_cls_host.is_pinned()):
+                raise ValueError("zero_copy needs pinned host tensors (the kernels dereference them directly)")
+            x_host = x_host.contiguous()
+            ws = self._ws(n)
+            with torch.cuda.device(self.device):
+                compute = torch.cuda.current_stream(self.device)
+                rc = self.lib.dce_forward(self._handle, self._p(x_host), n, None, self._p(out_cls_host), self._p(out_bits_host),
+                                          self._p(ws), ws.numel(), _lib.PRECISIONS[self.precision],
+                                          ctypes.c_void_p(compute.cuda_stream))
+                _lib.check(rc, "dce_forward")
+                self.last_launches = self.lib.dce_last_launch_count()
+                compute.synchronize()
             return out_cls_host, out_bits_host
         with torch.cuda.device(self.device):
             compute = torch.cuda.current_stream(self.device)
