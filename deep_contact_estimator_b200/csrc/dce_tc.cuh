@@ -674,6 +674,31 @@ __global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __rest
     }
 }
 
+// Conv layers in the fp16 + e4m3 format (option "conv_f16f8"): blocks of 192 * cout bytes, each covering 32 input
+// channels of all three taps; first the G = cin_pad / 32 e4m3 blocks [img: w8 | wl8][tap][2 chunks of 16][cout][16 B],
+// then the G fp16 blocks [tap][4 chunks of 8][cout][8 x 2 B] — the order the two-sweep issuers consume them
+// (block2's 24 KB weight ring at cout = 128; block1 keeps its four 12 KB blocks resident).
+__global__ void pack_conv_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int cout, int cin, int cin_pad,
+                                       const float* __restrict__ scale) {
+    const float sw = scale[0];
+    const int G = cin_pad / 32;
+    const size_t blk = (size_t)192 * cout;
+    const int total = cout * cin_pad * 3;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int tap = idx % 3, c = (idx / 3) % cin_pad, n = idx / (3 * cin_pad);
+        const float v = (c < cin ? W[((size_t)n * cin + c) * 3 + tap] : 0.f) * sw;
+        const __half h = __float2half_rn(v);
+        const float r = v - __half2float(h);
+        const int g = c / 32, cr = c % 32;
+        uint8_t* b8 = out + (size_t)g * blk;
+        uint8_t* b16 = out + (size_t)(G + g) * blk;
+        *reinterpret_cast<__half*>(b16 + ((size_t)(tap * 4 + cr / 8) * cout + n) * 16 + (cr % 8) * 2) = h;
+        const size_t o8 = ((size_t)(tap * 2 + cr / 16) * cout + n) * 16 + cr % 16;
+        b8[o8] = (uint8_t)__nv_cvt_float_to_fp8(v * (float)(1 << kF8EwH), __NV_SATFINITE, __NV_E4M3);
+        b8[blk / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ingest: fp32 windows -> layer-0 tape (54 channels padded to 64, bf16 hi/lo, guard rows zero)
 //   batch mode : x = [B][150][54]                                 (DataLoader batch, src/inference_one_seq.py:24)
@@ -816,7 +841,7 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 10;
+constexpr int kNumPacked = 14;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
@@ -826,7 +851,11 @@ constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // b
                                  {128, 3, 4, 4, 1, 0, 128, 6},     // block2.2 again, in 48 KB blocks (unused; kept for ablations)
                                  {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
                                  {256, 1, 4, 148, 8, 3, 4736, 8},  // fc.0 in the fp16 + e4m3 format (option "fc_f16f8")
-                                 {128, 1, 4, 64, 4, 4, 2048, 10}}; // fc.3 in the fp16 + e4m3 format
+                                 {128, 1, 4, 64, 4, 4, 2048, 10},  // fc.3 in the fp16 + e4m3 format
+                                 {64, 3, 2, 4, 1, 5, 54, 0},       // block1.0 in the fp16 + e4m3 format (option "conv_f16f8"): 2 * cin_pad/32 blocks
+                                 {64, 3, 2, 4, 1, 5, 64, 2},       // block1.2
+                                 {128, 3, 2, 4, 1, 5, 64, 4},      // block2.0
+                                 {128, 3, 2, 8, 1, 5, 128, 6}};    // block2.2
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t scales; size_t begin, end; };   // scales: [kNumPacked][4] floats {sw, 1/sw, absmax bits, -}
@@ -845,11 +874,16 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
         if (c.kind >= 3) {                                     // fp16 + e4m3 format: scale from max |w|, then the images
             float* sc = reinterpret_cast<float*>(buf + L.scales) + i * 4;
-            const size_t nw = (size_t)c.n_tiles * c.BN * c.cin;
+            const size_t nw = (size_t)c.n_tiles * c.BN * c.cin * c.TAPS;
             cudaError_t e = cudaMemsetAsync(sc, 0, 16, ctx.stream);
             if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             DCE_KL(ctx, "tc_absmax", absmax_kernel<<<1024, 256, 0, ctx.stream>>>(params[c.src], nw, reinterpret_cast<unsigned int*>(sc) + 2));
             DCE_KL(ctx, "tc_weight_scale", weight_scale_kernel<<<1, 1, 0, ctx.stream>>>(sc));
+            if (c.kind == 5) {                                 // conv: cin_pad = 16 * stages (2 blocks per 32 channels)
+                DCE_KL(ctx, "tc_pack_conv_f16f8", pack_conv_f16f8_kernel<<<96, 256, 0, ctx.stream>>>(
+                    params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.BN, c.cin, 16 * c.stages, sc));
+                continue;
+            }
             DCE_KL(ctx, "tc_pack_b_f16f8", pack_b_f16f8_kernel<<<4096, 256, 0, ctx.stream>>>(
                 params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.kind, c.cin, sc));
             continue;

@@ -90,7 +90,8 @@ __device__ __forceinline__ TileSegs tile_segs(const Block1Params& p, int r0) {
     return g;
 }
 
-template <bool STREAM>
+// F8 bit 0: write X2 in the fp16 + e4m3 format (dce_tc.cuh: split16_f16f8; option "conv_f16f8") for block2_kernel<.., F8IN>.
+template <bool STREAM, int F8 = 0>
 __global__ void __launch_bounds__(kB1Threads, 1)
 block1_kernel(const Block1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -420,7 +421,24 @@ block1_kernel(const Block1Params p) {
                 const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
                 y[i] = valid ? m : 0.f;
             }
-            if (store && !(p.dbg & 1)) {
+            if ((F8 & 1) && store && !(p.dbg & 1)) {
+                // X2 in the fp16 + e4m3 format: even lane -> the four fp16 chunks of its 32 channels (tape part 0, chunk
+                // h*4 + ..); odd lane -> lo8 chunks h*2 + hh and hi8 chunks 4 + h*2 + hh (tape part 1, 16 channels each)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 fa, fb, lo8, hi8;
+                    split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                    if (lane & 1) {
+                        uint8_t* d8 = p.out + p.out_part_stride + (size_t)(h * 2 + hh) * p.out_kch_stride + (size_t)(orow + kGuard) * 16;
+                        *reinterpret_cast<uint4*>(d8) = lo8;
+                        *reinterpret_cast<uint4*>(d8 + 4 * p.out_kch_stride) = hi8;
+                    } else {
+                        uint8_t* d16 = p.out + (size_t)(h * 4 + hh * 2) * p.out_kch_stride + (size_t)(orow + kGuard) * 16;
+                        *reinterpret_cast<uint4*>(d16) = fa;
+                        *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
+                    }
+                }
+            } else if (store && !(p.dbg & 1)) {
                 uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {

@@ -34,14 +34,21 @@ struct Block2Params {
     uint8_t* out; size_t out_part_stride, out_kch_stride; int out_rows_cap;
     int n_tiles;
     long long* trace;            // optional clock64 timeline of CTA 0 (DCE_TRACE builds)
+    const float* inv_sw3; const float* inv_sw4;     // F8IN: 1 / (power-of-two weight scale) of conv3 / conv4
 };
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
 // F8OUT: write the fc.0 operand in the fp16 + e4m3 format (dce_tc.cuh: split16_f16f8) instead of bf16 hi/lo.
-template <bool F8OUT>
+// F8IN : X2, X3 (slabB) and both weight images are in that format too (option "conv_f16f8").  A slab of C
+//        channels then holds C/8 fp16 chunks, C/16 lo8 chunks and C/16 hi8 chunks (the same 16 bytes per row and
+//        chunk, the same slab bytes), a 24 KB weight block covers 32 input channels of all three taps — first the
+//        conv's e4m3 blocks [w8 | wl8], then its fp16 blocks (pack_conv_f16f8_kernel) — and a block is 6 MMAs
+//        instead of 9.  Barriers, ring, TMEM and tiling are untouched.
+template <bool F8OUT, bool F8IN = false>
 __global__ void __launch_bounds__(kB2Threads, 1)
 block2_kernel(const Block2Params p) {
+    static_assert(F8OUT || !F8IN, "F8IN implies F8OUT");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* slabA = smem;
     uint8_t* slabB = smem + kB2SlabA;
@@ -132,6 +139,42 @@ block2_kernel(const Block2Params p) {
         auto stage_mmas = [&](uint32_t slab, int kch_total, int s, uint32_t d, bool first_stage) {
             const uint32_t slot = it % kB2Ring;
             const uint32_t b0 = rg + slot * kB2WBlock;
+            if (F8IN) {
+                constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, 128), id16 = ptx::make_idesc_f16_f32(128, 128);
+                const int half = kch_total >> 2;                   // e4m3 blocks of this conv (= its fp16 blocks)
+#pragma unroll
+                for (int tap = 0; tap < 3; ++tap) {
+                    if (s < half) {
+                        // corrections for input channels [32 s, 32 s + 32): one K = 32 MMA per product
+                        const uint32_t a_l = slab + (uint32_t)(kch_total + 2 * s) * kSlabBytes + tap * 16;
+                        const uint32_t a_h = a_l + (uint32_t)(kch_total >> 1) * kSlabBytes;
+                        const uint64_t da_l = ptx::make_smem_desc(a_l, kSlabBytes, 128);
+                        const uint64_t da_h = ptx::make_smem_desc(a_h, kSlabBytes, 128);
+                        const uint64_t db_h = ptx::make_smem_desc(b0 + tap * 4096, 2048, 128);
+                        const uint64_t db_l = ptx::make_smem_desc(b0 + 12288 + tap * 4096, 2048, 128);
+                        if (leader) {
+                            ptx::umma_e4m3_ss(d, da_l, db_h, id8, (first_stage && tap == 0) ? 0u : 1u);
+                            ptx::umma_e4m3_ss(d, da_h, db_l, id8, 1u);
+                        }
+                    } else {
+                        // main products for the same 32 channels: two K = 16 MMAs
+                        const int g = s - half;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t da = ptx::make_smem_desc(slab + (uint32_t)(4 * g + 2 * kk) * kSlabBytes + tap * 16, kSlabBytes, 128);
+                            const uint64_t db = ptx::make_smem_desc(b0 + tap * 8192 + kk * 4096, 2048, 128);
+                            if (leader) {
+                                if (s == half && tap == 0 && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
+                                else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
+                            }
+                        }
+                    }
+                    if (tap == 1 && it + 1 < total_blocks) {
+                        ptx::mbar_wait(&wfull[(it + 1) % kB2Ring], ((it + 1) / kB2Ring) & 1);
+                        ptx::tc_fence_after_sync();
+                    }
+                }
+            } else {
 #pragma unroll
             for (int tap = 0; tap < 3; ++tap) {
                 const uint32_t b_hi = b0 + tap * 2 * 2048;
@@ -149,6 +192,7 @@ block2_kernel(const Block2Params p) {
                     ptx::mbar_wait(&wfull[(it + 1) % kB2Ring], ((it + 1) / kB2Ring) & 1);
                     ptx::tc_fence_after_sync();
                 }
+            }
             }
             if (leader) ptx::umma_commit(&wempty[slot]);
             ++it;
@@ -186,6 +230,7 @@ block2_kernel(const Block2Params p) {
         const float* bias3 = s_bias + h * 64;
         const float* bias4 = s_bias + 128 + h * 64;
         const int NR = p.n_windows * kRW2;
+        const float inv3 = F8IN ? __ldg(p.inv_sw3) : 1.f, inv4 = F8IN ? __ldg(p.inv_sw4) : 1.f;
 
         auto epi1 = [&](int k) {
             const int tile = blockIdx.x + k * gridDim.x;
@@ -214,11 +259,32 @@ block2_kernel(const Block2Params p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias3 + c * 32 + i);
+                    if (F8IN) {
+                        y[i] = valid ? relu_nan(fmaf(__uint_as_float(v[i]), inv3, b4.x)) : 0.f;
+                        y[i + 1] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 1]), inv3, b4.y)) : 0.f;
+                        y[i + 2] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 2]), inv3, b4.z)) : 0.f;
+                        y[i + 3] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 3]), inv3, b4.w)) : 0.f;
+                        continue;
+                    }
                     y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
                     y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
                     y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
                     y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
                 }
+                if (F8IN) {
+                    // slabB: fp16 chunks 0..15, lo8 chunks 16..23, hi8 chunks 24..31 (16 channels per e4m3 chunk)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 fa, fb, lo8, hi8;
+                        split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                        uint8_t* d16 = slabB + (h * 8 + c * 4 + hh * 2) * kSlabBytes + (rit + 1) * 16;
+                        *reinterpret_cast<uint4*>(d16) = fa;
+                        *reinterpret_cast<uint4*>(d16 + kSlabBytes) = fb;
+                        uint8_t* d8 = slabB + (16 + h * 4 + c * 2 + hh) * kSlabBytes + (rit + 1) * 16;
+                        *reinterpret_cast<uint4*>(d8) = lo8;
+                        *reinterpret_cast<uint4*>(d8 + 8 * kSlabBytes) = hi8;
+                    }
+                } else {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     uint4 hi, lo;
@@ -226,6 +292,7 @@ block2_kernel(const Block2Params p) {
                     uint8_t* d = slabB + (h * 8 + c * 4 + qd) * kSlabBytes + (rit + 1) * 16;
                     *reinterpret_cast<uint4*>(d) = hi;
                     *reinterpret_cast<uint4*>(d + 16 * kSlabBytes) = lo;
+                }
                 }
             }
             ptx::fence_proxy_async_smem();
@@ -259,6 +326,13 @@ block2_kernel(const Block2Params p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias4 + c * 32 + i);
+                    if (F8IN) {
+                        y[i] = relu_nan(fmaf(__uint_as_float(v[i]), inv4, b4.x));
+                        y[i + 1] = relu_nan(fmaf(__uint_as_float(v[i + 1]), inv4, b4.y));
+                        y[i + 2] = relu_nan(fmaf(__uint_as_float(v[i + 2]), inv4, b4.z));
+                        y[i + 3] = relu_nan(fmaf(__uint_as_float(v[i + 3]), inv4, b4.w));
+                        continue;
+                    }
                     y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
                     y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
                     y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);

@@ -13,6 +13,7 @@ inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& fuse_fc3_flag() { static int v = 1; return v; }
 inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
+inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: X2 and the whole of block2 in that format too
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
@@ -46,6 +47,10 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
 
         int rc;
         TapGemmParams p{};
+        const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
+        const bool f8 = fc_f16f8_flag() && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
+        const bool f8c = f8 && conv_f16f8_flag() && fuse_block1_flag();
+        const float* scales = reinterpret_cast<const float*>(buf + L.scales);
         if (stream_mode) {
             static DeviceOnce st_once;
             if (st_once.need()) {
@@ -62,6 +67,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             if (attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
@@ -73,7 +80,11 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (stream_mode)
+            if (f8c && stream_mode)
+                DCE_KL(ctx, "tc_block1_stream_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<true, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
+            else if (f8c)
+                DCE_KL(ctx, "tc_block1_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<false, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
+            else if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
                 DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1_kernel<false>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
@@ -102,15 +113,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.out = x2; p.out_part_stride = W.x2.part_stride; p.out_kch_stride = W.x2.kch_stride; p.out_rows_cap = W.x2.m_tiles * 128;
         if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
         }
-        const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
-        const bool f8 = fc_f16f8_flag() && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
-        const float* scales = reinterpret_cast<const float*>(buf + L.scales);
         if (fuse_block2_flag() && !tiny) {
             // ---- fused conv3 + conv4 + pool + flatten (a7-a9): X2 -> X4, X3 stays in shared memory
             static DeviceOnce b2_once;
             if (b2_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
             Block2Params b{};
@@ -121,7 +130,11 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
             b.trace = (tapgemm_trace_layer() == 6) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (f8)
+            if (f8c) {
+                b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[12]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[13]);
+                b.inv_sw3 = scales + 12 * 4 + 1; b.inv_sw4 = scales + 13 * 4 + 1;
+                DCE_KL(ctx, "tc_block2_f16f8", { cudaError_t le_ = launch_pdl(block2_kernel<true, true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+            } else if (f8)
                 DCE_KL(ctx, "tc_block2_f8out", { cudaError_t le_ = launch_pdl(block2_kernel<true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
             else
                 DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel<false>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });

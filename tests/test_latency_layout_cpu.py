@@ -24,3 +24,5 @@ def test_f16f8_fc_layouts_match_float64():
     spec.loader.exec_module(mod)
     e_fc0, e_fc3 = mod.check(rows=3)
     assert e_fc0 <= 3e-5 and e_fc3 <= 3e-5
+    # option "conv_f16f8": block1's X2 writer, the conv weight blocks and block2_kernel<true, true> (slabs, issuer, pool)
+    assert mod.check_block2(windows=2) <= 3e-5

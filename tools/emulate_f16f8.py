@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""CPU emulation of the index arithmetic of the experimental fp16 + e4m3 FC mode (option "fc_f16f8"):
-    pack_b_f16f8_kernel, split16_f16f8, the two tape writers (tapgemm EPI_FC_TAPE with F8, block2_kernel<true>),
-    and the F8 producer / issuer of tapgemm_kernel (csrc/dce_tc.cuh, dce_tc_block2.cuh)
+"""CPU emulation of the index arithmetic of the experimental fp16 + e4m3 modes (options "fc_f16f8", "conv_f16f8"):
+    pack_b_f16f8_kernel, pack_conv_f16f8_kernel, split16_f16f8, the tape writers (tapgemm EPI_FC_TAPE with F8,
+    block2_kernel<true>, block1_kernel<.., 1>), the F8 producer / issuer of tapgemm_kernel and the slabs, weight
+    blocks and issuer of block2_kernel<true, true> (csrc/dce_tc.cuh, dce_tc_block1.cuh, dce_tc_block2.cuh)
 restated in numpy: bulk copies land in a byte array shaped like a ring stage, every MMA gathers its operands
 through the (start, LBO, SBO = 128) descriptor it would be issued with, corrections accumulate at 2^15 and the
 first fp16 MMA applies scale-input-d.  Checked against float64 x @ W^T.  No GPU: this pins the layout formulas and
@@ -202,6 +203,127 @@ def check(rows=5, seed=0):
     return max(errs), max(e3)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# conv_f16f8: block1's X2 writer, pack_conv_f16f8_kernel and block2_kernel<true, true> (slabs, weight blocks, issuer)
+# ---------------------------------------------------------------------------------------------------------
+def pack_conv_f16f8(W, cout, cin, cin_pad, sw):
+    """pack_conv_f16f8_kernel: W[cout][cin][3] -> 2 * cin_pad / 32 blocks of 192 * cout bytes."""
+    G, blk = cin_pad // 32, 192 * cout
+    out = np.zeros(2 * G * blk, np.uint8)
+    idx = np.arange(cout * cin_pad * 3, dtype=np.int64)
+    tap, c, n = idx % 3, (idx // 3) % cin_pad, idx // (3 * cin_pad)
+    v = np.where(c < cin, W.reshape(-1)[(n * cin + np.minimum(c, cin - 1)) * 3 + tap], 0.0).astype(np.float32) * sw
+    h = v.astype(np.float16)
+    r = v - h.astype(np.float32)
+    g, cr = c // 32, c % 32
+    o16 = (G + g) * blk + ((tap * 4 + cr // 8) * cout + n) * 16 + (cr % 8) * 2
+    hb = h.view(np.uint16)
+    out[o16] = (hb & 0xFF).astype(np.uint8)
+    out[o16 + 1] = (hb >> 8).astype(np.uint8)
+    o8 = g * blk + ((tap * 2 + cr // 16) * cout + n) * 16 + cr % 16
+    out[o8] = e4m3(v * 2.0 ** EWH)
+    out[o8 + blk // 2] = e4m3(r * 2.0 ** EWL)
+    return out
+
+
+def write_x2_tape(tape, y2):
+    """block1_kernel<.., 1> epi2: y2[w][75][64] pooled conv2 output -> X2 tape (76 rows per window, row 75 = guard)."""
+    for w in range(y2.shape[0]):
+        for t in range(75):
+            orow = w * 76 + t
+            for h in range(2):
+                for hh in range(2):
+                    f, lo, hi = split16(y2[w, t, h * 32 + hh * 16: h * 32 + hh * 16 + 16])
+                    d8 = tape["part_stride"] + (h * 2 + hh) * tape["kch_stride"] + (orow + GUARD) * 16
+                    tape["buf"][d8: d8 + 16] = lo
+                    tape["buf"][d8 + 4 * tape["kch_stride"]: d8 + 4 * tape["kch_stride"] + 16] = hi
+                    d16 = (h * 4 + hh * 2) * tape["kch_stride"] + (orow + GUARD) * 16
+                    tape["buf"][d16: d16 + 16] = f[:16]
+                    tape["buf"][d16 + tape["kch_stride"]: d16 + tape["kch_stride"] + 16] = f[16:]
+
+
+def conv_blocks(slab, wimg, kch_total):
+    """stage_mmas of block2_kernel<true, true> over all blocks of one conv: slab = uint8 [(kch_total * 2) * SLAB]."""
+    D = np.zeros((128, 128))
+    half, blk = kch_total // 4, 24576
+    for s in range(2 * half):
+        b0 = s * blk
+        for tap in range(3):
+            if s < half:
+                a_l = (kch_total + 2 * s) * SLAB + tap * 16
+                a_h = a_l + (kch_total // 2) * SLAB
+                D += gather(slab, a_l, SLAB, 128, 1) @ gather(wimg, b0 + tap * 4096, 2048, 128, 1).T
+                D += gather(slab, a_h, SLAB, 128, 1) @ gather(wimg, b0 + 12288 + tap * 4096, 2048, 128, 1).T
+            else:
+                g = s - half
+                for kk in range(2):
+                    if s == half and tap == 0 and kk == 0:
+                        D *= 2.0 ** -SCALE_D
+                    D += gather(slab, (4 * g + 2 * kk) * SLAB + tap * 16, SLAB, 128, 2) @ \
+                        gather(wimg, b0 + tap * 8192 + kk * 4096, 2048, 128, 2).T
+    return D
+
+
+def check_block2(windows=2, seed=0):
+    """X2 (block1 writer) -> conv3 -> slabB -> conv4 -> pool, tile by tile; returns the norm-wise error of the pooled output."""
+    from deep_contact_estimator_b200 import synth
+    import torch.nn.functional as F
+    P = synth.make_params(seed)
+    rng = np.random.default_rng(seed + 2)
+    y2 = np.maximum(rng.standard_normal((windows, 75, 64)), 0.0).astype(np.float32)
+    x2 = make_tape(windows * 76, 8)
+    write_x2_tape(x2, y2)
+    W3, W4 = P["block2.0.weight"].numpy(), P["block2.2.weight"].numpy()
+    b3, b4 = P["block2.0.bias"].numpy(), P["block2.2.bias"].numpy()
+    (sw3, inv3), (sw4, inv4) = weight_scale(W3), weight_scale(W4)
+    w3i, w4i = pack_conv_f16f8(W3, 128, 64, 64, sw3), pack_conv_f16f8(W4, 128, 128, 128, sw4)
+    with torch.no_grad():
+        t = torch.from_numpy(y2).double().permute(0, 2, 1)
+        a3 = F.relu(F.conv1d(t, P["block2.0.weight"].double(), P["block2.0.bias"].double(), padding=1))
+        a4 = F.relu(F.conv1d(a3, P["block2.2.weight"].double(), P["block2.2.bias"].double(), padding=1))
+        want = F.max_pool1d(a4, 2, 2).permute(0, 2, 1).numpy()                  # [w][37][128]
+    NR = windows * 76
+    got = np.zeros_like(want)
+    seen = np.zeros(want.shape[:2], bool)
+    for tile_i in range((NR + 123) // 124):
+        b = tile_i * 124
+        slabA = np.zeros(16 * SLAB, np.uint8)
+        src = (b - 3 + GUARD) * 16                                            # slabA loader: 16 bulk copies of 2080 B
+        for c in range(16):
+            o = src + (c >> 3) * x2["part_stride"] + (c & 7) * x2["kch_stride"]
+            slabA[c * SLAB:(c + 1) * SLAB] = x2["buf"][o: o + SLAB]
+        D3 = conv_blocks(slabA, w3i, 8)
+        slabB = np.zeros(32 * SLAB, np.uint8)
+        for rit in range(128):                                                 # epi1
+            r = b - 2 + rit
+            valid = r >= 0 and (r % 76) < 75
+            y = np.maximum(D3[rit] * float(inv3) + b3, 0.0).astype(np.float32) if valid else np.zeros(128, np.float32)
+            for h in range(2):
+                for c in range(2):
+                    for hh in range(2):
+                        ch0 = h * 64 + c * 32 + hh * 16
+                        f, lo, hi = split16(y[ch0: ch0 + 16])
+                        d16 = (h * 8 + c * 4 + hh * 2) * SLAB + (rit + 1) * 16
+                        slabB[d16: d16 + 16] = f[:16]
+                        slabB[d16 + SLAB: d16 + SLAB + 16] = f[16:]
+                        d8 = (16 + h * 4 + c * 2 + hh) * SLAB + (rit + 1) * 16
+                        slabB[d8: d8 + 16] = lo
+                        slabB[d8 + 8 * SLAB: d8 + 8 * SLAB + 16] = hi
+        D4 = conv_blocks(slabB, w4i, 16)
+        y4 = np.maximum(D4 * float(inv4) + b4, 0.0)
+        for rit in range(2, 126, 2):                                           # epi2: pool pairs (even, odd) rows
+            r = b - 2 + rit
+            if r < 0 or r >= NR:
+                continue
+            w, to = r // 76, (r % 76) >> 1
+            if to < 37:
+                got[w, to] = np.maximum(y4[rit], y4[rit + 1])
+                seen[w, to] = True
+    assert seen.all()
+    return np.abs(got - want).max() / np.abs(want).max()
+
+
 if __name__ == "__main__":
+    print(f"block2 (block1 X2 writer -> conv3 -> slabB -> conv4 -> pool): {check_block2():.2e}")
     e0, e3 = check()
     print(f"fc.0 (block2 writer -> F8 tile): {e0:.2e}   fc.3 (fc.0 writer -> F8 tile): {e3:.2e}")
