@@ -116,11 +116,17 @@ __device__ __forceinline__ float min_nan(float a, float b) {
 }
 // 16 consecutive K elements of one row -> two 16-byte fp16 chunks + one 16-byte chunk of each e4m3 image.
 // Activations saturate at the largest finite fp16 (65504); NaN propagates through all three images.
+// SIGNED = false: the values are ReLU outputs (>= 0 or NaN), only the upper clamp is needed.
+template <bool SIGNED = false>
 __device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
     uint32_t h[8], l[4], g[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float a = min_nan(y[2 * i], 65504.f), b = min_nan(y[2 * i + 1], 65504.f);
+        float a = min_nan(y[2 * i], 65504.f), b = min_nan(y[2 * i + 1], 65504.f);
+        if (SIGNED) {
+            asm("max.NaN.f32 %0, %0, %1;" : "+f"(a) : "f"(-65504.f));
+            asm("max.NaN.f32 %0, %0, %1;" : "+f"(b) : "f"(-65504.f));
+        }
         const __half2 hb = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(hb);
         h[i] = *reinterpret_cast<const uint32_t*>(&hb);
@@ -132,6 +138,10 @@ __device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4
     f16b = make_uint4(h[4], h[5], h[6], h[7]);
     lo8 = make_uint4(l[0], l[1], l[2], l[3]);
     hi8 = make_uint4(g[0], g[1], g[2], g[3]);
+}
+
+__device__ __forceinline__ void split16_f16f8_signed(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
+    split16_f16f8<true>(y, f16a, f16b, lo8, hi8);
 }
 
 // NaN-propagating max (FMNMX.NAN): torch's ReLU and MaxPool1d both propagate NaN.

@@ -13,7 +13,7 @@ inline int& fuse_block1_flag() { static int v = 1; return v; }
 inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& fuse_fc3_flag() { static int v = 1; return v; }
 inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
-inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: X2 and the whole of block2 in that format too
+inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: 1 = X2 and the whole of block2 in that format too; 2 = block1's two convolutions as well
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
@@ -69,6 +69,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
@@ -80,7 +82,16 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (f8c && stream_mode)
+            if (f8c && conv_f16f8_flag() >= 2) {            // conv1 / conv2 themselves in the fp16 + e4m3 format
+                Block1ParamsF8 b8{};
+                static_cast<Block1Params&>(b8) = b;
+                b8.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[10]); b8.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[11]);
+                b8.inv_sw1 = scales + 10 * 4 + 1; b8.inv_sw2 = scales + 11 * 4 + 1;
+                if (stream_mode)
+                    DCE_KL(ctx, "tc_block1_stream_f16f8", { cudaError_t le_ = launch_pdl(block1_kernel<true, 3>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b8); (void)le_; });
+                else
+                    DCE_KL(ctx, "tc_block1_f16f8", { cudaError_t le_ = launch_pdl(block1_kernel<false, 3>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b8); (void)le_; });
+            } else if (f8c && stream_mode)
                 DCE_KL(ctx, "tc_block1_stream_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<true, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else if (f8c)
                 DCE_KL(ctx, "tc_block1_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<false, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });

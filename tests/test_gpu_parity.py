@@ -473,19 +473,21 @@ def test_realtime_estimator_on_gpu(dev, params0):
 
 
 @pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
-                    reason="fp16 + e4m3 FC mode (option fc_f16f8) has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
+                    reason="the fp16 + e4m3 modes (options fc_f16f8 / conv_f16f8) have not run on a GPU yet: DCE_EXPERIMENTAL=1 to try them")
+@pytest.mark.parametrize("conv", [0, 1, 2])
 @pytest.mark.parametrize("scale", [1.0, 50.0])
-def test_experimental_fc_f16f8_matches_oracle(dev, scale):
-    """fc.0 / fc.3 with fp16 main products + e4m3 corrections (two MMA-slot equivalents instead of three): same
-    bar as bf16x3.  Off by default; the option is restored whatever happens."""
+def test_experimental_f16f8_matches_oracle(dev, scale, conv):
+    """fp16 main products + e4m3 corrections (two MMA-slot equivalents instead of three) in fc.0 / fc.3 (conv = 0),
+    plus block2 (1), plus block1 (2): same bar as bf16x3.  Off by default; the options are restored whatever happens."""
     eng = engine(dev, "bf16x3", 0, scale)
     x = synth.make_windows(300, seed=77)
     want = oracle_logits(synth.make_params(0, logit_scale=scale), x)
     try:
-        assert eng.lib.dce_set_option(b"fc_f16f8", 1) == 0
+        assert eng.lib.dce_set_option(b"fc_f16f8", 1) == 0 and eng.lib.dce_set_option(b"conv_f16f8", conv) == 0
         logits, cls, bits = eng.classify(x.to(dev))
         torch.cuda.synchronize()
     finally:
         eng.lib.dce_set_option(b"fc_f16f8", 0)
+        eng.lib.dce_set_option(b"conv_f16f8", 0)
     assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL["bf16x3"]
     assert np.array_equal(cls.cpu().numpy(), want.argmax(1))

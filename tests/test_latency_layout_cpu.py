@@ -26,3 +26,5 @@ def test_f16f8_fc_layouts_match_float64():
     assert e_fc0 <= 3e-5 and e_fc3 <= 3e-5
     # option "conv_f16f8": block1's X2 writer, the conv weight blocks and block2_kernel<true, true> (slabs, issuer, pool)
     assert mod.check_block2(windows=2) <= 3e-5
+    # option "conv_f16f8" = 2: block1's converter, both resident weight images, slab1 and the pooled X2 writer
+    assert mod.check_block1(windows=1) <= 4e-5

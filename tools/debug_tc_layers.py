@@ -2,9 +2,10 @@
 """GPU debugging aid: run the bf16x3 path on a few windows, decode every
 activation tape out of the workspace and compare layer by layer with the oracle
 (torch CPU fp32).  Not part of the product path.
-    python tools/debug_tc_layers.py [B] [--layerwise] [--block2] [--f16f8]
+    python tools/debug_tc_layers.py [B] [--layerwise] [--block2] [--f16f8] [--conv-f16f8=1|2]
 --f16f8 turns on the experimental fp16 + e4m3 FC mode (implies the fused block2 kernel) and decodes X4 / H1 in
-that format: value = fp16 + lo8 * 2^-12, and hi8 * 2^-1 must agree with it to e4m3 precision."""
+that format: value = fp16 + lo8 * 2^-12, and hi8 * 2^-1 must agree with it to e4m3 precision.
+--conv-f16f8=1 adds X2 and block2 in that format (X2 is decoded accordingly), =2 block1's convolutions too."""
 import os
 import sys
 
@@ -80,7 +81,12 @@ def main():
     f16f8 = "--f16f8" in sys.argv
     fused2 = "--block2" in sys.argv or f16f8
     eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
+    conv8 = max([int(a.split("=")[1]) for a in sys.argv if a.startswith("--conv-f16f8=")] or [0])
+    f16f8 = f16f8 or conv8 > 0
+    fused2 = fused2 or f16f8
+    eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
     assert eng.lib.dce_set_option(b"fc_f16f8", 1 if f16f8 else 0) == 0
+    assert eng.lib.dce_set_option(b"conv_f16f8", conv8) == 0
     logits, cls, bits = eng.classify(x.to(dev))
     torch.cuda.synchronize()
     ws = eng._workspace
@@ -107,7 +113,12 @@ def main():
         report("x0", x0[:, :150, :54], x)
         print("x0 pad channels / guard rows:", x0[:, :, 54:].abs().max().item(), x0[:, 150:, :].abs().max().item())
         conv_tape("x1", a1, 152, 150, 64)
-    conv_tape("x2", a2, 76, 75, 64)
+    if conv8:
+        got2 = decode_f16f8(ws, W["x2"], "x2").reshape(B, 76, -1)
+        print(f"x2: guard rows max |v| = {got2[:, 75:, :].abs().max().item():.3e}")
+        report("x2", got2[:, :75, :64], a2.permute(0, 2, 1))
+    else:
+        conv_tape("x2", a2, 76, 75, 64)
     if not fused2:
         conv_tape("x3", a3, 76, 75, 128)
     x4 = decode_f16f8(ws, W["x4"], "x4") if f16f8 else decode(ws, W["x4"])      # [B][592*8], k' = t*128 + c

@@ -69,9 +69,11 @@ def pack_b_f16f8(W, n_tiles, stages, BN, kind, K, sw):
     return out
 
 
-def split16(y):
+def split16(y, signed=False):
     """split16_f16f8 on [..., 16] -> (fp16 bytes [..., 32], lo8 [..., 16], hi8 [..., 16])."""
     a = np.minimum(y.astype(np.float32), np.float32(65504.0))
+    if signed:
+        a = np.maximum(a, np.float32(-65504.0))
     h = a.astype(np.float16)
     lo = e4m3((a - h.astype(np.float32)) * 2.0 ** EXL)
     hi = e4m3(a * 2.0 ** EXH)
@@ -323,7 +325,101 @@ def check_block2(windows=2, seed=0):
     return np.abs(got - want).max() / np.abs(want).max()
 
 
+def conv64_mmas(slab, wimg):
+    """conv_mmas of block1_kernel<.., 3>: 64 -> 64 channels, resident image [e4m3 g0][e4m3 g1][fp16 g0][fp16 g1]."""
+    D = np.zeros((128, 64))
+    for g in range(2):
+        for tap in range(3):
+            a_l = (8 + 2 * g) * SLAB + tap * 16
+            b_h = g * 12288 + tap * 2048
+            D += gather(slab, a_l, SLAB, 128, 1) @ gather(wimg, b_h, 1024, 64, 1).T
+            D += gather(slab, a_l + 4 * SLAB, SLAB, 128, 1) @ gather(wimg, b_h + 6144, 1024, 64, 1).T
+    for g in range(2):
+        for tap in range(3):
+            for kk in range(2):
+                if (g | tap | kk) == 0:
+                    D *= 2.0 ** -SCALE_D
+                D += gather(slab, (4 * g + 2 * kk) * SLAB + tap * 16, SLAB, 128, 2) @ \
+                    gather(wimg, (2 + g) * 12288 + tap * 4096 + kk * 2048, 1024, 64, 2).T
+    return D
+
+
+def put_row64(slab, row, y64):
+    """One 64-channel row in the slab format of block1: fp16 chunks 0..7, lo8 8..11, hi8 12..15."""
+    for c16 in range(4):
+        f, lo, hi = split16(y64[16 * c16: 16 * c16 + 16], signed=True)
+        slab[(2 * c16) * SLAB + row * 16: (2 * c16) * SLAB + row * 16 + 16] = f[:16]
+        slab[(2 * c16 + 1) * SLAB + row * 16: (2 * c16 + 1) * SLAB + row * 16 + 16] = f[16:]
+        slab[(8 + c16) * SLAB + row * 16: (8 + c16) * SLAB + row * 16 + 16] = lo
+        slab[(12 + c16) * SLAB + row * 16: (12 + c16) * SLAB + row * 16 + 16] = hi
+
+
+def check_block1(windows=1, seed=0):
+    """windows -> converter -> conv1 -> slab1 -> conv2 -> pool -> X2 tape (block1_kernel<false, 3>), decoded and compared."""
+    from deep_contact_estimator_b200 import synth
+    import torch.nn.functional as F
+    P = synth.make_params(seed)
+    x = synth.make_windows(windows, seed=seed + 3)                              # [w][150][54], z-scored, signed
+    W1, W2 = P["block1.0.weight"].numpy(), P["block1.2.weight"].numpy()
+    b1, b2 = P["block1.0.bias"].numpy(), P["block1.2.bias"].numpy()
+    (sw1, inv1), (sw2, inv2) = weight_scale(W1), weight_scale(W2)
+    w1i, w2i = pack_conv_f16f8(W1, 64, 54, 64, sw1), pack_conv_f16f8(W2, 64, 64, 64, sw2)
+    with torch.no_grad():
+        t = x.double().permute(0, 2, 1)
+        a1 = F.relu(F.conv1d(t, P["block1.0.weight"].double(), P["block1.0.bias"].double(), padding=1))
+        a2 = F.relu(F.conv1d(a1, P["block1.2.weight"].double(), P["block1.2.bias"].double(), padding=1))
+        want = F.max_pool1d(a2, 2, 2).permute(0, 2, 1).numpy()                  # [w][75][64]
+    xn = x.numpy()
+    NR = windows * 152
+    x2 = make_tape(windows * 76, 8)
+    cap_rows = x2["m_tiles"] * 128
+    for tile_i in range((NR + 123) // 124):
+        b = tile_i * 124
+        slab0 = np.zeros(16 * SLAB, np.uint8)
+        for srow in range(130):                                                # converters (rows 128, 129 by 8 threads)
+            r = b - 3 + srow
+            y = np.zeros(64, np.float32)
+            if 0 <= r < NR and r % 152 < 150:
+                y[:54] = xn[r // 152, r % 152]
+            put_row64(slab0, srow, y)
+        D1 = conv64_mmas(slab0, w1i)
+        slab1 = np.zeros(16 * SLAB, np.uint8)
+        for rit in range(128):                                                 # epi1 -> slab1 row rit + 1
+            r = b - 2 + rit
+            valid = r >= 0 and r % 152 < 150
+            y = np.maximum(D1[rit] * float(inv1) + b1, 0.0).astype(np.float32) if valid else np.zeros(64, np.float32)
+            put_row64(slab1, rit + 1, y)
+        D2 = conv64_mmas(slab1, w2i)
+        y2 = np.maximum(D2 * float(inv2) + b2, 0.0).astype(np.float32)
+        for rit in range(0, 128, 2):                                           # epi2: pooled pair (rit, rit + 1)
+            r = b - 2 + rit
+            orow = r >> 1
+            valid = r >= 0 and ((r % 152) >> 1) < 75
+            store = ((2 <= rit < 126) or (tile_i == 0 and rit < 2)) and orow < cap_rows
+            if not store:
+                continue
+            m = np.maximum(y2[rit], y2[rit + 1]) if valid else np.zeros(64, np.float32)
+            for h in range(2):
+                for hh in range(2):
+                    f, lo, hi = split16(m[h * 32 + hh * 16: h * 32 + hh * 16 + 16])
+                    d8 = x2["part_stride"] + (h * 2 + hh) * x2["kch_stride"] + (orow + GUARD) * 16
+                    x2["buf"][d8: d8 + 16] = lo
+                    x2["buf"][d8 + 4 * x2["kch_stride"]: d8 + 4 * x2["kch_stride"] + 16] = hi
+                    d16 = (h * 4 + hh * 2) * x2["kch_stride"] + (orow + GUARD) * 16
+                    x2["buf"][d16: d16 + 16] = f[:16]
+                    x2["buf"][d16 + x2["kch_stride"]: d16 + x2["kch_stride"] + 16] = f[16:]
+    # decode the X2 tape: value = fp16 + lo8 * 2^-12; guard row 75 of every window must be zero
+    cap, ks, ps = x2["cap"], x2["kch_stride"], x2["part_stride"]
+    f16 = x2["buf"][:ps].view(np.float16).reshape(8, cap, 8).astype(np.float64)
+    lo = e4m3_to_f(x2["buf"][ps: ps + 4 * ks]).reshape(4, cap, 16).astype(np.float64) * 2.0 ** -EXL
+    val = f16.transpose(1, 0, 2).reshape(cap, 64) + lo.transpose(1, 0, 2).reshape(cap, 64)
+    got = val[GUARD: GUARD + windows * 76].reshape(windows, 76, 64)
+    assert np.abs(got[:, 75]).max() == 0.0 and np.abs(val[GUARD - 1]).max() == 0.0
+    return np.abs(got[:, :75] - want).max() / np.abs(want).max()
+
+
 if __name__ == "__main__":
+    print(f"block1 (converter -> conv1 -> slab1 -> conv2 -> pool -> X2): {check_block1():.2e}")
     print(f"block2 (block1 X2 writer -> conv3 -> slabB -> conv4 -> pool): {check_block2():.2e}")
     e0, e3 = check()
     print(f"fc.0 (block2 writer -> F8 tile): {e0:.2e}   fc.3 (fc.0 writer -> F8 tile): {e3:.2e}")
