@@ -82,6 +82,8 @@ def main():
     fused2 = "--block2" in sys.argv or f16f8
     eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
     conv8 = max([int(a.split("=")[1]) for a in sys.argv if a.startswith("--conv-f16f8=")] or [0])
+    if layerwise:
+        conv8 = 0                      # the conv variants exist only in the fused block kernels
     f16f8 = f16f8 or conv8 > 0
     fused2 = fused2 or f16f8
     eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
