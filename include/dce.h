@@ -181,6 +181,12 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *   "latency_kernel" 1 (default): calls of <= 4 windows run the single cooperative latency kernel;
  *                  0: the per-layer kernels (tensor-core convolutions + fp32 GEMV Linear layers);
  *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel.
+ *   "fc_f16f8"     0 (default).  EXPERIMENTAL, written without a GPU and not yet run on one: 1 = fc.0 and fc.3 use
+ *                  fp16 main products + e4m3 correction products (two MMA-slot equivalents per K-step instead of
+ *                  the three of bf16x3; emulated at 6e-6 norm-wise; activations saturate at 65504).  Needs the
+ *                  default "fuse_block2" / "fuse_fc3"; calls of <= 4 windows are unaffected.
+ *   "conv_f16f8"   0 (default).  EXPERIMENTAL, as above, needs "fc_f16f8" = 1 and "fuse_block1": 1 = X2 and the whole
+ *                  of block2 in that format too, 2 = block1's two convolutions as well.
  * Returns DCE_EINVAL for an unknown key.
  */
 DCE_API int dce_set_option(const char *key, int value);
