@@ -45,10 +45,18 @@ struct Block2Params {
 //        chunk, the same slab bytes), a 24 KB weight block covers 32 input channels of all three taps — first the
 //        conv's e4m3 blocks [w8 | wl8], then its fp16 blocks (pack_conv_f16f8_kernel) — and a block is 6 MMAs
 //        instead of 9.  Barriers, ring, TMEM and tiling are untouched.
-template <bool F8OUT, bool F8IN = false>
+// CL = 2 or 4 (option "block2_cluster"): thread-block clusters of CL CTAs share the weight stream.  Every CTA consumes the
+//        SAME sequence of 24 KB weight blocks, so block i is fetched from L2 once per cluster — by the producer of CTA
+//        i % CL, with .multicast::cluster into the same ring slot of all CL CTAs — instead of once per CTA (L2 -> SM
+//        traffic per tile 321 KB -> 33 + 288 / CL KB).  A slot is refilled when the MMAs of ALL CL CTAs have drained it:
+//        every issuer's tcgen05.commit arrives on the `wempty` barrier of every CTA (count CL).  The CTAs of a cluster
+//        therefore walk the same number of tiles (`rounds`); a CTA without a tile in the last round runs it on stale
+//        operands with all stores predicated off.
+template <bool F8OUT, bool F8IN = false, int CL = 0>
 __global__ void __launch_bounds__(kB2Threads, 1)
 block2_kernel(const Block2Params p) {
     static_assert(F8OUT || !F8IN, "F8IN implies F8OUT");
+    static_assert(CL == 0 || CL == 2 || CL == 4, "cluster size (0: no clusters)");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* slabA = smem;
     uint8_t* slabB = smem + kB2SlabA;
@@ -68,10 +76,13 @@ block2_kernel(const Block2Params p) {
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // b3[128], b4[128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int real_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tiles this CTA walks: with clusters, the same for all CTAs (the last one may be a dummy for some of them)
+    const int my_tiles = (CL > 1) ? (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x : real_tiles;
+    constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kB2Ring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < kB2Ring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], CL ? CL : 1); }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&d3_full[i], 1); ptx::mbar_init(&d3_empty[i], 8);
             ptx::mbar_init(&d4_full[i], 1); ptx::mbar_init(&d4_empty[i], 8);
@@ -90,6 +101,7 @@ block2_kernel(const Block2Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (CL > 1) ptx::cluster_sync();      // every CTA's barriers exist before anything remote touches them
     pdl_wait();
 
     if (warp == 9) {
@@ -101,7 +113,13 @@ block2_kernel(const Block2Params p) {
                 ptx::mbar_wait_relaxed(&wempty[slot], ph ^ 1);
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&wfull[slot], kB2WBlock);
-                    ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
+                    if constexpr (CL > 1) {
+                        // all CL producers are here for the same block `it`; one of them fetches it for everybody
+                        if (it % CL == ptx::cluster_ctarank())
+                            ptx::bulk_g2s_multicast(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot], kClMask);
+                    } else {
+                        ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
+                    }
                 }
                 __syncwarp();
             }
@@ -116,6 +134,11 @@ block2_kernel(const Block2Params p) {
         for (int k = 0; k < my_tiles; ++k) {
             const int b = (int)(blockIdx.x + k * gridDim.x) * kB2Rows;
             ptx::mbar_wait_relaxed(a_empty, (k & 1) ^ 1);                       // conv3(k-1) has drained slabA
+            if (CL > 1 && k >= real_tiles) {                                    // dummy round: nothing to load
+                if (ptx::elect_one()) ptx::mbar_arrive(a_full);
+                __syncwarp();
+                continue;
+            }
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(a_full, kB2SlabA);
                 const uint8_t* src = p.x2 + (size_t)(b - 3 + kGuard) * 16;
@@ -194,7 +217,10 @@ block2_kernel(const Block2Params p) {
                 }
             }
             }
-            if (leader) ptx::umma_commit(&wempty[slot]);
+            if (leader) {
+                if constexpr (CL > 1) ptx::umma_commit_multicast(&wempty[slot], kClMask);   // the slot is free when all CL CTAs have drained it
+                else ptx::umma_commit(&wempty[slot]);
+            }
             ++it;
         };
         auto issue_c3 = [&](int k) {
@@ -378,6 +404,7 @@ block2_kernel(const Block2Params p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
+    if constexpr (CL > 1) ptx::cluster_sync();      // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
 }
 

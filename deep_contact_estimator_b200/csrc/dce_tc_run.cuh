@@ -14,10 +14,41 @@ inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& fuse_fc3_flag() { static int v = 1; return v; }
 inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
 inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: 1 = X2 and the whole of block2 in that format too; 2 = block1's two convolutions as well
+inline int& block2_cluster_flag() { static int v = 0; return v; }   // experimental: 2 or 4 = block2 in clusters that share the weight stream by multicast
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
 inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
 inline int& tapgemm_trace_layer() { static int v = -1; return v; }   // which layer (2..5) records into the trace buffer
+
+// block2 as thread-block clusters of CL CTAs (block2_kernel<.., CL>): the grid is a whole number of clusters, and no
+// more of them than the device can hold at once (with 1 CTA per SM a GPC whose SM count is not a multiple of CL
+// leaves SMs without a cluster; a second wave would double the kernel's time).
+template <bool F8OUT, bool F8IN, int CL>
+inline int launch_block2_cluster(Ctx& ctx, const char* name, int sm_count, const Block2Params& b) {
+    auto kern = block2_kernel<F8OUT, F8IN, CL>;
+    static DeviceOnce once;
+    static int max_clusters[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(sm_count / CL * CL)); cfg.blockDim = dim3(kB2Threads); cfg.dynamicSmemBytes = kB2SmemBytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n < 1) { ctx.err = (e != cudaSuccess) ? e : cudaErrorLaunchOutOfResources; return DCE_ECUDA; }
+        max_clusters[dev] = n;
+    }
+    int clusters = (b.n_tiles + CL - 1) / CL;
+    if (clusters > max_clusters[dev]) clusters = max_clusters[dev];
+    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl_cluster(kern, dim3((unsigned)(clusters * CL)), dim3(kB2Threads), kB2SmemBytes, ctx.stream, CL, b); (void)le_; });
+    return DCE_OK;
+}
 
 // pointers into the fp32 section of the packed buffer, passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
@@ -141,9 +172,18 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
             b.trace = (tapgemm_trace_layer() == 6) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
+            const int cl = block2_cluster_flag();
             if (f8c) {
                 b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[12]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[13]);
                 b.inv_sw3 = scales + 12 * 4 + 1; b.inv_sw4 = scales + 13 * 4 + 1;
+            }
+            if ((cl == 2 || cl == 4) && (f8c || !f8)) {
+                rc = f8c ? (cl == 2 ? launch_block2_cluster<true, true, 2>(ctx, "tc_block2_f16f8_cl2", sm_count, b)
+                                    : launch_block2_cluster<true, true, 4>(ctx, "tc_block2_f16f8_cl4", sm_count, b))
+                         : (cl == 2 ? launch_block2_cluster<false, false, 2>(ctx, "tc_block2_cl2", sm_count, b)
+                                    : launch_block2_cluster<false, false, 4>(ctx, "tc_block2_cl4", sm_count, b));
+                if (rc != DCE_OK) return rc;
+            } else if (f8c) {
                 DCE_KL(ctx, "tc_block2_f16f8", { cudaError_t le_ = launch_pdl(block2_kernel<true, true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
             } else if (f8)
                 DCE_KL(ctx, "tc_block2_f8out", { cudaError_t le_ = launch_pdl(block2_kernel<true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });

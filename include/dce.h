@@ -187,7 +187,9 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *                  default "fuse_block2" / "fuse_fc3"; calls of <= 4 windows are unaffected.
  *   "conv_f16f8"   0 (default).  EXPERIMENTAL, as above, needs "fc_f16f8" = 1 and "fuse_block1": 1 = X2 and the whole
  *                  of block2 in that format too, 2 = block1's two convolutions as well.
- * Returns DCE_EINVAL for an unknown key.
+ *   "block2_cluster" 0 (default).  EXPERIMENTAL, as above: 2 or 4 = the fused block2 kernel runs as thread-block
+ *                  clusters whose CTAs share one weight stream from L2 (bulk-TMA multicast); same results bit for bit.
+ * Returns DCE_EINVAL for an unknown key (or an unsupported value).
  */
 DCE_API int dce_set_option(const char *key, int value);
 /* "block1_trace" armed: copy the first n clock64 samples ([tile][16 events]) of CTA 0 to the host. */

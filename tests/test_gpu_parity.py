@@ -491,3 +491,23 @@ def test_experimental_f16f8_matches_oracle(dev, scale, conv):
         eng.lib.dce_set_option(b"conv_f16f8", 0)
     assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL["bf16x3"]
     assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
+
+
+@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
+                    reason="block2 in clusters (option block2_cluster) has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
+@pytest.mark.parametrize("cl", [2, 4])
+@pytest.mark.parametrize("batch", [7, 300, 4096])
+def test_experimental_block2_cluster_is_bit_identical(dev, cl, batch):
+    """block2 as clusters of 2 / 4 CTAs sharing the weight stream by multicast: same arithmetic, same bits — also when
+    the last round has CTAs without a tile (batch 7: 5 tiles on 2 clusters of 4, or 3 of 2) and with many rounds (4096)."""
+    eng = engine(dev, "bf16x3")
+    x = synth.make_windows(batch, seed=55).to(dev)
+    want, wc, _ = eng.classify(x)
+    torch.cuda.synchronize()
+    try:
+        assert eng.lib.dce_set_option(b"block2_cluster", cl) == 0
+        got, gc, _ = eng.classify(x)
+        torch.cuda.synchronize()
+    finally:
+        eng.lib.dce_set_option(b"block2_cluster", 0)
+    assert torch.equal(got, want) and torch.equal(gc, wc)
