@@ -351,6 +351,7 @@ int dce_set_option(const char* key, int value) {
     if (!strcmp(key, "fuse_fc3")) { dce::tc::fuse_fc3_flag() = value; return DCE_OK; }
     if (!strcmp(key, "fc_f16f8")) { dce::tc::fc_f16f8_flag() = value; return DCE_OK; }
     if (!strcmp(key, "conv_f16f8")) { dce::tc::conv_f16f8_flag() = value; return DCE_OK; }
+    if (!strcmp(key, "fc_cluster")) { if (value != 0 && value != 2) return DCE_EINVAL; dce::tc::fc_cluster_flag() = value; return DCE_OK; }
     if (!strcmp(key, "block2_cluster")) { if (value != 0 && value != 2 && value != 4) return DCE_EINVAL; dce::tc::block2_cluster_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { latency_kernel_flag() = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { dce::lat::coop_flag() = value; return DCE_OK; }

@@ -196,10 +196,15 @@ struct TapGemmCfg {
 // of p.stages / 2 stages each, 64 K-elements per stage and the same bytes per stage as the bf16x3 layout: sweep 1
 // streams the e4m3 images (A: [lo8 | hi8], B: [w8 | wl8]) and issues the correction MMAs, sweep 2 streams the
 // fp16 images and issues the main MMAs, the first of them with scale-input-d.
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0>
+// CL = 2 (Linear layers, option "fc_cluster"): launched as clusters of two CTAs with ONE tile per CTA; tiles 2j and
+// 2j + 1 share their M-tile(s) (n_tiles is even), so every activation slab of a stage is fetched from L2 by one of the
+// two CTAs and multicast to both (L2 -> SM bytes per stage: A + B -> A / 2 + B), and a ring slot is free when the
+// issuers of BOTH CTAs have drained it (multicast tcgen05.commit, `empty` count 2 MT).
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0, int CL = 0>
 __global__ void __launch_bounds__(tapgemm_threads(MT), 1)
 tapgemm_kernel(const TapGemmParams p) {
     static_assert(!F8 || (TAPS == 1 && KSA == 4 && WST == 0 && (EPI == EPI_FC_TAPE || EPI == EPI_FC_LOGITS)), "F8: Linear layers, 64 K-elements per stage");
+    static_assert(CL == 0 || (CL == 2 && TAPS == 1 && WST == 0), "clusters: pairs, Linear layers");
     constexpr int kProducerWarp0 = kEpiWarps + MT;
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     constexpr int NBUF = Cfg::NBUF;
@@ -219,7 +224,7 @@ tapgemm_kernel(const TapGemmParams p) {
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], MT); }
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], CL ? CL * MT : MT); }
         for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], MT); ptx::mbar_init(&tempty[b], kEpiWarps); }
         ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
@@ -230,6 +235,7 @@ tapgemm_kernel(const TapGemmParams p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (CL != 0) ptx::cluster_sync();                 // the peer's barriers exist before anything remote touches them
     pdl_wait();                                                 // everything the previous kernel wrote is visible from here on
 
     if (warp >= kProducerWarp0) {
@@ -272,6 +278,16 @@ tapgemm_kernel(const TapGemmParams p) {
                             const int c = c0 + pw;
                             if (c < NA) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
+                                if constexpr (CL != 0) {
+                                    // slab c of the stage: fetched by CTA c % 2 of the pair, delivered to both
+                                    const int half = p.stages >> 1;
+                                    size_t src_off = part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride;
+                                    if (F8) src_off = (s < half) ? p.a_part_stride + (size_t)(part * 2 * p.stages + s * KSA + j) * p.a_kch_stride
+                                                                 : (size_t)((s - half) * 2 * KSA + part * KSA + j) * p.a_kch_stride;
+                                    if ((uint32_t)(c & 1) == ptx::cluster_ctarank())
+                                        ptx::bulk_g2s_multicast(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                                                a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot], (uint16_t)0x3);
+                                } else
                                 if (F8) {
                                     // sweep 1: 16-element chunk s*4 + j of e4m3 image `part` (lo8 | hi8; an image has K/16 =
                                     // 2 * stages chunks, both live in tape part 1); sweep 2: 8-element fp16 chunk, tape part 0
@@ -396,6 +412,8 @@ tapgemm_kernel(const TapGemmParams p) {
                     }
                     }
                     if (leader) {
+                        if constexpr (CL != 0) ptx::umma_commit_multicast(&empty[slot], (uint16_t)0x3);   // ... in both CTAs of the pair
+                        else
                         ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
                         if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
                     }
@@ -596,6 +614,7 @@ tapgemm_kernel(const TapGemmParams p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
+    if constexpr (CL != 0) ptx::cluster_sync();                 // the peer may still multicast into this CTA or signal its barriers
     if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -927,10 +946,10 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0, int CL = 0>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, F8>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, F8, CL>;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
     if (F8 && ((p.stages & 1) || !p.acc_scale)) return DCE_EINVAL;
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
@@ -942,7 +961,30 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
+    if constexpr (CL != 0) {
+        // pairs need one tile per CTA, tiles 2j / 2j+1 on the same M-tile, and every pair resident at once
+        if (tiles > sm_count || (p.n_tiles & 1)) return DCE_EUNSUPPORTED;
+        static int max_clusters[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!max_clusters[dev]) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(sm_count & ~1)); cfg.blockDim = dim3(tapgemm_threads(MT)); cfg.dynamicSmemBytes = kSmem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+            if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+            max_clusters[dev] = n > 0 ? n : -1;
+        }
+        if (max_clusters[dev] * 2 < tiles) return DCE_EUNSUPPORTED;
+        DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl_cluster(kern, dim3(tiles), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, 2, p); (void)le_; });
+    } else {
+        DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
+    }
     return DCE_OK;
 }
 

@@ -14,6 +14,7 @@ inline int& fuse_block2_flag() { static int v = 1; return v; }
 inline int& fuse_fc3_flag() { static int v = 1; return v; }
 inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
 inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: 1 = X2 and the whole of block2 in that format too; 2 = block1's two convolutions as well
+inline int& fc_cluster_flag() { static int v = 0; return v; }       // experimental: 2 = fc.0 / fc.3 as CTA pairs that share the activation slabs by multicast
 inline int& block2_cluster_flag() { static int v = 0; return v; }   // experimental: 2 or 4 = block2 in clusters that share the weight stream by multicast
 inline int& block1_dbg_flag() { static int v = 0; return v; }
 inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
@@ -241,11 +242,14 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.N = 2048; p.rw = 1; p.tv = 1;
         p.dbg = tapgemm_dbg_flag();
         p.trace = (tapgemm_trace_layer() == 4) ? block1_trace_ptr() : nullptr;
+        const bool fcl = fc_cluster_flag() == 2;
         if (f8) {
             p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[8]); p.acc_scale = scales + 8 * 4 + 1;
-            rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1_f16f8", sm_count, p);
+            rc = fcl ? launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1, 2>(ctx, "tc_fc1_f16f8_cl2", sm_count, p) : DCE_EUNSUPPORTED;
+            if (rc == DCE_EUNSUPPORTED) rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1_f16f8", sm_count, p);
         } else {
-            rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
+            rc = fcl ? launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 0, 2>(ctx, "tc_fc1_cl2", sm_count, p) : DCE_EUNSUPPORTED;
+            if (rc == DCE_EUNSUPPORTED) rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
         }
         if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
@@ -259,9 +263,11 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             p.w3t = bp.w3;
             if (f8) {
                 p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[9]); p.acc_scale = scales + 9 * 4 + 1;
-                rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1>(ctx, "tc_fc2_fc3_f16f8", sm_count, p);
+                rc = fcl ? launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1, 2>(ctx, "tc_fc2_fc3_f16f8_cl2", sm_count, p) : DCE_EUNSUPPORTED;
+                if (rc == DCE_EUNSUPPORTED) rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1>(ctx, "tc_fc2_fc3_f16f8", sm_count, p);
             } else {
-                rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
+                rc = fcl ? launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 0, 2>(ctx, "tc_fc2_fc3_cl2", sm_count, p) : DCE_EUNSUPPORTED;
+                if (rc == DCE_EUNSUPPORTED) rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
             }
             if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,

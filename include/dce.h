@@ -189,6 +189,8 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *                  of block2 in that format too, 2 = block1's two convolutions as well.
  *   "block2_cluster" 0 (default).  EXPERIMENTAL, as above: 2 or 4 = the fused block2 kernel runs as thread-block
  *                  clusters whose CTAs share one weight stream from L2 (bulk-TMA multicast); same results bit for bit.
+ *   "fc_cluster"   0 (default).  EXPERIMENTAL, as above: 2 = fc.0 and fc.3 run as CTA pairs on the same M-tile that
+ *                  fetch each activation slab once and multicast it to both; same results bit for bit.
  * Returns DCE_EINVAL for an unknown key (or an unsupported value).
  */
 DCE_API int dce_set_option(const char *key, int value);

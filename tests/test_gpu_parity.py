@@ -495,7 +495,7 @@ def test_experimental_f16f8_matches_oracle(dev, scale, conv):
 
 @pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
                     reason="block2 in clusters (option block2_cluster) has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
-@pytest.mark.parametrize("cl", [2, 4])
+@pytest.mark.parametrize("cl", [2, 4, -2])
 @pytest.mark.parametrize("batch", [7, 300, 4096])
 def test_experimental_block2_cluster_is_bit_identical(dev, cl, batch):
     """block2 as clusters of 2 / 4 CTAs sharing the weight stream by multicast: same arithmetic, same bits — also when
@@ -505,9 +505,13 @@ def test_experimental_block2_cluster_is_bit_identical(dev, cl, batch):
     want, wc, _ = eng.classify(x)
     torch.cuda.synchronize()
     try:
-        assert eng.lib.dce_set_option(b"block2_cluster", cl) == 0
+        if cl > 0:
+            assert eng.lib.dce_set_option(b"block2_cluster", cl) == 0
+        else:                                   # -2: fc.0 / fc.3 as CTA pairs sharing the activation slabs
+            assert eng.lib.dce_set_option(b"fc_cluster", 2) == 0
         got, gc, _ = eng.classify(x)
         torch.cuda.synchronize()
     finally:
         eng.lib.dce_set_option(b"block2_cluster", 0)
+        eng.lib.dce_set_option(b"fc_cluster", 0)
     assert torch.equal(got, want) and torch.equal(gc, wc)
