@@ -237,10 +237,15 @@ def dominant_kernel(profile_runs):
 
 
 def kernel_flops(name: str) -> int:
-    """Algorithmic FLOPs per window a kernel covers, from its name."""
-    for key in ("conv1", "conv2", "conv3", "conv4", "fc1", "fc2", "fc3"):
-        if key in name:
-            return LAYER_FLOP[key]
+    """Algorithmic FLOPs per window a kernel covers, from its profiler name (dce_forward_profile): a kernel's name
+    lists the layers it fuses (`tc_block1` = conv1 + conv2, `tc_block2` = conv3 + conv4, `tc_fc2_fc3` = fc.3 + fc.6)."""
+    if "block1" in name:
+        return LAYER_FLOP["conv1"] + LAYER_FLOP["conv2"]
+    if "block2" in name:
+        return LAYER_FLOP["conv3"] + LAYER_FLOP["conv4"]
+    total = sum(LAYER_FLOP[key] for key in ("conv1", "conv2", "conv3", "conv4", "fc1", "fc2", "fc3") if key in name)
+    if total:
+        return total
     if "conv" in name:
         return LAYER_FLOP["conv"]
     return 0
@@ -255,6 +260,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
+                    help="dce_set_option(KEY, VALUE) before timing (A/B of experimental kernels; recorded in config.options)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -281,6 +288,12 @@ def main():
 
     # weights: rank 0 packs (K0), one NCCL broadcast of the packed buffer, outside the timed region
     eng = dce.ContactEngine(synth.make_params(0) if rank == 0 else None, dev, precision)
+    options = {}
+    for kv in args.set:
+        key, _, val = kv.partition("=")
+        if eng.lib.dce_set_option(key.encode(), int(val)) != 0:
+            raise SystemExit(f"bench.py: dce_set_option({key!r}, {val}) was rejected")
+        options[key] = int(val)
     bcast_ms = None
     if world > 1:
         torch.cuda.synchronize(); dist.barrier()
@@ -376,7 +389,8 @@ def main():
             "bound": "tensor", "kernel": dom, "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / peak, "traffic": traffic,
             "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
-            "note": "algorithmic FLOPs (bf16x3 split passes count once; ceiling of frac is 1/3 in bf16x3 mode)",
+            "note": "algorithmic FLOPs (split-precision passes count once; ceiling of frac is 1/3 with three bf16 passes"
+                    + (", 1/2 with the fp16 + e4m3 passes of this run's options)" if options.get("fc_f16f8") else ")"),
             "kernel_share_of_step": per_kernel_ms[dom] / step_kernel_ms,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in per_kernel_ms.items()},
             "whole_step": {"achieved_tflops": value / world * FLOP_PER_WINDOW / 1e12,
@@ -394,7 +408,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3_f32acc" if precision == "bf16x3" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(B),
-                   "precision": precision, "weights": "seeded random init (synth.make_params(0))",
+                   "precision": precision, **({"options": options} if options else {}),
+                   "weights": "seeded random init (synth.make_params(0))",
                    "l2": f"inputs rotate over {NBUF} resident batches of {B * 32400 / 1e6:.1f} MB each (> 126 MB L2 in total)",
                    "parallelism": f"window-range shards x{world}, one-time NCCL weight broadcast"
                                   + (f" ({bcast_ms:.1f} ms, untimed)" if bcast_ms else "")},
