@@ -109,7 +109,7 @@ int run_fp32(const dce_weights* w, const float* x, bool normalize, int64_t first
     using namespace dce::fp32;
     const Fp32Layout& L = w->f32;
     static dce::DeviceOnce attr_once;
-    if (attr_once.need()) {
+    if (auto first_ = attr_once.need()) {
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
         DCE_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
         DCE_CUDA(cudaFuncSetAttribute(fc3_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFc3SmemBytes));

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "../../include/dce.h"
 
 namespace dce {
@@ -39,16 +40,27 @@ struct Ctx {
     }
 };
 
-// cudaFuncSetAttribute is per device: remember which devices a kernel's attributes were set on.
+// cudaFuncSetAttribute is per device: remember which devices a kernel's attributes were set on.  Handles are shared
+// across host threads (include/dce.h), so the first call per device runs its set-up under a lock the others wait on:
+//     static DeviceOnce once;
+//     if (auto first = once.need()) { ... cudaFuncSetAttribute(...) ... }      // lock held until `first` goes out of scope
 struct DeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
-    bool need() {
+    struct Guard {
+        DeviceOnce* o; int d; bool first;
+        Guard(DeviceOnce* o_, int d_, bool first_) : o(o_), d(d_), first(first_) {}
+        Guard(const Guard&) = delete;
+        Guard& operator=(const Guard&) = delete;
+        ~Guard() { if (first) o->done[d] = true; o->mu.unlock(); }
+        explicit operator bool() const { return first; }
+    };
+    Guard need() {
         int d = 0;
         cudaGetDevice(&d);
         d &= 63;
-        if (done[d]) return false;
-        done[d] = true;
-        return true;
+        mu.lock();
+        return Guard(this, d, !done[d]);
     }
 };
 

@@ -524,7 +524,7 @@ inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mo
     const int grid = sm_count / 4 * 4;
     if (grid < kSlices || n < 1 || n > kMaxB) return DCE_EUNSUPPORTED;
     static DeviceOnce once;
-    if (once.need()) {
+    if (auto first_ = once.need()) {
         cudaError_t e = cudaFuncSetAttribute(latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
     }

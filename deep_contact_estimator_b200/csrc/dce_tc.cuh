@@ -955,7 +955,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
     static_assert(kSmem <= 232448, "exceeds 227 KB");
     static DeviceOnce attr_once;
-    if (attr_once.need()) {
+    if (auto first_ = attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
     }
@@ -965,10 +965,11 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
         // pairs need one tile per CTA, tiles 2j / 2j+1 on the same M-tile, and every pair resident at once
         if (tiles > sm_count || (p.n_tiles & 1)) return DCE_EUNSUPPORTED;
         static int max_clusters[64] = {};
+        static DeviceOnce cl_once;
         int dev = 0;
         cudaGetDevice(&dev);
         dev &= 63;
-        if (!max_clusters[dev]) {
+        if (auto first_ = cl_once.need()) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)(sm_count & ~1)); cfg.blockDim = dim3(tapgemm_threads(MT)); cfg.dynamicSmemBytes = kSmem;
             cudaLaunchAttribute at[1];

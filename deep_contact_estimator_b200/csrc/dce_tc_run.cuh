@@ -32,7 +32,7 @@ inline int launch_block2_cluster(Ctx& ctx, const char* name, int sm_count, const
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (once.need()) {
+    if (auto first_ = once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(sm_count / CL * CL)); cfg.blockDim = dim3(kB2Threads); cfg.dynamicSmemBytes = kB2SmemBytes;
@@ -59,7 +59,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
     cudaStream_t s = ctx.stream;
     {
         static DeviceOnce fc3_once;
-        if (fc3_once.need()) {
+        if (auto first_ = fc3_once.need()) {
             cudaError_t e = cudaFuncSetAttribute(fp32::fc3_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fp32::kFc3SmemBytes);
             if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
         }
@@ -85,7 +85,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         const float* scales = reinterpret_cast<const float*>(buf + L.scales);
         if (stream_mode) {
             static DeviceOnce st_once;
-            if (st_once.need()) {
+            if (auto first_ = st_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatSmemBytes);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
@@ -96,7 +96,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         if (fuse_block1_flag()) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static DeviceOnce attr_once;
-            if (attr_once.need()) {
+            if (auto first_ = attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
@@ -159,7 +159,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         if (fuse_block2_flag() && !tiny) {
             // ---- fused conv3 + conv4 + pool + flatten (a7-a9): X2 -> X4, X3 stays in shared memory
             static DeviceOnce b2_once;
-            if (b2_once.need()) {
+            if (auto first_ = b2_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
@@ -223,7 +223,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             static DeviceOnce gemv_once;
             auto k1 = gemv_bias_relu_kernel<4736, 2048, 16, true>;
             auto k2 = gemv_bias_relu_kernel<2048, 512, 8, false>;
-            if (gemv_once.need()) {
+            if (auto first_ = gemv_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxB * 4736 * 4);
                 if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
             }
