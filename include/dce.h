@@ -15,6 +15,9 @@
  *     owns the packed-weight buffer inside a dce_weights handle);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
  *     nothing synchronises, nothing allocates: calls are CUDA-graph capturable;
+ *   - the handle's device must be the calling thread's current device when a
+ *     call enqueues work (as for any launch on a cudaStream_t); only
+ *     dce_weights_create() switches devices itself, and restores the caller's;
  *   - return value: 0 = DCE_OK, negative = DCE_E*; never throws or aborts;
  *   - a handle is immutable after dce_weights_pack() and may be shared by
  *     host threads; dce_forward / dce_stream are re-entrant given distinct
