@@ -28,3 +28,22 @@ def test_f16f8_fc_layouts_match_float64():
     assert mod.check_block2(windows=2) <= 3e-5
     # option "conv_f16f8" = 2: block1's converter, both resident weight images, slab1 and the pooled X2 writer
     assert mod.check_block1(windows=1) <= 4e-5
+
+
+def test_block2_barrier_protocol_simulation():
+    """tools/simulate_block2_protocol.py: every warp role of block2_kernel as a coroutine under a random scheduler, with
+    and without clusters (option "block2_cluster": multicast weight blocks, multicast slot release, dummy last rounds):
+    no deadlock, no parity aliasing, no operand overwritten under a pending MMA, one L2 fetch per block and cluster."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "simulate_block2_protocol.py")
+    spec = importlib.util.spec_from_file_location("simulate_block2_protocol", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check(runs=80, seed=3) == 80
+    # the simulation must be able to fail: releasing a ring slot to the local CTA only deadlocks or corrupts a cluster
+    import random
+    src = open(path).read()
+    bad = {}
+    exec(compile(src.replace("for dst in (ctas if cl > 1 else [c]):", "for dst in [c]:", 1), "mutant", "exec"), bad)
+    import pytest
+    with pytest.raises(AssertionError):
+        bad["simulate"](2, 3, [3, 3], random.Random(1).randrange(1 << 30))
