@@ -961,6 +961,10 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;
+    // With a single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM) the issuer's mid-stage probe of the next
+    // tile's `tempty` would wait for an epilogue that cannot start before the current tile's `tfull` commit: a CTA must
+    // not get a second tile (tools/simulate_block2_protocol.py).  128 tiles on a B200's 148 SMs: never the case here.
+    if (Cfg::NBUF == 1 && tiles > grid) return DCE_EUNSUPPORTED;
     if constexpr (CL != 0) {
         // pairs need one tile per CTA, tiles 2j / 2j+1 on the same M-tile, and every pair resident at once
         if (tiles > sm_count || (p.n_tiles & 1)) return DCE_EUNSUPPORTED;

@@ -39,11 +39,14 @@ def test_block2_barrier_protocol_simulation():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check(runs=80, seed=3) == 80
+    assert mod.check_tapgemm(runs=60, seed=4) == 60            # fc.0 / fc.3 / conv configurations, plain and as CTA pairs
+    import pytest
+    with pytest.raises(AssertionError, match="deadlock"):      # the one combination launch_layer() refuses (see its comment)
+        mod.simulate_tapgemm(1, 2, 3, 4, 2, 5, nbuf=1)
     # the simulation must be able to fail: releasing a ring slot to the local CTA only deadlocks or corrupts a cluster
     import random
     src = open(path).read()
     bad = {}
     exec(compile(src.replace("for dst in (ctas if cl > 1 else [c]):", "for dst in [c]:", 1), "mutant", "exec"), bad)
-    import pytest
     with pytest.raises(AssertionError):
         bad["simulate"](2, 3, [3, 3], random.Random(1).randrange(1 << 30))

@@ -236,6 +236,145 @@ def simulate(cl, rounds, real_tiles, seed):
     return True
 
 
+def simulate_tapgemm(cl, mt, nstage, stages, tiles, seed, ksa=4, nbuf=2):
+    """tapgemm_kernel (csrc/dce_tc.cuh): 4 producer warps, MT issuers, 8 epilogue warps per CTA; cl = 2: a CTA pair with
+    one tile each that shares the activation slabs by multicast (option "fc_cluster"), cl = 1: the plain kernel with
+    `tiles` tiles per CTA.  nbuf = accumulator buffers in TMEM (1 for fc.0, whose two 256-column accumulators fill it).
+    Same checks as `simulate`.
+
+    Found with this simulation: with nbuf = 1 and MORE THAN ONE tile per CTA the kernel deadlocks — the issuer probes the
+    next tile's `tempty` in the middle of the current tile's last stage, i.e. before it has committed `tfull` for the
+    buffer the epilogue must drain first.  fc.0 is the only nbuf = 1 layer and always runs one tile per CTA on a B200
+    (128 tiles, 148 SMs); launch_layer() now refuses the combination instead of hanging on a smaller device."""
+    rng = random.Random(seed)
+    ncta = cl
+    NA, SLABB, BB = mt * 2 * ksa, 2080, 32768
+
+    class T:
+        pass
+    ctas = []
+    for r in range(ncta):
+        c = T()
+        c.rank = r
+        c.full = [Barrier(f"cta{r}.full{i}", 4) for i in range(nstage)]
+        c.empty = [Barrier(f"cta{r}.empty{i}", mt * cl) for i in range(nstage)]
+        c.tfull = [Barrier(f"cta{r}.tfull{i}", mt) for i in range(2)]
+        c.tempty = [Barrier(f"cta{r}.tempty{i}", 8) for i in range(2)]
+        c.slot_stage = [[None] * (NA + 1) for _ in range(nstage)]       # which stage `it` each piece of a slot holds
+        c.slot_readers = [0] * nstage
+        c.pipes = [[] for _ in range(mt)]                               # MMAs retire in order per issuer (conservative)
+        ctas.append(c)
+    inflight = []
+    fetched = {}
+
+    def producer(c, pw):
+        my = [cc for cc in range(pw, NA + 1, 4)]
+        my_bytes = sum(SLABB if cc < NA else BB for cc in my)
+        it = 0
+        for _t in range(tiles):
+            for _s in range(stages):
+                slot, use = it % nstage, it // nstage
+                while not c.empty[slot].ready(use - 1, (use & 1) ^ 1):
+                    yield
+                c.full[slot].arrive(1, tx=my_bytes)
+                for cc in my:
+                    if cc < NA and cl > 1:
+                        if (cc & 1) != c.rank:
+                            continue
+                        dsts = ctas
+                    else:
+                        dsts = [c]
+                    if cc < NA:
+                        fetched[(it, cc)] = fetched.get((it, cc), 0) + 1
+                    for dst in dsts:
+                        def land(dst=dst, slot=slot, cc=cc, it=it):
+                            assert dst.slot_readers[slot] == 0, f"stage {it} piece {cc} lands in a slot an MMA still reads (cta{dst.rank})"
+                            dst.slot_stage[slot][cc] = it
+                            dst.full[slot].complete_tx(SLABB if cc < NA else BB)
+                        inflight.append(land)
+                it += 1
+                yield
+
+    def issuer(c, m):
+        total = tiles * stages
+        it = 0
+        if tiles > 0:
+            while not c.tempty[0].ready(-1, 1):
+                yield
+            while not c.full[0].ready(0, 0):
+                yield
+        for tcount in range(tiles):
+            buf = tcount % nbuf
+            for s in range(stages):
+                slot = it % nstage
+                assert all(v == it for v in c.slot_stage[slot]), f"cta{c.rank}: MMAs of stage {it} issued on {c.slot_stage[slot]}"
+                c.slot_readers[slot] += 1
+                yield
+                if it + 1 < total:
+                    if s == stages - 1:
+                        nt = tcount + 1
+                        while not c.tempty[nt % nbuf].ready(nt // nbuf - 1, ((nt // nbuf) & 1) ^ 1):
+                            yield
+                    nuse = (it + 1) // nstage
+                    while not c.full[(it + 1) % nstage].ready(nuse, nuse & 1):
+                        yield
+                def retire(slot=slot):
+                    c.slot_readers[slot] -= 1
+                    for dst in (ctas if cl > 1 else [c]):
+                        dst.empty[slot].arrive(1)
+                c.pipes[m].append(retire)
+                if s == stages - 1:
+                    c.pipes[m].append(lambda buf=buf: c.tfull[buf].arrive(1))
+                it += 1
+
+    def epilogue(c):
+        for tcount in range(tiles):
+            buf, tph = tcount % nbuf, (tcount // nbuf) & 1
+            while not c.tfull[buf].ready(tcount // nbuf, tph):
+                yield
+            yield
+            c.tempty[buf].arrive(8)
+
+    alive = []
+    for c in ctas:
+        alive += [producer(c, pw) for pw in range(4)] + [issuer(c, m) for m in range(mt)] + [epilogue(c)]
+    idle = 0
+    while alive:
+        progressed = False
+        if inflight and rng.random() < 0.5:
+            inflight.pop(rng.randrange(len(inflight)))()
+            progressed = True
+        for c in ctas:
+            for pipe in c.pipes:
+                if pipe and rng.random() < 0.5:
+                    pipe.pop(0)()
+                    progressed = True
+        r = rng.choice(alive)
+        before = [(b.phase, b.pending, b.tx) for c in ctas for b in c.full + c.empty + c.tfull + c.tempty]
+        try:
+            next(r)
+        except StopIteration:
+            alive.remove(r)
+            progressed = True
+        if before != [(b.phase, b.pending, b.tx) for c in ctas for b in c.full + c.empty + c.tfull + c.tempty]:
+            progressed = True
+        idle = 0 if progressed else idle + 1
+        if idle > 20000 and not inflight and not any(p for c in ctas for p in c.pipes):
+            raise AssertionError(f"deadlock: {len(alive)} roles waiting (cl={cl}, mt={mt}, nstage={nstage}, stages={stages}, tiles={tiles}, seed={seed})")
+    assert all(v == 1 for v in fetched.values()), "an activation slab was not fetched exactly once per pair"
+    return True
+
+
+def check_tapgemm(runs=40, seed=0):
+    rng = random.Random(seed)
+    for _ in range(runs):
+        cl = rng.choice([1, 2])
+        mt, nstage, nbuf = rng.choice([(2, 3, 1), (1, 6, 2), (2, 3, 2), (2, 4, 2)])     # fc.0, fc.3, conv3, conv4 configurations
+        tiles = 1 if (cl == 2 or nbuf == 1) else rng.choice([1, 2, 3, 4])
+        simulate_tapgemm(cl, mt, nstage, rng.choice([4, 7, 12]), tiles, rng.randrange(1 << 30), nbuf=nbuf)
+    return runs
+
+
 def snapshot(ctas):
     out = []
     for c in ctas:
@@ -260,5 +399,6 @@ def check(runs=60, seed=0):
 
 if __name__ == "__main__":
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    print(f"tapgemm (fc.0 / fc.3, plain and as CTA pairs): {check_tapgemm(runs // 2)} randomised runs passed")
     print(f"{check(runs)} randomised runs (clusters of 1 / 2 / 4, 1-5 rounds, dummy last rounds): no deadlock, no phase aliasing, "
           f"no operand overwritten under a pending MMA, every weight block fetched once per cluster")
