@@ -96,6 +96,7 @@ class Scheme:
             return op(rnd(x, torch.bfloat16), rnd(w, torch.bfloat16))
         # fp16 main term; the weight is pre-scaled into fp16's normal range by a per-layer power of two
         sw = 1.0 / pow2_floor(w.abs().max())
+        x = x.clamp(-65504.0, 65504.0)                                   # split16_f16f8 saturates activations at the fp16 maximum
         xh, wh = rnd(x, torch.float16), rnd(w * sw, torch.float16) / sw
         main = op(xh, wh)
         if n == "f16x1":
@@ -157,6 +158,9 @@ def main():
     ap.add_argument("--logit-scale", type=float, default=1.0)
     ap.add_argument("--weight-spread", type=float, default=0.0,
                     help="multiply every weight by 10**U(-s, s) per output row: trained-like dynamic range")
+    ap.add_argument("--outliers", type=float, default=0.0,
+                    help="multiply a random 0.1 %% of every weight tensor by this factor: heavy-tailed weights stress the "
+                         "static per-layer scales of the e4m3 corrections (small weights fall below their range)")
     args = ap.parse_args()
     torch.set_grad_enabled(False)
     params = synth.make_params(0, logit_scale=args.logit_scale)
@@ -166,9 +170,15 @@ def main():
             if k.endswith("weight"):
                 s = 10.0 ** ((torch.rand(params[k].shape[0], generator=g) * 2 - 1) * args.weight_spread)
                 params[k] = params[k] * s.reshape(-1, *([1] * (params[k].dim() - 1)))
+    if args.outliers:
+        g = torch.Generator().manual_seed(11)
+        for k in list(params):
+            if k.endswith("weight"):
+                m = torch.rand(params[k].shape, generator=g) < 1e-3
+                params[k] = torch.where(m, params[k] * args.outliers, params[k])
     x = synth.make_windows(args.windows, seed=1)
     want = forward(params, x, Scheme("f64"))
-    print(f"{args.windows} windows, logit scale {args.logit_scale}, weight spread {args.weight_spread}; "
+    print(f"{args.windows} windows, logit scale {args.logit_scale}, weight spread {args.weight_spread}, outliers x{args.outliers}; "
           f"error = max|d| / max|logit| per window")
     print(f"{'scheme':<12} {'passes':>6} {'max':>10} {'median':>10} {'argmax flips':>13}")
     for name, cost in (("bf16x1", 1), ("bf16x3", 3), ("f16x1", 1), ("f16x3", 3), ("f16+e4m3", 2), ("f16+e5m2", 2),
