@@ -109,27 +109,42 @@ __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
 constexpr int kF8ExL = 12, kF8EwH = 3, kF8ExH = 1, kF8EwL = 14, kF8ScaleD = 15;
 static_assert(kF8ExL + kF8EwH == kF8ScaleD && kF8ExH + kF8EwL == kF8ScaleD, "both correction products carry the same scale");
 
-__device__ __forceinline__ float min_nan(float a, float b) {
+// NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
+// conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
+__host__ __device__ __forceinline__ float min_nan(float a, float b) {
+#ifdef __CUDA_ARCH__
     float d;
     asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
+#else
+    return (a != a || b != b) ? (a + b) : (a < b ? a : b);
+#endif
+}
+__host__ __device__ __forceinline__ float max_nan_hd(float a, float b) {
+#ifdef __CUDA_ARCH__
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+#else
+    return (a != a || b != b) ? (a + b) : (a > b ? a : b);
+#endif
 }
 // 16 consecutive K elements of one row -> two 16-byte fp16 chunks + one 16-byte chunk of each e4m3 image.
 // Activations saturate at the largest finite fp16 (65504); NaN propagates through all three images.
 // SIGNED = false: the values are ReLU outputs (>= 0 or NaN), only the upper clamp is needed.
 template <bool SIGNED = false>
-__device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
+__host__ __device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
     uint32_t h[8], l[4], g[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float a = min_nan(y[2 * i], 65504.f), b = min_nan(y[2 * i + 1], 65504.f);
         if (SIGNED) {
-            asm("max.NaN.f32 %0, %0, %1;" : "+f"(a) : "f"(-65504.f));
-            asm("max.NaN.f32 %0, %0, %1;" : "+f"(b) : "f"(-65504.f));
+            a = max_nan_hd(a, -65504.f);
+            b = max_nan_hd(b, -65504.f);
         }
         const __half2 hb = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(hb);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        h[i] = (uint32_t)__half_as_ushort(__low2half(hb)) | ((uint32_t)__half_as_ushort(__high2half(hb)) << 16);
         const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2((a - hf.x) * (float)(1 << kF8ExL), (b - hf.y) * (float)(1 << kF8ExL)), __NV_SATFINITE, __NV_E4M3);
         const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a * (float)(1 << kF8ExH), b * (float)(1 << kF8ExH)), __NV_SATFINITE, __NV_E4M3);
         if (i & 1) { l[i >> 1] |= lo << 16; g[i >> 1] |= hi << 16; } else { l[i >> 1] = lo; g[i >> 1] = hi; }
@@ -140,7 +155,7 @@ __device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4
     hi8 = make_uint4(g[0], g[1], g[2], g[3]);
 }
 
-__device__ __forceinline__ void split16_f16f8_signed(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
+__host__ __device__ __forceinline__ void split16_f16f8_signed(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
     split16_f16f8<true>(y, f16a, f16b, lo8, hi8);
 }
 
@@ -677,13 +692,12 @@ __global__ void weight_scale_kernel(float* __restrict__ scale) {
     scale[0] = ldexpf(1.f, 1 - e);
     scale[1] = ldexpf(1.f, e - 1);
 }
-__global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
-                                    int BN, int kind, int K, const float* __restrict__ scale) {
-    const float sw = scale[0];
-    const size_t total = (size_t)n_tiles * BN * K;
+// one weight element (idx = n * K + k) of a Linear layer -> its three images
+__host__ __device__ __forceinline__ void pack_b_f16f8_elem(const float* __restrict__ W, uint8_t* __restrict__ out, size_t idx,
+                                                           int stages, int BN, int kind, int K, float sw) {
     const size_t blk_bytes = (size_t)8 * BN * 16;
     const int half = stages / 2;                               // K == 64 * half
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    {
         const int k = (int)(idx % K);
         const int n = (int)(idx / K);
         const int nt = n / BN, nn = n % BN;
@@ -702,18 +716,23 @@ __global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __rest
         corr[blk_bytes / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
     }
 }
+__global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
+                                    int BN, int kind, int K, const float* __restrict__ scale) {
+    const float sw = scale[0];
+    const size_t total = (size_t)n_tiles * BN * K;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+        pack_b_f16f8_elem(W, out, idx, stages, BN, kind, K, sw);
+}
 
 // Conv layers in the fp16 + e4m3 format (option "conv_f16f8"): blocks of 192 * cout bytes, each covering 32 input
 // channels of all three taps; first the G = cin_pad / 32 e4m3 blocks [img: w8 | wl8][tap][2 chunks of 16][cout][16 B],
 // then the G fp16 blocks [tap][4 chunks of 8][cout][8 x 2 B] — the order the two-sweep issuers consume them
 // (block2's 24 KB weight ring at cout = 128; block1 keeps its four 12 KB blocks resident).
-__global__ void pack_conv_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int cout, int cin, int cin_pad,
-                                       const float* __restrict__ scale) {
-    const float sw = scale[0];
+__host__ __device__ __forceinline__ void pack_conv_f16f8_elem(const float* __restrict__ W, uint8_t* __restrict__ out, int idx,
+                                                              int cout, int cin, int cin_pad, float sw) {
     const int G = cin_pad / 32;
     const size_t blk = (size_t)192 * cout;
-    const int total = cout * cin_pad * 3;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    {
         const int tap = idx % 3, c = (idx / 3) % cin_pad, n = idx / (3 * cin_pad);
         const float v = (c < cin ? W[((size_t)n * cin + c) * 3 + tap] : 0.f) * sw;
         const __half h = __float2half_rn(v);
@@ -726,6 +745,13 @@ __global__ void pack_conv_f16f8_kernel(const float* __restrict__ W, uint8_t* __r
         b8[o8] = (uint8_t)__nv_cvt_float_to_fp8(v * (float)(1 << kF8EwH), __NV_SATFINITE, __NV_E4M3);
         b8[blk / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
     }
+}
+__global__ void pack_conv_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int cout, int cin, int cin_pad,
+                                       const float* __restrict__ scale) {
+    const float sw = scale[0];
+    const int total = cout * cin_pad * 3;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+        pack_conv_f16f8_elem(W, out, idx, cout, cin, cin_pad, sw);
 }
 
 // ---------------------------------------------------------------------------------------------

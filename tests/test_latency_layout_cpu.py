@@ -50,3 +50,54 @@ def test_block2_barrier_protocol_simulation():
     exec(compile(src.replace("for dst in (ctas if cl > 1 else [c]):", "for dst in [c]:", 1), "mutant", "exec"), bad)
     with pytest.raises(AssertionError):
         bad["simulate"](2, 3, [3, 3], random.Random(1).randrange(1 << 30))
+
+
+def test_cuda_source_matches_numpy_emulation_byte_for_byte(tmp_path):
+    """The numpy emulation above consumes ITS OWN packers; this ties them to the CUDA source: split16_f16f8,
+    pack_b_f16f8_elem and pack_conv_f16f8_elem of csrc/dce_tc.cuh are __host__ __device__, tools/host_check_f16f8.cu
+    runs them on the CPU (nvcc-compiled, no CUDA call) and their bytes must equal the emulation's."""
+    import shutil
+    import subprocess
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_check_f16f8")
+    res = subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                          os.path.join(root, "tools", "host_check_f16f8.cu")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    spec = importlib.util.spec_from_file_location("emulate_f16f8", os.path.join(root, "tools", "emulate_f16f8.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)
+    rng = np.random.default_rng(5)
+    for signed, fc_kind in ((0, 4), (1, 3)):
+        y = (rng.standard_normal((64, 16)) * np.exp(rng.uniform(-9, 5, (64, 1)))).astype(np.float32)
+        y[3, 5], y[7, 0], y[9, 9] = np.nan, 7.0e4, 0.0                        # NaN propagates, saturation at 65504, zero
+        if not signed:
+            y = np.where(np.isnan(y), y, np.abs(y))
+        else:
+            y[11, 2] = -9.0e4
+        fc_n, fc_k, fc_bn = (256, 4736, 256) if fc_kind == 3 else (256, 2048, 128)
+        wfc = (rng.uniform(-1, 1, (fc_n, fc_k)) / np.sqrt(fc_k)).astype(np.float32)
+        cout, cin, cin_pad = (64, 54, 64) if signed else (128, 128, 128)
+        wcv = (rng.uniform(-1, 1, (cout, cin, 3)) / np.sqrt(3 * cin)).astype(np.float32)
+        sw_fc, _ = emu.weight_scale(wfc)
+        sw_cv, _ = emu.weight_scale(wcv)
+        src, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        with open(src, "wb") as f:
+            f.write(np.array([64, signed, fc_n, fc_k, fc_bn, fc_kind, cout, cin, cin_pad], np.int32).tobytes())
+            f.write(np.array([sw_fc, sw_cv], np.float32).tobytes())
+            f.write(y.tobytes()); f.write(wfc.tobytes()); f.write(wcv.tobytes())
+        assert subprocess.run([exe, src, out]).returncode == 0
+        got = np.fromfile(out, np.uint8)
+        f16, lo, hi = emu.split16(y, signed=bool(signed))
+        want_split = np.concatenate([f16, lo, hi], axis=1).reshape(-1)
+        n = want_split.size
+        nan_rows = np.isnan(y).any(axis=1)
+        ok = (got[:n].reshape(64, 64) == want_split.reshape(64, 64)) | nan_rows[:, None]     # NaN payload bits may differ
+        assert ok.all()
+        g_nan = got[:n].reshape(64, 64)[3]
+        assert np.isnan(g_nan[:32].view(np.float16)[5]) and g_nan[32 + 5] & 0x7F == 0x7F and g_nan[48 + 5] & 0x7F == 0x7F
+        want_fc = emu.pack_b_f16f8(wfc, fc_n // fc_bn, fc_k // 32, fc_bn, fc_kind, fc_k, sw_fc)
+        assert np.array_equal(got[n:n + want_fc.size], want_fc)
+        want_cv = emu.pack_conv_f16f8(wcv, cout, cin, cin_pad, sw_cv)
+        assert np.array_equal(got[n + want_fc.size:], want_cv)
