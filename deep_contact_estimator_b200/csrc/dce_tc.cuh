@@ -109,6 +109,35 @@ __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
 constexpr int kF8ExL = 12, kF8EwH = 3, kF8ExH = 1, kF8EwL = 14, kF8ScaleD = 15;
 static_assert(kF8ExL + kF8EwH == kF8ScaleD && kF8ExH + kF8EwL == kF8ScaleD, "both correction products carry the same scale");
 
+// One layout rule for every tensor in this format: a row with C channels is C/8 fp16 chunks (8 channels, 16 bytes
+// each), then C/16 lo8 chunks, then C/16 hi8 chunks (16 channels, 16 bytes each).  In a tape the fp16 chunks are
+// part 0 and the e4m3 chunks part 1 (chunk pitch kch_stride); in a shared-memory slab all C/4 chunks follow each
+// other (pitch kSlabBytes: C/8 fp16, C/16 lo8, C/16 hi8).  Writers and readers below go through these helpers, and
+// tools/host_check_f16f8.cu tabulates them on the host for the CPU tests.
+struct F8Dst { size_t f16, lo8, hi8; };      // byte offsets of fp16 chunk 2*g16 (chunk 2*g16+1 follows one pitch later), lo8 / hi8 chunk g16
+__host__ __device__ __forceinline__ F8Dst f8_tape_dst(int g16, int C, size_t part_stride, size_t kch_stride) {
+    F8Dst d;
+    d.f16 = (size_t)(2 * g16) * kch_stride;
+    d.lo8 = part_stride + (size_t)g16 * kch_stride;
+    d.hi8 = part_stride + (size_t)(C / 16 + g16) * kch_stride;
+    return d;
+}
+__host__ __device__ __forceinline__ F8Dst f8_slab_dst(int g16, int C) {
+    F8Dst d;
+    d.f16 = (size_t)(2 * g16) * (130 * 16);
+    d.lo8 = (size_t)(C / 8 + g16) * (130 * 16);
+    d.hi8 = (size_t)(C / 8 + C / 16 + g16) * (130 * 16);
+    return d;
+}
+// tapgemm F8 producer: tape offset of activation copy (part, j) of stage s (K = 32 * stages, KSA = 4 chunks per part).
+// Sweep 1 (s < stages/2) streams 16-element chunks s*4 + j of e4m3 image `part` (0 = lo8, 1 = hi8); sweep 2 streams
+// fp16 chunks (s - stages/2)*8 + part*4 + j.
+__host__ __device__ __forceinline__ size_t f8_stage_src(int s, int stages, int part, int j, size_t part_stride, size_t kch_stride) {
+    const int half = stages >> 1;
+    return (s < half) ? part_stride + (size_t)(part * 2 * stages + s * 4 + j) * kch_stride
+                      : (size_t)((s - half) * 8 + part * 4 + j) * kch_stride;
+}
+
 // NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
 // conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
 __host__ __device__ __forceinline__ float min_nan(float a, float b) {
@@ -295,20 +324,14 @@ tapgemm_kernel(const TapGemmParams p) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
                                 if constexpr (CL != 0) {
                                     // slab c of the stage: fetched by CTA c % 2 of the pair, delivered to both
-                                    const int half = p.stages >> 1;
                                     size_t src_off = part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride;
-                                    if (F8) src_off = (s < half) ? p.a_part_stride + (size_t)(part * 2 * p.stages + s * KSA + j) * p.a_kch_stride
-                                                                 : (size_t)((s - half) * 2 * KSA + part * KSA + j) * p.a_kch_stride;
+                                    if (F8) src_off = f8_stage_src(s, p.stages, part, j, p.a_part_stride, p.a_kch_stride);
                                     if ((uint32_t)(c & 1) == ptx::cluster_ctarank())
                                         ptx::bulk_g2s_multicast(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
                                                                 a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot], (uint16_t)0x3);
                                 } else
                                 if (F8) {
-                                    // sweep 1: 16-element chunk s*4 + j of e4m3 image `part` (lo8 | hi8; an image has K/16 =
-                                    // 2 * stages chunks, both live in tape part 1); sweep 2: 8-element fp16 chunk, tape part 0
-                                    const int half = p.stages >> 1;
-                                    const size_t src_off = (s < half) ? p.a_part_stride + (size_t)(part * 2 * p.stages + s * KSA + j) * p.a_kch_stride
-                                                                      : (size_t)((s - half) * 2 * KSA + part * KSA + j) * p.a_kch_stride;
+                                    const size_t src_off = f8_stage_src(s, p.stages, part, j, p.a_part_stride, p.a_kch_stride);
                                     ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
                                                   a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot]);
                                 } else {
@@ -554,13 +577,12 @@ tapgemm_kernel(const TapGemmParams p) {
                     for (int hh = 0; hh < 2; ++hh) {
                         uint4 fa, fb, lo8, hi8;
                         split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                        const int k16 = (n0 + c0) / 16 + hh;
-                        uint8_t* d16 = p.out + (size_t)(2 * k16) * p.out_kch_stride + out_off[mt];
-                        *reinterpret_cast<uint4*>(d16) = fa;
-                        *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
-                        uint8_t* d8 = p.out + p.out_part_stride + (size_t)k16 * p.out_kch_stride + out_off[mt];
-                        *reinterpret_cast<uint4*>(d8) = lo8;
-                        *reinterpret_cast<uint4*>(d8 + (size_t)(p.N / 16) * p.out_kch_stride) = hi8;
+                        const F8Dst d = f8_tape_dst((n0 + c0) / 16 + hh, p.N, p.out_part_stride, p.out_kch_stride);
+                        uint8_t* row = p.out + out_off[mt];
+                        *reinterpret_cast<uint4*>(row + d.f16) = fa;
+                        *reinterpret_cast<uint4*>(row + d.f16 + p.out_kch_stride) = fb;
+                        *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
+                        *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
                     }
                     return;
                 }

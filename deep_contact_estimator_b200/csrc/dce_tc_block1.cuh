@@ -257,11 +257,12 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                     }
                     uint4 fa, fb, lo8, hi8;
                     split16_f16f8_signed(y, fa, fb, lo8, hi8);
+                    const F8Dst o = f8_slab_dst(c16, 64);
                     uint8_t* d = dst0 + tid * 16;
-                    *reinterpret_cast<uint4*>(d + (2 * c16) * kSlabBytes) = fa;
-                    *reinterpret_cast<uint4*>(d + (2 * c16 + 1) * kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + (8 + c16) * kSlabBytes) = lo8;
-                    *reinterpret_cast<uint4*>(d + (12 + c16) * kSlabBytes) = hi8;
+                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
+                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
+                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
+                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
                 }
                 if (tid < 8) {
                     float y[16];
@@ -269,11 +270,12 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                     for (int i = 0; i < 8; ++i) { y[2 * i] = g8[i].x; y[2 * i + 1] = g8[i].y; }
                     uint4 fa, fb, lo8, hi8;
                     split16_f16f8_signed(y, fa, fb, lo8, hi8);
+                    const F8Dst o = f8_slab_dst(c8, 64);
                     uint8_t* d = dst0 + s8 * 16;
-                    *reinterpret_cast<uint4*>(d + (2 * c8) * kSlabBytes) = fa;
-                    *reinterpret_cast<uint4*>(d + (2 * c8 + 1) * kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + (8 + c8) * kSlabBytes) = lo8;
-                    *reinterpret_cast<uint4*>(d + (12 + c8) * kSlabBytes) = hi8;
+                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
+                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
+                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
+                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
                 }
             } else {
 #pragma unroll
@@ -372,10 +374,11 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                     for (int g = 0; g < 2; ++g) {
 #pragma unroll
                         for (int tap = 0; tap < 3; ++tap) {
-                            const uint32_t a_l = a_base + (8 + 2 * g) * kSlabBytes + tap * 16;
+                            const F8Dst o = f8_slab_dst(2 * g, 64);              // the slab's 16-channel groups 2g, 2g + 1
+                            const uint32_t a_l = a_base + (uint32_t)o.lo8 + tap * 16, a_h = a_base + (uint32_t)o.hi8 + tap * 16;
                             const uint32_t b_h = w_base + g * 12288 + tap * 2048;
                             ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_l, kSlabBytes, 128), ptx::make_smem_desc(b_h, 1024, 128), id8, (g | tap) ? 1u : 0u);
-                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_l + 4 * kSlabBytes, kSlabBytes, 128), ptx::make_smem_desc(b_h + 6144, 1024, 128), id8, 1u);
+                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_h, kSlabBytes, 128), ptx::make_smem_desc(b_h + 6144, 1024, 128), id8, 1u);
                         }
                     }
 #pragma unroll
@@ -384,7 +387,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                         for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
-                                const uint64_t da = ptx::make_smem_desc(a_base + (4 * g + 2 * kk) * kSlabBytes + tap * 16, kSlabBytes, 128);
+                                const uint64_t da = ptx::make_smem_desc(a_base + (uint32_t)f8_slab_dst(2 * g + kk, 64).f16 + tap * 16, kSlabBytes, 128);
                                 const uint64_t db = ptx::make_smem_desc(w_base + (2 + g) * 12288 + tap * 4096 + kk * 2048, 1024, 128);
                                 if ((g | tap | kk) == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
                                 else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
@@ -484,11 +487,12 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 for (int hh = 0; hh < 2; ++hh) {
                     uint4 fa, fb, lo8, hi8;
                     split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                    const F8Dst o = f8_slab_dst(h * 2 + hh, 64);
                     uint8_t* d = slab1 + (rit + 1) * 16;
-                    *reinterpret_cast<uint4*>(d + (h * 4 + hh * 2) * kSlabBytes) = fa;
-                    *reinterpret_cast<uint4*>(d + (h * 4 + hh * 2 + 1) * kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + (8 + h * 2 + hh) * kSlabBytes) = lo8;
-                    *reinterpret_cast<uint4*>(d + (12 + h * 2 + hh) * kSlabBytes) = hi8;
+                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
+                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
+                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
+                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
                 }
             } else {
 #pragma unroll
@@ -550,14 +554,14 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 for (int hh = 0; hh < 2; ++hh) {
                     uint4 fa, fb, lo8, hi8;
                     split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                    const F8Dst o = f8_tape_dst(h * 2 + hh, 64, p.out_part_stride, p.out_kch_stride);
+                    uint8_t* row = p.out + (size_t)(orow + kGuard) * 16;
                     if (lane & 1) {
-                        uint8_t* d8 = p.out + p.out_part_stride + (size_t)(h * 2 + hh) * p.out_kch_stride + (size_t)(orow + kGuard) * 16;
-                        *reinterpret_cast<uint4*>(d8) = lo8;
-                        *reinterpret_cast<uint4*>(d8 + 4 * p.out_kch_stride) = hi8;
+                        *reinterpret_cast<uint4*>(row + o.lo8) = lo8;
+                        *reinterpret_cast<uint4*>(row + o.hi8) = hi8;
                     } else {
-                        uint8_t* d16 = p.out + (size_t)(h * 4 + hh * 2) * p.out_kch_stride + (size_t)(orow + kGuard) * 16;
-                        *reinterpret_cast<uint4*>(d16) = fa;
-                        *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
+                        *reinterpret_cast<uint4*>(row + o.f16) = fa;
+                        *reinterpret_cast<uint4*>(row + o.f16 + p.out_kch_stride) = fb;
                     }
                 }
             } else if (store && !(p.dbg & 1)) {

@@ -169,8 +169,9 @@ block2_kernel(const Block2Params p) {
                 for (int tap = 0; tap < 3; ++tap) {
                     if (s < half) {
                         // corrections for input channels [32 s, 32 s + 32): one K = 32 MMA per product
-                        const uint32_t a_l = slab + (uint32_t)(kch_total + 2 * s) * kSlabBytes + tap * 16;
-                        const uint32_t a_h = a_l + (uint32_t)(kch_total >> 1) * kSlabBytes;
+                        const F8Dst o = f8_slab_dst(2 * s, kch_total * 8);      // the slab's 16-channel groups 2s, 2s + 1
+                        const uint32_t a_l = slab + (uint32_t)o.lo8 + tap * 16;
+                        const uint32_t a_h = slab + (uint32_t)o.hi8 + tap * 16;
                         const uint64_t da_l = ptx::make_smem_desc(a_l, kSlabBytes, 128);
                         const uint64_t da_h = ptx::make_smem_desc(a_h, kSlabBytes, 128);
                         const uint64_t db_h = ptx::make_smem_desc(b0 + tap * 4096, 2048, 128);
@@ -184,7 +185,7 @@ block2_kernel(const Block2Params p) {
                         const int g = s - half;
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t da = ptx::make_smem_desc(slab + (uint32_t)(4 * g + 2 * kk) * kSlabBytes + tap * 16, kSlabBytes, 128);
+                            const uint64_t da = ptx::make_smem_desc(slab + (uint32_t)f8_slab_dst(2 * g + kk, kch_total * 8).f16 + tap * 16, kSlabBytes, 128);
                             const uint64_t db = ptx::make_smem_desc(b0 + tap * 8192 + kk * 4096, 2048, 128);
                             if (leader) {
                                 if (s == half && tap == 0 && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
@@ -303,12 +304,12 @@ block2_kernel(const Block2Params p) {
                     for (int hh = 0; hh < 2; ++hh) {
                         uint4 fa, fb, lo8, hi8;
                         split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                        uint8_t* d16 = slabB + (h * 8 + c * 4 + hh * 2) * kSlabBytes + (rit + 1) * 16;
-                        *reinterpret_cast<uint4*>(d16) = fa;
-                        *reinterpret_cast<uint4*>(d16 + kSlabBytes) = fb;
-                        uint8_t* d8 = slabB + (16 + h * 4 + c * 2 + hh) * kSlabBytes + (rit + 1) * 16;
-                        *reinterpret_cast<uint4*>(d8) = lo8;
-                        *reinterpret_cast<uint4*>(d8 + 8 * kSlabBytes) = hi8;
+                        const F8Dst d = f8_slab_dst(h * 4 + c * 2 + hh, 128);        // 16-channel group of the 128 X3 channels
+                        uint8_t* row = slabB + (rit + 1) * 16;
+                        *reinterpret_cast<uint4*>(row + d.f16) = fa;
+                        *reinterpret_cast<uint4*>(row + d.f16 + kSlabBytes) = fb;
+                        *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
+                        *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
                     }
                 } else {
 #pragma unroll
@@ -374,14 +375,15 @@ block2_kernel(const Block2Params p) {
                         for (int hh = 0; hh < 2; ++hh) {
                             uint4 fa, fb, lo8, hi8;
                             split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
+                            // fc.0 operand row of window w: K index k' = to*128 + channel, 4736 "channels" in all
+                            const F8Dst d = f8_tape_dst(to * 8 + h * 4 + c * 2 + hh, 4736, p.out_part_stride, p.out_kch_stride);
+                            uint8_t* row = p.out + (size_t)(w + kGuard) * 16;
                             if (lane & 1) {
-                                uint8_t* d8 = p.out + p.out_part_stride + (size_t)(to * 8 + h * 4 + c * 2 + hh) * p.out_kch_stride + (size_t)(w + kGuard) * 16;
-                                *reinterpret_cast<uint4*>(d8) = lo8;
-                                *reinterpret_cast<uint4*>(d8 + (size_t)(37 * 8) * p.out_kch_stride) = hi8;
+                                *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
+                                *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
                             } else {
-                                uint8_t* d16 = p.out + (size_t)(to * 16 + h * 8 + c * 4 + hh * 2) * p.out_kch_stride + (size_t)(w + kGuard) * 16;
-                                *reinterpret_cast<uint4*>(d16) = fa;
-                                *reinterpret_cast<uint4*>(d16 + p.out_kch_stride) = fb;
+                                *reinterpret_cast<uint4*>(row + d.f16) = fa;
+                                *reinterpret_cast<uint4*>(row + d.f16 + p.out_kch_stride) = fb;
                             }
                         }
                     }

@@ -100,4 +100,19 @@ def test_cuda_source_matches_numpy_emulation_byte_for_byte(tmp_path):
         want_fc = emu.pack_b_f16f8(wfc, fc_n // fc_bn, fc_k // 32, fc_bn, fc_kind, fc_k, sw_fc)
         assert np.array_equal(got[n:n + want_fc.size], want_fc)
         want_cv = emu.pack_conv_f16f8(wcv, cout, cin, cin_pad, sw_cv)
-        assert np.array_equal(got[n + want_fc.size:], want_cv)
+        assert np.array_equal(got[n + want_fc.size:n + want_fc.size + want_cv.size], want_cv)
+        # the layout helpers every f16f8 writer and reader goes through (f8_tape_dst, f8_slab_dst, f8_stage_src)
+        tab = got[n + want_fc.size + want_cv.size:].view(np.uint64).astype(np.int64)
+        P, K, SLAB = 1 << 40, 1 << 20, 130 * 16
+        want_tab = []
+        for C in (64, 128, 2048, 4736):
+            for g in range(C // 16):
+                # fp16 chunks in tape part 0 (chunk 2 g), lo8 chunk g and hi8 chunk C/16 + g in part 1; slab: C/8 fp16, C/16 lo8, C/16 hi8
+                want_tab += [2 * g * K, P + g * K, P + (C // 16 + g) * K, 2 * g * SLAB, (C // 8 + g) * SLAB, (C // 8 + C // 16 + g) * SLAB]
+        for stages in (148, 64):
+            half = stages // 2
+            for s_ in range(stages):
+                for part in range(2):
+                    for j in range(4):
+                        want_tab.append(P + (part * 2 * stages + s_ * 4 + j) * K if s_ < half else ((s_ - half) * 8 + part * 4 + j) * K)
+        assert np.array_equal(tab, np.array(want_tab, np.int64))

@@ -47,6 +47,25 @@ int main(int argc, char** argv) {
             dce::tc::pack_conv_f16f8_elem(wcv.data(), img.data(), idx, cout, cin, cin_pad, sw[1]);
         fwrite(img.data(), 1, img.size(), o);
     }
+    // layout helper tables (all as uint64): for C in {64, 128, 2048, 4736}: per 16-channel group g16 the tape
+    // destinations (part_stride = 1 << 40, kch_stride = 1 << 20, so chunk indices can be read off) and the slab
+    // destinations; then f8_stage_src for fc.0 (148 stages) and fc.3 (64 stages), [s][part][j]
+    const int Cs[4] = {64, 128, 2048, 4736};
+    for (int ci = 0; ci < 4; ++ci)
+        for (int g = 0; g < Cs[ci] / 16; ++g) {
+            const dce::tc::F8Dst t = dce::tc::f8_tape_dst(g, Cs[ci], (size_t)1 << 40, (size_t)1 << 20);
+            const dce::tc::F8Dst sl = dce::tc::f8_slab_dst(g, Cs[ci]);
+            const unsigned long long v[6] = {t.f16, t.lo8, t.hi8, sl.f16, sl.lo8, sl.hi8};
+            fwrite(v, 8, 6, o);
+        }
+    const int St[2] = {148, 64};
+    for (int li = 0; li < 2; ++li)
+        for (int s = 0; s < St[li]; ++s)
+            for (int part = 0; part < 2; ++part)
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long v = dce::tc::f8_stage_src(s, St[li], part, j, (size_t)1 << 40, (size_t)1 << 20);
+                    fwrite(&v, 8, 1, o);
+                }
     fclose(o);
     return 0;
 }
