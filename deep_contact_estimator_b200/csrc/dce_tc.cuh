@@ -138,6 +138,12 @@ __host__ __device__ __forceinline__ size_t f8_stage_src(int s, int stages, int p
                       : (size_t)((s - half) * 8 + part * 4 + j) * kch_stride;
 }
 
+// B-operand offsets inside one conv weight block of 192 * cout bytes (pack_conv_f16f8_kernel): an e4m3 block is
+// [img: w8 | wl8][tap][2 chunks of 16 channels][cout][16 B], an fp16 block [tap][4 chunks of 8 channels][cout][16 B];
+// the descriptor's LBO (distance between the two K chunks of one MMA) is 16 * cout in both.
+__host__ __device__ __forceinline__ uint32_t f8_wblk_e4m3(int cout, int img, int tap) { return (uint32_t)((img * 3 + tap) * 32 * cout); }
+__host__ __device__ __forceinline__ uint32_t f8_wblk_f16(int cout, int tap, int kk) { return (uint32_t)((tap * 2 + kk) * 32 * cout); }
+
 // NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
 // conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
 __host__ __device__ __forceinline__ float min_nan(float a, float b) {

@@ -376,9 +376,9 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                         for (int tap = 0; tap < 3; ++tap) {
                             const F8Dst o = f8_slab_dst(2 * g, 64);              // the slab's 16-channel groups 2g, 2g + 1
                             const uint32_t a_l = a_base + (uint32_t)o.lo8 + tap * 16, a_h = a_base + (uint32_t)o.hi8 + tap * 16;
-                            const uint32_t b_h = w_base + g * 12288 + tap * 2048;
+                            const uint32_t b_h = w_base + g * 12288 + f8_wblk_e4m3(64, 0, tap), b_l = w_base + g * 12288 + f8_wblk_e4m3(64, 1, tap);
                             ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_l, kSlabBytes, 128), ptx::make_smem_desc(b_h, 1024, 128), id8, (g | tap) ? 1u : 0u);
-                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_h, kSlabBytes, 128), ptx::make_smem_desc(b_h + 6144, 1024, 128), id8, 1u);
+                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_h, kSlabBytes, 128), ptx::make_smem_desc(b_l, 1024, 128), id8, 1u);
                         }
                     }
 #pragma unroll
@@ -388,7 +388,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk) {
                                 const uint64_t da = ptx::make_smem_desc(a_base + (uint32_t)f8_slab_dst(2 * g + kk, 64).f16 + tap * 16, kSlabBytes, 128);
-                                const uint64_t db = ptx::make_smem_desc(w_base + (2 + g) * 12288 + tap * 4096 + kk * 2048, 1024, 128);
+                                const uint64_t db = ptx::make_smem_desc(w_base + (2 + g) * 12288 + f8_wblk_f16(64, tap, kk), 1024, 128);
                                 if ((g | tap | kk) == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
                                 else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
                             }

@@ -174,8 +174,8 @@ block2_kernel(const Block2Params p) {
                         const uint32_t a_h = slab + (uint32_t)o.hi8 + tap * 16;
                         const uint64_t da_l = ptx::make_smem_desc(a_l, kSlabBytes, 128);
                         const uint64_t da_h = ptx::make_smem_desc(a_h, kSlabBytes, 128);
-                        const uint64_t db_h = ptx::make_smem_desc(b0 + tap * 4096, 2048, 128);
-                        const uint64_t db_l = ptx::make_smem_desc(b0 + 12288 + tap * 4096, 2048, 128);
+                        const uint64_t db_h = ptx::make_smem_desc(b0 + f8_wblk_e4m3(128, 0, tap), 2048, 128);
+                        const uint64_t db_l = ptx::make_smem_desc(b0 + f8_wblk_e4m3(128, 1, tap), 2048, 128);
                         if (leader) {
                             ptx::umma_e4m3_ss(d, da_l, db_h, id8, (first_stage && tap == 0) ? 0u : 1u);
                             ptx::umma_e4m3_ss(d, da_h, db_l, id8, 1u);
@@ -186,7 +186,7 @@ block2_kernel(const Block2Params p) {
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
                             const uint64_t da = ptx::make_smem_desc(slab + (uint32_t)f8_slab_dst(2 * g + kk, kch_total * 8).f16 + tap * 16, kSlabBytes, 128);
-                            const uint64_t db = ptx::make_smem_desc(b0 + tap * 8192 + kk * 4096, 2048, 128);
+                            const uint64_t db = ptx::make_smem_desc(b0 + f8_wblk_f16(128, tap, kk), 2048, 128);
                             if (leader) {
                                 if (s == half && tap == 0 && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
                                 else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc

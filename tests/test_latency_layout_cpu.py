@@ -115,4 +115,7 @@ def test_cuda_source_matches_numpy_emulation_byte_for_byte(tmp_path):
                 for part in range(2):
                     for j in range(4):
                         want_tab.append(P + (part * 2 * stages + s_ * 4 + j) * K if s_ < half else ((s_ - half) * 8 + part * 4 + j) * K)
+        # B-operand offsets inside a conv weight block, as the numpy issuers use them (conv64_mmas / conv_blocks)
+        want_tab += [0, 2048, 4096, 6144, 8192, 10240] + [0, 2048, 4096, 6144, 8192, 10240]                 # cout 64: e4m3 [img][tap], fp16 [tap][kk]
+        want_tab += [0, 4096, 8192, 12288, 16384, 20480] + [0, 4096, 8192, 12288, 16384, 20480]             # cout 128
         assert np.array_equal(tab, np.array(want_tab, np.int64))

@@ -66,6 +66,13 @@ int main(int argc, char** argv) {
                     const unsigned long long v = dce::tc::f8_stage_src(s, St[li], part, j, (size_t)1 << 40, (size_t)1 << 20);
                     fwrite(&v, 8, 1, o);
                 }
+    // B-operand offsets inside a conv weight block: [cout in {64, 128}][img][tap] e4m3, then [cout][tap][kk] fp16
+    for (int cout_ : {64, 128}) {
+        for (int img = 0; img < 2; ++img)
+            for (int tap = 0; tap < 3; ++tap) { const unsigned long long v = dce::tc::f8_wblk_e4m3(cout_, img, tap); fwrite(&v, 8, 1, o); }
+        for (int tap = 0; tap < 3; ++tap)
+            for (int kk = 0; kk < 2; ++kk) { const unsigned long long v = dce::tc::f8_wblk_f16(cout_, tap, kk); fwrite(&v, 8, 1, o); }
+    }
     fclose(o);
     return 0;
 }
