@@ -388,9 +388,14 @@ tapgemm_kernel(const TapGemmParams p) {
                         constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, BN), id16 = ptx::make_idesc_f16_f32(128, BN);
                         const int half = p.stages >> 1;
                         const uint32_t ac = a0 + 16;                       // Linear layers read the centre row of a slab
+                        // With a single accumulator buffer the next tile's `tempty` (= this tile's epilogue) cannot
+                        // complete before this tile's `tfull` commit at the end of the stage: wait for it at the top of
+                        // the next tile instead of mid-stage (the bf16x3 loop below has the mid-stage wait and is kept to
+                        // one tile per CTA by launch_layer; tools/simulate_block2_protocol.py).
+                        if (NBUF == 1 && s == 0 && tcount > 0) { ptx::mbar_wait(&tempty[0], (tcount & 1) ^ 1); ptx::tc_fence_after_sync(); }
                         auto probe_next = [&]() {                          // as below: probe the next stage mid-stage
                             if (it + 1 < total_stages) {
-                                if (s == p.stages - 1) {
+                                if (NBUF > 1 && s == p.stages - 1) {
                                     const uint32_t nt = tcount + 1;
                                     ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
                                 }
@@ -1018,7 +1023,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     // With a single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM) the issuer's mid-stage probe of the next
     // tile's `tempty` would wait for an epilogue that cannot start before the current tile's `tfull` commit: a CTA must
     // not get a second tile (tools/simulate_block2_protocol.py).  128 tiles on a B200's 148 SMs: never the case here.
-    if (Cfg::NBUF == 1 && tiles > grid) return DCE_EUNSUPPORTED;
+    if (Cfg::NBUF == 1 && tiles > grid && !F8) return DCE_EUNSUPPORTED;
     if constexpr (CL != 0) {
         // pairs need one tile per CTA, tiles 2j / 2j+1 on the same M-tile, and every pair resident at once
         if (tiles > sm_count || (p.n_tiles & 1)) return DCE_EUNSUPPORTED;

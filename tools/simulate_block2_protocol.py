@@ -236,7 +236,7 @@ def simulate(cl, rounds, real_tiles, seed):
     return True
 
 
-def simulate_tapgemm(cl, mt, nstage, stages, tiles, seed, ksa=4, nbuf=2):
+def simulate_tapgemm(cl, mt, nstage, stages, tiles, seed, ksa=4, nbuf=2, top_of_tile_wait=False):
     """tapgemm_kernel (csrc/dce_tc.cuh): 4 producer warps, MT issuers, 8 epilogue warps per CTA; cl = 2: a CTA pair with
     one tile each that shares the activation slabs by multicast (option "fc_cluster"), cl = 1: the plain kernel with
     `tiles` tiles per CTA.  nbuf = accumulator buffers in TMEM (1 for fc.0, whose two 256-column accumulators fill it).
@@ -245,7 +245,9 @@ def simulate_tapgemm(cl, mt, nstage, stages, tiles, seed, ksa=4, nbuf=2):
     Found with this simulation: with nbuf = 1 and MORE THAN ONE tile per CTA the kernel deadlocks — the issuer probes the
     next tile's `tempty` in the middle of the current tile's last stage, i.e. before it has committed `tfull` for the
     buffer the epilogue must drain first.  fc.0 is the only nbuf = 1 layer and always runs one tile per CTA on a B200
-    (128 tiles, 148 SMs); launch_layer() now refuses the combination instead of hanging on a smaller device."""
+    (128 tiles, 148 SMs); launch_layer() now refuses the combination instead of hanging on a smaller device.
+    top_of_tile_wait = True is the repaired order the F8 issue loop uses: with one buffer, `tempty` is awaited at the
+    top of the next tile."""
     rng = random.Random(seed)
     ncta = cl
     NA, SLABB, BB = mt * 2 * ksa, 2080, 32768
@@ -307,11 +309,14 @@ def simulate_tapgemm(cl, mt, nstage, stages, tiles, seed, ksa=4, nbuf=2):
             buf = tcount % nbuf
             for s in range(stages):
                 slot = it % nstage
+                if top_of_tile_wait and nbuf == 1 and s == 0 and tcount > 0:
+                    while not c.tempty[0].ready(tcount - 1, (tcount & 1) ^ 1):
+                        yield
                 assert all(v == it for v in c.slot_stage[slot]), f"cta{c.rank}: MMAs of stage {it} issued on {c.slot_stage[slot]}"
                 c.slot_readers[slot] += 1
                 yield
                 if it + 1 < total:
-                    if s == stages - 1:
+                    if s == stages - 1 and not (top_of_tile_wait and nbuf == 1):
                         nt = tcount + 1
                         while not c.tempty[nt % nbuf].ready(nt // nbuf - 1, ((nt // nbuf) & 1) ^ 1):
                             yield
@@ -370,8 +375,9 @@ def check_tapgemm(runs=40, seed=0):
     for _ in range(runs):
         cl = rng.choice([1, 2])
         mt, nstage, nbuf = rng.choice([(2, 3, 1), (1, 6, 2), (2, 3, 2), (2, 4, 2)])     # fc.0, fc.3, conv3, conv4 configurations
-        tiles = 1 if (cl == 2 or nbuf == 1) else rng.choice([1, 2, 3, 4])
-        simulate_tapgemm(cl, mt, nstage, rng.choice([4, 7, 12]), tiles, rng.randrange(1 << 30), nbuf=nbuf)
+        fixed = nbuf == 1 and cl == 1 and rng.random() < 0.5           # the F8 loop's order: any number of tiles with one buffer
+        tiles = rng.choice([1, 2, 3, 4]) if (fixed or (cl == 1 and nbuf > 1)) else 1
+        simulate_tapgemm(cl, mt, nstage, rng.choice([4, 7, 12]), tiles, rng.randrange(1 << 30), nbuf=nbuf, top_of_tile_wait=fixed)
     return runs
 
 
