@@ -18,6 +18,7 @@ One JSON line on stdout (rank 0):
   roofline     dominant kernel: algorithmic FLOPs / its CUDA-event duration vs measured bf16 peak
   cpu_baseline the oracle (torch CPU restatement of the reference forward) on this box's host cores
   latency_b1   BASELINE.json's second headline: p50 per-window microseconds at batch 1 (graph replay)
+  torch_eager_gpu  the same module's stock PyTorch layers in eager mode on the same GPU (informational)
 --impl reference times that CPU path alone, same metric/config.
 """
 from __future__ import annotations
@@ -236,6 +237,43 @@ def dominant_kernel(profile_runs):
     return per_step, launches
 
 
+def torch_eager_gpu(dev, x, ours_logits, steps: int = 20):
+    """the stock PyTorch layers of the same model (what the reference runs on a GPU: cuDNN / cuBLAS eager
+    kernels, PyTorch's default TF32 policy) on the same B200, same batch, CUDA-event timed.  Informational — it is not
+    the reference arm (the reference ships no GPU kernel of its own) — and never allowed to fail the bench."""
+    try:
+        import torch
+        import deep_contact_estimator_b200 as dce
+        from deep_contact_estimator_b200 import synth
+        model = dce.contact_cnn()
+        model.load_state_dict(synth.make_params(0))
+        model = model.eval().to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                y = model._forward_torch(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                y = model._forward_torch(x)
+                pred = torch.max(y, 1)[1]
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        num = (y - ours_logits).abs().amax(dim=1)
+        den = ours_logits.abs().amax(dim=1)
+        return {"value": x.shape[0] / (ms * 1e-3), "unit": "windows/s", "ms_per_step": ms, "steps": steps,
+                "what": "stock nn.Conv1d / nn.Linear layers of the same module in PyTorch eager mode on this GPU, "
+                        "forward + argmax, inputs resident",
+                "flags": {"cudnn.allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                          "cuda.matmul.allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                          "torch": torch.__version__},
+                "normwise_diff_vs_this_path": float((num / den).max()),
+                "classes_equal_to_this_path": bool((pred == ours_logits.argmax(1)).all())}
+    except Exception as e:                                    # pragma: no cover - informational only
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def kernel_flops(name: str) -> int:
     """Algorithmic FLOPs per window a kernel covers, from its profiler name (dce_forward_profile): a kernel's name
     lists the layers it fuses (`tc_block1` = conv1 + conv2, `tc_block2` = conv3 + conv4, `tc_fc2_fc3` = fc.3 + fc.6)."""
@@ -370,6 +408,7 @@ def main():
         return
 
     latency = gpu_latency_b1(eng, dev)
+    eager = torch_eager_gpu(dev, xs[0], eng.classify(xs[0], want_logits=True)[0])
     peaks, peak_src = load_peaks()
     dom = max(per_kernel_ms, key=per_kernel_ms.get) if per_kernel_ms else None
     roofline = None
@@ -416,7 +455,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * 32400, "d2h_bytes_per_step": B * 8,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "api": "ContactEngine.classify_host (pinned host windows -> host cls+bits)"},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "latency_b1": latency,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "latency_b1": latency, "torch_eager_gpu": eager,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
