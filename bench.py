@@ -133,7 +133,8 @@ def gpu_latency_b1(eng, dev, calls: int = 500):
     pinned host memory.
       host_us   wall clock of step() (graph launch -> results visible on the host)
       gpu_us    CUDA events around one graph launch on an idle stream (includes launch latency)
-      gpu_us_back_to_back   `calls` launches queued without waiting / calls: the device time one step occupies"""
+      gpu_us_back_to_back   `calls` launches queued without waiting / calls: the device time one step occupies
+      host_us_*_at_1khz     host_us with one step per millisecond (the GPU idles between steps, as in the control loop)"""
     import numpy as np
     import torch
     from deep_contact_estimator_b200 import synth
@@ -157,9 +158,20 @@ def gpu_latency_b1(eng, dev, calls: int = 500):
     b.record(run.stream)
     b.synchronize()
     b2b = a.elapsed_time(b) * 1e3 / calls
+    # the same call paced at the 1 kHz of the control loop (BASELINE configs[4]): the GPU idles ~960 us between steps
+    paced = []
+    t_next = time.perf_counter()
+    for _ in range(300):
+        t_next += 1e-3
+        while time.perf_counter() < t_next:
+            pass
+        t0 = time.perf_counter()
+        run.step()
+        paced.append((time.perf_counter() - t0) * 1e6)
     return {"gpu_us_p50": float(np.percentile(gpu, 50)), "gpu_us_p99": float(np.percentile(gpu, 99)),
             "gpu_us_back_to_back": b2b,
             "host_us_p50": float(np.percentile(host, 50)), "host_us_p99": float(np.percentile(host, 99)),
+            "host_us_p50_at_1khz": float(np.percentile(paced, 50)), "host_us_p99_at_1khz": float(np.percentile(paced, 99)),
             "calls": calls, "launches_per_call": run.launches, "bits": run.bits_host.tolist(),
             "what": "batch=1 through ContactEngine.latency_runner().step(): one graph launch of the fused latency kernel, which reads the "
                     "window (32.4 KB) from pinned host memory and writes class + contact bits to pinned host memory"}
