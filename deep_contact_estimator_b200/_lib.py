@@ -19,7 +19,8 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "dce.h")
 DCE_OK = 0
 DCE_PREC_FP32 = 0
 DCE_PREC_BF16X3 = 1
-PRECISIONS = {"fp32": DCE_PREC_FP32, "bf16x3": DCE_PREC_BF16X3}
+DCE_PREC_F16F8 = 2            # experimental (include/dce.h): fp16 + e4m3 corrections, not yet run on a GPU
+PRECISIONS = {"fp32": DCE_PREC_FP32, "bf16x3": DCE_PREC_BF16X3, "f16f8": DCE_PREC_F16F8}
 
 _lib = None
 

@@ -143,7 +143,7 @@ int check_common(const dce_weights* w, const void* ws, size_t ws_bytes, int64_t 
     if (!w) return DCE_EINVAL;
     if (!w->packed) return DCE_ENOTPACKED;
     if (n < 0) return DCE_EINVAL;
-    if (precision != DCE_PREC_FP32 && precision != DCE_PREC_BF16X3) return DCE_EINVAL;
+    if (precision != DCE_PREC_FP32 && precision != DCE_PREC_BF16X3 && precision != DCE_PREC_F16F8) return DCE_EINVAL;
     if (n > 0) {
         if (!ws) return DCE_EINVAL;
         if ((uintptr_t)ws % 256) return DCE_EALIGN;
@@ -232,7 +232,7 @@ size_t dce_workspace_bytes(int64_t max_windows, int precision) {
     if (precision == DCE_PREC_FP32) {
         const int64_t n = max_windows < kChunkFp32 ? max_windows : kChunkFp32;
         need = fp32_workspace(n).end;
-    } else if (precision == DCE_PREC_BF16X3) {
+    } else if (precision == DCE_PREC_BF16X3 || precision == DCE_PREC_F16F8) {
         need = dce::tc::workspace_bytes(max_windows);
     } else {
         return 0;
@@ -277,7 +277,8 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
         dce::tc::BiasPtrs bp;
         for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
         bp.w3 = at<float>(w, L.f3t); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
-        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx);
+        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx,
+                          precision == DCE_PREC_F16F8);
     }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
     return rc;

@@ -54,9 +54,13 @@ inline int launch_block2_cluster(Ctx& ctx, const char* name, int sm_count, const
 // pointers into the fp32 section of the packed buffer, passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
 
+// f16f8_call: this call asked for DCE_PREC_F16F8 (fp16 + e4m3 everywhere) — same as the "fc_f16f8" = 1, "conv_f16f8" = 2
+// options, but per call instead of process-wide.
 inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
-               int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+               int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx,
+               bool f16f8_call = false) {
     cudaStream_t s = ctx.stream;
+    const int opt_fc8 = f16f8_call ? 1 : fc_f16f8_flag(), opt_conv8 = f16f8_call ? 2 : conv_f16f8_flag();
     {
         static DeviceOnce fc3_once;
         if (auto first_ = fc3_once.need()) {
@@ -80,8 +84,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         int rc;
         TapGemmParams p{};
         const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
-        const bool f8 = fc_f16f8_flag() && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
-        const bool f8c = f8 && conv_f16f8_flag() && fuse_block1_flag();
+        const bool f8 = opt_fc8 && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
+        const bool f8c = f8 && opt_conv8 && fuse_block1_flag();
         const float* scales = reinterpret_cast<const float*>(buf + L.scales);
         if (stream_mode) {
             static DeviceOnce st_once;
@@ -114,7 +118,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (f8c && conv_f16f8_flag() >= 2) {            // conv1 / conv2 themselves in the fp16 + e4m3 format
+            if (f8c && opt_conv8 >= 2) {                    // conv1 / conv2 themselves in the fp16 + e4m3 format
                 Block1ParamsF8 b8{};
                 static_cast<Block1Params&>(b8) = b;
                 b8.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[10]); b8.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[11]);

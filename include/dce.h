@@ -61,6 +61,9 @@ extern "C" {
 /* arithmetic mode of the forward pass */
 #define DCE_PREC_FP32    0       /* fp32 FFMA kernels (exact-order-free fp32) */
 #define DCE_PREC_BF16X3  1       /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
+#define DCE_PREC_F16F8   2       /* EXPERIMENTAL, not yet run on a GPU: fp16 products + two e4m3 correction products per
+                                    K-step (2 MMA-slot equivalents instead of 3), every layer; the per-call form of the
+                                    "fc_f16f8" = 1 / "conv_f16f8" = 2 options.  Activations saturate at 65504. */
 
 typedef struct dce_weights dce_weights;
 

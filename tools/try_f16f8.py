@@ -45,6 +45,17 @@ for scale in (1.0, 50.0):
               f"classes exact {same}, {eng.last_launches} launches", flush=True)
     set_mode(eng, 0, 0, 0, 0)
 
+# the per-call form: precision "f16f8" (DCE_PREC_F16F8) = fc_f16f8 1 + conv_f16f8 2 without touching the global options
+if "--fc-only" not in sys.argv and "--cluster-only" not in sys.argv:
+    e8 = dce.ContactEngine(synth.make_params(0), dev, "f16f8")
+    x = synth.make_windows(512, seed=1)
+    with torch.no_grad():
+        want = oracle.forward_torch(synth.make_params(0), x)
+    logits, cls, _ = e8.classify(x.to(dev))
+    torch.cuda.synchronize()
+    print(f'precision "f16f8": normwise err {oracle.normwise_rel_err(logits.cpu().numpy(), want.numpy()):.2e}, classes exact '
+          f"{bool((cls.cpu().long() == oracle.argmax_class(want)).all())}", flush=True)
+
 eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 xs = [synth.make_windows(4096, seed=5 + i).to(dev) for i in range(4)]
 
