@@ -54,6 +54,7 @@ _SIGNATURES = {
     "dce_stream_profile": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                    c_int, c_void_p, c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int)]),
     "dce_set_option": (c_int, [c_char_p, c_int]),
+    "dce_f16f8_status": (c_int, [c_void_p, c_void_p, c_int]),
     "dce_debug_read_trace": (c_int, [c_void_p, c_int]),
     "dce_decimal2binary": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dce_accuracy_counts": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -369,6 +369,14 @@ int dce_set_option(const char* key, int value) {
     return DCE_EINVAL;
 }
 
+int dce_f16f8_status(dce_weights* w, uint32_t* host_out, int reset) {
+    if (!w || !host_out) return DCE_EINVAL;
+    unsigned int* d = reinterpret_cast<unsigned int*>(w->buf + w->tc.scales) + dce::tc::kF8StatusWord;
+    DCE_CUDA(cudaMemcpy(host_out, d, 4, cudaMemcpyDeviceToHost));        // synchronises: a diagnostic, not a hot-path call
+    if (reset) DCE_CUDA(cudaMemset(d, 0, 4));
+    return DCE_OK;
+}
+
 int dce_debug_read_trace(long long* host_out, int n) {
     long long* t = dce::tc::block1_trace_ptr();
     if (!t || !host_out || n <= 0 || n > 60 * 16) return DCE_EINVAL;

@@ -70,6 +70,7 @@ struct TapGemmParams {
     long long* trace;            // optional clock64 timeline of CTA 0: [tile][8] (tools/trace_tapgemm.py)
     int dbg;                     // timing ablations (results invalid): 1 = every tile loads the A slabs of tile 0; 2 = skip epilogue stores
     const float* acc_scale;      // F8 kernels: one float, 1 / (the layer's power-of-two weight scale), applied to the accumulator
+    unsigned int* f8_status;     // F8 kernels: range diagnostic word (f8_range_note), or nullptr
 };
 
 struct Tape {
@@ -143,6 +144,16 @@ __host__ __device__ __forceinline__ size_t f8_stage_src(int s, int stages, int p
 // the descriptor's LBO (distance between the two K chunks of one MMA) is 16 * cout in both.
 __host__ __device__ __forceinline__ uint32_t f8_wblk_e4m3(int cout, int img, int tap) { return (uint32_t)((img * 3 + tap) * 32 * cout); }
 __host__ __device__ __forceinline__ uint32_t f8_wblk_f16(int cout, int tap, int kk) { return (uint32_t)((tap * 2 + kk) * 32 * cout); }
+
+// Range diagnostic of the format (dce_f16f8_status): bit `layer` of *status is set when a layer wrote an activation
+// above 224 (the e4m3 image of 2 x saturates, so that element's second correction term is lost: fp16-only accuracy for
+// it), bit 8 + layer when it wrote one above 65504 (the fp16 image itself saturated).  Layers: 0 conv1, 1 conv2,
+// 2 conv3, 3 conv4, 4 fc.0.  Thread-local test, an atomic only in the abnormal case.
+__device__ __forceinline__ void f8_range_note(const float* y, int n, unsigned int* status, int layer) {
+    float mx = 0.f;
+    for (int i = 0; i < n; ++i) mx = fmaxf(mx, y[i]);
+    if (status && mx > 224.f) atomicOr(status, (1u << layer) | (mx > 65504.f ? (256u << layer) : 0u));
+}
 
 // NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
 // conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
@@ -582,6 +593,7 @@ tapgemm_kernel(const TapGemmParams p) {
                     return;
                 }
                 if (F8 && EPI == EPI_FC_TAPE) {
+                    f8_range_note(y, 32, p.f8_status, 4);
                     // next layer's operand in the fp16 + e4m3 format: fp16 chunks in tape part 0, the two e4m3 images
                     // (N / 16 chunks each: lo8, then hi8) in tape part 1
 #pragma unroll
@@ -946,7 +958,8 @@ constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // b
                                  {128, 3, 2, 8, 1, 5, 128, 6}};    // block2.2
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
-struct PackedLayout { size_t w[kNumPacked]; size_t scales; size_t begin, end; };   // scales: [kNumPacked][4] floats {sw, 1/sw, absmax bits, -}
+struct PackedLayout { size_t w[kNumPacked]; size_t scales; size_t begin, end; };   // scales: [kNumPacked][4] floats {sw, 1/sw, absmax bits, -}; then the
+constexpr int kF8StatusWord = 60;                                                  // f8 range-status word: 32-bit word 60 of that 256-byte block
 inline PackedLayout make_packed_layout(size_t base) {
     PackedLayout L; L.begin = base; size_t o = base;
     for (int i = 0; i < kNumPacked; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }

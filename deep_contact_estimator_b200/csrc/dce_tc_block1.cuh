@@ -52,6 +52,7 @@ struct Block1Params {
 // with it their generated code — stays exactly what was measured.
 struct Block1ParamsF8 : Block1Params {
     const float* inv_sw1; const float* inv_sw2;   // 1 / (power-of-two weight scale) of conv1 / conv2
+    unsigned int* f8_status;                      // range diagnostic word (f8_range_note), or nullptr
 };
 
 #define B1_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
@@ -481,6 +482,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
             ptx::mbar_wait_relaxed(x1_empty, (k & 1) ^ 1);    // conv2 of the previous tile has finished reading slab1
             if (warp == 4) B1_TRACE(k, 9);
             if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
+            if constexpr ((F8 & 2) != 0) f8_range_note(y, 32, p.f8_status, 0);
             if (F8 & 2) {
                 // slab1: fp16 chunks 0..7, lo8 chunks 8..11, hi8 chunks 12..15
 #pragma unroll
@@ -547,6 +549,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
                 y[i] = valid ? m : 0.f;
             }
+            if constexpr ((F8 & 2) != 0) { if (store) f8_range_note(y, 32, p.f8_status, 1); }
             if ((F8 & 1) && store && !(p.dbg & 1)) {
                 // X2 in the fp16 + e4m3 format: even lane -> the four fp16 chunks of its 32 channels (tape part 0, chunk
                 // h*4 + ..); odd lane -> lo8 chunks h*2 + hh and hi8 chunks 4 + h*2 + hh (tape part 1, 16 channels each)

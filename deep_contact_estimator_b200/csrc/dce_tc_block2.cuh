@@ -35,6 +35,7 @@ struct Block2Params {
     int n_tiles;
     long long* trace;            // optional clock64 timeline of CTA 0 (DCE_TRACE builds)
     const float* inv_sw3; const float* inv_sw4;     // F8IN: 1 / (power-of-two weight scale) of conv3 / conv4
+    unsigned int* f8_status;                        // F8OUT / F8IN: range diagnostic word (f8_range_note), or nullptr
 };
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
@@ -299,6 +300,7 @@ block2_kernel(const Block2Params p) {
                     y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
                 }
                 if (F8IN) {
+                    f8_range_note(y, 32, p.f8_status, 2);
                     // slabB: fp16 chunks 0..15, lo8 chunks 16..23, hi8 chunks 24..31 (16 channels per e4m3 chunk)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
@@ -371,6 +373,7 @@ block2_kernel(const Block2Params p) {
                     // k' = to*128 + channel.  Even lane: the four fp16 chunks (tape part 0, chunk to*16 + channel/8);
                     // odd lane: the e4m3 images (tape part 1: lo8 chunks [0, 296), hi8 chunks [296, 592), chunk to*8 + channel/16)
                     if (store) {
+                        f8_range_note(y, 32, p.f8_status, 3);
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             uint4 fa, fb, lo8, hi8;

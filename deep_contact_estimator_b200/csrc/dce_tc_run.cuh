@@ -87,6 +87,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         const bool f8 = opt_fc8 && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
         const bool f8c = f8 && opt_conv8 && fuse_block1_flag();
         const float* scales = reinterpret_cast<const float*>(buf + L.scales);
+        unsigned int* f8_status = reinterpret_cast<unsigned int*>(const_cast<char*>(buf) + L.scales) + kF8StatusWord;
         if (stream_mode) {
             static DeviceOnce st_once;
             if (auto first_ = st_once.need()) {
@@ -122,7 +123,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
                 Block1ParamsF8 b8{};
                 static_cast<Block1Params&>(b8) = b;
                 b8.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[10]); b8.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[11]);
-                b8.inv_sw1 = scales + 10 * 4 + 1; b8.inv_sw2 = scales + 11 * 4 + 1;
+                b8.inv_sw1 = scales + 10 * 4 + 1; b8.inv_sw2 = scales + 11 * 4 + 1; b8.f8_status = f8_status;
                 if (stream_mode)
                     DCE_KL(ctx, "tc_block1_stream_f16f8", { cudaError_t le_ = launch_pdl(block1_kernel<true, 3>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b8); (void)le_; });
                 else
@@ -182,6 +183,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
                 b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[12]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[13]);
                 b.inv_sw3 = scales + 12 * 4 + 1; b.inv_sw4 = scales + 13 * 4 + 1;
             }
+            b.f8_status = f8 ? f8_status : nullptr;
             if ((cl == 2 || cl == 4) && (f8c || !f8)) {
                 rc = f8c ? (cl == 2 ? launch_block2_cluster<true, true, 2>(ctx, "tc_block2_f16f8_cl2", sm_count, b)
                                     : launch_block2_cluster<true, true, 4>(ctx, "tc_block2_f16f8_cl4", sm_count, b))
@@ -248,7 +250,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.trace = (tapgemm_trace_layer() == 4) ? block1_trace_ptr() : nullptr;
         const bool fcl = fc_cluster_flag() == 2;
         if (f8) {
-            p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[8]); p.acc_scale = scales + 8 * 4 + 1;
+            p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[8]); p.acc_scale = scales + 8 * 4 + 1; p.f8_status = f8_status;
             rc = fcl ? launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1, 2>(ctx, "tc_fc1_f16f8_cl2", sm_count, p) : DCE_EUNSUPPORTED;
             if (rc == DCE_EUNSUPPORTED) rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1_f16f8", sm_count, p);
         } else {

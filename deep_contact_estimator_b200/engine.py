@@ -344,6 +344,15 @@ class ContactEngine:
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
         return LatencyRunner(self, n, want_logits, use_graph)
 
+    def f16f8_status(self, reset: bool = True) -> int:
+        """Range diagnostic of the experimental "f16f8" arithmetic (``dce_f16f8_status``): 0 = every activation
+        since the last reset stayed inside the range its error model assumes; bit l = layer l (0 conv1 .. 4 fc.0)
+        wrote a value above 224, bit 8 + l above 65504.  Synchronises the device."""
+        out = ctypes.c_uint32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dce_f16f8_status(self._handle, ctypes.byref(out), 1 if reset else 0), "dce_f16f8_status")
+        return int(out.value)
+
     # -- small helpers on the same ABI ------------------------------------------
     def decimal2binary(self, x: torch.Tensor) -> torch.Tensor:
         flat = x.reshape(-1).to(torch.int64).contiguous()

@@ -200,6 +200,15 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  * Returns DCE_EINVAL for an unknown key (or an unsupported value).
  */
 DCE_API int dce_set_option(const char *key, int value);
+
+/*
+ * Range diagnostic of the experimental fp16 + e4m3 arithmetic (DCE_PREC_F16F8 / "fc_f16f8"): a word the kernels of
+ * that mode OR into.  Bit l (l = 0 conv1, 1 conv2, 2 conv3, 3 conv4, 4 fc.0): layer l wrote an activation above 224,
+ * whose second correction term is lost (fp16-only accuracy for that element); bit 8 + l: above 65504, the value
+ * itself saturated.  0 = the mode's error model held for everything classified since the last reset.  Synchronises
+ * the device (a diagnostic, not a hot-path call); `reset` != 0 clears the word after reading it.
+ */
+DCE_API int dce_f16f8_status(dce_weights *w, uint32_t *host_out, int reset);
 /* "block1_trace" armed: copy the first n clock64 samples ([tile][16 events]) of CTA 0 to the host. */
 DCE_API int dce_debug_read_trace(long long *host_out, int n);
 

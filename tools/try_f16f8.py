@@ -42,7 +42,7 @@ for scale in (1.0, 50.0):
         err = oracle.normwise_rel_err(logits.cpu().numpy(), want.numpy())
         same = bool((cls.cpu().long() == oracle.argmax_class(want)).all())
         print(f"logit scale {scale:4.0f}  fc_f16f8={fc} conv_f16f8={conv} block2_cluster={cl} fc_cluster={fcl}: normwise err {err:.2e}, "
-              f"classes exact {same}, {eng.last_launches} launches", flush=True)
+              f"classes exact {same}, {eng.last_launches} launches, range status {eng.f16f8_status():#x}", flush=True)
     set_mode(eng, 0, 0, 0, 0)
 
 # the per-call form: precision "f16f8" (DCE_PREC_F16F8) = fc_f16f8 1 + conv_f16f8 2 without touching the global options
