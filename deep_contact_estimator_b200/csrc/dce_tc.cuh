@@ -155,6 +155,52 @@ __device__ __forceinline__ void f8_range_note(const float* y, int n, unsigned in
     if (status && mx > 224.f) atomicOr(status, (1u << layer) | (mx > 65504.f ? (256u << layer) : 0u));
 }
 
+// The issue plans of the format, as host-callable functions: which operands MMA i of a stage / weight block reads, of
+// which kind, and how it treats the accumulator.  The kernels issue exactly what these return, and
+// tools/host_check_f16f8.cu dumps them so that the numpy emulation executes the SAME plan on real packed bytes.
+struct F8Mma {
+    uint32_t a_off, b_off;   // byte offsets: A relative to the M-tile's stage image (tapgemm) or the slab (fused kernels), B relative to the block
+    uint8_t e4m3;            // 1: kind::f8f6f4, K = 32 (two 16-element chunks); 0: kind::f16, K = 16 (two 8-element chunks)
+    uint8_t mode;            // 0: D = A*B;  1: D += A*B;  2: D = A*B + D * 2^-15 (scale-input-d: the corrections come down to the main scale)
+};
+// tapgemm, Linear layers: MMA i = 0..3 of stage s (stages/2 correction stages, then stages/2 main stages; 64 K-elements each).
+// Stage image of an M-tile: [part 0: 4 slabs][part 1: 4 slabs]; B block: [part 0: 4 chunks][part 1: 4 chunks] of b_tapch bytes.
+__host__ __device__ __forceinline__ F8Mma f8_fc_mma(int s, int stages, int i, uint32_t a_part, uint32_t b_part, uint32_t b_tapch) {
+    F8Mma m;
+    const int half = stages >> 1;
+    if (s < half) {                     // i = 2 kk + product: product 0 = (x - f16 x) * w, 1 = x * (w - f16 w); centre row of the slab: + 16
+        const int kk = i >> 1, prod = i & 1;
+        m.a_off = 16 + prod * a_part + 2 * kk * (130 * 16);
+        m.b_off = prod * b_part + 2 * kk * b_tapch;
+        m.e4m3 = 1;
+        m.mode = (s == 0 && i == 0) ? 0 : 1;
+    } else {                            // 8 consecutive fp16 chunks of A (both parts) and of B
+        m.a_off = 16 + 2 * i * (130 * 16);
+        m.b_off = 2 * i * b_tapch;
+        m.e4m3 = 0;
+        m.mode = (s == half && i == 0) ? 2 : 1;
+    }
+    return m;
+}
+// fused conv kernels: MMA i = 0..1 of tap `tap` of weight block s (half e4m3 blocks, then half fp16 blocks, 32 input channels
+// each); C = channels of the slab, cout = output channels (block = 192 * cout bytes); A offset includes the tap's row shift.
+__host__ __device__ __forceinline__ F8Mma f8_conv_mma(int s, int half, int tap, int i, int C, int cout) {
+    F8Mma m;
+    if (s < half) {                     // i = product: 0 = (x - f16 x) * w (lo8 image, w8 image), 1 = x * (w - f16 w) (hi8, wl8)
+        const F8Dst o = f8_slab_dst(2 * s, C);              // the slab's 16-channel groups 2s, 2s + 1
+        m.a_off = (uint32_t)(i ? o.hi8 : o.lo8) + tap * 16;
+        m.b_off = f8_wblk_e4m3(cout, i, tap);
+        m.e4m3 = 1;
+        m.mode = (s == 0 && tap == 0 && i == 0) ? 0 : 1;
+    } else {                            // i = kk: fp16 chunks 4g + 2kk, 4g + 2kk + 1 of the slab, g = s - half
+        m.a_off = (uint32_t)f8_slab_dst(2 * (s - half) + i, C).f16 + tap * 16;
+        m.b_off = f8_wblk_f16(cout, tap, i);
+        m.e4m3 = 0;
+        m.mode = (s == half && tap == 0 && i == 0) ? 2 : 1;
+    }
+    return m;
+}
+
 // NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
 // conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
 __host__ __device__ __forceinline__ float min_nan(float a, float b) {
@@ -397,8 +443,6 @@ tapgemm_kernel(const TapGemmParams p) {
                     const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
                     if (F8) {
                         constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, BN), id16 = ptx::make_idesc_f16_f32(128, BN);
-                        const int half = p.stages >> 1;
-                        const uint32_t ac = a0 + 16;                       // Linear layers read the centre row of a slab
                         // With a single accumulator buffer the next tile's `tempty` (= this tile's epilogue) cannot
                         // complete before this tile's `tfull` commit at the end of the stage: wait for it at the top of
                         // the next tile instead of mid-stage (the bf16x3 loop below has the mid-stage wait and is kept to
@@ -414,32 +458,18 @@ tapgemm_kernel(const TapGemmParams p) {
                                 ptx::tc_fence_after_sync();
                             }
                         };
-                        if (s < half) {
-                            // corrections: (x - f16 x) 2^12 * w 2^3  and  x 2^1 * (w - f16 w) 2^14, K = 32 per MMA
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                const uint64_t da_l = ptx::make_smem_desc(ac + 2 * kk * kSlabBytes, kSlabBytes, 128);
-                                const uint64_t da_h = ptx::make_smem_desc(ac + Cfg::A_PART + 2 * kk * kSlabBytes, kSlabBytes, 128);
-                                const uint64_t db_h = ptx::make_smem_desc(b0 + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
-                                const uint64_t db_l = ptx::make_smem_desc(b0 + Cfg::B_PART + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
-                                if (leader) {
-                                    ptx::umma_e4m3_ss(d, da_l, db_h, id8, (s == 0 && kk == 0) ? 0u : 1u);
-                                    ptx::umma_e4m3_ss(d, da_h, db_l, id8, 1u);
-                                }
-                                if (kk == 0) probe_next();
+                        for (int i = 0; i < 4; ++i) {
+                            // sweep 1: (x - f16 x) 2^12 * w 2^3 and x 2^1 * (w - f16 w) 2^14, K = 32 per MMA; sweep 2: the fp16 products
+                            const F8Mma m = f8_fc_mma(s, p.stages, i, Cfg::A_PART, Cfg::B_PART, Cfg::B_TAPCH);
+                            const uint64_t da = ptx::make_smem_desc(a0 + m.a_off, kSlabBytes, 128);
+                            const uint64_t db = ptx::make_smem_desc(b0 + m.b_off, Cfg::B_TAPCH, 128);
+                            if (leader) {
+                                if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
+                                else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
+                                else ptx::umma_bf16_ss(d, da, db, id16, 1u);              // kind::f16; the operand format is in the idesc
                             }
-                        } else {
-                            // main products: the stage holds 8 consecutive fp16 chunks of A (both "parts") and of B
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint64_t da = ptx::make_smem_desc(ac + 2 * kk * kSlabBytes, kSlabBytes, 128);
-                                const uint64_t db = ptx::make_smem_desc(b0 + 2 * kk * Cfg::B_TAPCH, Cfg::B_TAPCH, 128);
-                                if (leader) {
-                                    if (s == half && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
-                                    else ptx::umma_bf16_ss(d, da, db, id16, 1u);          // kind::f16; the operand format is in the idesc
-                                }
-                                if (kk == 1) probe_next();
-                            }
+                            if (i == 1) probe_next();
                         }
                     } else {
 #pragma unroll

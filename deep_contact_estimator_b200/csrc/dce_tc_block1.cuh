@@ -371,26 +371,18 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 if ((F8 & 2) && ptx::elect_one()) {
                     // weight image: [e4m3 block g0][e4m3 g1][fp16 g0][fp16 g1], 12288 B each (32 input channels, 3 taps)
                     constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, 64), id16 = ptx::make_idesc_f16_f32(128, 64);
+                    // four blocks (e4m3 g0, e4m3 g1, fp16 g0, fp16 g1) x 3 taps x 2 MMAs: the plan of f8_conv_mma with half = 2
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-#pragma unroll
-                        for (int tap = 0; tap < 3; ++tap) {
-                            const F8Dst o = f8_slab_dst(2 * g, 64);              // the slab's 16-channel groups 2g, 2g + 1
-                            const uint32_t a_l = a_base + (uint32_t)o.lo8 + tap * 16, a_h = a_base + (uint32_t)o.hi8 + tap * 16;
-                            const uint32_t b_h = w_base + g * 12288 + f8_wblk_e4m3(64, 0, tap), b_l = w_base + g * 12288 + f8_wblk_e4m3(64, 1, tap);
-                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_l, kSlabBytes, 128), ptx::make_smem_desc(b_h, 1024, 128), id8, (g | tap) ? 1u : 0u);
-                            ptx::umma_e4m3_ss(d, ptx::make_smem_desc(a_h, kSlabBytes, 128), ptx::make_smem_desc(b_l, 1024, 128), id8, 1u);
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
+                    for (int s = 0; s < 4; ++s) {
 #pragma unroll
                         for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                const uint64_t da = ptx::make_smem_desc(a_base + (uint32_t)f8_slab_dst(2 * g + kk, 64).f16 + tap * 16, kSlabBytes, 128);
-                                const uint64_t db = ptx::make_smem_desc(w_base + (2 + g) * 12288 + f8_wblk_f16(64, tap, kk), 1024, 128);
-                                if ((g | tap | kk) == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
+                            for (int i = 0; i < 2; ++i) {
+                                const F8Mma m = f8_conv_mma(s, 2, tap, i, 64, 64);
+                                const uint64_t da = ptx::make_smem_desc(a_base + m.a_off, kSlabBytes, 128);
+                                const uint64_t db = ptx::make_smem_desc(w_base + s * 12288 + m.b_off, 1024, 128);
+                                if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
+                                else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
                                 else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
                             }
                         }

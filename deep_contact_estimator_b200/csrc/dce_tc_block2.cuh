@@ -168,30 +168,17 @@ block2_kernel(const Block2Params p) {
                 const int half = kch_total >> 2;                   // e4m3 blocks of this conv (= its fp16 blocks)
 #pragma unroll
                 for (int tap = 0; tap < 3; ++tap) {
-                    if (s < half) {
-                        // corrections for input channels [32 s, 32 s + 32): one K = 32 MMA per product
-                        const F8Dst o = f8_slab_dst(2 * s, kch_total * 8);      // the slab's 16-channel groups 2s, 2s + 1
-                        const uint32_t a_l = slab + (uint32_t)o.lo8 + tap * 16;
-                        const uint32_t a_h = slab + (uint32_t)o.hi8 + tap * 16;
-                        const uint64_t da_l = ptx::make_smem_desc(a_l, kSlabBytes, 128);
-                        const uint64_t da_h = ptx::make_smem_desc(a_h, kSlabBytes, 128);
-                        const uint64_t db_h = ptx::make_smem_desc(b0 + f8_wblk_e4m3(128, 0, tap), 2048, 128);
-                        const uint64_t db_l = ptx::make_smem_desc(b0 + f8_wblk_e4m3(128, 1, tap), 2048, 128);
-                        if (leader) {
-                            ptx::umma_e4m3_ss(d, da_l, db_h, id8, (first_stage && tap == 0) ? 0u : 1u);
-                            ptx::umma_e4m3_ss(d, da_h, db_l, id8, 1u);
-                        }
-                    } else {
-                        // main products for the same 32 channels: two K = 16 MMAs
-                        const int g = s - half;
+                    // e4m3 block s < half: the two correction products for input channels [32 s, 32 s + 32), one K = 32 MMA each;
+                    // fp16 block: the main products of channels [32 (s - half), + 32), two K = 16 MMAs (f8_conv_mma)
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t da = ptx::make_smem_desc(slab + (uint32_t)f8_slab_dst(2 * g + kk, kch_total * 8).f16 + tap * 16, kSlabBytes, 128);
-                            const uint64_t db = ptx::make_smem_desc(b0 + f8_wblk_f16(128, tap, kk), 2048, 128);
-                            if (leader) {
-                                if (s == half && tap == 0 && kk == 0) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
-                                else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
-                            }
+                    for (int i = 0; i < 2; ++i) {
+                        const F8Mma m = f8_conv_mma(s, half, tap, i, kch_total * 8, 128);
+                        const uint64_t da = ptx::make_smem_desc(slab + m.a_off, kSlabBytes, 128);
+                        const uint64_t db = ptx::make_smem_desc(b0 + m.b_off, 2048, 128);
+                        if (leader) {
+                            if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
+                            else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
+                            else ptx::umma_bf16_ss(d, da, db, id16, 1u);           // kind::f16; fp16 operands per the idesc
                         }
                     }
                     if (tap == 1 && it + 1 < total_blocks) {

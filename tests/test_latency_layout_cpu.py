@@ -118,4 +118,29 @@ def test_cuda_source_matches_numpy_emulation_byte_for_byte(tmp_path):
         # B-operand offsets inside a conv weight block, as the numpy issuers use them (conv64_mmas / conv_blocks)
         want_tab += [0, 2048, 4096, 6144, 8192, 10240] + [0, 2048, 4096, 6144, 8192, 10240]                 # cout 64: e4m3 [img][tap], fp16 [tap][kk]
         want_tab += [0, 4096, 8192, 12288, 16384, 20480] + [0, 4096, 8192, 12288, 16384, 20480]             # cout 128
-        assert np.array_equal(tab, np.array(want_tab, np.int64))
+        n_tab = len(want_tab)
+        assert np.array_equal(tab[:n_tab], np.array(want_tab, np.int64))
+        plans = tab[n_tab:]
+    # the issue plans dumped from the CUDA source (f8_fc_mma, f8_conv_mma): first they must equal the emulation's own
+    # formulas, then the emulation runs ON them — packed bytes, writers, producer addressing and the kernels' own MMA
+    # plan together must reproduce float64 x @ W^T
+    off = 0
+    dumped = {}
+    for stages, bn in ((148, 256), (64, 128)):
+        k = stages * 4 * 4
+        dumped[("fc", stages, bn)] = plans[off:off + k].reshape(stages, 4, 4); off += k
+    for half, C, cout in ((2, 64, 64), (2, 64, 128), (4, 128, 128)):
+        k = 2 * half * 3 * 2 * 4
+        dumped[("conv", half, C, cout)] = plans[off:off + k].reshape(2 * half, 3, 2, 4); off += k
+    assert off == plans.size
+    for (kind, *cfg), table in dumped.items():
+        for idx in np.ndindex(*table.shape[:-1]):
+            own = emu.fc_plan(idx[0], cfg[0], idx[1], 4 * emu.SLAB, 4 * cfg[1] * 16, cfg[1] * 16) if kind == "fc" \
+                else emu.conv_plan(idx[0], cfg[0], idx[1], idx[2], cfg[1], cfg[2])
+            assert tuple(int(v) for v in table[idx]) == own, (kind, cfg, idx)
+    emu.PLANS.update(dumped)
+    try:
+        e_fc0, e_fc3 = emu.check(rows=2)
+        assert e_fc0 <= 3e-5 and e_fc3 <= 3e-5 and emu.check_block2(windows=2) <= 3e-5 and emu.check_block1(windows=1) <= 4e-5
+    finally:
+        emu.PLANS.clear()

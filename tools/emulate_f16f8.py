@@ -113,6 +113,43 @@ def write_block2_tape(tape, y4):
                         tape["buf"][d16 + tape["kch_stride"]: d16 + tape["kch_stride"] + 16] = f[16:]
 
 
+# Issue plans.  By default computed here with the formulas of f8_fc_mma / f8_conv_mma (csrc/dce_tc.cuh); the CPU test
+# replaces them with the tables tools/host_check_f16f8.cu dumps from the CUDA source, so that the emulated MMAs below
+# execute the kernels' own plan.  A plan entry is (a_off, b_off, e4m3, mode), mode 0 = overwrite, 1 = accumulate,
+# 2 = accumulate after scaling D by 2^-15.
+PLANS = {}
+
+
+def fc_plan(s, stages, i, a_part, b_part, b_tapch):
+    key = ("fc", stages, b_tapch // 16)
+    if key in PLANS:
+        return tuple(int(v) for v in PLANS[key][s][i])
+    half = stages // 2
+    if s < half:
+        kk, prod = i >> 1, i & 1
+        return (16 + prod * a_part + 2 * kk * SLAB, prod * b_part + 2 * kk * b_tapch, 1, 0 if (s == 0 and i == 0) else 1)
+    return (16 + 2 * i * SLAB, 2 * i * b_tapch, 0, 2 if (s == half and i == 0) else 1)
+
+
+def conv_plan(s, half, tap, i, C, cout):
+    key = ("conv", half, C, cout)
+    if key in PLANS:
+        return tuple(int(v) for v in PLANS[key][s][tap][i])
+    if s < half:
+        g16 = 2 * s
+        a = ((C // 8 + C // 16 + g16) if i else (C // 8 + g16)) * SLAB + tap * 16
+        return (a, (i * 3 + tap) * 32 * cout, 1, 0 if (s == 0 and tap == 0 and i == 0) else 1)
+    return (2 * (2 * (s - half) + i) * SLAB + tap * 16, (tap * 2 + i) * 32 * cout, 0, 2 if (s == half and tap == 0 and i == 0) else 1)
+
+
+def apply_mma(D, a, b, mode):
+    if mode == 0:
+        D[:] = 0.0
+    elif mode == 2:
+        D *= 2.0 ** -SCALE_D
+    D += a @ b.T
+
+
 def gather(smem, start, lbo, rows, elem_bytes):
     """Operand of one MMA through its SWIZZLE_NONE K-major descriptor: two 16-byte K chunks, SBO = 128 (row pitch 16)."""
     out = []
@@ -144,26 +181,13 @@ def tile(tape, wpk, m, n, stages, BN, MT):
             st[dst: dst + SLAB] = tape["buf"][src: src + SLAB]
         wsrc = (n * stages + s) * B_BYTES                       # producer: the B block
         st[A_BYTES: A_BYTES + B_BYTES] = wpk[wsrc: wsrc + B_BYTES]
-        for mt in range(MT):                                    # issuers
-            a0, b0 = mt * A_TILE, A_BYTES
-            ac = a0 + 16
-            if s < half:
-                for kk in range(2):
-                    a_l = gather(st, ac + 2 * kk * SLAB, SLAB, 128, 1)
-                    a_h = gather(st, ac + A_PART + 2 * kk * SLAB, SLAB, 128, 1)
-                    b_h = gather(st, b0 + 2 * kk * B_TAPCH, B_TAPCH, BN, 1)
-                    b_l = gather(st, b0 + B_PART + 2 * kk * B_TAPCH, B_TAPCH, BN, 1)
-                    if s == 0 and kk == 0:
-                        D[mt] = 0.0
-                    D[mt] += a_l @ b_h.T
-                    D[mt] += a_h @ b_l.T
-            else:
-                for kk in range(4):
-                    a = gather(st, ac + 2 * kk * SLAB, SLAB, 128, 2)
-                    b = gather(st, b0 + 2 * kk * B_TAPCH, B_TAPCH, BN, 2)
-                    if s == half and kk == 0:
-                        D[mt] *= 2.0 ** -SCALE_D
-                    D[mt] += a @ b.T
+        for mt in range(MT):                                    # issuers: the plan of f8_fc_mma
+            for i in range(4):
+                a_off, b_off, e4m3_, mode = fc_plan(s, stages, i, A_PART, B_PART, B_TAPCH)
+                eb = 1 if e4m3_ else 2
+                a = gather(st, mt * A_TILE + a_off, SLAB, 128, eb)
+                b = gather(st, A_BYTES + b_off, B_TAPCH, BN, eb)
+                apply_mma(D[mt], a, b, mode)
     return D
 
 
@@ -249,20 +273,11 @@ def conv_blocks(slab, wimg, kch_total):
     D = np.zeros((128, 128))
     half, blk = kch_total // 4, 24576
     for s in range(2 * half):
-        b0 = s * blk
         for tap in range(3):
-            if s < half:
-                a_l = (kch_total + 2 * s) * SLAB + tap * 16
-                a_h = a_l + (kch_total // 2) * SLAB
-                D += gather(slab, a_l, SLAB, 128, 1) @ gather(wimg, b0 + tap * 4096, 2048, 128, 1).T
-                D += gather(slab, a_h, SLAB, 128, 1) @ gather(wimg, b0 + 12288 + tap * 4096, 2048, 128, 1).T
-            else:
-                g = s - half
-                for kk in range(2):
-                    if s == half and tap == 0 and kk == 0:
-                        D *= 2.0 ** -SCALE_D
-                    D += gather(slab, (4 * g + 2 * kk) * SLAB + tap * 16, SLAB, 128, 2) @ \
-                        gather(wimg, b0 + tap * 8192 + kk * 4096, 2048, 128, 2).T
+            for i in range(2):                                  # the plan of f8_conv_mma
+                a_off, b_off, e4m3_, mode = conv_plan(s, half, tap, i, kch_total * 8, 128)
+                eb = 1 if e4m3_ else 2
+                apply_mma(D, gather(slab, a_off, SLAB, 128, eb), gather(wimg, s * blk + b_off, 2048, 128, eb), mode)
     return D
 
 
@@ -328,19 +343,12 @@ def check_block2(windows=2, seed=0):
 def conv64_mmas(slab, wimg):
     """conv_mmas of block1_kernel<.., 3>: 64 -> 64 channels, resident image [e4m3 g0][e4m3 g1][fp16 g0][fp16 g1]."""
     D = np.zeros((128, 64))
-    for g in range(2):
+    for s in range(4):
         for tap in range(3):
-            a_l = (8 + 2 * g) * SLAB + tap * 16
-            b_h = g * 12288 + tap * 2048
-            D += gather(slab, a_l, SLAB, 128, 1) @ gather(wimg, b_h, 1024, 64, 1).T
-            D += gather(slab, a_l + 4 * SLAB, SLAB, 128, 1) @ gather(wimg, b_h + 6144, 1024, 64, 1).T
-    for g in range(2):
-        for tap in range(3):
-            for kk in range(2):
-                if (g | tap | kk) == 0:
-                    D *= 2.0 ** -SCALE_D
-                D += gather(slab, (4 * g + 2 * kk) * SLAB + tap * 16, SLAB, 128, 2) @ \
-                    gather(wimg, (2 + g) * 12288 + tap * 4096 + kk * 2048, 1024, 64, 2).T
+            for i in range(2):                                  # the plan of f8_conv_mma with half = 2
+                a_off, b_off, e4m3_, mode = conv_plan(s, 2, tap, i, 64, 64)
+                eb = 1 if e4m3_ else 2
+                apply_mma(D, gather(slab, a_off, SLAB, 128, eb), gather(wimg, s * 12288 + b_off, 1024, 64, eb), mode)
     return D
 
 

@@ -73,6 +73,25 @@ int main(int argc, char** argv) {
         for (int tap = 0; tap < 3; ++tap)
             for (int kk = 0; kk < 2; ++kk) { const unsigned long long v = dce::tc::f8_wblk_f16(cout_, tap, kk); fwrite(&v, 8, 1, o); }
     }
+    // issue plans, 4 x uint64 per MMA {a_off, b_off, e4m3, mode}: f8_fc_mma for fc.0 (148 stages, BN 256) and fc.3 (64, BN 128)
+    // as [s][i]; f8_conv_mma for block1 (half 2, C 64, cout 64), conv3 (2, 64, 128), conv4 (4, 128, 128) as [s][tap][i]
+    const int fc_cfg[2][2] = {{148, 256}, {64, 128}};
+    for (auto& c : fc_cfg)
+        for (int s = 0; s < c[0]; ++s)
+            for (int i = 0; i < 4; ++i) {
+                const dce::tc::F8Mma m = dce::tc::f8_fc_mma(s, c[0], i, 4 * 130 * 16, 4 * c[1] * 16, c[1] * 16);
+                const unsigned long long v[4] = {m.a_off, m.b_off, m.e4m3, m.mode};
+                fwrite(v, 8, 4, o);
+            }
+    const int cv_cfg[3][3] = {{2, 64, 64}, {2, 64, 128}, {4, 128, 128}};
+    for (auto& c : cv_cfg)
+        for (int s = 0; s < 2 * c[0]; ++s)
+            for (int tap = 0; tap < 3; ++tap)
+                for (int i = 0; i < 2; ++i) {
+                    const dce::tc::F8Mma m = dce::tc::f8_conv_mma(s, c[0], tap, i, c[1], c[2]);
+                    const unsigned long long v[4] = {m.a_off, m.b_off, m.e4m3, m.mode};
+                    fwrite(v, 8, 4, o);
+                }
     fclose(o);
     return 0;
 }
