@@ -14,6 +14,7 @@
 // Part 2 (rate): cycles per 32 K-elements of one M = 128 tile for the three issue patterns, all SMs busy.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_f16f8 umma_f16f8.cu && ./umma_f16f8
+//   ./umma_f16f8 --cpu   prints only the errors exact arithmetic on the rounded operands gives (no GPU needed)
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -169,7 +170,7 @@ static float gauss() {
     return sqrtf(-2.f * logf(u1)) * cosf(6.2831853f * u2);
 }
 
-static void numerics(int K, int N, bool relu_inputs) {
+static void numerics(int K, int N, bool relu_inputs, bool cpu_only) {
     std::vector<float> x((size_t)128 * K), w((size_t)N * K);
     const float bound = 1.f / sqrtf((float)K);
     float wmax = 0.f;
@@ -195,15 +196,56 @@ static void numerics(int K, int N, bool relu_inputs) {
             put(b8h, N, n, k, h_e4m3(ldexpf(vs, kEwH)));
             put(b8l, N, n, k, h_e4m3(ldexpf(vs - f_f16(hh), kEwL)));
         }
-    Images bx{upload(a_bh), upload(a_bl), upload(b_bh), upload(b_bl), nullptr, nullptr, nullptr, nullptr, K, N};
-    Images fx{upload(a_h), nullptr, upload(b_h), nullptr, upload(a8l), upload(a8h), upload(b8h), upload(b8l), K, N};
-    float* dD; cudaMalloc(&dD, (size_t)128 * N * 4);
+    Images bx{}, fx{};
+    float* dD = nullptr;
+    if (!cpu_only) {
+    bx = Images{upload(a_bh), upload(a_bl), upload(b_bh), upload(b_bl), nullptr, nullptr, nullptr, nullptr, K, N};
+    fx = Images{upload(a_h), nullptr, upload(b_h), nullptr, upload(a8l), upload(a8h), upload(b8h), upload(b8l), K, N};
+    cudaMalloc(&dD, (size_t)128 * N * 4);
+    }
     std::vector<double> ref((size_t)128 * N);
     for (int r = 0; r < 128; ++r)
         for (int n = 0; n < N; ++n) {
             double s = 0; for (int k = 0; k < K; ++k) s += (double)x[(size_t)r * K + k] * w[(size_t)n * K + k];
             ref[(size_t)r * N + n] = s;
         }
+    // what the rounded operands give in exact arithmetic (double accumulation): the error the GPU result should show,
+    // up to fp32 accumulation (~1e-7).  Computed from the same rounding functions the images were built with.
+    double model[3] = {0, 0, 0};
+    {
+        std::vector<float> xh((size_t)128 * K), xl(xh.size()), xf(xh.size()), x8l(xh.size()), x8h(xh.size());
+        std::vector<float> wh((size_t)N * K), wl(wh.size()), wf(wh.size()), w8h(wh.size()), w8l(wh.size());
+        auto e4 = [](float v) { return (float)__half2float(__nv_cvt_fp8_to_halfraw(h_e4m3(v), __NV_E4M3)); };
+        for (size_t i = 0; i < xh.size(); ++i) {
+            const float v = x[i];
+            xh[i] = f_bf16(h_bf16(v)); xl[i] = f_bf16(h_bf16(v - xh[i]));
+            xf[i] = f_f16(h_f16(v)); x8l[i] = e4(ldexpf(v - xf[i], kExL)); x8h[i] = e4(ldexpf(v, kExH));
+        }
+        for (size_t i = 0; i < wh.size(); ++i) {
+            const float v = w[i], vs = v * sw;
+            wh[i] = f_bf16(h_bf16(v)); wl[i] = f_bf16(h_bf16(v - wh[i]));
+            wf[i] = f_f16(h_f16(vs)); w8h[i] = e4(ldexpf(vs, kEwH)); w8l[i] = e4(ldexpf(vs - wf[i], kEwL));
+        }
+        for (int r = 0; r < 128; ++r) {
+            double num[3] = {0, 0, 0}, den = 0;
+            for (int n = 0; n < N; ++n) {
+                double b3 = 0, corr = 0, main16 = 0;
+                for (int k = 0; k < K; ++k) {
+                    const size_t a = (size_t)r * K + k, b = (size_t)n * K + k;
+                    b3 += (double)xh[a] * wl[b] + (double)xl[a] * wh[b] + (double)xh[a] * wh[b];
+                    corr += (double)x8l[a] * w8h[b] + (double)x8h[a] * w8l[b];
+                    main16 += (double)xf[a] * wf[b];
+                }
+                const double want = ref[(size_t)r * N + n];
+                num[0] = fmax(num[0], fabs(b3 - want));
+                num[1] = fmax(num[1], fabs((main16 + ldexp(corr, -kScaleD)) / sw - want));
+                num[2] = fmax(num[2], fabs(main16 / sw - want));
+                den = fmax(den, fabs(want));
+            }
+            for (int m = 0; m < 3; ++m) model[m] = fmax(model[m], num[m] / den);
+        }
+    }
+    int which = 0;
     auto report = [&](const char* name, float post) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("  %-10s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
@@ -215,13 +257,18 @@ static void numerics(int K, int N, bool relu_inputs) {
             for (int n = 0; n < N; ++n) { num = fmax(num, fabs(d[(size_t)r * N + n] * post - ref[(size_t)r * N + n])); den = fmax(den, fabs(ref[(size_t)r * N + n])); }
             worst = fmax(worst, num / den);
         }
-        printf("  %-10s max over rows of max|d| / max|ref| = %.3e\n", name, worst);
+        printf("  %-10s max over rows of max|d| / max|ref| = %.3e   (exact arithmetic on the rounded operands: %.3e)\n",
+               name, worst, model[which++]);
     };
+    printf("K = %d, N = %d, %s inputs\n", K, N, relu_inputs ? "ReLU(N(0,1))" : "N(0,1)");
+    if (cpu_only) {
+        printf("  exact arithmetic on the rounded operands: bf16x3 %.3e   f16+e4m3 %.3e   f16 %.3e\n", model[0], model[1], model[2]);
+        return;
+    }
     constexpr int kSmem = 4 * 32768;
     cudaFuncSetAttribute(gemm_check<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(gemm_check<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(gemm_check<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    printf("K = %d, N = %d, %s inputs\n", K, N, relu_inputs ? "ReLU(N(0,1))" : "N(0,1)");
     gemm_check<0><<<1, 128, kSmem>>>(bx, dD); report("bf16x3", 1.f);
     gemm_check<1><<<1, 128, kSmem>>>(fx, dD); report("f16+e4m3", 1.f / sw);
     gemm_check<2><<<1, 128, kSmem>>>(fx, dD); report("f16", 1.f / sw);
@@ -292,11 +339,13 @@ static double run_rate(int N, int pattern, long long* d_out) {
     return (double)h / reps;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool cpu_only = argc > 1 && !strcmp(argv[1], "--cpu");      // the model column alone: runs without a GPU
     srand(1);
-    numerics(512, 128, false);
-    numerics(4736, 256, true);       // fc.0's contraction length, post-ReLU operands
-    numerics(192, 64, false);        // a conv-sized contraction
+    numerics(512, 128, false, cpu_only);
+    numerics(4736, 256, true, cpu_only);       // fc.0's contraction length, post-ReLU operands
+    numerics(192, 64, false, cpu_only);        // a conv-sized contraction
+    if (cpu_only) return 0;
     long long* d_out; cudaMalloc(&d_out, 8);
     printf("cycles per 32 K-elements of one M = 128 tile (148 CTAs)\n");
     for (int N : {64, 128, 256})
