@@ -409,11 +409,17 @@ class LatencyRunner:
         ws = torch.zeros(eng.lib.dce_workspace_bytes(n, _lib.PRECISIONS[eng.precision]), dtype=torch.uint8, device=dev)
         P = ContactEngine._p
 
+        # pinned host pointers are device-accessible under unified addressing: the kernel dereferences them directly.
+        # The buffers live as long as the runner, so the ctypes arguments are built once (a few microseconds per step
+        # of a ~40 us call); only the handle is looked up per call, so a closed engine fails cleanly.
+        forward = eng.lib.dce_forward
+        rest = (P(self.x_host), n, P(self.logits_host), P(self.cls_host), P(self.bits_host), P(ws), ws.numel(),
+                _lib.PRECISIONS[eng.precision], ctypes.c_void_p(self.stream.cuda_stream))
+
         def launch():
-            # pinned host pointers are device-accessible under unified addressing: the kernel dereferences them directly
-            rc = eng.lib.dce_forward(eng._handle, P(self.x_host), n, P(self.logits_host), P(self.cls_host), P(self.bits_host),
-                                     P(ws), ws.numel(), _lib.PRECISIONS[eng.precision], ctypes.c_void_p(self.stream.cuda_stream))
-            _lib.check(rc, "dce_forward")
+            rc = forward(eng._handle, *rest)
+            if rc:
+                _lib.check(rc, "dce_forward")
 
         self._launch = launch
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
