@@ -1,6 +1,6 @@
 // Runs the REAL fp16 + e4m3 operand conversion (split16_f16f8) and weight packers (pack_b_f16f8_elem,
 // pack_conv_f16f8_elem) of csrc/dce_tc.cuh ON THE HOST — they are __host__ __device__ — and writes their bytes to a
-// file, so tests/test_latency_layout_cpu.py can compare the CUDA source byte for byte with the numpy emulation
+// file, so tests/test_f16f8_models_cpu.py can compare the CUDA source byte for byte with the numpy emulation
 // (tools/emulate_f16f8.py) whose layouts the emulated MMAs consume.  No GPU, no CUDA call.
 //   nvcc -std=c++17 -O1 -o /tmp/host_check_f16f8 tools/host_check_f16f8.cu && /tmp/host_check_f16f8 in.bin out.bin
 // in.bin : int32 header {n_split, signed, fc_n, fc_k, fc_bn, fc_kind, conv_cout, conv_cin, conv_cin_pad}, float sw_fc, float sw_conv,
