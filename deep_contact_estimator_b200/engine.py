@@ -49,6 +49,11 @@ class ContactEngine:
         _lib.check(self.lib.dce_weights_create(ctypes.byref(self._handle), self.device.index), "dce_weights_create")
         self._workspace: Optional[torch.Tensor] = None
         self.last_launches = 0
+        # precision "f16f8" only: after every classify() / stream() read the kernels' range word (one device
+        # synchronisation per call) and redo the call in bf16x3 when an activation left the range the fp16 + e4m3
+        # error model assumes.  Off by default: the check costs the asynchrony of the call.
+        self.guard = os.environ.get("DCE_F16F8_GUARD", "0") == "1"
+        self.fallbacks = 0
         if params is not None:
             self.pack(params)
 
@@ -139,6 +144,13 @@ class ContactEngine:
                                       ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_forward")
         self.last_launches = self.lib.dce_last_launch_count()
+        if self.guard and self.precision == "f16f8" and self.f16f8_status(reset=True):
+            self.fallbacks += 1
+            with torch.cuda.device(self.device):
+                rc = self.lib.dce_forward(self._handle, self._p(x), n, self._p(logits), self._p(cls), self._p(bits),
+                                          self._p(ws), ws.numel(), _lib.PRECISIONS["bf16x3"], ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "dce_forward")
+            self.last_launches += self.lib.dce_last_launch_count()
         return logits, cls, bits
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -286,6 +298,14 @@ class ContactEngine:
                                      _lib.PRECISIONS[self.precision], ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_stream")
         self.last_launches = self.lib.dce_last_launch_count()
+        if self.guard and self.precision == "f16f8" and self.f16f8_status(reset=True):
+            self.fallbacks += 1
+            with torch.cuda.device(self.device):
+                rc = self.lib.dce_stream(self._handle, self._p(data), T, first_window, n_windows,
+                                         self._p(logits), self._p(cls), self._p(bits), self._p(ws), ws.numel(),
+                                         _lib.PRECISIONS["bf16x3"], ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "dce_stream")
+            self.last_launches += self.lib.dce_last_launch_count()
         return logits, cls, bits
 
     def stream_host(self, log_host: torch.Tensor, chunk_rows: int = 1 << 18, out_bits_host: Optional[torch.Tensor] = None,

@@ -518,3 +518,24 @@ def test_experimental_block2_cluster_is_bit_identical(dev, cl, batch):
         eng.lib.dce_set_option(b"block2_cluster", 0)
         eng.lib.dce_set_option(b"fc_cluster", 0)
     assert torch.equal(got, want) and torch.equal(gc, wc)
+
+
+@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
+                    reason="the fp16 + e4m3 mode has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
+def test_experimental_f16f8_guard_falls_back_to_bf16x3(dev, params0):
+    """ContactEngine.guard: windows whose activations leave the range the fp16 + e4m3 error model assumes (here inputs
+    3000x too large: conv1 writes values far above 224) set the kernels' range word; the call is then redone in
+    bf16x3 and returns exactly what a bf16x3 engine returns.  In-range windows never fall back."""
+    eng8 = dce.ContactEngine(params0, dev, "f16f8")
+    eng8.guard = True
+    ref = engine(dev, "bf16x3")
+    x = synth.make_windows(64, seed=9).to(dev)
+    got = eng8.classify(x)
+    assert eng8.fallbacks == 0 and eng8.f16f8_status() == 0
+    assert torch.equal(got[1], ref.classify(x)[1])
+    big = x * 3000.0
+    got = eng8.classify(big)
+    want = ref.classify(big)
+    assert eng8.fallbacks == 1
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+    eng8.close()
