@@ -308,10 +308,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
-    ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32", "f16f8"])
+    ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
-                    help="dce_set_option(KEY, VALUE) before timing (A/B of experimental kernels; recorded in config.options)")
+                    help="dce_weights_set_option(KEY, VALUE) before timing (A/B of ablation switches; recorded in config.options)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -341,8 +341,8 @@ def main():
     options = {}
     for kv in args.set:
         key, _, val = kv.partition("=")
-        if eng.lib.dce_set_option(key.encode(), int(val)) != 0:
-            raise SystemExit(f"bench.py: dce_set_option({key!r}, {val}) was rejected")
+        if eng.set_option(key, int(val)) != 0:
+            raise SystemExit(f"bench.py: dce_weights_set_option({key!r}, {val}) was rejected")
         options[key] = int(val)
     bcast_ms = None
     if world > 1:
@@ -440,8 +440,7 @@ def main():
             "bound": "tensor", "kernel": dom, "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / peak, "traffic": traffic,
             "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
-            "note": "algorithmic FLOPs (split-precision passes count once; ceiling of frac is 1/3 with three bf16 passes"
-                    + (", 1/2 with the fp16 + e4m3 passes of this run)" if (options.get("fc_f16f8") or precision == "f16f8") else ")"),
+            "note": "algorithmic FLOPs (split-precision passes count once; ceiling of frac is 1/3 with three bf16 passes)",
             "kernel_share_of_step": per_kernel_ms[dom] / step_kernel_ms,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in per_kernel_ms.items()},
             "whole_step": {"achieved_tflops": value / world * FLOP_PER_WINDOW / 1e12,
@@ -457,7 +456,7 @@ def main():
         "metric": "contact windows/sec at batch=4096", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3_f32acc", "f16f8": "f16+2xe4m3_f32acc"}.get(precision, "f32"), "data": "synthetic",
+        "dtype": {"bf16x3": "bf16x3_f32acc"}.get(precision, "f32"), "data": "synthetic",
         "config": {"workload": workload_name(B),
                    "precision": precision, **({"options": options} if options else {}),
                    "weights": "seeded random init (synth.make_params(0))",

@@ -19,8 +19,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "dce.h")
 DCE_OK = 0
 DCE_PREC_FP32 = 0
 DCE_PREC_BF16X3 = 1
-DCE_PREC_F16F8 = 2            # experimental (include/dce.h): fp16 + e4m3 corrections, not yet run on a GPU
-PRECISIONS = {"fp32": DCE_PREC_FP32, "bf16x3": DCE_PREC_BF16X3, "f16f8": DCE_PREC_F16F8}
+PRECISIONS = {"fp32": DCE_PREC_FP32, "bf16x3": DCE_PREC_BF16X3}
 
 _lib = None
 
@@ -53,9 +52,8 @@ _SIGNATURES = {
                                     c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int)]),
     "dce_stream_profile": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                    c_int, c_void_p, c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int)]),
-    "dce_set_option": (c_int, [c_char_p, c_int]),
-    "dce_f16f8_status": (c_int, [c_void_p, c_void_p, c_int]),
-    "dce_debug_read_trace": (c_int, [c_void_p, c_int]),
+    "dce_weights_set_option": (c_int, [c_void_p, c_char_p, c_int]),
+    "dce_debug_read_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "dce_decimal2binary": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dce_accuracy_counts": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dce_ingest_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

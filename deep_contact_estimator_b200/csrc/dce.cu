@@ -59,12 +59,12 @@ struct dce_weights {
     size_t bytes = 0;
     Fp32Layout f32;
     dce::tc::PackedLayout tc;
+    dce::tc::Options opt;           // ablation / debugging switches (dce_weights_set_option); read-only for dce_forward / dce_stream
 };
 
 namespace {
 
 constexpr int64_t kChunkFp32 = 4096;   // windows per internal pass (bounds the workspace)
-inline int& latency_kernel_flag() { static int v = 1; return v; }   // dce_set_option("latency_kernel", 0): per-layer kernels for B <= 4
 
 struct Fp32Workspace { size_t act4, h1, h2, end; };
 Fp32Workspace fp32_workspace(int64_t n) {
@@ -143,7 +143,7 @@ int check_common(const dce_weights* w, const void* ws, size_t ws_bytes, int64_t 
     if (!w) return DCE_EINVAL;
     if (!w->packed) return DCE_ENOTPACKED;
     if (n < 0) return DCE_EINVAL;
-    if (precision != DCE_PREC_FP32 && precision != DCE_PREC_BF16X3 && precision != DCE_PREC_F16F8) return DCE_EINVAL;
+    if (precision != DCE_PREC_FP32 && precision != DCE_PREC_BF16X3) return DCE_EINVAL;
     if (n > 0) {
         if (!ws) return DCE_EINVAL;
         if ((uintptr_t)ws % 256) return DCE_EALIGN;
@@ -180,17 +180,17 @@ int dce_weights_create(dce_weights** out, int device) {
     *out = nullptr;
     cudaDeviceProp prop;
     DCE_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return DCE_EARCH;
+    if (prop.major != 10 || prop.minor != 0) return DCE_EARCH;      // the library holds sm_100a code only
+    int prev = 0;
+    DCE_CUDA(cudaGetDevice(&prev));
+    DCE_CUDA(cudaSetDevice(device));
     dce_weights* w = new (std::nothrow) dce_weights();
-    if (!w) return DCE_EINVAL;
+    if (!w) { cudaSetDevice(prev); return DCE_EINVAL; }
     w->device = device;
     w->sm_count = prop.multiProcessorCount;
     w->f32 = make_fp32_layout(0);
     w->tc = dce::tc::make_packed_layout(w->f32.end);
     w->bytes = w->tc.end;
-    int prev = 0;
-    DCE_CUDA(cudaGetDevice(&prev));
-    DCE_CUDA(cudaSetDevice(device));
     cudaError_t e = cudaMalloc(&w->buf, w->bytes);
     if (e == cudaSuccess) e = cudaMemset(w->buf, 0, w->bytes);
     cudaSetDevice(prev);
@@ -201,6 +201,7 @@ int dce_weights_create(dce_weights** out, int device) {
 
 int dce_weights_destroy(dce_weights* w) {
     if (!w) return DCE_OK;
+    if (w->opt.trace) cudaFree(w->opt.trace);
     if (w->buf) cudaFree(w->buf);
     delete w;
     return DCE_OK;
@@ -232,7 +233,7 @@ size_t dce_workspace_bytes(int64_t max_windows, int precision) {
     if (precision == DCE_PREC_FP32) {
         const int64_t n = max_windows < kChunkFp32 ? max_windows : kChunkFp32;
         need = fp32_workspace(n).end;
-    } else if (precision == DCE_PREC_BF16X3 || precision == DCE_PREC_F16F8) {
+    } else if (precision == DCE_PREC_BF16X3) {
         need = dce::tc::workspace_bytes(max_windows);
     } else {
         return 0;
@@ -259,14 +260,15 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
     if ((uintptr_t)src % 16 || (logits && (uintptr_t)logits % 16) || (bits && (uintptr_t)bits % 4) || (cls && (uintptr_t)cls % 4))
         return DCE_EALIGN;
     rc = DCE_EUNSUPPORTED;
-    if (n <= dce::lat::kMaxB && latency_kernel_flag()) {
+    if (n <= dce::lat::kMaxB && w->opt.latency_kernel) {
         // latency mode (K3): one cooperative fp32 kernel for the whole path, both precision modes
         const Fp32Layout& L = w->f32;
         dce::lat::Weights wt;
         wt.w1 = at<float>(w, L.w1); wt.w2 = at<float>(w, L.w2); wt.w3 = at<float>(w, L.w3); wt.w4q = at<float>(w, L.w4q);
         wt.f1s = at<float>(w, L.f1s); wt.f2s = at<float>(w, L.f2s); wt.f3t = at<float>(w, L.f3t);
         for (int i = 0; i < 7; ++i) wt.b[i] = at<float>(w, L.b[i]);
-        rc = dce::lat::run(wt, w->sm_count, src, is_stream, first, (int)n, logits, cls, bits, (char*)ws, ctx);
+        rc = dce::lat::run(wt, w->sm_count, src, is_stream, first, (int)n, logits, cls, bits, (char*)ws, ctx,
+                           w->opt.latency_coop, w->opt.latency_tma_in);
     }
     if (rc != DCE_EUNSUPPORTED) { /* done (or failed) in the latency kernel */ }
     else if (precision == DCE_PREC_FP32)
@@ -277,8 +279,7 @@ int run_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, i
         dce::tc::BiasPtrs bp;
         for (int i = 0; i < 7; ++i) bp.b[i] = at<float>(w, L.b[i]);
         bp.w3 = at<float>(w, L.f3t); bp.f1 = at<float>(w, L.f1); bp.f2 = at<float>(w, L.f2);
-        rc = dce::tc::run(w->buf, w->tc, bp, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx,
-                          precision == DCE_PREC_F16F8);
+        rc = dce::tc::run(w->buf, w->tc, bp, w->opt, w->sm_count, src, is_stream, T, first, n, logits, cls, bits, (char*)ws, ctx);
     }
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
     return rc;
@@ -345,42 +346,34 @@ int dce_stream_profile(const dce_weights* w, const float* data_dev, int64_t T, i
                        workspace_bytes, precision, stream, max_kernels, ms_out, names_out, n_out);
 }
 
-int dce_set_option(const char* key, int value) {
-    if (!key) return DCE_EINVAL;
-    if (!strcmp(key, "fuse_block1")) { dce::tc::fuse_block1_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "fuse_block2")) { dce::tc::fuse_block2_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "fuse_fc3")) { dce::tc::fuse_fc3_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "fc_f16f8")) { dce::tc::fc_f16f8_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "conv_f16f8")) { dce::tc::conv_f16f8_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "fc_cluster")) { if (value != 0 && value != 2) return DCE_EINVAL; dce::tc::fc_cluster_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "block2_cluster")) { if (value != 0 && value != 2 && value != 4) return DCE_EINVAL; dce::tc::block2_cluster_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "latency_kernel")) { latency_kernel_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "latency_coop")) { dce::lat::coop_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "latency_tma_in")) { dce::lat::tma_in_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "block1_dbg")) { dce::tc::block1_dbg_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "tapgemm_dbg")) { dce::tc::tapgemm_dbg_flag() = value; return DCE_OK; }
-    if (!strcmp(key, "trace_layer")) { dce::tc::tapgemm_trace_layer() = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3
-    if (!strcmp(key, "block1_trace")) {          // value != 0: allocate (once) and arm a 60-tile x 16-event clock64 trace of CTA 0
-        long long*& t = dce::tc::block1_trace_ptr();
-        if (value && !t) { if (cudaMalloc(&t, 60 * 16 * 8) != cudaSuccess) return DCE_ECUDA; cudaMemset(t, 0, 60 * 16 * 8); }
-        if (!value && t) { cudaFree(t); t = nullptr; }
-        return DCE_OK;
+int dce_weights_set_option(dce_weights* w, const char* key, int value) {
+    if (!w || !key) return DCE_EINVAL;
+    dce::tc::Options& o = w->opt;
+    if (!strcmp(key, "fuse_block1")) { o.fuse_block1 = value; return DCE_OK; }
+    if (!strcmp(key, "fuse_block2")) { o.fuse_block2 = value; return DCE_OK; }
+    if (!strcmp(key, "fuse_fc3")) { o.fuse_fc3 = value; return DCE_OK; }
+    if (!strcmp(key, "latency_kernel")) { o.latency_kernel = value; return DCE_OK; }
+    if (!strcmp(key, "latency_coop")) { o.latency_coop = value; return DCE_OK; }
+    if (!strcmp(key, "latency_tma_in")) { o.latency_tma_in = value; return DCE_OK; }
+    if (!strcmp(key, "block1_dbg")) { o.block1_dbg = value; return DCE_OK; }
+    if (!strcmp(key, "tapgemm_dbg")) { o.tapgemm_dbg = value; return DCE_OK; }
+    if (!strcmp(key, "trace_layer")) { o.trace_layer = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3; 6: block2
+    if (!strcmp(key, "trace")) {                 // value != 0: allocate (once) and arm a 60-tile x 16-event clock64 trace of CTA 0
+        int prev = 0;
+        DCE_CUDA(cudaGetDevice(&prev));
+        DCE_CUDA(cudaSetDevice(w->device));
+        cudaError_t e = cudaSuccess;
+        if (value && !o.trace) { e = cudaMalloc(&o.trace, 60 * 16 * 8); if (e == cudaSuccess) e = cudaMemset(o.trace, 0, 60 * 16 * 8); }
+        if (!value && o.trace) { cudaFree(o.trace); o.trace = nullptr; }
+        cudaSetDevice(prev);
+        return e == cudaSuccess ? DCE_OK : cuda_fail(e);
     }
     return DCE_EINVAL;
 }
 
-int dce_f16f8_status(dce_weights* w, uint32_t* host_out, int reset) {
-    if (!w || !host_out) return DCE_EINVAL;
-    unsigned int* d = reinterpret_cast<unsigned int*>(w->buf + w->tc.scales) + dce::tc::kF8StatusWord;
-    DCE_CUDA(cudaMemcpy(host_out, d, 4, cudaMemcpyDeviceToHost));        // synchronises: a diagnostic, not a hot-path call
-    if (reset) DCE_CUDA(cudaMemset(d, 0, 4));
-    return DCE_OK;
-}
-
-int dce_debug_read_trace(long long* host_out, int n) {
-    long long* t = dce::tc::block1_trace_ptr();
-    if (!t || !host_out || n <= 0 || n > 60 * 16) return DCE_EINVAL;
-    return cudaMemcpy(host_out, t, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? DCE_OK : DCE_ECUDA;
+int dce_debug_read_trace(dce_weights* w, long long* host_out, int n) {
+    if (!w || !w->opt.trace || !host_out || n <= 0 || n > 60 * 16) return DCE_EINVAL;
+    return cudaMemcpy(host_out, w->opt.trace, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? DCE_OK : DCE_ECUDA;
 }
 
 int dce_decimal2binary(const int64_t* cls_dev, int64_t n, uint8_t* bits_dev, void* stream) {

@@ -52,8 +52,10 @@ struct DeviceOnce {
         Guard(DeviceOnce* o_, int d_, bool first_) : o(o_), d(d_), first(first_) {}
         Guard(const Guard&) = delete;
         Guard& operator=(const Guard&) = delete;
-        ~Guard() { if (first) o->done[d] = true; o->mu.unlock(); }
+        ~Guard() { if (first && ok) o->done[d] = true; o->mu.unlock(); }
         explicit operator bool() const { return first; }
+        void fail() { ok = false; }              // the set-up did not complete: the next call on this device retries it
+        bool ok = true;
     };
     Guard need() {
         int d = 0;
@@ -74,19 +76,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-// the same, as thread-block clusters of `cluster` CTAs along x (grid.x must be a multiple of it)
-template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    at[1].id = cudaLaunchAttributeClusterDimension;
-    at[1].val.clusterDim.x = (unsigned)cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

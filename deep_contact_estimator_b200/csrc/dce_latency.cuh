@@ -515,22 +515,20 @@ struct Weights {                  // pointers into the packed buffer
     const float *w1, *w2, *w3, *w4q, *f1s, *f2s, *f3t, *b[7];
 };
 
-inline int& coop_flag() { static int v = 1; return v; }
-inline int& tma_in_flag() { static int v = 1; return v; }
-
 // -> DCE_EUNSUPPORTED when the device cannot co-schedule the grid (the caller then uses the per-layer kernels)
+// coop / tma_in: launch-attribute and input-staging ablations (dce_weights_set_option "latency_coop", "latency_tma_in")
 inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mode, int64_t first, int n,
-               float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx) {
+               float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx, int coop = 1, int tma_in = 1) {
     const int grid = sm_count / 4 * 4;
     if (grid < kSlices || n < 1 || n > kMaxB) return DCE_EUNSUPPORTED;
     static DeviceOnce once;
     if (auto first_ = once.need()) {
         cudaError_t e = cudaFuncSetAttribute(latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+        if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
     }
     const Workspace W = make_workspace(n);
     Params p{};
-    p.x = src; p.stream = stream_mode ? 1 : 0; p.tma_in = tma_in_flag(); p.first = first; p.B = n;
+    p.x = src; p.stream = stream_mode ? 1 : 0; p.tma_in = tma_in; p.first = first; p.B = n;
     p.w1 = wt.w1; p.w2 = wt.w2; p.w3 = wt.w3; p.w4q = wt.w4q; p.f1s = wt.f1s; p.f2s = wt.f2s; p.f3t = wt.f3t;
     p.b1 = wt.b[0]; p.b2 = wt.b[1]; p.b3 = wt.b[2]; p.b4 = wt.b[3]; p.bf1 = wt.b[4]; p.bf2 = wt.b[5]; p.bf3 = wt.b[6];
     p.p1 = reinterpret_cast<float*>(ws + W.p1); p.a4 = reinterpret_cast<float*>(ws + W.a4);
@@ -542,7 +540,7 @@ inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mo
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;        // the launch fails instead of deadlocking if the grid cannot be co-resident
     at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = coop_flag() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
     DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel, p); (void)le_; });
     return DCE_OK;
 }

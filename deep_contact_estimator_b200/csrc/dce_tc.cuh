@@ -32,8 +32,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <cuda_fp8.h>
 #include <stdint.h>
 #include "dce_common.cuh"
 #include "dce_tc_ptx.cuh"
@@ -69,8 +67,6 @@ struct TapGemmParams {
     int n_valid;                 // EPI_FC_F32: valid rows
     long long* trace;            // optional clock64 timeline of CTA 0: [tile][8] (tools/trace_tapgemm.py)
     int dbg;                     // timing ablations (results invalid): 1 = every tile loads the A slabs of tile 0; 2 = skip epilogue stores
-    const float* acc_scale;      // F8 kernels: one float, 1 / (the layer's power-of-two weight scale), applied to the accumulator
-    unsigned int* f8_status;     // F8 kernels: range diagnostic word (f8_range_note), or nullptr
 };
 
 struct Tape {
@@ -101,156 +97,6 @@ __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// ---- fp16 main + e4m3 corrections (experimental FC operand format, option "fc_f16f8") ----------------
-//     x * w ~= f16(x) * f16(w sw) + e4m3((x - f16(x)) 2^12) * e4m3(w sw 2^3) + e4m3(x 2^1) * e4m3((w sw - f16(w sw)) 2^14)
-// sw = the layer's power-of-two weight scale (max |w sw| in [1, 2)).  Both correction products carry 2^15 and
-// are accumulated first; the first fp16 MMA rescales the accumulator by 2^-15 (scale-input-d).  fp8 MMAs take
-// K = 32 per instruction, so a K-step costs 2 + 2 MMA slots per 32 elements instead of 6
-// (tools/emulate_split_precision.py: 6e-6 norm-wise on the logits; tools/microbench/umma_f16f8.cu).
-constexpr int kF8ExL = 12, kF8EwH = 3, kF8ExH = 1, kF8EwL = 14, kF8ScaleD = 15;
-static_assert(kF8ExL + kF8EwH == kF8ScaleD && kF8ExH + kF8EwL == kF8ScaleD, "both correction products carry the same scale");
-
-// One layout rule for every tensor in this format: a row with C channels is C/8 fp16 chunks (8 channels, 16 bytes
-// each), then C/16 lo8 chunks, then C/16 hi8 chunks (16 channels, 16 bytes each).  In a tape the fp16 chunks are
-// part 0 and the e4m3 chunks part 1 (chunk pitch kch_stride); in a shared-memory slab all C/4 chunks follow each
-// other (pitch kSlabBytes: C/8 fp16, C/16 lo8, C/16 hi8).  Writers and readers below go through these helpers, and
-// tools/host_check_f16f8.cu tabulates them on the host for the CPU tests.
-struct F8Dst { size_t f16, lo8, hi8; };      // byte offsets of fp16 chunk 2*g16 (chunk 2*g16+1 follows one pitch later), lo8 / hi8 chunk g16
-__host__ __device__ __forceinline__ F8Dst f8_tape_dst(int g16, int C, size_t part_stride, size_t kch_stride) {
-    F8Dst d;
-    d.f16 = (size_t)(2 * g16) * kch_stride;
-    d.lo8 = part_stride + (size_t)g16 * kch_stride;
-    d.hi8 = part_stride + (size_t)(C / 16 + g16) * kch_stride;
-    return d;
-}
-__host__ __device__ __forceinline__ F8Dst f8_slab_dst(int g16, int C) {
-    F8Dst d;
-    d.f16 = (size_t)(2 * g16) * (130 * 16);
-    d.lo8 = (size_t)(C / 8 + g16) * (130 * 16);
-    d.hi8 = (size_t)(C / 8 + C / 16 + g16) * (130 * 16);
-    return d;
-}
-// tapgemm F8 producer: tape offset of activation copy (part, j) of stage s (K = 32 * stages, KSA = 4 chunks per part).
-// Sweep 1 (s < stages/2) streams 16-element chunks s*4 + j of e4m3 image `part` (0 = lo8, 1 = hi8); sweep 2 streams
-// fp16 chunks (s - stages/2)*8 + part*4 + j.
-__host__ __device__ __forceinline__ size_t f8_stage_src(int s, int stages, int part, int j, size_t part_stride, size_t kch_stride) {
-    const int half = stages >> 1;
-    return (s < half) ? part_stride + (size_t)(part * 2 * stages + s * 4 + j) * kch_stride
-                      : (size_t)((s - half) * 8 + part * 4 + j) * kch_stride;
-}
-
-// B-operand offsets inside one conv weight block of 192 * cout bytes (pack_conv_f16f8_kernel): an e4m3 block is
-// [img: w8 | wl8][tap][2 chunks of 16 channels][cout][16 B], an fp16 block [tap][4 chunks of 8 channels][cout][16 B];
-// the descriptor's LBO (distance between the two K chunks of one MMA) is 16 * cout in both.
-__host__ __device__ __forceinline__ uint32_t f8_wblk_e4m3(int cout, int img, int tap) { return (uint32_t)((img * 3 + tap) * 32 * cout); }
-__host__ __device__ __forceinline__ uint32_t f8_wblk_f16(int cout, int tap, int kk) { return (uint32_t)((tap * 2 + kk) * 32 * cout); }
-
-// Range diagnostic of the format (dce_f16f8_status): bit `layer` of *status is set when a layer wrote an activation
-// above 224 (the e4m3 image of 2 x saturates, so that element's second correction term is lost: fp16-only accuracy for
-// it), bit 8 + layer when it wrote one above 65504 (the fp16 image itself saturated).  Layers: 0 conv1, 1 conv2,
-// 2 conv3, 3 conv4, 4 fc.0.  Thread-local test, an atomic only in the abnormal case.
-__device__ __forceinline__ void f8_range_note(const float* y, int n, unsigned int* status, int layer) {
-    float mx = 0.f;
-    for (int i = 0; i < n; ++i) mx = fmaxf(mx, y[i]);
-    if (status && mx > 224.f) atomicOr(status, (1u << layer) | (mx > 65504.f ? (256u << layer) : 0u));
-}
-
-// The issue plans of the format, as host-callable functions: which operands MMA i of a stage / weight block reads, of
-// which kind, and how it treats the accumulator.  The kernels issue exactly what these return, and
-// tools/host_check_f16f8.cu dumps them so that the numpy emulation executes the SAME plan on real packed bytes.
-struct F8Mma {
-    uint32_t a_off, b_off;   // byte offsets: A relative to the M-tile's stage image (tapgemm) or the slab (fused kernels), B relative to the block
-    uint8_t e4m3;            // 1: kind::f8f6f4, K = 32 (two 16-element chunks); 0: kind::f16, K = 16 (two 8-element chunks)
-    uint8_t mode;            // 0: D = A*B;  1: D += A*B;  2: D = A*B + D * 2^-15 (scale-input-d: the corrections come down to the main scale)
-};
-// tapgemm, Linear layers: MMA i = 0..3 of stage s (stages/2 correction stages, then stages/2 main stages; 64 K-elements each).
-// Stage image of an M-tile: [part 0: 4 slabs][part 1: 4 slabs]; B block: [part 0: 4 chunks][part 1: 4 chunks] of b_tapch bytes.
-__host__ __device__ __forceinline__ F8Mma f8_fc_mma(int s, int stages, int i, uint32_t a_part, uint32_t b_part, uint32_t b_tapch) {
-    F8Mma m;
-    const int half = stages >> 1;
-    if (s < half) {                     // i = 2 kk + product: product 0 = (x - f16 x) * w, 1 = x * (w - f16 w); centre row of the slab: + 16
-        const int kk = i >> 1, prod = i & 1;
-        m.a_off = 16 + prod * a_part + 2 * kk * (130 * 16);
-        m.b_off = prod * b_part + 2 * kk * b_tapch;
-        m.e4m3 = 1;
-        m.mode = (s == 0 && i == 0) ? 0 : 1;
-    } else {                            // 8 consecutive fp16 chunks of A (both parts) and of B
-        m.a_off = 16 + 2 * i * (130 * 16);
-        m.b_off = 2 * i * b_tapch;
-        m.e4m3 = 0;
-        m.mode = (s == half && i == 0) ? 2 : 1;
-    }
-    return m;
-}
-// fused conv kernels: MMA i = 0..1 of tap `tap` of weight block s (half e4m3 blocks, then half fp16 blocks, 32 input channels
-// each); C = channels of the slab, cout = output channels (block = 192 * cout bytes); A offset includes the tap's row shift.
-__host__ __device__ __forceinline__ F8Mma f8_conv_mma(int s, int half, int tap, int i, int C, int cout) {
-    F8Mma m;
-    if (s < half) {                     // i = product: 0 = (x - f16 x) * w (lo8 image, w8 image), 1 = x * (w - f16 w) (hi8, wl8)
-        const F8Dst o = f8_slab_dst(2 * s, C);              // the slab's 16-channel groups 2s, 2s + 1
-        m.a_off = (uint32_t)(i ? o.hi8 : o.lo8) + tap * 16;
-        m.b_off = f8_wblk_e4m3(cout, i, tap);
-        m.e4m3 = 1;
-        m.mode = (s == 0 && tap == 0 && i == 0) ? 0 : 1;
-    } else {                            // i = kk: fp16 chunks 4g + 2kk, 4g + 2kk + 1 of the slab, g = s - half
-        m.a_off = (uint32_t)f8_slab_dst(2 * (s - half) + i, C).f16 + tap * 16;
-        m.b_off = f8_wblk_f16(cout, tap, i);
-        m.e4m3 = 0;
-        m.mode = (s == half && tap == 0 && i == 0) ? 2 : 1;
-    }
-    return m;
-}
-
-// NaN-propagating min / max that also compile for the host, so tools/host_check_f16f8.cu can run the operand
-// conversion and the weight packers below on the CPU and compare them byte for byte with the numpy emulation.
-__host__ __device__ __forceinline__ float min_nan(float a, float b) {
-#ifdef __CUDA_ARCH__
-    float d;
-    asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-#else
-    return (a != a || b != b) ? (a + b) : (a < b ? a : b);
-#endif
-}
-__host__ __device__ __forceinline__ float max_nan_hd(float a, float b) {
-#ifdef __CUDA_ARCH__
-    float d;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-#else
-    return (a != a || b != b) ? (a + b) : (a > b ? a : b);
-#endif
-}
-// 16 consecutive K elements of one row -> two 16-byte fp16 chunks + one 16-byte chunk of each e4m3 image.
-// Activations saturate at the largest finite fp16 (65504); NaN propagates through all three images.
-// SIGNED = false: the values are ReLU outputs (>= 0 or NaN), only the upper clamp is needed.
-template <bool SIGNED = false>
-__host__ __device__ __forceinline__ void split16_f16f8(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
-    uint32_t h[8], l[4], g[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float a = min_nan(y[2 * i], 65504.f), b = min_nan(y[2 * i + 1], 65504.f);
-        if (SIGNED) {
-            a = max_nan_hd(a, -65504.f);
-            b = max_nan_hd(b, -65504.f);
-        }
-        const __half2 hb = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hb);
-        h[i] = (uint32_t)__half_as_ushort(__low2half(hb)) | ((uint32_t)__half_as_ushort(__high2half(hb)) << 16);
-        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2((a - hf.x) * (float)(1 << kF8ExL), (b - hf.y) * (float)(1 << kF8ExL)), __NV_SATFINITE, __NV_E4M3);
-        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a * (float)(1 << kF8ExH), b * (float)(1 << kF8ExH)), __NV_SATFINITE, __NV_E4M3);
-        if (i & 1) { l[i >> 1] |= lo << 16; g[i >> 1] |= hi << 16; } else { l[i >> 1] = lo; g[i >> 1] = hi; }
-    }
-    f16a = make_uint4(h[0], h[1], h[2], h[3]);
-    f16b = make_uint4(h[4], h[5], h[6], h[7]);
-    lo8 = make_uint4(l[0], l[1], l[2], l[3]);
-    hi8 = make_uint4(g[0], g[1], g[2], g[3]);
-}
-
-__host__ __device__ __forceinline__ void split16_f16f8_signed(const float* y, uint4& f16a, uint4& f16b, uint4& lo8, uint4& hi8) {
-    split16_f16f8<true>(y, f16a, f16b, lo8, hi8);
-}
-
 // NaN-propagating max (FMNMX.NAN): torch's ReLU and MaxPool1d both propagate NaN.
 __device__ __forceinline__ float max_nan(float a, float b) {
     float d;
@@ -299,19 +145,9 @@ struct TapGemmCfg {
 #endif
 #define TG_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
-// F8 = 1 (Linear layers only): operands in the fp16 + e4m3 format (split16_f16f8).  A tile's K loop is two sweeps
-// of p.stages / 2 stages each, 64 K-elements per stage and the same bytes per stage as the bf16x3 layout: sweep 1
-// streams the e4m3 images (A: [lo8 | hi8], B: [w8 | wl8]) and issues the correction MMAs, sweep 2 streams the
-// fp16 images and issues the main MMAs, the first of them with scale-input-d.
-// CL = 2 (Linear layers, option "fc_cluster"): launched as clusters of two CTAs with ONE tile per CTA; tiles 2j and
-// 2j + 1 share their M-tile(s) (n_tiles is even), so every activation slab of a stage is fetched from L2 by one of the
-// two CTAs and multicast to both (L2 -> SM bytes per stage: A + B -> A / 2 + B), and a ring slot is free when the
-// issuers of BOTH CTAs have drained it (multicast tcgen05.commit, `empty` count 2 MT).
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0, int CL = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
 __global__ void __launch_bounds__(tapgemm_threads(MT), 1)
 tapgemm_kernel(const TapGemmParams p) {
-    static_assert(!F8 || (TAPS == 1 && KSA == 4 && WST == 0 && (EPI == EPI_FC_TAPE || EPI == EPI_FC_LOGITS)), "F8: Linear layers, 64 K-elements per stage");
-    static_assert(CL == 0 || (CL == 2 && TAPS == 1 && WST == 0), "clusters: pairs, Linear layers");
     constexpr int kProducerWarp0 = kEpiWarps + MT;
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
     constexpr int NBUF = Cfg::NBUF;
@@ -331,7 +167,7 @@ tapgemm_kernel(const TapGemmParams p) {
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], CL ? CL * MT : MT); }
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], MT); }
         for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], MT); ptx::mbar_init(&tempty[b], kEpiWarps); }
         ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
@@ -342,7 +178,6 @@ tapgemm_kernel(const TapGemmParams p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    if constexpr (CL != 0) ptx::cluster_sync();                 // the peer's barriers exist before anything remote touches them
     pdl_wait();                                                 // everything the previous kernel wrote is visible from here on
 
     if (warp >= kProducerWarp0) {
@@ -385,23 +220,9 @@ tapgemm_kernel(const TapGemmParams p) {
                             const int c = c0 + pw;
                             if (c < NA) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
-                                if constexpr (CL != 0) {
-                                    // slab c of the stage: fetched by CTA c % 2 of the pair, delivered to both
-                                    size_t src_off = part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride;
-                                    if (F8) src_off = f8_stage_src(s, p.stages, part, j, p.a_part_stride, p.a_kch_stride);
-                                    if ((uint32_t)(c & 1) == ptx::cluster_ctarank())
-                                        ptx::bulk_g2s_multicast(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
-                                                                a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot], (uint16_t)0x3);
-                                } else
-                                if (F8) {
-                                    const size_t src_off = f8_stage_src(s, p.stages, part, j, p.a_part_stride, p.a_kch_stride);
-                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
-                                                  a_row + (size_t)mt * 2048 + src_off, kSlabBytes, &full[slot]);
-                                } else {
-                                    ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
-                                                  a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
-                                                  kSlabBytes, &full[slot]);
-                                }
+                                ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
+                                              a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
+                                              kSlabBytes, &full[slot]);
                             } else if (c == NA && !WST) {
                                 ptx::bulk_g2s(st + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[slot]);
                             }
@@ -435,43 +256,17 @@ tapgemm_kernel(const TapGemmParams p) {
                 const uint32_t buf = tcount % NBUF;
                 if (mt == 0) TG_TRACE(tcount, 2);
                 const uint32_t d = tmem_base + buf * (MT * BN) + mt * BN;
+                // A single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM): the epilogue that frees it cannot start
+                // before this issuer's own `tfull` commit of the previous tile, so the buffer is awaited here, at the top of
+                // the tile, not by the mid-stage probe below (which would wait for it BEFORE that commit: a deadlock found
+                // by tools/simulate_block2_protocol.py).
+                if (NBUF == 1 && tcount > 0) { ptx::mbar_wait(&tempty[0], (tcount & 1) ^ 1); ptx::tc_fence_after_sync(); }
                 for (int s = 0; s < p.stages; ++s, ++it) {
                     const uint32_t slot = it % NSTAGE;
                     if (mt == 0 && s == 0) TG_TRACE(tcount, 4);
                     if (mt == 0 && s == p.stages - 1) TG_TRACE(tcount, 5);
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + mt * Cfg::A_TILE;
                     const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
-                    if (F8) {
-                        constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, BN), id16 = ptx::make_idesc_f16_f32(128, BN);
-                        // With a single accumulator buffer the next tile's `tempty` (= this tile's epilogue) cannot
-                        // complete before this tile's `tfull` commit at the end of the stage: wait for it at the top of
-                        // the next tile instead of mid-stage (the bf16x3 loop below has the mid-stage wait and is kept to
-                        // one tile per CTA by launch_layer; tools/simulate_block2_protocol.py).
-                        if (NBUF == 1 && s == 0 && tcount > 0) { ptx::mbar_wait(&tempty[0], (tcount & 1) ^ 1); ptx::tc_fence_after_sync(); }
-                        auto probe_next = [&]() {                          // as below: probe the next stage mid-stage
-                            if (it + 1 < total_stages) {
-                                if (NBUF > 1 && s == p.stages - 1) {
-                                    const uint32_t nt = tcount + 1;
-                                    ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
-                                }
-                                ptx::mbar_wait(&full[(it + 1) % NSTAGE], ((it + 1) / NSTAGE) & 1);
-                                ptx::tc_fence_after_sync();
-                            }
-                        };
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            // sweep 1: (x - f16 x) 2^12 * w 2^3 and x 2^1 * (w - f16 w) 2^14, K = 32 per MMA; sweep 2: the fp16 products
-                            const F8Mma m = f8_fc_mma(s, p.stages, i, Cfg::A_PART, Cfg::B_PART, Cfg::B_TAPCH);
-                            const uint64_t da = ptx::make_smem_desc(a0 + m.a_off, kSlabBytes, 128);
-                            const uint64_t db = ptx::make_smem_desc(b0 + m.b_off, Cfg::B_TAPCH, 128);
-                            if (leader) {
-                                if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
-                                else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
-                                else ptx::umma_bf16_ss(d, da, db, id16, 1u);              // kind::f16; the operand format is in the idesc
-                            }
-                            if (i == 1) probe_next();
-                        }
-                    } else {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
                         const int arow = (TAPS == 1) ? 1 : tap;            // Linear layers read the centre row only
@@ -491,7 +286,7 @@ tapgemm_kernel(const TapGemmParams p) {
                             }
                             // mid-stage: probe what the NEXT stage needs while MMAs of this one are still queued
                             if (tap == (TAPS - 1) / 2 && kk == (KSA / 2 - 1) / 2 && it + 1 < total_stages) {
-                                if (s == p.stages - 1) {                       // next stage opens the next tile
+                                if (NBUF > 1 && s == p.stages - 1) {           // next stage opens the next tile
                                     const uint32_t nt = tcount + 1;
                                     ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
                                 }
@@ -500,10 +295,7 @@ tapgemm_kernel(const TapGemmParams p) {
                             }
                         }
                     }
-                    }
                     if (leader) {
-                        if constexpr (CL != 0) ptx::umma_commit_multicast(&empty[slot], (uint16_t)0x3);   // ... in both CTAs of the pair
-                        else
                         ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
                         if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
                     }
@@ -517,7 +309,6 @@ tapgemm_kernel(const TapGemmParams p) {
         const int q = warp & 3, h = warp >> 2;
         const int row_in_tile = q * 32 + lane;
         float* my_bias = s_bias + warp * HALF;               // warp-private copy of this warp's bias slice
-        const float acc_scale = F8 ? __ldg(p.acc_scale) : 1.f;   // F8: the weights were packed times a power of two
         uint32_t tcount = 0;
         int last_n = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -585,13 +376,6 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c0 + i);     // smem broadcast
-                    if (F8) {
-                        y[i] = relu_nan(fmaf(__uint_as_float(v[i]), acc_scale, b4.x));
-                        y[i + 1] = relu_nan(fmaf(__uint_as_float(v[i + 1]), acc_scale, b4.y));
-                        y[i + 2] = relu_nan(fmaf(__uint_as_float(v[i + 2]), acc_scale, b4.z));
-                        y[i + 3] = relu_nan(fmaf(__uint_as_float(v[i + 3]), acc_scale, b4.w));
-                        continue;
-                    }
                     y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
                     y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
                     y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
@@ -619,23 +403,6 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
-                    }
-                    return;
-                }
-                if (F8 && EPI == EPI_FC_TAPE) {
-                    f8_range_note(y, 32, p.f8_status, 4);
-                    // next layer's operand in the fp16 + e4m3 format: fp16 chunks in tape part 0, the two e4m3 images
-                    // (N / 16 chunks each: lo8, then hi8) in tape part 1
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint4 fa, fb, lo8, hi8;
-                        split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                        const F8Dst d = f8_tape_dst((n0 + c0) / 16 + hh, p.N, p.out_part_stride, p.out_kch_stride);
-                        uint8_t* row = p.out + out_off[mt];
-                        *reinterpret_cast<uint4*>(row + d.f16) = fa;
-                        *reinterpret_cast<uint4*>(row + d.f16 + p.out_kch_stride) = fb;
-                        *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
-                        *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
                     }
                     return;
                 }
@@ -704,7 +471,6 @@ tapgemm_kernel(const TapGemmParams p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if constexpr (CL != 0) ptx::cluster_sync();                 // the peer may still multicast into this CTA or signal its barriers
     if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -739,94 +505,6 @@ __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__
         *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
         *reinterpret_cast<__nv_bfloat16*>(out + blk + per_part * 2 + within) = l;
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K0, fp16 + e4m3 format (option "fc_f16f8"; Linear layers): per n-tile, `stages` blocks of 8 * BN * 16 bytes in
-// the order the F8 kernel streams them: stages/2 correction blocks [w8 | wl8] (4 chunks of 16 e4m3 each) covering
-// 64 K-elements apiece, then stages/2 main blocks (8 chunks of 8 fp16).  Weights are multiplied by the layer's
-// power-of-two scale sw first (max |w sw| in [1, 2)), so small weights stay clear of the fp16 subnormals.
-// kind 3: fc.0 (K index k' = t*128 + c), kind 4: fc.3.
-// ---------------------------------------------------------------------------------------------
-__global__ void absmax_kernel(const float* __restrict__ W, size_t n, unsigned int* __restrict__ out_bits) {
-    float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float a = fabsf(W[i]);
-        if (a <= 3.0e38f) m = fmaxf(m, a);                     // NaN / inf weights do not set the scale
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));      // non-negative floats order like their bits
-}
-// scale[0] = sw = 2^-floor(log2 max|w|), scale[1] = 1 / sw; scale[2] holds the absmax bits on entry
-__global__ void weight_scale_kernel(float* __restrict__ scale) {
-    const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]);
-    int e = 1;
-    if (m > 0.f) frexpf(m, &e);                                // m = f * 2^e, f in [0.5, 1)  ->  floor(log2 m) = e - 1
-    e = e < -100 ? -100 : (e > 100 ? 100 : e);
-    scale[0] = ldexpf(1.f, 1 - e);
-    scale[1] = ldexpf(1.f, e - 1);
-}
-// one weight element (idx = n * K + k) of a Linear layer -> its three images
-__host__ __device__ __forceinline__ void pack_b_f16f8_elem(const float* __restrict__ W, uint8_t* __restrict__ out, size_t idx,
-                                                           int stages, int BN, int kind, int K, float sw) {
-    const size_t blk_bytes = (size_t)8 * BN * 16;
-    const int half = stages / 2;                               // K == 64 * half
-    {
-        const int k = (int)(idx % K);
-        const int n = (int)(idx / K);
-        const int nt = n / BN, nn = n % BN;
-        float v;
-        if (kind == 3) { const int t = k / 128, ch = k % 128; v = W[(size_t)n * 4736 + ch * 37 + t]; }
-        else v = W[(size_t)n * K + k];
-        v *= sw;
-        const __half h = __float2half_rn(v);
-        const float r = v - __half2float(h);
-        const int s = k / 64, kr = k % 64;
-        uint8_t* corr = out + ((size_t)nt * stages + s) * blk_bytes;
-        uint8_t* mainb = out + ((size_t)nt * stages + half + s) * blk_bytes;
-        *reinterpret_cast<__half*>(mainb + (((size_t)(kr / 8) * BN + nn) * 8 + kr % 8) * 2) = h;
-        const size_t o8 = ((size_t)(kr / 16) * BN + nn) * 16 + kr % 16;
-        corr[o8] = (uint8_t)__nv_cvt_float_to_fp8(v * (float)(1 << kF8EwH), __NV_SATFINITE, __NV_E4M3);
-        corr[blk_bytes / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
-    }
-}
-__global__ void pack_b_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
-                                    int BN, int kind, int K, const float* __restrict__ scale) {
-    const float sw = scale[0];
-    const size_t total = (size_t)n_tiles * BN * K;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
-        pack_b_f16f8_elem(W, out, idx, stages, BN, kind, K, sw);
-}
-
-// Conv layers in the fp16 + e4m3 format (option "conv_f16f8"): blocks of 192 * cout bytes, each covering 32 input
-// channels of all three taps; first the G = cin_pad / 32 e4m3 blocks [img: w8 | wl8][tap][2 chunks of 16][cout][16 B],
-// then the G fp16 blocks [tap][4 chunks of 8][cout][8 x 2 B] — the order the two-sweep issuers consume them
-// (block2's 24 KB weight ring at cout = 128; block1 keeps its four 12 KB blocks resident).
-__host__ __device__ __forceinline__ void pack_conv_f16f8_elem(const float* __restrict__ W, uint8_t* __restrict__ out, int idx,
-                                                              int cout, int cin, int cin_pad, float sw) {
-    const int G = cin_pad / 32;
-    const size_t blk = (size_t)192 * cout;
-    {
-        const int tap = idx % 3, c = (idx / 3) % cin_pad, n = idx / (3 * cin_pad);
-        const float v = (c < cin ? W[((size_t)n * cin + c) * 3 + tap] : 0.f) * sw;
-        const __half h = __float2half_rn(v);
-        const float r = v - __half2float(h);
-        const int g = c / 32, cr = c % 32;
-        uint8_t* b8 = out + (size_t)g * blk;
-        uint8_t* b16 = out + (size_t)(G + g) * blk;
-        *reinterpret_cast<__half*>(b16 + ((size_t)(tap * 4 + cr / 8) * cout + n) * 16 + (cr % 8) * 2) = h;
-        const size_t o8 = ((size_t)(tap * 2 + cr / 16) * cout + n) * 16 + cr % 16;
-        b8[o8] = (uint8_t)__nv_cvt_float_to_fp8(v * (float)(1 << kF8EwH), __NV_SATFINITE, __NV_E4M3);
-        b8[blk / 2 + o8] = (uint8_t)__nv_cvt_float_to_fp8(r * (float)(1 << kF8EwL), __NV_SATFINITE, __NV_E4M3);
-    }
-}
-__global__ void pack_conv_f16f8_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int cout, int cin, int cin_pad,
-                                       const float* __restrict__ scale) {
-    const float sw = scale[0];
-    const int total = cout * cin_pad * 3;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
-        pack_conv_f16f8_elem(W, out, idx, cout, cin, cin_pad, sw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -971,29 +649,21 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 14;
+constexpr int kNumPacked = 7;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
-                                 {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0
+                                 {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0 (layer-wise conv3: resident image)
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
-                                 {128, 3, 4, 4, 1, 0, 128, 6},     // block2.2 again, in 48 KB blocks (unused; kept for ablations)
-                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
-                                 {256, 1, 4, 148, 8, 3, 4736, 8},  // fc.0 in the fp16 + e4m3 format (option "fc_f16f8")
-                                 {128, 1, 4, 64, 4, 4, 2048, 10},  // fc.3 in the fp16 + e4m3 format
-                                 {64, 3, 2, 4, 1, 5, 54, 0},       // block1.0 in the fp16 + e4m3 format (option "conv_f16f8"): 2 * cin_pad/32 blocks
-                                 {64, 3, 2, 4, 1, 5, 64, 2},       // block1.2
-                                 {128, 3, 2, 4, 1, 5, 64, 4},      // block2.0
-                                 {128, 3, 2, 8, 1, 5, 128, 6}};    // block2.2
+                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+constexpr int kLayerConv3Ring = 6;
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
-struct PackedLayout { size_t w[kNumPacked]; size_t scales; size_t begin, end; };   // scales: [kNumPacked][4] floats {sw, 1/sw, absmax bits, -}; then the
-constexpr int kF8StatusWord = 60;                                                  // f8 range-status word: 32-bit word 60 of that 256-byte block
+struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
 inline PackedLayout make_packed_layout(size_t base) {
     PackedLayout L; L.begin = base; size_t o = base;
     for (int i = 0; i < kNumPacked; ++i) { L.w[i] = o; o = align_up(o + layer_packed_bytes(kLayers[i]), 256); }
-    L.scales = o; o = align_up(o + kNumPacked * 16, 256);
     L.end = o;
     return L;
 }
@@ -1003,22 +673,6 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
         const LayerCfg& c = kLayers[i];
         const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-        if (c.kind >= 3) {                                     // fp16 + e4m3 format: scale from max |w|, then the images
-            float* sc = reinterpret_cast<float*>(buf + L.scales) + i * 4;
-            const size_t nw = (size_t)c.n_tiles * c.BN * c.cin * c.TAPS;
-            cudaError_t e = cudaMemsetAsync(sc, 0, 16, ctx.stream);
-            if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
-            DCE_KL(ctx, "tc_absmax", absmax_kernel<<<1024, 256, 0, ctx.stream>>>(params[c.src], nw, reinterpret_cast<unsigned int*>(sc) + 2));
-            DCE_KL(ctx, "tc_weight_scale", weight_scale_kernel<<<1, 1, 0, ctx.stream>>>(sc));
-            if (c.kind == 5) {                                 // conv: cin_pad = 16 * stages (2 blocks per 32 channels)
-                DCE_KL(ctx, "tc_pack_conv_f16f8", pack_conv_f16f8_kernel<<<96, 256, 0, ctx.stream>>>(
-                    params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.BN, c.cin, 16 * c.stages, sc));
-                continue;
-            }
-            DCE_KL(ctx, "tc_pack_b_f16f8", pack_b_f16f8_kernel<<<4096, 256, 0, ctx.stream>>>(
-                params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.kind, c.cin, sc));
-            continue;
-        }
         DCE_KL(ctx, "tc_pack_b", pack_b_kernel<<<blocks, 256, 0, ctx.stream>>>(
             params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin));
     }
@@ -1048,50 +702,21 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int F8 = 0, int CL = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
     using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, F8, CL>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST>;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
-    if (F8 && ((p.stages & 1) || !p.acc_scale)) return DCE_EINVAL;
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
     static_assert(kSmem <= 232448, "exceeds 227 KB");
     static DeviceOnce attr_once;
     if (auto first_ = attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+        if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
-    const int grid = tiles < sm_count ? tiles : sm_count;
-    // With a single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM) the issuer's mid-stage probe of the next
-    // tile's `tempty` would wait for an epilogue that cannot start before the current tile's `tfull` commit: a CTA must
-    // not get a second tile (tools/simulate_block2_protocol.py).  128 tiles on a B200's 148 SMs: never the case here.
-    if (Cfg::NBUF == 1 && tiles > grid && !F8) return DCE_EUNSUPPORTED;
-    if constexpr (CL != 0) {
-        // pairs need one tile per CTA, tiles 2j / 2j+1 on the same M-tile, and every pair resident at once
-        if (tiles > sm_count || (p.n_tiles & 1)) return DCE_EUNSUPPORTED;
-        static int max_clusters[64] = {};
-        static DeviceOnce cl_once;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev &= 63;
-        if (auto first_ = cl_once.need()) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(sm_count & ~1)); cfg.blockDim = dim3(tapgemm_threads(MT)); cfg.dynamicSmemBytes = kSmem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int n = 0;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-            if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
-            max_clusters[dev] = n > 0 ? n : -1;
-        }
-        if (max_clusters[dev] * 2 < tiles) return DCE_EUNSUPPORTED;
-        DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl_cluster(kern, dim3(tiles), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, 2, p); (void)le_; });
-    } else {
-        DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
-    }
+    const int grid = tiles < sm_count ? tiles : sm_count;         // persistent: a CTA walks tiles blockIdx.x, + gridDim.x, ...
+    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
     return DCE_OK;
 }
 

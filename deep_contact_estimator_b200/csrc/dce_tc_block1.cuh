@@ -20,7 +20,6 @@
 //   warp 14    : conv2 MMA issuer — separate issuers, so the tensor pipe always has the other conv's MMAs queued
 //                             while one issuer is between tiles or waiting for epi1 to fill slab1
 #pragma once
-#include <type_traits>
 #include "dce_tc.cuh"
 
 namespace dce {
@@ -48,13 +47,6 @@ struct Block1Params {
     int dbg;                     // timing ablations only (results invalid when non-zero)
     long long* trace;            // optional: CTA 0 records clock64() per role per tile ([tile][16])
 };
-// F8 bit 1 kernels take two more pointers.  A separate parameter type, so the default kernels' parameter block — and
-// with it their generated code — stays exactly what was measured.
-struct Block1ParamsF8 : Block1Params {
-    const float* inv_sw1; const float* inv_sw2;   // 1 / (power-of-two weight scale) of conv1 / conv2
-    unsigned int* f8_status;                      // range diagnostic word (f8_range_note), or nullptr
-};
-
 #define B1_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -97,13 +89,9 @@ __device__ __forceinline__ TileSegs tile_segs(const Block1Params& p, int r0) {
     return g;
 }
 
-// F8 bit 0: write X2 in the fp16 + e4m3 format (dce_tc.cuh: split16_f16f8; option "conv_f16f8") for block2_kernel<.., F8IN>.
-// F8 bit 1: slab0, slab1 and both resident weight images are in that format too (option "conv_f16f8" >= 2): a 64-channel
-//           slab is 8 fp16 chunks + 4 lo8 chunks + 4 hi8 chunks (the same 16 slab units), a weight image is four
-//           12 KB blocks (pack_conv_f16f8_kernel), and a convolution is 12 e4m3 + 12 fp16 MMAs instead of 36.
-template <bool STREAM, int F8 = 0>
+template <bool STREAM>
 __global__ void __launch_bounds__(kB1Threads, 1)
-block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Params> p) {
+block1_kernel(const Block1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* w1s = smem;
     uint8_t* w2s = smem + kB1WBytes;
@@ -223,62 +211,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                     }
                 }
             }
-            float2 g8[8];                                                            // F8: rows 128, 129 in 16-channel pieces
-            int w8r = 0;
-            const int s8 = 128 + tid / 4, c8 = tid % 4;
-            if (F8 & 2) {
-                const bool v8 = (tid < 8) && row_window(r0 + s8, w8r);
-                const uint8_t* src8 = row_ptr(s8);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    g8[i] = (v8 && c8 * 8 + i < 27) ? *reinterpret_cast<const float2*>(src8 + c8 * 64 + 8 * i) : make_float2(0.f, 0.f);
-                if (STREAM && v8) {
-                    const float2* mu = reinterpret_cast<const float2*>(s_nrm + (w8r - wbase) * 128 + c8 * 16);
-                    const float2* sd = mu + 32;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (c8 * 8 + i < 27) {
-                            const float2 m2 = mu[i], s2 = sd[i];
-                            g8[i].x = (g8[i].x - m2.x) * s2.x; g8[i].y = (g8[i].y - m2.y) * s2.y;
-                        }
-                    }
-                }
-            }
             asm volatile("bar.sync 1, 128;" ::: "memory");                           // all raw reads done: overwrite in place
-            if (F8 & 2) {
-                // slab0 in the fp16 + e4m3 format: fp16 chunks 0..7, lo8 chunks 8..11, hi8 chunks 12..15 (channels 54..63 are zero)
-#pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) {
-                    float y[16];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool have = c16 * 8 + i < 27;
-                        y[2 * i] = have ? f[(c16 * 8 + i) % 27].x : 0.f;
-                        y[2 * i + 1] = have ? f[(c16 * 8 + i) % 27].y : 0.f;
-                    }
-                    uint4 fa, fb, lo8, hi8;
-                    split16_f16f8_signed(y, fa, fb, lo8, hi8);
-                    const F8Dst o = f8_slab_dst(c16, 64);
-                    uint8_t* d = dst0 + tid * 16;
-                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
-                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
-                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
-                }
-                if (tid < 8) {
-                    float y[16];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { y[2 * i] = g8[i].x; y[2 * i + 1] = g8[i].y; }
-                    uint4 fa, fb, lo8, hi8;
-                    split16_f16f8_signed(y, fa, fb, lo8, hi8);
-                    const F8Dst o = f8_slab_dst(c8, 64);
-                    uint8_t* d = dst0 + s8 * 16;
-                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
-                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
-                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
-                }
-            } else {
 #pragma unroll
             for (int kch = 0; kch < 7; ++kch) {
                 float y[8];
@@ -307,7 +240,6 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
             }
             if (tid < 2) *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + (128 + tid) * 16) = make_uint4(0, 0, 0, 0);
-            }
             ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
             ptx::mbar_arrive(&x0_full[buf]);
             if (warp == 0) B1_TRACE(k, 3);
@@ -368,29 +300,7 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
 
             // 36 MMAs: 3 taps x 4 kchunk pairs x (hi*lo, lo*hi, hi*hi); then the two completion commits
             auto conv_mmas = [&](uint32_t a_base, uint32_t w_base, uint32_t d, uint64_t* bar_a, uint64_t* bar_b) {
-                if ((F8 & 2) && ptx::elect_one()) {
-                    // weight image: [e4m3 block g0][e4m3 g1][fp16 g0][fp16 g1], 12288 B each (32 input channels, 3 taps)
-                    constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, 64), id16 = ptx::make_idesc_f16_f32(128, 64);
-                    // four blocks (e4m3 g0, e4m3 g1, fp16 g0, fp16 g1) x 3 taps x 2 MMAs: the plan of f8_conv_mma with half = 2
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-#pragma unroll
-                        for (int tap = 0; tap < 3; ++tap) {
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const F8Mma m = f8_conv_mma(s, 2, tap, i, 64, 64);
-                                const uint64_t da = ptx::make_smem_desc(a_base + m.a_off, kSlabBytes, 128);
-                                const uint64_t db = ptx::make_smem_desc(w_base + s * 12288 + m.b_off, 1024, 128);
-                                if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
-                                else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
-                                else ptx::umma_bf16_ss(d, da, db, id16, 1u);       // kind::f16; fp16 operands per the idesc
-                            }
-                        }
-                    }
-                    ptx::umma_commit(bar_a);
-                    ptx::umma_commit(bar_b);
-                }
-                if (!(F8 & 2) && ptx::elect_one()) {
+                if (ptx::elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
@@ -436,8 +346,6 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
         const int rit = q * 32 + lane;                        // MMA row this thread owns
         const float* bias1 = s_bias + h * 32;
         const float* bias2 = s_bias + 64 + h * 32;
-        float inv1 = 1.f, inv2 = 1.f;
-        if constexpr ((F8 & 2) != 0) { inv1 = __ldg(p.inv_sw1); inv2 = __ldg(p.inv_sw2); }
 
         auto epi1 = [&](int k) {
             const int tile = blockIdx.x + k * gridDim.x;
@@ -458,37 +366,15 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias1 + i);
-                if (F8 & 2) {
-                    y[i] = valid ? relu_nan(fmaf(__uint_as_float(v[i]), inv1, b4.x)) : 0.f;
-                    y[i + 1] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 1]), inv1, b4.y)) : 0.f;
-                    y[i + 2] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 2]), inv1, b4.z)) : 0.f;
-                    y[i + 3] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 3]), inv1, b4.w)) : 0.f;
-                } else {
-                    y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
-                    y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
-                    y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
-                    y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
-                }
+                y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
+                y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
+                y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
+                y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
             }
             if (warp == 4) B1_TRACE(k, 8);
             ptx::mbar_wait_relaxed(x1_empty, (k & 1) ^ 1);    // conv2 of the previous tile has finished reading slab1
             if (warp == 4) B1_TRACE(k, 9);
             if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
-            if constexpr ((F8 & 2) != 0) f8_range_note(y, 32, p.f8_status, 0);
-            if (F8 & 2) {
-                // slab1: fp16 chunks 0..7, lo8 chunks 8..11, hi8 chunks 12..15
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint4 fa, fb, lo8, hi8;
-                    split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                    const F8Dst o = f8_slab_dst(h * 2 + hh, 64);
-                    uint8_t* d = slab1 + (rit + 1) * 16;
-                    *reinterpret_cast<uint4*>(d + o.f16) = fa;
-                    *reinterpret_cast<uint4*>(d + o.f16 + kSlabBytes) = fb;
-                    *reinterpret_cast<uint4*>(d + o.lo8) = lo8;
-                    *reinterpret_cast<uint4*>(d + o.hi8) = hi8;
-                }
-            } else {
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
                 uint4 hi, lo;
@@ -496,7 +382,6 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
                 uint8_t* d = slab1 + (h * 4 + qd) * kSlabBytes + (rit + 1) * 16;
                 *reinterpret_cast<uint4*>(d) = hi;
                 *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
-            }
             }
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(x1_full);
@@ -524,42 +409,17 @@ block1_kernel(const std::conditional_t<(F8 & 2) != 0, Block1ParamsF8, Block1Para
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias2 + i);
-                if (F8 & 2) {
-                    y[i] = relu_nan(fmaf(__uint_as_float(v[i]), inv2, b4.x));
-                    y[i + 1] = relu_nan(fmaf(__uint_as_float(v[i + 1]), inv2, b4.y));
-                    y[i + 2] = relu_nan(fmaf(__uint_as_float(v[i + 2]), inv2, b4.z));
-                    y[i + 3] = relu_nan(fmaf(__uint_as_float(v[i + 3]), inv2, b4.w));
-                } else {
-                    y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
-                    y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
-                    y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
-                    y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
-                }
+                y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
+                y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
+                y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
+                y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
                 y[i] = valid ? m : 0.f;
             }
-            if constexpr ((F8 & 2) != 0) { if (store) f8_range_note(y, 32, p.f8_status, 1); }
-            if ((F8 & 1) && store && !(p.dbg & 1)) {
-                // X2 in the fp16 + e4m3 format: even lane -> the four fp16 chunks of its 32 channels (tape part 0, chunk
-                // h*4 + ..); odd lane -> lo8 chunks h*2 + hh and hi8 chunks 4 + h*2 + hh (tape part 1, 16 channels each)
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint4 fa, fb, lo8, hi8;
-                    split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                    const F8Dst o = f8_tape_dst(h * 2 + hh, 64, p.out_part_stride, p.out_kch_stride);
-                    uint8_t* row = p.out + (size_t)(orow + kGuard) * 16;
-                    if (lane & 1) {
-                        *reinterpret_cast<uint4*>(row + o.lo8) = lo8;
-                        *reinterpret_cast<uint4*>(row + o.hi8) = hi8;
-                    } else {
-                        *reinterpret_cast<uint4*>(row + o.f16) = fa;
-                        *reinterpret_cast<uint4*>(row + o.f16 + p.out_kch_stride) = fb;
-                    }
-                }
-            } else if (store && !(p.dbg & 1)) {
+            if (store && !(p.dbg & 1)) {
                 uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {

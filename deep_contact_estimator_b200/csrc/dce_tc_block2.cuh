@@ -34,30 +34,12 @@ struct Block2Params {
     uint8_t* out; size_t out_part_stride, out_kch_stride; int out_rows_cap;
     int n_tiles;
     long long* trace;            // optional clock64 timeline of CTA 0 (DCE_TRACE builds)
-    const float* inv_sw3; const float* inv_sw4;     // F8IN: 1 / (power-of-two weight scale) of conv3 / conv4
-    unsigned int* f8_status;                        // F8OUT / F8IN: range diagnostic word (f8_range_note), or nullptr
 };
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
-// F8OUT: write the fc.0 operand in the fp16 + e4m3 format (dce_tc.cuh: split16_f16f8) instead of bf16 hi/lo.
-// F8IN : X2, X3 (slabB) and both weight images are in that format too (option "conv_f16f8").  A slab of C
-//        channels then holds C/8 fp16 chunks, C/16 lo8 chunks and C/16 hi8 chunks (the same 16 bytes per row and
-//        chunk, the same slab bytes), a 24 KB weight block covers 32 input channels of all three taps — first the
-//        conv's e4m3 blocks [w8 | wl8], then its fp16 blocks (pack_conv_f16f8_kernel) — and a block is 6 MMAs
-//        instead of 9.  Barriers, ring, TMEM and tiling are untouched.
-// CL = 2 or 4 (option "block2_cluster"): thread-block clusters of CL CTAs share the weight stream.  Every CTA consumes the
-//        SAME sequence of 24 KB weight blocks, so block i is fetched from L2 once per cluster — by the producer of CTA
-//        i % CL, with .multicast::cluster into the same ring slot of all CL CTAs — instead of once per CTA (L2 -> SM
-//        traffic per tile 321 KB -> 33 + 288 / CL KB).  A slot is refilled when the MMAs of ALL CL CTAs have drained it:
-//        every issuer's tcgen05.commit arrives on the `wempty` barrier of every CTA (count CL).  The CTAs of a cluster
-//        therefore walk the same number of tiles (`rounds`); a CTA without a tile in the last round runs it on stale
-//        operands with all stores predicated off.
-template <bool F8OUT, bool F8IN = false, int CL = 0>
 __global__ void __launch_bounds__(kB2Threads, 1)
 block2_kernel(const Block2Params p) {
-    static_assert(F8OUT || !F8IN, "F8IN implies F8OUT");
-    static_assert(CL == 0 || CL == 2 || CL == 4, "cluster size (0: no clusters)");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* slabA = smem;
     uint8_t* slabB = smem + kB2SlabA;
@@ -77,13 +59,10 @@ block2_kernel(const Block2Params p) {
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // b3[128], b4[128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int real_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // tiles this CTA walks: with clusters, the same for all CTAs (the last one may be a dummy for some of them)
-    const int my_tiles = (CL > 1) ? (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x : real_tiles;
-    constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1);
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kB2Ring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], CL ? CL : 1); }
+        for (int i = 0; i < kB2Ring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&d3_full[i], 1); ptx::mbar_init(&d3_empty[i], 8);
             ptx::mbar_init(&d4_full[i], 1); ptx::mbar_init(&d4_empty[i], 8);
@@ -102,7 +81,6 @@ block2_kernel(const Block2Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    if constexpr (CL > 1) ptx::cluster_sync();      // every CTA's barriers exist before anything remote touches them
     pdl_wait();
 
     if (warp == 9) {
@@ -114,13 +92,7 @@ block2_kernel(const Block2Params p) {
                 ptx::mbar_wait_relaxed(&wempty[slot], ph ^ 1);
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&wfull[slot], kB2WBlock);
-                    if constexpr (CL > 1) {
-                        // all CL producers are here for the same block `it`; one of them fetches it for everybody
-                        if (it % CL == ptx::cluster_ctarank())
-                            ptx::bulk_g2s_multicast(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot], kClMask);
-                    } else {
-                        ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
-                    }
+                    ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
                 }
                 __syncwarp();
             }
@@ -135,11 +107,6 @@ block2_kernel(const Block2Params p) {
         for (int k = 0; k < my_tiles; ++k) {
             const int b = (int)(blockIdx.x + k * gridDim.x) * kB2Rows;
             ptx::mbar_wait_relaxed(a_empty, (k & 1) ^ 1);                       // conv3(k-1) has drained slabA
-            if (CL > 1 && k >= real_tiles) {                                    // dummy round: nothing to load
-                if (ptx::elect_one()) ptx::mbar_arrive(a_full);
-                __syncwarp();
-                continue;
-            }
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(a_full, kB2SlabA);
                 const uint8_t* src = p.x2 + (size_t)(b - 3 + kGuard) * 16;
@@ -163,30 +130,6 @@ block2_kernel(const Block2Params p) {
         auto stage_mmas = [&](uint32_t slab, int kch_total, int s, uint32_t d, bool first_stage) {
             const uint32_t slot = it % kB2Ring;
             const uint32_t b0 = rg + slot * kB2WBlock;
-            if (F8IN) {
-                constexpr uint32_t id8 = ptx::make_idesc_e4m3_f32(128, 128), id16 = ptx::make_idesc_f16_f32(128, 128);
-                const int half = kch_total >> 2;                   // e4m3 blocks of this conv (= its fp16 blocks)
-#pragma unroll
-                for (int tap = 0; tap < 3; ++tap) {
-                    // e4m3 block s < half: the two correction products for input channels [32 s, 32 s + 32), one K = 32 MMA each;
-                    // fp16 block: the main products of channels [32 (s - half), + 32), two K = 16 MMAs (f8_conv_mma)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const F8Mma m = f8_conv_mma(s, half, tap, i, kch_total * 8, 128);
-                        const uint64_t da = ptx::make_smem_desc(slab + m.a_off, kSlabBytes, 128);
-                        const uint64_t db = ptx::make_smem_desc(b0 + m.b_off, 2048, 128);
-                        if (leader) {
-                            if (m.e4m3) ptx::umma_e4m3_ss(d, da, db, id8, m.mode);
-                            else if (m.mode == 2) ptx::umma_f16_ss_scale_d<kF8ScaleD>(d, da, db, id16);
-                            else ptx::umma_bf16_ss(d, da, db, id16, 1u);           // kind::f16; fp16 operands per the idesc
-                        }
-                    }
-                    if (tap == 1 && it + 1 < total_blocks) {
-                        ptx::mbar_wait(&wfull[(it + 1) % kB2Ring], ((it + 1) / kB2Ring) & 1);
-                        ptx::tc_fence_after_sync();
-                    }
-                }
-            } else {
 #pragma unroll
             for (int tap = 0; tap < 3; ++tap) {
                 const uint32_t b_hi = b0 + tap * 2 * 2048;
@@ -205,11 +148,7 @@ block2_kernel(const Block2Params p) {
                     ptx::tc_fence_after_sync();
                 }
             }
-            }
-            if (leader) {
-                if constexpr (CL > 1) ptx::umma_commit_multicast(&wempty[slot], kClMask);   // the slot is free when all CL CTAs have drained it
-                else ptx::umma_commit(&wempty[slot]);
-            }
+            if (leader) ptx::umma_commit(&wempty[slot]);
             ++it;
         };
         auto issue_c3 = [&](int k) {
@@ -245,7 +184,6 @@ block2_kernel(const Block2Params p) {
         const float* bias3 = s_bias + h * 64;
         const float* bias4 = s_bias + 128 + h * 64;
         const int NR = p.n_windows * kRW2;
-        const float inv3 = F8IN ? __ldg(p.inv_sw3) : 1.f, inv4 = F8IN ? __ldg(p.inv_sw4) : 1.f;
 
         auto epi1 = [&](int k) {
             const int tile = blockIdx.x + k * gridDim.x;
@@ -274,33 +212,11 @@ block2_kernel(const Block2Params p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias3 + c * 32 + i);
-                    if (F8IN) {
-                        y[i] = valid ? relu_nan(fmaf(__uint_as_float(v[i]), inv3, b4.x)) : 0.f;
-                        y[i + 1] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 1]), inv3, b4.y)) : 0.f;
-                        y[i + 2] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 2]), inv3, b4.z)) : 0.f;
-                        y[i + 3] = valid ? relu_nan(fmaf(__uint_as_float(v[i + 3]), inv3, b4.w)) : 0.f;
-                        continue;
-                    }
                     y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
                     y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
                     y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
                     y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
                 }
-                if (F8IN) {
-                    f8_range_note(y, 32, p.f8_status, 2);
-                    // slabB: fp16 chunks 0..15, lo8 chunks 16..23, hi8 chunks 24..31 (16 channels per e4m3 chunk)
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint4 fa, fb, lo8, hi8;
-                        split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                        const F8Dst d = f8_slab_dst(h * 4 + c * 2 + hh, 128);        // 16-channel group of the 128 X3 channels
-                        uint8_t* row = slabB + (rit + 1) * 16;
-                        *reinterpret_cast<uint4*>(row + d.f16) = fa;
-                        *reinterpret_cast<uint4*>(row + d.f16 + kSlabBytes) = fb;
-                        *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
-                        *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
-                    }
-                } else {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     uint4 hi, lo;
@@ -308,7 +224,6 @@ block2_kernel(const Block2Params p) {
                     uint8_t* d = slabB + (h * 8 + c * 4 + qd) * kSlabBytes + (rit + 1) * 16;
                     *reinterpret_cast<uint4*>(d) = hi;
                     *reinterpret_cast<uint4*>(d + 16 * kSlabBytes) = lo;
-                }
                 }
             }
             ptx::fence_proxy_async_smem();
@@ -342,13 +257,6 @@ block2_kernel(const Block2Params p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias4 + c * 32 + i);
-                    if (F8IN) {
-                        y[i] = relu_nan(fmaf(__uint_as_float(v[i]), inv4, b4.x));
-                        y[i + 1] = relu_nan(fmaf(__uint_as_float(v[i + 1]), inv4, b4.y));
-                        y[i + 2] = relu_nan(fmaf(__uint_as_float(v[i + 2]), inv4, b4.z));
-                        y[i + 3] = relu_nan(fmaf(__uint_as_float(v[i + 3]), inv4, b4.w));
-                        continue;
-                    }
                     y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
                     y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
                     y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
@@ -356,28 +264,7 @@ block2_kernel(const Block2Params p) {
                 }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
-                if (F8OUT) {
-                    // k' = to*128 + channel.  Even lane: the four fp16 chunks (tape part 0, chunk to*16 + channel/8);
-                    // odd lane: the e4m3 images (tape part 1: lo8 chunks [0, 296), hi8 chunks [296, 592), chunk to*8 + channel/16)
-                    if (store) {
-                        f8_range_note(y, 32, p.f8_status, 3);
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            uint4 fa, fb, lo8, hi8;
-                            split16_f16f8(y + hh * 16, fa, fb, lo8, hi8);
-                            // fc.0 operand row of window w: K index k' = to*128 + channel, 4736 "channels" in all
-                            const F8Dst d = f8_tape_dst(to * 8 + h * 4 + c * 2 + hh, 4736, p.out_part_stride, p.out_kch_stride);
-                            uint8_t* row = p.out + (size_t)(w + kGuard) * 16;
-                            if (lane & 1) {
-                                *reinterpret_cast<uint4*>(row + d.lo8) = lo8;
-                                *reinterpret_cast<uint4*>(row + d.hi8) = hi8;
-                            } else {
-                                *reinterpret_cast<uint4*>(row + d.f16) = fa;
-                                *reinterpret_cast<uint4*>(row + d.f16 + p.out_kch_stride) = fb;
-                            }
-                        }
-                    }
-                } else if (store) {
+                if (store) {
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) {
                         uint4 hi, lo;
@@ -396,7 +283,6 @@ block2_kernel(const Block2Params p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if constexpr (CL > 1) ptx::cluster_sync();      // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
 }
 

@@ -61,18 +61,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- thread-block clusters: multicast bulk copy, multicast MMA-completion arrive (experimental block2 variant) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// One copy from global memory lands at the same shared-memory offset in every CTA of `cta_mask`, and completes
-// `bytes` on the mbarrier at the same offset as `bar` in each of them (SASS UBLKCP.S.G.MULTICAST).
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-
 // ---- TMEM ---------------------------------------------------------------------
 // Whole warp executes alloc/dealloc (.sync.aligned). ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -119,43 +107,10 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// ---- fp16 main + e4m3 corrections (experimental FC mode, dce_tc_f16f8.cuh) -----------------------
-// kind::f16 with fp16 operands, and kind::f8f6f4 with e4m3 operands (K = 32 per instruction: two 16-byte
-// K chunks of 16 elements, same descriptors as above).  Both accumulate in fp32 in the same TMEM columns.
-__host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // A = B = F16 (format 0)
-}
-__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // A = B = E4M3 (format 0 of kind::f8f6f4)
-}
-__device__ __forceinline__ void umma_e4m3_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// D = A * B + D * 2^-S (scale-input-d, kind::f16 only): brings an accumulator that holds the e4m3 correction
-// products at scale 2^S down to the scale of the fp16 main products.
-template <int S>
-__device__ __forceinline__ void umma_f16_ss_scale_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
-    static_assert(S >= 0 && S <= 15, "scale-input-d is a 4-bit immediate");
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.eq.b32 p, %3, %3;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(S) : "memory");
-}
 // mbarrier arrives when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// the same arrive, delivered to the mbarrier at this offset in every CTA of `cta_mask` (SASS UTCBAR.MULTICAST)
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns ---------------

@@ -8,59 +8,27 @@
 namespace dce {
 namespace tc {
 
-// debug/ablation switch: 0 = one kernel per layer (ingest, conv1, conv2 as separate launches)
-inline int& fuse_block1_flag() { static int v = 1; return v; }
-inline int& fuse_block2_flag() { static int v = 1; return v; }
-inline int& fuse_fc3_flag() { static int v = 1; return v; }
-inline int& fc_f16f8_flag() { static int v = 0; return v; }        // experimental: fc.0 / fc.3 operands as fp16 + e4m3 corrections (dce_tc.cuh)
-inline int& conv_f16f8_flag() { static int v = 0; return v; }      // experimental, needs fc_f16f8: 1 = X2 and the whole of block2 in that format too; 2 = block1's two convolutions as well
-inline int& fc_cluster_flag() { static int v = 0; return v; }       // experimental: 2 = fc.0 / fc.3 as CTA pairs that share the activation slabs by multicast
-inline int& block2_cluster_flag() { static int v = 0; return v; }   // experimental: 2 or 4 = block2 in clusters that share the weight stream by multicast
-inline int& block1_dbg_flag() { static int v = 0; return v; }
-inline long long*& block1_trace_ptr() { static long long* v = nullptr; return v; }
-inline int& tapgemm_dbg_flag() { static int v = 0; return v; }
-inline int& tapgemm_trace_layer() { static int v = -1; return v; }   // which layer (2..5) records into the trace buffer
-
-// block2 as thread-block clusters of CL CTAs (block2_kernel<.., CL>): the grid is a whole number of clusters, and no
-// more of them than the device can hold at once (with 1 CTA per SM a GPC whose SM count is not a multiple of CL
-// leaves SMs without a cluster; a second wave would double the kernel's time).
-template <bool F8OUT, bool F8IN, int CL>
-inline int launch_block2_cluster(Ctx& ctx, const char* name, int sm_count, const Block2Params& b) {
-    auto kern = block2_kernel<F8OUT, F8IN, CL>;
-    static DeviceOnce once;
-    static int max_clusters[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (auto first_ = once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(sm_count / CL * CL)); cfg.blockDim = dim3(kB2Threads); cfg.dynamicSmemBytes = kB2SmemBytes;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int n = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-        if (e != cudaSuccess || n < 1) { ctx.err = (e != cudaSuccess) ? e : cudaErrorLaunchOutOfResources; return DCE_ECUDA; }
-        max_clusters[dev] = n;
-    }
-    int clusters = (b.n_tiles + CL - 1) / CL;
-    if (clusters > max_clusters[dev]) clusters = max_clusters[dev];
-    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl_cluster(kern, dim3((unsigned)(clusters * CL)), dim3(kB2Threads), kB2SmemBytes, ctx.stream, CL, b); (void)le_; });
-    return DCE_OK;
-}
+// Ablation / debugging switches.  They live in the dce_weights handle (dce_weights_set_option), not in process-wide
+// state: two handles in one process do not see each other's switches, and dce_forward / dce_stream only read them.
+struct Options {
+    int fuse_block1 = 1;         // 0: ingest, conv1, conv2 as separate launches (activations round-trip through HBM)
+    int fuse_block2 = 1;         // 0: conv3, conv4 as separate launches
+    int fuse_fc3 = 1;            // 0: fc.3 writes H2, a separate kernel does fc.6 + argmax + bits
+    int latency_kernel = 1;      // 0: calls of <= 4 windows take the per-layer kernels
+    int latency_coop = 1, latency_tma_in = 1;
+    int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
+    int tapgemm_dbg = 0;
+    int trace_layer = -1;        // which kernel records into `trace`: -1 block1, 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2
+    long long* trace = nullptr;  // device buffer [60 tiles][16 events] of clock64 samples of CTA 0 (DCE_TRACE builds)
+};
 
 // pointers into the fp32 section of the packed buffer, passed in by dce.cu
 struct BiasPtrs { const float* b[7]; const float* w3; const float* f1; const float* f2; };
 
-// f16f8_call: this call asked for DCE_PREC_F16F8 (fp16 + e4m3 everywhere) — same as the "fc_f16f8" = 1, "conv_f16f8" = 2
-// options, but per call instead of process-wide.
-inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int sm_count, const float* src, bool stream_mode,
-               int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx,
-               bool f16f8_call = false) {
+inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const Options& opt, int sm_count, const float* src,
+               bool stream_mode, int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits,
+               char* ws, Ctx& ctx) {
     cudaStream_t s = ctx.stream;
-    const int opt_fc8 = f16f8_call ? 1 : fc_f16f8_flag(), opt_conv8 = f16f8_call ? 2 : conv_f16f8_flag();
     {
         static DeviceOnce fc3_once;
         if (auto first_ = fc3_once.need()) {
@@ -84,10 +52,6 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         int rc;
         TapGemmParams p{};
         const bool tiny = m <= small::kMaxB;       // latency mode: one M-tile per CTA tile (the second would be padding)
-        const bool f8 = opt_fc8 && fuse_block2_flag() && fuse_fc3_flag() && !tiny;
-        const bool f8c = f8 && opt_conv8 && fuse_block1_flag();
-        const float* scales = reinterpret_cast<const float*>(buf + L.scales);
-        unsigned int* f8_status = reinterpret_cast<unsigned int*>(const_cast<char*>(buf) + L.scales) + kF8StatusWord;
         if (stream_mode) {
             static DeviceOnce st_once;
             if (auto first_ = st_once.need()) {
@@ -96,19 +60,15 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             }
             const int64_t fa = first + c0;
             const int tiles = (int)((fa + m - 1) / kStatWT - fa / kStatWT + 1);       // tiles are aligned to absolute window indices
-            DCE_KL(ctx, "tc_window_stats", { cudaError_t le_ = launch_pdl(window_stats_kernel, dim3(tiles), dim3(256), kStatSmemBytes, s, src, fa, m, total_rows, mean, sdev, fuse_block1_flag() ? 1 : 0); (void)le_; });
+            DCE_KL(ctx, "tc_window_stats", { cudaError_t le_ = launch_pdl(window_stats_kernel, dim3(tiles), dim3(256), kStatSmemBytes, s, src, fa, m, total_rows, mean, sdev, opt.fuse_block1 ? 1 : 0); (void)le_; });
         }
-        if (fuse_block1_flag()) {
+        if (opt.fuse_block1) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static DeviceOnce attr_once;
             if (auto first_ = attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+                if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
             b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m; b.total_rows = total_rows;
@@ -117,22 +77,9 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
-            b.dbg = block1_dbg_flag(); b.trace = (tapgemm_trace_layer() < 0) ? block1_trace_ptr() : nullptr;
+            b.dbg = opt.block1_dbg; b.trace = (opt.trace_layer < 0) ? opt.trace : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (f8c && opt_conv8 >= 2) {                    // conv1 / conv2 themselves in the fp16 + e4m3 format
-                Block1ParamsF8 b8{};
-                static_cast<Block1Params&>(b8) = b;
-                b8.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[10]); b8.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[11]);
-                b8.inv_sw1 = scales + 10 * 4 + 1; b8.inv_sw2 = scales + 11 * 4 + 1; b8.f8_status = f8_status;
-                if (stream_mode)
-                    DCE_KL(ctx, "tc_block1_stream_f16f8", { cudaError_t le_ = launch_pdl(block1_kernel<true, 3>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b8); (void)le_; });
-                else
-                    DCE_KL(ctx, "tc_block1_f16f8", { cudaError_t le_ = launch_pdl(block1_kernel<false, 3>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b8); (void)le_; });
-            } else if (f8c && stream_mode)
-                DCE_KL(ctx, "tc_block1_stream_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<true, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
-            else if (f8c)
-                DCE_KL(ctx, "tc_block1_f8out", { cudaError_t le_ = launch_pdl(block1_kernel<false, 1>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
-            else if (stream_mode)
+            if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
                 DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1_kernel<false>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
@@ -161,41 +108,22 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.out = x2; p.out_part_stride = W.x2.part_stride; p.out_kch_stride = W.x2.kch_stride; p.out_rows_cap = W.x2.m_tiles * 128;
         if ((rc = launch_layer<64, 3, 4, 4, EPI_POOL_TAPE>(ctx, "tc_conv2_pool", sm_count, p)) != DCE_OK) return rc;
         }
-        if (fuse_block2_flag() && !tiny) {
+        if (opt.fuse_block2 && !tiny) {
             // ---- fused conv3 + conv4 + pool + flatten (a7-a9): X2 -> X4, X3 stays in shared memory
             static DeviceOnce b2_once;
             if (auto first_ = b2_once.need()) {
-                cudaError_t e = cudaFuncSetAttribute(block2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
-                if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
+                cudaError_t e = cudaFuncSetAttribute(block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block2Params b{};
             b.x2 = x2; b.x2_part_stride = W.x2.part_stride; b.x2_kch_stride = W.x2.kch_stride; b.n_windows = m;
-            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[7]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[3]);
+            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv3Ring]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[3]);
             b.b3 = bp.b[2]; b.b4 = bp.b[3];
             b.out = x4; b.out_part_stride = W.x4.part_stride; b.out_kch_stride = W.x4.kch_stride; b.out_rows_cap = W.x4.m_tiles * 128;
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
-            b.trace = (tapgemm_trace_layer() == 6) ? block1_trace_ptr() : nullptr;
+            b.trace = (opt.trace_layer == 6) ? opt.trace : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            const int cl = block2_cluster_flag();
-            if (f8c) {
-                b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[12]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[13]);
-                b.inv_sw3 = scales + 12 * 4 + 1; b.inv_sw4 = scales + 13 * 4 + 1;
-            }
-            b.f8_status = f8 ? f8_status : nullptr;
-            if ((cl == 2 || cl == 4) && (f8c || !f8)) {
-                rc = f8c ? (cl == 2 ? launch_block2_cluster<true, true, 2>(ctx, "tc_block2_f16f8_cl2", sm_count, b)
-                                    : launch_block2_cluster<true, true, 4>(ctx, "tc_block2_f16f8_cl4", sm_count, b))
-                         : (cl == 2 ? launch_block2_cluster<false, false, 2>(ctx, "tc_block2_cl2", sm_count, b)
-                                    : launch_block2_cluster<false, false, 4>(ctx, "tc_block2_cl4", sm_count, b));
-                if (rc != DCE_OK) return rc;
-            } else if (f8c) {
-                DCE_KL(ctx, "tc_block2_f16f8", { cudaError_t le_ = launch_pdl(block2_kernel<true, true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
-            } else if (f8)
-                DCE_KL(ctx, "tc_block2_f8out", { cudaError_t le_ = launch_pdl(block2_kernel<true>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
-            else
-                DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel<false>, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+            DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
         } else {
         p = TapGemmParams{};
         p.n_tiles = 1;
@@ -205,8 +133,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.x2.m_tiles; p.stages = kLayers[2].stages;
         p.out = x3; p.out_part_stride = W.x3.part_stride; p.out_kch_stride = W.x3.kch_stride; p.out_rows_cap = W.x3.m_tiles * 128;
         p.N = 128; p.rw = kRW2; p.tv = 75;
-        p.dbg = tapgemm_dbg_flag();
-        p.trace = (tapgemm_trace_layer() == 2) ? block1_trace_ptr() : nullptr;
+        p.dbg = opt.tapgemm_dbg;
+        p.trace = (opt.trace_layer == 2) ? opt.trace : nullptr;
         if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
         rc = tiny ? launch_layer<128, 3, 4, 3, EPI_TAPE, 1, 2>(ctx, "tc_conv3", sm_count, p)
                   : launch_layer<128, 3, 4, 3, EPI_TAPE, 2, 2>(ctx, "tc_conv3", sm_count, p);
@@ -216,7 +144,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
         p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
         p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
-        p.trace = (tapgemm_trace_layer() == 3) ? block1_trace_ptr() : nullptr;
+        p.trace = (opt.trace_layer == 3) ? opt.trace : nullptr;
         if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
         rc = tiny ? launch_layer<128, 3, 2, 6, EPI_POOL_FC, 1>(ctx, "tc_conv4_pool", sm_count, p)
                   : launch_layer<128, 3, 2, 4, EPI_POOL_FC, 2>(ctx, "tc_conv4_pool", sm_count, p);
@@ -246,35 +174,20 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, int s
         p.m_tiles = W.x4.m_tiles; p.n_tiles = kLayers[4].n_tiles; p.stages = kLayers[4].stages;
         p.out = h1; p.out_part_stride = W.h1.part_stride; p.out_kch_stride = W.h1.kch_stride; p.out_rows_cap = W.h1.m_tiles * 128;
         p.N = 2048; p.rw = 1; p.tv = 1;
-        p.dbg = tapgemm_dbg_flag();
-        p.trace = (tapgemm_trace_layer() == 4) ? block1_trace_ptr() : nullptr;
-        const bool fcl = fc_cluster_flag() == 2;
-        if (f8) {
-            p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[8]); p.acc_scale = scales + 8 * 4 + 1; p.f8_status = f8_status;
-            rc = fcl ? launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1, 2>(ctx, "tc_fc1_f16f8_cl2", sm_count, p) : DCE_EUNSUPPORTED;
-            if (rc == DCE_EUNSUPPORTED) rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1_f16f8", sm_count, p);
-        } else {
-            rc = fcl ? launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2, 0, 0, 2>(ctx, "tc_fc1_cl2", sm_count, p) : DCE_EUNSUPPORTED;
-            if (rc == DCE_EUNSUPPORTED) rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
-        }
+        p.dbg = opt.tapgemm_dbg;
+        p.trace = (opt.trace_layer == 4) ? opt.trace : nullptr;
+        rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
         if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
         p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[5]); p.bias = bp.b[5];
         p.m_tiles = W.h1.m_tiles; p.n_tiles = kLayers[5].n_tiles; p.stages = kLayers[5].stages;
         p.out = nullptr; p.out_f32 = h2; p.N = 512; p.n_valid = m;
-        p.trace = (tapgemm_trace_layer() == 5) ? block1_trace_ptr() : nullptr;
-        if (fuse_fc3_flag()) {
+        p.trace = (opt.trace_layer == 5) ? opt.trace : nullptr;
+        if (opt.fuse_fc3) {
             // ---- fc.3 + ReLU with fc.6 folded into the epilogue (a11, a12): H2 stays in registers; 8 logit shares per window
             p.w3t = bp.w3;
-            if (f8) {
-                p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[9]); p.acc_scale = scales + 9 * 4 + 1;
-                rc = fcl ? launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1, 2>(ctx, "tc_fc2_fc3_f16f8_cl2", sm_count, p) : DCE_EUNSUPPORTED;
-                if (rc == DCE_EUNSUPPORTED) rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 1>(ctx, "tc_fc2_fc3_f16f8", sm_count, p);
-            } else {
-                rc = fcl ? launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 0, 2>(ctx, "tc_fc2_fc3_cl2", sm_count, p) : DCE_EUNSUPPORTED;
-                if (rc == DCE_EUNSUPPORTED) rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
-            }
+            rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
             if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,
                 (const float*)h2, bp.b[6], (int64_t)m, 2 * kLayers[5].n_tiles, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,

@@ -49,11 +49,6 @@ class ContactEngine:
         _lib.check(self.lib.dce_weights_create(ctypes.byref(self._handle), self.device.index), "dce_weights_create")
         self._workspace: Optional[torch.Tensor] = None
         self.last_launches = 0
-        # precision "f16f8" only: after every classify() / stream() read the kernels' range word (one device
-        # synchronisation per call) and redo the call in bf16x3 when an activation left the range the fp16 + e4m3
-        # error model assumes.  Off by default: the check costs the asynchrony of the call.
-        self.guard = os.environ.get("DCE_F16F8_GUARD", "0") == "1"
-        self.fallbacks = 0
         if params is not None:
             self.pack(params)
 
@@ -144,13 +139,6 @@ class ContactEngine:
                                       ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_forward")
         self.last_launches = self.lib.dce_last_launch_count()
-        if self.guard and self.precision == "f16f8" and self.f16f8_status(reset=True):
-            self.fallbacks += 1
-            with torch.cuda.device(self.device):
-                rc = self.lib.dce_forward(self._handle, self._p(x), n, self._p(logits), self._p(cls), self._p(bits),
-                                          self._p(ws), ws.numel(), _lib.PRECISIONS["bf16x3"], ctypes.c_void_p(stream.cuda_stream))
-            _lib.check(rc, "dce_forward")
-            self.last_launches += self.lib.dce_last_launch_count()
         return logits, cls, bits
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -298,14 +286,6 @@ class ContactEngine:
                                      _lib.PRECISIONS[self.precision], ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_stream")
         self.last_launches = self.lib.dce_last_launch_count()
-        if self.guard and self.precision == "f16f8" and self.f16f8_status(reset=True):
-            self.fallbacks += 1
-            with torch.cuda.device(self.device):
-                rc = self.lib.dce_stream(self._handle, self._p(data), T, first_window, n_windows,
-                                         self._p(logits), self._p(cls), self._p(bits), self._p(ws), ws.numel(),
-                                         _lib.PRECISIONS["bf16x3"], ctypes.c_void_p(stream.cuda_stream))
-            _lib.check(rc, "dce_stream")
-            self.last_launches += self.lib.dce_last_launch_count()
         return logits, cls, bits
 
     def stream_host(self, log_host: torch.Tensor, chunk_rows: int = 1 << 18, out_bits_host: Optional[torch.Tensor] = None,
@@ -364,14 +344,18 @@ class ContactEngine:
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
         return LatencyRunner(self, n, want_logits, use_graph)
 
-    def f16f8_status(self, reset: bool = True) -> int:
-        """Range diagnostic of the experimental "f16f8" arithmetic (``dce_f16f8_status``): 0 = every activation
-        since the last reset stayed inside the range its error model assumes; bit l = layer l (0 conv1 .. 4 fc.0)
-        wrote a value above 224, bit 8 + l above 65504.  Synchronises the device."""
-        out = ctypes.c_uint32(0)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.dce_f16f8_status(self._handle, ctypes.byref(out), 1 if reset else 0), "dce_f16f8_status")
-        return int(out.value)
+    def set_option(self, key, value: int) -> int:
+        """``dce_weights_set_option``: an ablation / debugging switch of THIS engine's handle (include/dce.h);
+        returns the ABI's code (0, or -1 for an unknown key)."""
+        if isinstance(key, str):
+            key = key.encode()
+        return int(self.lib.dce_weights_set_option(self._handle, key, int(value)))
+
+    def read_trace(self, n: int = 60 * 16):
+        """clock64 samples of CTA 0 recorded by the kernel ``trace_layer`` selects (DCE_TRACE=1 builds, option "trace")."""
+        buf = (ctypes.c_longlong * n)()
+        _lib.check(self.lib.dce_debug_read_trace(self._handle, buf, n), "dce_debug_read_trace")
+        return list(buf)
 
     # -- small helpers on the same ABI ------------------------------------------
     def decimal2binary(self, x: torch.Tensor) -> torch.Tensor:

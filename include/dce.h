@@ -19,9 +19,10 @@
  *     call enqueues work (as for any launch on a cudaStream_t); only
  *     dce_weights_create() switches devices itself, and restores the caller's;
  *   - return value: 0 = DCE_OK, negative = DCE_E*; never throws or aborts;
- *   - a handle is immutable after dce_weights_pack() and may be shared by
- *     host threads; dce_forward / dce_stream are re-entrant given distinct
- *     workspaces.
+ *   - a handle is immutable after dce_weights_pack() (its debugging switches,
+ *     dce_weights_set_option, aside) and may be shared by host threads;
+ *     dce_forward / dce_stream keep no state outside the handle and the
+ *     caller's buffers and are re-entrant given distinct workspaces.
  */
 #ifndef DCE_H_
 #define DCE_H_
@@ -61,9 +62,6 @@ extern "C" {
 /* arithmetic mode of the forward pass */
 #define DCE_PREC_FP32    0       /* fp32 FFMA kernels (exact-order-free fp32) */
 #define DCE_PREC_BF16X3  1       /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
-#define DCE_PREC_F16F8   2       /* EXPERIMENTAL, not yet run on a GPU: fp16 products + two e4m3 correction products per
-                                    K-step (2 MMA-slot equivalents instead of 3), every layer; the per-call form of the
-                                    "fc_f16f8" = 1 / "conv_f16f8" = 2 options.  Activations saturate at 65504. */
 
 typedef struct dce_weights dce_weights;
 
@@ -176,41 +174,24 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
                         int64_t *counts_dev, void *stream);
 
 /*
- * Ablation / debugging switches (process-wide).  Keys:
- *   "block1_dbg"   bit mask of timing ablations inside the fused block1 kernel (results invalid);
- *   "block1_trace" 1: record a per-role clock64 timeline of CTA 0 (tools/trace_block1.py);
+ * Ablation / debugging switches OF ONE HANDLE (not process-wide: two handles never see each other's switches).
+ * Not part of the hot path: set them between calls, from one thread, while no call on the handle is in flight.  Keys:
+ *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
+ *                  0: one kernel per layer (activations round-trip through HBM);
  *   "fuse_block2"  1 (default): conv3 + conv4 + pool run as ONE kernel (X3 stays in shared memory); 0: two launches;
  *   "fuse_fc3"     1 (default): fc.6 is folded into fc.3's epilogue (logit shares + a small reduce/argmax kernel);
  *                  0: fc.3 writes H2, a separate kernel does fc.6 + argmax + bits;
- *   "fuse_block1"  1 (default): ingest + conv1 + conv2 + pool run as ONE kernel;
- *                  0: one kernel per layer (activations round-trip through HBM).
  *   "latency_kernel" 1 (default): calls of <= 4 windows run the single cooperative latency kernel;
  *                  0: the per-layer kernels (tensor-core convolutions + fp32 GEMV Linear layers);
- *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel.
- *   "fc_f16f8"     0 (default).  EXPERIMENTAL, written without a GPU and not yet run on one: 1 = fc.0 and fc.3 use
- *                  fp16 main products + e4m3 correction products (two MMA-slot equivalents per K-step instead of
- *                  the three of bf16x3; emulated at 6e-6 norm-wise; activations saturate at 65504).  Needs the
- *                  default "fuse_block2" / "fuse_fc3"; calls of <= 4 windows are unaffected.
- *   "conv_f16f8"   0 (default).  EXPERIMENTAL, as above, needs "fc_f16f8" = 1 and "fuse_block1": 1 = X2 and the whole
- *                  of block2 in that format too, 2 = block1's two convolutions as well.
- *   "block2_cluster" 0 (default).  EXPERIMENTAL, as above: 2 or 4 = the fused block2 kernel runs as thread-block
- *                  clusters whose CTAs share one weight stream from L2 (bulk-TMA multicast); same results bit for bit.
- *   "fc_cluster"   0 (default).  EXPERIMENTAL, as above: 2 = fc.0 and fc.3 run as CTA pairs on the same M-tile that
- *                  fetch each activation slab once and multicast it to both; same results bit for bit.
- * Returns DCE_EINVAL for an unknown key (or an unsupported value).
+ *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel;
+ *   "block1_dbg" / "tapgemm_dbg"  bit masks of timing ablations inside the kernels (results invalid);
+ *   "trace" 1: allocate and arm a per-role clock64 timeline of CTA 0 (libraries built with -DDCE_TRACE=1);
+ *   "trace_layer"  which kernel records it: -1 block1 (default), 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2.
+ * Returns DCE_EINVAL for an unknown key.
  */
-DCE_API int dce_set_option(const char *key, int value);
-
-/*
- * Range diagnostic of the experimental fp16 + e4m3 arithmetic (DCE_PREC_F16F8 / "fc_f16f8"): a word the kernels of
- * that mode OR into.  Bit l (l = 0 conv1, 1 conv2, 2 conv3, 3 conv4, 4 fc.0): layer l wrote an activation above 224,
- * whose second correction term is lost (fp16-only accuracy for that element); bit 8 + l: above 65504, the value
- * itself saturated.  0 = the mode's error model held for everything classified since the last reset.  Synchronises
- * the device (a diagnostic, not a hot-path call); `reset` != 0 clears the word after reading it.
- */
-DCE_API int dce_f16f8_status(dce_weights *w, uint32_t *host_out, int reset);
-/* "block1_trace" armed: copy the first n clock64 samples ([tile][16 events]) of CTA 0 to the host. */
-DCE_API int dce_debug_read_trace(long long *host_out, int n);
+DCE_API int dce_weights_set_option(dce_weights *w, const char *key, int value);
+/* "trace" armed: copy the first n clock64 samples ([tile][16 events]) of CTA 0 to the host. */
+DCE_API int dce_debug_read_trace(dce_weights *w, long long *host_out, int n);
 
 /* How many kernel launches the last dce_forward / dce_stream on this thread enqueued. */
 DCE_API int dce_last_launch_count(void);

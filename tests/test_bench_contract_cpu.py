@@ -33,12 +33,11 @@ def test_product_arm_refuses_to_run_without_a_gpu():
 def test_kernel_flops_cover_the_whole_path():
     """roofline.achieved is algorithmic FLOPs of the dominant kernel: the per-kernel figures, keyed by the profiler
     names of dce_forward_profile, must add up to SURVEY.md §8d's 39 368 192 per window — for the default kernels and
-    for the experimental variants alike."""
+    for the layer-wise ablation alike."""
     sys.path.insert(0, ROOT)
     import bench
     default = ["tc_block1", "tc_block2", "tc_fc1", "tc_fc2_fc3", "logits_argmax_bits"]
     layerwise = ["tc_ingest", "tc_conv1", "tc_conv2_pool", "tc_conv3", "tc_conv4_pool", "tc_fc1", "tc_fc2", "fc3_argmax_bits"]
-    experimental = ["tc_block1_f16f8", "tc_block2_f16f8_cl4", "tc_fc1_f16f8_cl2", "tc_fc2_fc3_f16f8", "logits_argmax_bits"]
-    for names in (default, layerwise, experimental):
+    for names in (default, layerwise):
         assert sum(bench.kernel_flops(n) for n in names) == bench.FLOP_PER_WINDOW, names
     assert bench.kernel_flops("tc_fc1") == 19_398_656 and bench.kernel_flops("tc_window_stats") == 0

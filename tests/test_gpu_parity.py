@@ -19,10 +19,8 @@ from oracle import contact_oracle as oracle
 pytestmark = pytest.mark.gpu
 
 NORTH_STAR_TOL = 1e-4
-TOL = {"fp32": 1e-5, "bf16x3": 3e-5, "f16f8": 3e-5}
+TOL = {"fp32": 1e-5, "bf16x3": 3e-5}
 PRECISIONS = ["fp32", "bf16x3"]
-if os.environ.get("DCE_EXPERIMENTAL") == "1":       # the whole parity suite for the per-call form of the experimental mode too
-    PRECISIONS.append("f16f8")
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +47,28 @@ def engine(dev, precision, seed=0, scale=1.0):
 def oracle_logits(params, x, bs=256):
     with torch.no_grad():
         return torch.cat([oracle.forward_torch(params, x[i:i + bs]) for i in range(0, x.shape[0], bs)]).numpy()
+
+
+def oracle_logits64(params, x, bs=256):
+    """The reference forward in float64 (`model.double()`): the arbiter when two fp32 results pick different classes."""
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        return torch.cat([oracle.forward_torch(p64, x[i:i + bs].double()) for i in range(0, x.shape[0], bs)]).numpy()
+
+
+def assert_classes_exact_up_to_reference_rounding(got_cls, want32, want64):
+    """argmax bit-exact (north star) wherever the reference's own answer is determined by the arithmetic: a window may
+    differ from the reference's fp32 class ONLY if, in float64, the two classes in question are closer than the
+    reference's fp32 logits are to the float64 ones for that window — i.e. the reference itself picks that class by
+    rounding noise (torch fp32 vs torch fp64 of the same module).  Returns the number of such windows."""
+    got_cls = np.asarray(got_cls).astype(np.int64)
+    ref_cls = want32.argmax(1)
+    bad = np.nonzero(got_cls != ref_cls)[0]
+    for i in bad:
+        gap64 = abs(want64[i, got_cls[i]] - want64[i, ref_cls[i]])
+        ref_noise = np.abs(want32[i].astype(np.float64) - want64[i]).max()
+        assert gap64 <= 2.0 * ref_noise, (int(i), int(got_cls[i]), int(ref_cls[i]), float(gap64), float(ref_noise))
+    return len(bad)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -94,10 +114,9 @@ def test_forward_unnormalised_inputs_and_big_logits(dev, precision):
 
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_full_size_batch_properties(dev, params0, precision):
-    """BASELINE config 2 (B=4096): checked through size-independent properties —
+    """BASELINE config 2 (B=4096): every window against the oracle, plus size-independent properties —
     batch invariance (same window, same answer wherever it sits in the batch),
-    bits == decimal2binary(cls), cls == argmax(logits) — plus the oracle on a
-    512-window sample."""
+    bits == decimal2binary(cls), cls == argmax(logits)."""
     eng = engine(dev, precision)
     x = synth.make_windows(4096, seed=1).to(dev)
     logits, cls, bits = eng.classify(x)
@@ -113,10 +132,60 @@ def test_full_size_batch_properties(dev, params0, precision):
     assert torch.equal(cl, cls[1000:1003])
     assert torch.equal(cls.long(), logits.argmax(1))
     assert torch.equal(bits, dce.decimal2binary(cls.long()))
-    idx = torch.arange(0, 4096, 8)
-    want = oracle_logits(params0, x[idx.to(dev)].cpu())
-    assert oracle.normwise_rel_err(logits[idx.to(dev)].cpu().numpy(), want) <= TOL[precision]
-    assert np.array_equal(cls[idx.to(dev)].cpu().numpy(), want.argmax(1))
+    want = oracle_logits(params0, x.cpu())                                   # all 4096 windows
+    assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL[precision]
+    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
+    assert np.array_equal(bits.cpu().numpy(), oracle.decimal2binary_numpy(want.argmax(1)))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("batch", [4097, 8192 + 37, 32768])
+def test_batches_beyond_one_internal_chunk(dev, params0, precision, batch):
+    """dce_forward walks batches of more than 4096 windows in internal chunks (the reference loop it replaces:
+    src/inference_one_seq.py:19-30): a ragged second chunk of ONE window, two chunks + a ragged third, and the
+    per-rank share of BASELINE configs[3] (262 144 windows over 8 GPUs = 32 768) — every window against the oracle."""
+    if precision == "fp32" and batch > 9000:
+        pytest.skip("fp32 arm: the two smaller sizes cover its chunk loop")
+    eng = engine(dev, precision)
+    x = synth.make_windows(batch, seed=200 + batch % 97)
+    want = oracle_logits(params0, x, bs=1024)
+    logits, cls, bits = eng.classify(x.to(dev))
+    torch.cuda.synchronize()
+    assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL[precision]
+    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
+    assert np.array_equal(bits.cpu().numpy(), oracle.decimal2binary_numpy(want.argmax(1)))
+    # chunk boundaries do not show: a window's answer does not depend on where it sits in the call
+    lo2, cl2, _ = eng.classify(x[4000:4200].to(dev))
+    assert torch.equal(lo2, logits[4000:4200]) and torch.equal(cl2, cls[4000:4200])
+
+
+def test_stream_far_positions_of_a_long_log(dev, params0):
+    """BASELINE configs[2] (streaming over a long contiguous log), at the positions that stress it: 64 windows
+    around each of 40 positions spread over a 2 M-step log, where the random-walk channels have drifted to offsets of
+    tens of sigma (utils/data_handler.py:55-57 recomputed per window by the oracle).  Contact bits exact; the windowed
+    prefix-sum statistics must not lose what the reference's two-pass fp32 statistics keep."""
+    T = 2_000_000
+    log = synth.make_sensor_log(T, seed=2)
+    eng = engine(dev, "bf16x3")
+    logd = log.to(dev)
+    n = oracle.num_windows(T)
+    firsts = [int(v) for v in np.linspace(0, n - 64, 40)]
+    firsts[1] += 1                                               # odd first rows too (rows are 216 B: 8-byte aligned only)
+    firsts[-2] -= 17
+    # the whole log in one call (2 M windows, 489 internal chunks), and the 40 spots as separate small calls
+    _, cl_all, bi_all = eng.stream(logd)
+    n_noise = 0
+    for f in firsts:
+        x = oracle.extract_windows(log, f, 64)
+        want32 = oracle_logits(params0, x)
+        lg, cl, bi = eng.stream(logd, f, 64, want_logits=True)
+        assert torch.equal(cl, cl_all[f:f + 64]) and torch.equal(bi, bi_all[f:f + 64])
+        assert oracle.normwise_rel_err(lg.cpu().numpy(), want32) <= NORTH_STAR_TOL
+        if not np.array_equal(cl.cpu().numpy(), want32.argmax(1)):
+            n_noise += assert_classes_exact_up_to_reference_rounding(cl.cpu().numpy(), want32, oracle_logits64(params0, x))
+        else:
+            assert np.array_equal(bi.cpu().numpy(), oracle.decimal2binary_numpy(want32.argmax(1)))
+    assert n_noise <= 2, n_noise                                 # of 2560 windows
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -325,14 +394,14 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
     ref_logits, ref_cls, _ = eng.classify(x)
     try:
         for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3"):
-            assert eng.lib.dce_set_option(key, 0) == 0
+            assert eng.set_option(key, 0) == 0
             lo, cl, _ = eng.classify(x)
             assert torch.equal(cl, ref_cls)
             assert oracle.normwise_rel_err(lo.cpu().numpy(), ref_logits.cpu().numpy()) <= 1e-5
-            assert eng.lib.dce_set_option(key, 1) == 0
-        assert eng.lib.dce_set_option(b"no_such_option", 1) == -1
+            assert eng.set_option(key, 1) == 0
+        assert eng.set_option(b"no_such_option", 1) == -1
     finally:
-        eng.lib.dce_set_option(b"fuse_block1", 1); eng.lib.dce_set_option(b"fuse_block2", 1); eng.lib.dce_set_option(b"fuse_fc3", 1)
+        eng.set_option(b"fuse_block1", 1); eng.set_option(b"fuse_block2", 1); eng.set_option(b"fuse_fc3", 1)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -361,12 +430,12 @@ def test_latency_kernel_batch_and_stream(dev, params0, precision):
             assert oracle.normwise_rel_err(ls.cpu().numpy(), wl.numpy()[first:first + B]) <= 1e-5
             assert np.array_equal(bs.cpu().numpy(), wb.numpy()[first:first + B])
         try:
-            assert eng.lib.dce_set_option(b"latency_kernel", 0) == 0
+            assert eng.set_option(b"latency_kernel", 0) == 0
             lo, co, _ = eng.classify(x.to(dev))
             assert eng.last_launches > 1
             assert torch.equal(co, cl) and oracle.normwise_rel_err(lo.cpu().numpy(), lg.cpu().numpy()) <= TOL[precision]
         finally:
-            eng.lib.dce_set_option(b"latency_kernel", 1)
+            eng.set_option(b"latency_kernel", 1)
     # a bigger batch in between reuses the same workspace (tapes over the latency buffers): the header with the
     # barrier counters must survive it
     eng.classify(synth.make_windows(300, seed=3).to(dev))
@@ -386,7 +455,11 @@ def test_stream_statistics_offsets_and_nonfinite(dev, params0, precision):
     lg, cl, bi = eng.stream(log.to(dev), want_logits=True)
     # the reference's own fp32 mean loses ~2e-5 sigma at these offsets: compare at the north-star bar
     assert oracle.normwise_rel_err(lg.cpu().numpy(), wl.numpy()) <= NORTH_STAR_TOL
-    assert (cl.cpu().numpy() == wc.numpy()).mean() >= 0.995
+    # argmax exact wherever the reference's own class is not decided by its rounding noise: every window whose class
+    # differs must have a float64 top-2 gap below the reference's own fp32-vs-fp64 distance
+    x = oracle.extract_windows(log, 0, oracle.num_windows(700))
+    n_noise = assert_classes_exact_up_to_reference_rounding(cl.cpu().numpy(), wl.numpy(), oracle_logits64(params0, x))
+    assert n_noise <= 3, n_noise
     bad = synth.make_sensor_log(700, seed=18)
     bad[333, 7] = float("nan")
     bad[500, 20] = float("inf")
@@ -472,70 +545,3 @@ def test_realtime_estimator_on_gpu(dev, params0):
     got = [est.push_row(log[t]) for t in range(log.shape[0])]
     assert all(g is None for g in got[:149])
     assert [g[0] for g in got[149:]] == wc.tolist() and [list(g[1]) for g in got[149:]] == wb.tolist()
-
-
-@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
-                    reason="the fp16 + e4m3 modes (options fc_f16f8 / conv_f16f8) have not run on a GPU yet: DCE_EXPERIMENTAL=1 to try them")
-@pytest.mark.parametrize("conv", [0, 1, 2])
-@pytest.mark.parametrize("scale", [1.0, 50.0])
-def test_experimental_f16f8_matches_oracle(dev, scale, conv):
-    """fp16 main products + e4m3 corrections (two MMA-slot equivalents instead of three) in fc.0 / fc.3 (conv = 0),
-    plus block2 (1), plus block1 (2): same bar as bf16x3.  Off by default; the options are restored whatever happens."""
-    eng = engine(dev, "bf16x3", 0, scale)
-    x = synth.make_windows(300, seed=77)
-    want = oracle_logits(synth.make_params(0, logit_scale=scale), x)
-    try:
-        assert eng.lib.dce_set_option(b"fc_f16f8", 1) == 0 and eng.lib.dce_set_option(b"conv_f16f8", conv) == 0
-        logits, cls, bits = eng.classify(x.to(dev))
-        torch.cuda.synchronize()
-        assert eng.f16f8_status() == 0          # z-scored inputs, default-init weights: nothing near the e4m3 / fp16 range limits
-    finally:
-        eng.lib.dce_set_option(b"fc_f16f8", 0)
-        eng.lib.dce_set_option(b"conv_f16f8", 0)
-    assert oracle.normwise_rel_err(logits.cpu().numpy(), want) <= TOL["bf16x3"]
-    assert np.array_equal(cls.cpu().numpy(), want.argmax(1))
-
-
-@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
-                    reason="block2 in clusters (option block2_cluster) has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
-@pytest.mark.parametrize("cl", [2, 4, -2])
-@pytest.mark.parametrize("batch", [7, 300, 4096])
-def test_experimental_block2_cluster_is_bit_identical(dev, cl, batch):
-    """block2 as clusters of 2 / 4 CTAs sharing the weight stream by multicast: same arithmetic, same bits — also when
-    the last round has CTAs without a tile (batch 7: 5 tiles on 2 clusters of 4, or 3 of 2) and with many rounds (4096)."""
-    eng = engine(dev, "bf16x3")
-    x = synth.make_windows(batch, seed=55).to(dev)
-    want, wc, _ = eng.classify(x)
-    torch.cuda.synchronize()
-    try:
-        if cl > 0:
-            assert eng.lib.dce_set_option(b"block2_cluster", cl) == 0
-        else:                                   # -2: fc.0 / fc.3 as CTA pairs sharing the activation slabs
-            assert eng.lib.dce_set_option(b"fc_cluster", 2) == 0
-        got, gc, _ = eng.classify(x)
-        torch.cuda.synchronize()
-    finally:
-        eng.lib.dce_set_option(b"block2_cluster", 0)
-        eng.lib.dce_set_option(b"fc_cluster", 0)
-    assert torch.equal(got, want) and torch.equal(gc, wc)
-
-
-@pytest.mark.skipif(os.environ.get("DCE_EXPERIMENTAL") != "1",
-                    reason="the fp16 + e4m3 mode has not run on a GPU yet: DCE_EXPERIMENTAL=1 to try it")
-def test_experimental_f16f8_guard_falls_back_to_bf16x3(dev, params0):
-    """ContactEngine.guard: windows whose activations leave the range the fp16 + e4m3 error model assumes (here inputs
-    3000x too large: conv1 writes values far above 224) set the kernels' range word; the call is then redone in
-    bf16x3 and returns exactly what a bf16x3 engine returns.  In-range windows never fall back."""
-    eng8 = dce.ContactEngine(params0, dev, "f16f8")
-    eng8.guard = True
-    ref = engine(dev, "bf16x3")
-    x = synth.make_windows(64, seed=9).to(dev)
-    got = eng8.classify(x)
-    assert eng8.fallbacks == 0 and eng8.f16f8_status() == 0
-    assert torch.equal(got[1], ref.classify(x)[1])
-    big = x * 3000.0
-    got = eng8.classify(big)
-    want = ref.classify(big)
-    assert eng8.fallbacks == 1
-    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
-    eng8.close()

@@ -18,9 +18,9 @@ def step_us(n=60):
 for key in [k.encode() for k in sys.argv[1:]] or [b"fuse_fc3"]:
     res = {}
     for v in (1, 0, 1, 0):
-        eng.lib.dce_set_option(key, v)
+        eng.set_option(key, v)
         res.setdefault(v, []).append(round(step_us(), 1))
-    eng.lib.dce_set_option(key, 1)
+    eng.set_option(key, 1)
     prof = {}
     for i in range(10):
         for n, ms in eng.profile_forward(xs[i % 4]): prof[n] = prof.get(n, 0) + ms * 100

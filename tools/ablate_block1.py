@@ -12,7 +12,7 @@ eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 xs = [synth.make_windows(4096, seed=10 + i).to(dev) for i in range(3)]
 key = b"tapgemm_dbg" if "--tapgemm" in sys.argv else b"block1_dbg"
 for dbg in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [0, 1, 2, 4, 8, 9, 11, 15]:
-    eng.lib.dce_set_option(key, dbg)
+    eng.set_option(key, dbg)
     for i in range(3):
         eng.classify(xs[i % 3])
     tot = {}

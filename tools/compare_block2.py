@@ -7,7 +7,7 @@ eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 xs = [synth.make_windows(4096, seed=10 + i).to(dev) for i in range(3)]
 ref = None
 for fuse in (0, 1):
-    eng.lib.dce_set_option(b"fuse_block2", fuse)
+    eng.set_option(b"fuse_block2", fuse)
     for i in range(3): out = eng.classify(xs[0])
     torch.cuda.synchronize()
     if ref is None: ref = [t.clone() for t in out]

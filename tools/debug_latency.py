@@ -79,7 +79,7 @@ x = synth.make_windows(1, seed=5).to(dev)
 for label, opts in (("fused coop", {b"latency_kernel": 1, b"latency_coop": 1}), ("fused non-coop", {b"latency_kernel": 1, b"latency_coop": 0}),
                     ("per-layer", {b"latency_kernel": 0})):
     for k, v in opts.items():
-        eng.lib.dce_set_option(k, v)
+        eng.set_option(k, v)
     try:
         s = torch.cuda.Stream(dev)
         with torch.cuda.stream(s):
@@ -98,7 +98,7 @@ for label, opts in (("fused coop", {b"latency_kernel": 1, b"latency_coop": 1}), 
     except Exception as e:                                # e.g. cooperative launch not capturable
         print(f"{label}: FAILED {type(e).__name__}: {e}", flush=True)
         ok = False
-eng.lib.dce_set_option(b"latency_kernel", 1); eng.lib.dce_set_option(b"latency_coop", 1)
+eng.set_option(b"latency_kernel", 1); eng.set_option(b"latency_coop", 1)
 # phase timeline (clock64 of the first and last CTA, written behind the barrier counters)
 NAMES = ["start", "A done", "bar1", "B done", "bar2", "C done", "bar3", "D done", "E done (last CTA only)", "exit"]
 for mode in ("batch", "stream"):

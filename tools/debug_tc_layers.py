@@ -2,10 +2,7 @@
 """GPU debugging aid: run the bf16x3 path on a few windows, decode every
 activation tape out of the workspace and compare layer by layer with the oracle
 (torch CPU fp32).  Not part of the product path.
-    python tools/debug_tc_layers.py [B] [--layerwise] [--block2] [--f16f8] [--conv-f16f8=1|2]
---f16f8 turns on the experimental fp16 + e4m3 FC mode (implies the fused block2 kernel) and decodes X4 / H1 in
-that format: value = fp16 + lo8 * 2^-12, and hi8 * 2^-1 must agree with it to e4m3 precision.
---conv-f16f8=1 adds X2 and block2 in that format (X2 is decoded accordingly), =2 block1's convolutions too."""
+    python tools/debug_tc_layers.py [B] [--layerwise] [--block2]"""
 import os
 import sys
 
@@ -47,21 +44,6 @@ def decode(ws, t):
     return v.permute(1, 0, 2).reshape(t["cap"], t["kch"] * 8)[GUARD:GUARD + t["rows"]].cpu()
 
 
-def decode_f16f8(ws, t, name):
-    """fp16 chunks in part 0, e4m3 images (lo8 then hi8, K/16 chunks each) in part 1."""
-    cap, kch = t["cap"], t["kch"]
-    part = cap * 16 * kch
-    f16 = ws[t["off"]: t["off"] + part].view(torch.float16).view(kch, cap, 8).float()
-    f8 = ws[t["off"] + part: t["off"] + 2 * part].view(torch.float8_e4m3fn).view(2, kch // 2, cap, 16).float()
-    main = f16.permute(1, 0, 2).reshape(cap, kch * 8)[GUARD:GUARD + t["rows"]].cpu()
-    lo = f8[0].permute(1, 0, 2).reshape(cap, kch * 8)[GUARD:GUARD + t["rows"]].cpu() * 2.0 ** -12
-    hi = f8[1].permute(1, 0, 2).reshape(cap, kch * 8)[GUARD:GUARD + t["rows"]].cpu() * 0.5
-    v = main + lo
-    dev = ((hi - v).abs() / v.abs().clamp_min(2.0 ** -7)).max().item()
-    print(f"{name}: hi8 image vs value, max relative deviation {dev:.3f} (e4m3: <= 0.0625 for |v| >= 2^-7)")
-    return v
-
-
 def report(name, got, want):
     err = (got - want).abs().max().item()
     ref = want.abs().max().item()
@@ -77,18 +59,9 @@ def main():
     params = synth.make_params(0)
     x = synth.make_windows(B, seed=1)
     eng = dce.ContactEngine(params, dev, "bf16x3")
-    eng.lib.dce_set_option(b"fuse_block1", 0 if layerwise else 1)
-    f16f8 = "--f16f8" in sys.argv
-    fused2 = "--block2" in sys.argv or f16f8
-    eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
-    conv8 = max([int(a.split("=")[1]) for a in sys.argv if a.startswith("--conv-f16f8=")] or [0])
-    if layerwise:
-        conv8 = 0                      # the conv variants exist only in the fused block kernels
-    f16f8 = f16f8 or conv8 > 0
-    fused2 = fused2 or f16f8
-    eng.lib.dce_set_option(b"fuse_block2", 1 if fused2 else 0)
-    assert eng.lib.dce_set_option(b"fc_f16f8", 1 if f16f8 else 0) == 0
-    assert eng.lib.dce_set_option(b"conv_f16f8", conv8) == 0
+    eng.set_option(b"fuse_block1", 0 if layerwise else 1)
+    fused2 = "--block2" in sys.argv
+    eng.set_option(b"fuse_block2", 1 if fused2 else 0)
     logits, cls, bits = eng.classify(x.to(dev))
     torch.cuda.synchronize()
     ws = eng._workspace
@@ -115,17 +88,12 @@ def main():
         report("x0", x0[:, :150, :54], x)
         print("x0 pad channels / guard rows:", x0[:, :, 54:].abs().max().item(), x0[:, 150:, :].abs().max().item())
         conv_tape("x1", a1, 152, 150, 64)
-    if conv8:
-        got2 = decode_f16f8(ws, W["x2"], "x2").reshape(B, 76, -1)
-        print(f"x2: guard rows max |v| = {got2[:, 75:, :].abs().max().item():.3e}")
-        report("x2", got2[:, :75, :64], a2.permute(0, 2, 1))
-    else:
-        conv_tape("x2", a2, 76, 75, 64)
+    conv_tape("x2", a2, 76, 75, 64)
     if not fused2:
         conv_tape("x3", a3, 76, 75, 128)
-    x4 = decode_f16f8(ws, W["x4"], "x4") if f16f8 else decode(ws, W["x4"])      # [B][592*8], k' = t*128 + c
+    x4 = decode(ws, W["x4"])      # [B][592*8], k' = t*128 + c
     report("x4", x4.reshape(B, 37, 128), a4.permute(0, 2, 1))
-    report("h1", decode_f16f8(ws, W["h1"], "h1") if f16f8 else decode(ws, W["h1"]), f1)
+    report("h1", decode(ws, W["h1"]), f1)
     h2 = ws[W["h2"]["off"]: W["h2"]["off"] + B * 512 * 4].view(torch.float32).view(B, 512).cpu()
     report("h2", h2, f2)
     report("logits", logits.cpu(), want)

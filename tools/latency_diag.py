@@ -11,8 +11,8 @@ dev = torch.device("cuda", 0)
 eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 N = 2000
 for coop, tma in ((1, 1), (1, 0), (0, 1)):
-    eng.lib.dce_set_option(b"latency_coop", coop)
-    eng.lib.dce_set_option(b"latency_tma_in", tma)
+    eng.set_option(b"latency_coop", coop)
+    eng.set_option(b"latency_tma_in", tma)
     run = eng.latency_runner(1)
     run.x_host.copy_(synth.make_windows(1, seed=6))
     for _ in range(50):
@@ -43,7 +43,7 @@ for coop, tma in ((1, 1), (1, 0), (0, 1)):
         t1 = time.perf_counter()
         b.record(s); b.synchronize()
     print(f"device-resident coop={coop} tma_in={tma}: host enqueue {1e6 * (t1 - t0) / N:.1f} us/call, device back-to-back {a.elapsed_time(b) * 1e3 / N:.1f} us/call", flush=True)
-eng.lib.dce_set_option(b"latency_coop", 1); eng.lib.dce_set_option(b"latency_tma_in", 1)
+eng.set_option(b"latency_coop", 1); eng.set_option(b"latency_tma_in", 1)
 
 # direct C-ABI launches (no CUDA graph) on the runner's stream: host cost per call and device period
 import ctypes

@@ -10,10 +10,9 @@ dev = torch.device("cuda", 0)
 eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 x = synth.make_windows(4096, seed=1).to(dev)
 for _ in range(3): eng.classify(x)
-eng.lib.dce_set_option(b"block1_trace", 1); eng.lib.dce_set_option(b"trace_layer", layer)
+eng.set_option(b"trace", 1); eng.set_option(b"trace_layer", layer)
 eng.classify(x); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (60 * 16))()
-assert eng.lib.dce_debug_read_trace(buf, 60 * 16) == 0
+buf = eng.read_trace(60 * 16)
 t = np.array(buf, dtype=np.int64).reshape(60, 16)
 t0 = t[t > 0].min()
 names = ["ld:first", "ld:last", "mma:start", "mma:tempty", "mma:full0", "mma:fullL", "ep:start", "ep:tfull", "ep:done", "s1:pre", "s1:post", "s2:pre", "s2:post", "s3:pre", "s3:post"]
