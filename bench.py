@@ -16,8 +16,15 @@ One JSON line on stdout (rank 0):
   e2e          same metric through ContactEngine.classify_host(): pinned HOST windows in,
                host class/bits out, H2D + D2H inside the timed region
   roofline     dominant kernel: algorithmic FLOPs / its CUDA-event duration vs measured bf16 peak
-  cpu_baseline the oracle (torch CPU restatement of the reference forward) on this box's host cores
-  latency_b1   BASELINE.json's second headline: p50 per-window microseconds at batch 1 (graph replay)
+               (burst or sustained, chosen from the timed region's length and clocks; both fractions printed)
+  cpu_baseline the reference's own contact_cnn (oracle/_ref, byte-compiled from /root/reference; else the oracle
+               port) on this box's host cores
+  stream       BASELINE configs[2]: dce_stream over a long contiguous synthetic log (kernel-only and, through
+               ContactEngine.stream_host, end to end from a pinned HOST log: 216 B per window over PCIe)
+  batch_32768_per_gpu   BASELINE configs[3]: 32 768 windows per rank in ONE dce_forward call (262 144 over 8 GPUs)
+  h2d          the box's pinned host->device copy rate with all ranks copying at once (the e2e ceiling), and
+               classify_host(zero_copy=True) beside the staged default
+  latency_b1   BASELINE.json's second headline: p50 per-window microseconds at batch 1
   torch_eager_gpu  the same module's stock PyTorch layers in eager mode on the same GPU (informational)
 --impl reference times that CPU path alone, same metric/config.
 """
@@ -103,26 +110,41 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def reference_forward(params):
+    """-> (callable x -> logits, kind, description): the reference's own ``contact_cnn`` from oracle/_ref (the module
+    byte-compiled from /root/reference/src/contact_cnn.py by oracle/make_ref.py) when it travelled with the snapshot,
+    else the oracle port (the same ATen ops restated)."""
+    from oracle import make_ref
+    if make_ref.available():
+        ref_cnn, _ = make_ref.load()
+        model = ref_cnn()
+        model.load_state_dict(params)
+        model = model.eval()
+        return model, "reference", "oracle/_ref contact_cnn (the reference's own module, byte-compiled from /root/reference/src/contact_cnn.py)"
+    from oracle import contact_oracle as oracle
+    return (lambda x: oracle.forward_torch(params, x)), "port", "oracle.forward_torch (the reference's contact_cnn ops restated)"
+
+
 def cpu_forward_baseline(batch: int, budget_s: float = 20.0, max_runs: int = 5):
-    """The reference's CPU forward (oracle port: same ATen ops) on all host cores."""
+    """The reference's CPU forward on all host cores, on a bounded sample of the workload."""
     import torch
     from deep_contact_estimator_b200 import synth
-    from oracle import contact_oracle as oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     params = synth.make_params(0)
+    fwd, kind, what = reference_forward(params)
     x = synth.make_windows(batch, seed=1)
     with torch.no_grad():
-        oracle.forward_torch(params, x[:256])                 # warm-up
+        fwd(x[:256])                                          # warm-up
         times, t_begin = [], time.perf_counter()
         while len(times) < max_runs and (time.perf_counter() - t_begin < budget_s or not times):
             t0 = time.perf_counter()
-            y = oracle.forward_torch(params, x)
+            y = fwd(x)
             times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": batch / med, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} x forward of {batch} windows (oracle.forward_torch = reference contact_cnn ops, fp32, "
-                      f"torch {torch.__version__} CPU), median {med * 1e3:.1f} ms",
+    return {"value": batch / med, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} x forward of {batch} windows through {what}, fp32, torch {torch.__version__} CPU, "
+                      f"median {med * 1e3:.1f} ms",
             "ms_per_batch": med * 1e3}, y
 
 
@@ -178,27 +200,29 @@ def gpu_latency_b1(eng, dev, calls: int = 500):
 
 
 def cpu_latency_b1(params, calls: int = 100):
-    """The reference's forward at batch 1 on the host cores (oracle port), p50 microseconds per window."""
+    """The reference's forward at batch 1 on the host cores, p50 microseconds per window."""
     import numpy as np
     import torch
     from deep_contact_estimator_b200 import synth
     from oracle import contact_oracle as oracle
+    fwd, kind, what = reference_forward(params)
     x = synth.make_windows(1, seed=5)
     t = []
     with torch.no_grad():
         for i in range(calls + 5):
             t0 = time.perf_counter()
-            logits = oracle.forward_torch(params, x)
+            logits = fwd(x)
             oracle.decimal2binary(oracle.argmax_class(logits))
             if i >= 5:
                 t.append((time.perf_counter() - t0) * 1e6)
     return {"host_us_p50": float(np.percentile(t, 50)), "host_us_p99": float(np.percentile(t, 99)), "calls": calls,
-            "what": "batch=1 forward + argmax + bits through the oracle port (reference ops) on the host cores"}
+            "what": f"batch=1 forward + argmax + bits through {what} on the host cores", "kind": kind}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path (the
-    oracle port: /root/reference is Python and cannot travel to the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores — oracle/_ref
+    (its contact_cnn byte-compiled from /root/reference, which travels with the snapshot) or, without it, the
+    oracle port.  Under torchrun rank 0 alone runs and prints; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -208,15 +232,16 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     params = synth.make_params(0)
+    fwd, kind, what = reference_forward(params)
     batch = args.batch
     x = synth.make_windows(batch, seed=1)
     with torch.no_grad():
         for _ in range(max(args.warmup, 1)):
-            oracle.forward_torch(params, x[: min(batch, 512)])
+            fwd(x[: min(batch, 512)])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            logits = oracle.forward_torch(params, x)
-            cls = oracle.argmax_class(logits)
+            logits = fwd(x)
+            cls = oracle.argmax_class(logits)                 # torch.max(output, 1) + decimal2binary: src/inference_one_seq.py:26-27
             oracle.decimal2binary(cls)
         dt = time.perf_counter() - t0
     v = batch * args.steps / dt
@@ -227,8 +252,8 @@ def run_reference_arm(args):
         "config": {"workload": workload_name(batch), "precision": "fp32 (ATen CPU kernels)",
                    "weights": "seeded random init (synth.make_params(0))",
                    "host": f"{cores} CPU threads, torch {torch.__version__}"},
-        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} windows through oracle.forward_torch (reference ops on CPU)"},
+        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{args.steps} steps x {batch} windows through {what}"},
         "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "latency_b1": cpu_latency_b1(params),
@@ -286,6 +311,80 @@ def torch_eager_gpu(dev, x, ours_logits, steps: int = 20):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def stream_leg(eng, dev, rank, sync_all, max_over_ranks, steps: int):
+    """BASELINE configs[2]: streaming inference over a long contiguous synthetic sensor log (one log per rank, weak
+    scaling).  `value`: ONE dce_stream call over the device-resident log (window extraction + z-score + forward +
+    argmax + bits, overlapping windows read once).  `e2e`: ContactEngine.stream_host from a PINNED HOST log — the
+    216 B/step upload runs on a side stream under the kernels, classes + bits are read back — so, unlike the batch
+    e2e (32 400 B per window over PCIe), it is not bound by the wire."""
+    import torch
+    from deep_contact_estimator_b200 import synth
+    log = synth.make_sensor_log(steps, seed=2 + rank)
+    n = steps - 149
+    pinned = log.pin_memory()
+    logd = log.to(dev)
+    eng.stream(logd, 0, min(n, 65536))
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps, launches = 2, 0
+    e0.record()
+    for _ in range(reps):
+        eng.stream(logd)
+        launches += eng.last_launches
+    e1.record()
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    del logd
+    out_b = torch.empty((n, 4), dtype=torch.uint8).pin_memory()
+    out_c = torch.empty((n,), dtype=torch.int32).pin_memory()
+    eng.stream_host(pinned[: 300000], out_bits_host=out_b[: 300000 - 149], out_cls_host=out_c[: 300000 - 149])      # warm-up: copy stream, staging
+    sync_all()
+    t0 = time.perf_counter()
+    eng.stream_host(pinned, out_bits_host=out_b, out_cls_host=out_c)                 # returns after the D2H read completed
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    return {"steps_per_gpu": steps, "windows_per_gpu": n, "ms": ms, "e2e_ms": e2e_ms, "launches": launches // reps,
+            "h2d_bytes": steps * 216, "d2h_bytes": n * 8}
+
+
+def big_batch_leg(eng, dev, rank, sync_all, max_over_ranks, per_gpu: int = 32768, reps: int = 3):
+    """BASELINE configs[3]: 262 144 windows sharded over 8 GPUs = 32 768 windows per rank in ONE dce_forward call (the
+    library walks them in internal chunks of 4 096).  Inputs resident in HBM (1.06 GB per rank, far beyond L2), generated
+    on the device with seed 1000 + rank."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x = torch.randn(per_gpu, 150, 54, generator=g, device=dev, dtype=torch.float32)
+    x = ((x - x.mean(dim=1, keepdim=True)) / x.std(dim=1, keepdim=True)).contiguous()
+    eng.classify(x[:8192], want_logits=True)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(reps):
+        eng.classify(x, want_logits=True)
+        launches += eng.last_launches
+    e1.record()
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    return {"windows_per_gpu": per_gpu, "ms_per_call": ms, "launches_per_call": launches // reps}
+
+
+def h2d_leg(dev, pinned, sync_all, max_over_ranks, reps: int = 6):
+    """The box's pinned host -> device copy rate with EVERY rank copying at once (plain cudaMemcpyAsync of one 132.7 MB
+    batch, CUDA-event timed, max over ranks): the ceiling of the batch-mode e2e figure at this N."""
+    import torch
+    dst = torch.empty_like(pinned, device=dev)
+    dst.copy_(pinned, non_blocking=True)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(pinned, non_blocking=True)
+    e1.record()
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    return pinned.numel() * 4 / (ms * 1e-3) / 1e9
+
+
 def kernel_flops(name: str) -> int:
     """Algorithmic FLOPs per window a kernel covers, from its profiler name (dce_forward_profile): a kernel's name
     lists the layers it fuses (`tc_block1` = conv1 + conv2, `tc_block2` = conv3 + conv4, `tc_fc2_fc3` = fc.3 + fc.6)."""
@@ -310,6 +409,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stream-steps", type=int, default=2_000_000, help="rows of the synthetic log of the `stream` leg per GPU (0: skip)")
+    ap.add_argument("--big-batch", type=int, default=32768, help="windows per GPU of the one-call big-batch leg, BASELINE configs[3] (0: skip)")
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
                     help="dce_weights_set_option(KEY, VALUE) before timing (A/B of ablation switches; recorded in config.options)")
     args = ap.parse_args()
@@ -414,6 +515,27 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
 
+    # ---- the box's concurrent pinned H2D rate (the ceiling of `e2e`), and the zero-copy variant of the same call ----
+    h2d_gbs = h2d_leg(dev, pinned[0], sync_all, max_over_ranks)
+    zc = None
+    try:
+        eng.classify_host(pinned[0], out_bits_host, out_cls_host, zero_copy=True)
+        sync_all()
+        t0 = time.perf_counter()
+        zc_steps = min(args.steps, 20)
+        for i in range(zc_steps):
+            eng.classify_host(pinned[i % NBUF], out_bits_host, out_cls_host, zero_copy=True)
+        zc_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / zc_steps
+        zc = {"value": world * B / (zc_ms * 1e-3), "unit": "windows/s", "ms_per_step": zc_ms, "steps": zc_steps,
+              "what": "classify_host(zero_copy=True): no staging copy, block1's bulk-TMA loader reads the pinned windows in place over PCIe"}
+    except Exception as e:                                    # informational leg
+        zc = {"error": f"{type(e).__name__}: {e}"[:200]}
+        sync_all()
+
+    # ---- BASELINE configs[2] and configs[3] ----------------------------------------
+    stream = stream_leg(eng, dev, rank, sync_all, max_over_ranks, args.stream_steps) if args.stream_steps >= 300000 else None
+    big = big_batch_leg(eng, dev, rank, sync_all, max_over_ranks, args.big_batch) if args.big_batch > 0 else None
+
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -430,7 +552,14 @@ def main():
         avg_launch_ms = per_kernel_ms[dom] / n_launch
         flops_per_launch = kernel_flops(dom) * B / n_launch
         achieved_tflops = flops_per_launch / (avg_launch_ms * 1e-3) / 1e12
-        peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        # which measured peak applies: the burst figure for a short timed region at full clocks (a kernel "timed
+        # alone"), the sustained one for a long, power-capped region — both fractions are printed either way
+        p_burst = peaks.get("bf16_tflops") or peaks.get("bf16_tflops_sustained")
+        p_sust = peaks.get("bf16_tflops_sustained") or p_burst
+        capped = bool(clocks and ("sw_power_cap" in (clocks.get("reasons") or []) or
+                                  (clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] < 0.97 * clocks["sm_max_mhz"])))
+        use_burst = (ms_total < 100.0) and not capped
+        peak = p_burst if use_burst else p_sust
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and B == 4096:
@@ -439,7 +568,9 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": dom, "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / peak, "traffic": traffic,
-            "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
+            "frac_of_burst_peak": achieved_tflops / p_burst, "frac_of_sustained_peak": achieved_tflops / p_sust,
+            "peak_source": f"{peak_src} cuBLAS bf16 " + (f"burst ({p_burst} TFLOP/s): timed region of {ms_total:.1f} ms at full clocks, per-kernel times from individually synchronised calls"
+                                                         if use_burst else f"sustained ({p_sust} TFLOP/s): timed region of {ms_total:.1f} ms" + (", power-capped / clocks below max" if capped else "")),
             "note": "algorithmic FLOPs (split-precision passes count once; ceiling of frac is 1/3 with three bf16 passes)",
             "kernel_share_of_step": per_kernel_ms[dom] / step_kernel_ms,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in per_kernel_ms.items()},
@@ -449,8 +580,8 @@ def main():
         }
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (the other ranks' processes share the host cores)
-        cpu, _ = cpu_forward_baseline(B)
+    if not args.no_cpu_baseline:     # rank 0, after every rank's GPU work is done (the others idle at the final barrier); a shorter sample at N > 1
+        cpu, _ = cpu_forward_baseline(B, budget_s=20.0 if world == 1 else 6.0, max_runs=5 if world == 1 else 2)
 
     line = {
         "metric": "contact windows/sec at batch=4096", "value": value, "unit": "windows/s", "n_gpus": world,
@@ -467,7 +598,26 @@ def main():
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "api": "ContactEngine.classify_host (pinned host windows -> host cls+bits)"},
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "latency_b1": latency, "torch_eager_gpu": eager,
+        "h2d": {"pinned_h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs, "e2e_h2d_gbs_per_gpu": B * 32400 / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                "e2e_frac_of_h2d": (B * 32400 / (e2e_ms / e2e_steps * 1e-3) / 1e9) / h2d_gbs, "zero_copy": zc},
     }
+    if stream:
+        n_w = stream["windows_per_gpu"]
+        line["stream"] = {
+            "workload": f"dce_stream over one contiguous synthetic {stream['steps_per_gpu']}-step x 54 fp32 sensor log per GPU "
+                        f"({n_w} windows; BASELINE configs[2], synth.make_sensor_log seed 2 + rank)",
+            "value": world * n_w / (stream["ms"] * 1e-3), "unit": "windows/s", "ms_per_log": stream["ms"],
+            "gpu_launches_per_log": stream["launches"],
+            "e2e": {"value": world * n_w / (stream["e2e_ms"] * 1e-3), "unit": "windows/s", "ms_per_log": stream["e2e_ms"],
+                    "h2d_bytes_per_step": stream["h2d_bytes"], "d2h_bytes_per_step": stream["d2h_bytes"],
+                    "api": "ContactEngine.stream_host (pinned host log -> chunked upload under the kernels -> host cls+bits)"}}
+    if big:
+        tot = world * big["windows_per_gpu"]
+        line["batch_%d" % tot if world == 8 else "batch_32768_per_gpu"] = {
+            "workload": f"{tot} windows over {world} GPU(s): ONE dce_forward call of {big['windows_per_gpu']} resident windows per rank "
+                        f"(BASELINE configs[3] is this at 8 GPUs = 262144)",
+            "value": tot / (big["ms_per_call"] * 1e-3), "unit": "windows/s", "ms_per_call": big["ms_per_call"],
+            "gpu_launches_per_call": big["launches_per_call"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -9,11 +9,12 @@ from .synth import WINDOW, CHANNELS, CLASSES, PARAM_NAMES, PARAM_SHAPES
 from .engine import ContactEngine, LatencyRunner, default_precision
 from .contact_cnn import contact_cnn
 from .data_handler import contact_dataset
-from .inference import inference, inference_and_compute_acc, compute_accuracy, decimal2binary
+from .inference import (inference, inference_and_compute_acc, compute_accuracy, decimal2binary, evaluate,
+                        metrics_from_counts, counts_from_arrays)
 from .realtime import RealtimeContactEstimator
 
 __all__ = [
     "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "RealtimeContactEstimator", "inference", "inference_and_compute_acc",
-    "compute_accuracy", "decimal2binary", "default_precision",
+    "compute_accuracy", "decimal2binary", "default_precision", "evaluate", "metrics_from_counts", "counts_from_arrays",
     "WINDOW", "CHANNELS", "CLASSES", "PARAM_NAMES", "PARAM_SHAPES",
 ]

@@ -19,6 +19,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "dce.h")
 DCE_OK = 0
 DCE_PREC_FP32 = 0
 DCE_PREC_BF16X3 = 1
+DCE_NUM_COUNTS = 277
 PRECISIONS = {"fp32": DCE_PREC_FP32, "bf16x3": DCE_PREC_BF16X3}
 
 _lib = None
@@ -85,6 +86,25 @@ def load(build_if_missing: bool = False):
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+TORCH_LIB_PATH = os.path.join(PKG_DIR, "_dce_torch.so")
+_torch_ops = False          # False: not tried yet; None: unavailable
+
+
+def torch_ops():
+    """``torch.ops.dce`` (csrc/dce_torch.cpp: forward / stream / accuracy_counts registered with the PyTorch dispatcher
+    over the same C ABI), or None when ``_dce_torch.so`` has not been built or ``DCE_BINDING=ctypes`` asks for the
+    plain ctypes binding.  Either way the kernels run: the two bindings call the same ``dce_forward`` / ``dce_stream``."""
+    global _torch_ops
+    if _torch_ops is False:
+        _torch_ops = None
+        if os.environ.get("DCE_BINDING", "torch") != "ctypes" and os.path.exists(TORCH_LIB_PATH):
+            import torch
+            load()                                   # libdce_b200.so first: _dce_torch.so links against it
+            torch.ops.load_library(TORCH_LIB_PATH)
+            _torch_ops = torch.ops.dce
+    return _torch_ops
 
 
 def dce_strerror(code: int) -> str:

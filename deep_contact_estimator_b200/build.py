@@ -1,6 +1,10 @@
-"""Build libdce_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""Build the two in-tree shared objects (both cross-compile without a GPU):
 
-    python -m deep_contact_estimator_b200.build [--force]
+    libdce_b200.so   csrc/dce.cu      nvcc, sm_100a: the kernels + the C ABI of include/dce.h (no torch types)
+    _dce_torch.so    csrc/dce_torch.cpp   g++: the torch extension (TORCH_LIBRARY `dce`: torch.ops.dce.forward / stream /
+                     accuracy_counts) that binds that C ABI to the PyTorch dispatcher; links libdce_b200.so ($ORIGIN rpath)
+
+    python -m deep_contact_estimator_b200.build [--force] [-v]
 """
 from __future__ import annotations
 
@@ -52,5 +56,41 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+TORCH_LIB_PATH = os.path.join(PKG_DIR, "_dce_torch.so")
+TORCH_SOURCES = ["dce_torch.cpp"]
+
+
+def torch_extension_is_stale() -> bool:
+    if not os.path.exists(TORCH_LIB_PATH):
+        return True
+    t = os.path.getmtime(TORCH_LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in TORCH_SOURCES] + [os.path.join(PKG_DIR, "..", "include", "dce.h"), LIB_PATH]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_torch_extension(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/dce_torch.cpp -> _dce_torch.so against this interpreter's torch headers (no nvcc: it holds no kernels)."""
+    build_library(force=False)
+    if not force and not torch_extension_is_stale():
+        return TORCH_LIB_PATH
+    import torch
+    from torch.utils import cpp_extension
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cuda_home = os.environ.get("CUDA_HOME") or os.path.dirname(os.path.dirname(_nvcc()))
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    cmd += ["-I" + p for p in cpp_extension.include_paths()] + ["-I" + os.path.join(cuda_home, "include")]
+    cmd += TORCH_SOURCES + ["-o", TORCH_LIB_PATH]
+    cmd += ["-L" + p for p in cpp_extension.library_paths()] + ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch"]
+    cmd += ["-L" + PKG_DIR, "-l:libdce_b200.so", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return TORCH_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -357,6 +357,7 @@ int dce_weights_set_option(dce_weights* w, const char* key, int value) {
     if (!strcmp(key, "latency_tma_in")) { o.latency_tma_in = value; return DCE_OK; }
     if (!strcmp(key, "block1_dbg")) { o.block1_dbg = value; return DCE_OK; }
     if (!strcmp(key, "tapgemm_dbg")) { o.tapgemm_dbg = value; return DCE_OK; }
+    if (!strcmp(key, "sm_limit")) { if (value < 0) return DCE_EINVAL; o.sm_limit = value; return DCE_OK; }
     if (!strcmp(key, "trace_layer")) { o.trace_layer = value; return DCE_OK; }   // -1: block1; 2..5: conv3, conv4, fc.0, fc.3; 6: block2
     if (!strcmp(key, "trace")) {                 // value != 0: allocate (once) and arm a 60-tile x 16-event clock64 trace of CTA 0
         int prev = 0;
@@ -408,7 +409,8 @@ int dce_accuracy_counts(const int32_t* cls_dev, const int64_t* labels_dev, int64
     if (n == 0) return DCE_OK;
     if (!cls_dev || !labels_dev || !counts_dev) return DCE_EINVAL;
     if ((uintptr_t)cls_dev % 4 || (uintptr_t)labels_dev % 8 || (uintptr_t)counts_dev % 8) return DCE_EALIGN;
-    int64_t blocks = (n + 255) / 256; if (blocks > 1184) blocks = 1184;
+    static_assert(dce::fp32::kNumCounts == DCE_NUM_COUNTS, "include/dce.h and the kernel agree on the counter layout");
+    int64_t blocks = (n + 255) / 256; if (blocks > 592) blocks = 592;
     Ctx ctx; ctx.stream = (cudaStream_t)stream;
     ctx.begin("accuracy_counts");
     dce::fp32::accuracy_counts_kernel<<<(unsigned)blocks, 256, 0, ctx.stream>>>(

@@ -409,22 +409,44 @@ __global__ void ingest_f64_kernel(const double* __restrict__ src, float* __restr
     }
 }
 
-__global__ void accuracy_counts_kernel(const int32_t* __restrict__ cls, const int64_t* __restrict__ labels, int64_t n,
-                                       unsigned long long* __restrict__ counts) {
+// counts[0] class agreement, [1..4] per-leg bit agreement, [5 + 4 leg + 2 gt + pred] the four 2x2 per-leg confusion
+// matrices (rows = ground truth, columns = prediction, as sklearn's confusion_matrix(gt, pred): src/test.py:19-27),
+// [21 + 16 gt + pred] the 16x16 class confusion matrix (what precision_score / jaccard_score(average='weighted') of
+// src/test.py:50-70 are functions of).  Labels outside [0, 16) only count as class disagreements.
+constexpr int kNumCounts = 5 + 16 + 256;
+__global__ void __launch_bounds__(256)
+accuracy_counts_kernel(const int32_t* __restrict__ cls, const int64_t* __restrict__ labels, int64_t n,
+                       unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int h[kNumCounts];
+    for (int j = threadIdx.x; j < kNumCounts; j += blockDim.x) h[j] = 0;
+    __syncthreads();
     unsigned int c[5] = {0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = cls[i], g = labels[i];
         c[0] += (p == g);
+        if ((unsigned long long)g < 16ull && (unsigned long long)p < 16ull) {
+            unsigned int legs = 0;                       // 4 x 4-bit fields: which cell of each leg's 2x2 matrix
 #pragma unroll
-        for (int l = 0; l < 4; ++l) c[1 + l] += (((p >> (3 - l)) & 1) == ((g >> (3 - l)) & 1));
+            for (int l = 0; l < 4; ++l) {
+                const unsigned int pb = (unsigned int)(p >> (3 - l)) & 1u, gb = (unsigned int)(g >> (3 - l)) & 1u;
+                c[1 + l] += (pb == gb);
+                legs |= (2u * gb + pb) << (4 * l);
+            }
+#pragma unroll
+            for (int l = 0; l < 4; ++l) atomicAdd(&h[5 + 4 * l + ((legs >> (4 * l)) & 3u)], 1u);
+            atomicAdd(&h[21 + 16 * (int)g + (int)p], 1u);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         unsigned int v = c[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(counts + j, (unsigned long long)v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&h[j], v);
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kNumCounts; j += blockDim.x)
+        if (h[j]) atomicAdd(counts + j, (unsigned long long)h[j]);
 }
 
 }  // namespace fp32

@@ -18,6 +18,7 @@ struct Options {
     int latency_coop = 1, latency_tma_in = 1;
     int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
     int tapgemm_dbg = 0;
+    int sm_limit = 0;            // > 0: the batch kernels use at most this many CTAs (what a MIG slice / smaller part would give them)
     int trace_layer = -1;        // which kernel records into `trace`: -1 block1, 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2
     long long* trace = nullptr;  // device buffer [60 tiles][16 events] of clock64 samples of CTA 0 (DCE_TRACE builds)
 };
@@ -29,6 +30,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
                bool stream_mode, int64_t total_rows, int64_t first, int64_t n, float* logits, int32_t* cls, uint8_t* bits,
                char* ws, Ctx& ctx) {
     cudaStream_t s = ctx.stream;
+    if (opt.sm_limit > 0 && opt.sm_limit < sm_count) sm_count = opt.sm_limit;
     {
         static DeviceOnce fc3_once;
         if (auto first_ = fc3_once.need()) {
@@ -36,8 +38,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             if (e != cudaSuccess) { ctx.err = e; return DCE_ECUDA; }
         }
     }
-    for (int64_t c0 = 0; c0 < n; c0 += kChunk) {
-        const int m = (int)((n - c0 < kChunk) ? n - c0 : kChunk);
+    int m = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += m) {
+        // chunks of kChunk windows; a tail of <= 4 windows would take the small-batch Linear kernels (fp32 GEMV: the same
+        // logits to rounding, not to the bit), so the chunk before it gives up 64 windows: a window's result never
+        // depends on where it sits in a call of more than 4 windows
+        const int64_t rem = n - c0;
+        m = (int)(rem <= kChunk ? rem : (rem - kChunk <= small::kMaxB ? kChunk - 64 : kChunk));
         const Workspace W = make_workspace(m);
         uint8_t* x0 = reinterpret_cast<uint8_t*>(ws + W.o_x0);
         uint8_t* x1 = reinterpret_cast<uint8_t*>(ws + W.o_x1);

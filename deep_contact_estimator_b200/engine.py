@@ -33,6 +33,11 @@ class ContactEngine:
     ``params``: mapping with the reference's 14 ``state_dict`` keys
     (src/contact_cnn.py:10-58); tensors may live anywhere, they are copied to
     ``device`` as fp32 and repacked once (K0).
+
+    Streams: calls enqueue on the CURRENT torch stream and share one workspace (and, for the host-buffer entry
+    points, one staging area and copy stream) per engine, as include/dce.h's "one workspace serves one call at a
+    time" requires — issue the calls of one engine from one stream (or order the streams yourself); use one engine
+    per concurrent stream otherwise.  ``LatencyRunner`` owns a workspace and stream of its own.
     """
 
     def __init__(self, params: Optional[Mapping[str, torch.Tensor]], device, precision: Optional[str] = None):
@@ -127,7 +132,16 @@ class ContactEngine:
         if x.device != self.device or x.dtype != torch.float32:
             raise ValueError(f"expected float32 on {self.device}, got {x.dtype} on {x.device}")
         x = x.contiguous()
+        if x.data_ptr() % 16:             # a view into a larger buffer at an odd offset
+            x = x.clone()
         n = x.shape[0]
+        ops = _lib.torch_ops()
+        if ops is not None and n:
+            # contact_cnn.forward -> torch.ops.dce.forward -> dce_forward (SURVEY.md §8b "who calls it")
+            logits, cls, bits = ops.forward(self._handle.value, x, self._ws(n), _lib.PRECISIONS[self.precision],
+                                            want_logits, want_cls, want_bits)
+            self.last_launches = self.lib.dce_last_launch_count()
+            return (logits if want_logits else None), (cls if want_cls else None), (bits if want_bits else None)
         logits, cls, bits = self._outs(n, want_logits, want_cls, want_bits)
         if n == 0:
             return logits, cls, bits
@@ -166,6 +180,8 @@ class ContactEngine:
     def profile_stream(self, data: torch.Tensor, first_window: int, n_windows: int):
         """Per-kernel CUDA-event durations of one ``dce_stream`` call (synchronises)."""
         data = data.contiguous()
+        if data.data_ptr() % 16:
+            data = data.clone()
         logits, cls, bits = self._outs(n_windows, False, True, True)
         ws = self._ws(n_windows)
         cap = 64
@@ -269,12 +285,20 @@ class ContactEngine:
         if data.device != self.device or data.dtype != torch.float32:
             raise ValueError(f"expected float32 on {self.device}, got {data.dtype} on {data.device}")
         data = data.contiguous()
+        if data.data_ptr() % 16:          # e.g. log[k:] with odd k: rows are 216 B, the ABI wants a 16-byte aligned base
+            data = data.clone()
         T = data.shape[0]
         total = max(T - WINDOW + 1, 0)
         if n_windows is None:
             n_windows = total - first_window
         if first_window < 0 or n_windows < 0 or first_window + n_windows > total:
             raise ValueError(f"window range [{first_window}, {first_window + n_windows}) outside [0, {total})")
+        ops = _lib.torch_ops()
+        if ops is not None and n_windows:
+            logits, cls, bits = ops.stream(self._handle.value, data, first_window, n_windows, self._ws(n_windows),
+                                           _lib.PRECISIONS[self.precision], want_logits, want_cls, want_bits)
+            self.last_launches = self.lib.dce_last_launch_count()
+            return (logits if want_logits else None), (cls if want_cls else None), (bits if want_bits else None)
         logits, cls, bits = self._outs(n_windows, want_logits, want_cls, want_bits)
         if n_windows == 0:
             return logits, cls, bits
@@ -368,13 +392,17 @@ class ContactEngine:
         return out.reshape(*x.shape, 4)
 
     def accuracy_counts(self, cls: torch.Tensor, labels: torch.Tensor, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """counts[0] += #(cls == label); counts[1+l] += #(bit l agrees)  (int64[5], on device)."""
+        """``dce_accuracy_counts``: counts[0] += #(cls == label); counts[1+l] += #(bit l agrees); counts[5:21] the four
+        per-leg 2x2 confusion matrices; counts[21:277] the 16x16 class confusion matrix (int64[277], on device)."""
         if counts is None:
-            counts = torch.zeros(5, dtype=torch.int64, device=self.device)
+            counts = torch.zeros(_lib.DCE_NUM_COUNTS, dtype=torch.int64, device=self.device)
         cls = cls.to(torch.int32).contiguous()
         labels = labels.reshape(-1).to(torch.int64).contiguous()
         if cls.numel() != labels.numel():
             raise ValueError("cls and labels differ in length")
+        ops = _lib.torch_ops()
+        if ops is not None and cls.numel():
+            return ops.accuracy_counts(cls, labels, counts)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
             rc = self.lib.dce_accuracy_counts(self._p(cls), self._p(labels), cls.numel(), self._p(counts),
@@ -420,8 +448,15 @@ class LatencyRunner:
         rest = (P(self.x_host), n, P(self.logits_host), P(self.cls_host), P(self.bits_host), P(ws), ws.numel(),
                 _lib.PRECISIONS[eng.precision], ctypes.c_void_p(self.stream.cuda_stream))
 
+        index = dev.index
+
         def launch():
-            rc = forward(eng._handle, *rest)
+            # the C ABI launches on the calling thread's current device (include/dce.h): make it the engine's
+            if torch.cuda.current_device() != index:
+                with torch.cuda.device(index):
+                    rc = forward(eng._handle, *rest)
+            else:
+                rc = forward(eng._handle, *rest)
             if rc:
                 _lib.check(rc, "dce_forward")
 
@@ -443,7 +478,7 @@ class LatencyRunner:
         if self.graph is None:
             self._launch()                                       # enqueues on self.stream (passed to the C ABI)
         else:
-            with torch.cuda.stream(self.stream):
+            with torch.cuda.device(self.eng.device), torch.cuda.stream(self.stream):
                 self.graph.replay()
 
     def step(self, window: Optional[torch.Tensor] = None):

@@ -3,8 +3,10 @@
 
 Same flow and config keys as /root/reference/src/test.py:113-220 (config/test_params.yaml):
 evaluate the test split, print accuracy / precision / Jaccard / confusion statistics.  The
-forward + argmax + bits of the whole split is one `dce_stream` call; the sklearn metrics
-(src/test.py:19-70) are host post-processing and are computed exactly as the reference does.
+forward + argmax + bits of the whole split is one `dce_stream` call and the metrics of src/test.py:19-70 come
+from counters accumulated on the device (`dce_accuracy_counts`: per-leg 2x2 and 16x16 class confusion matrices),
+so no per-window array crosses PCIe; `compute_metrics` below is the reference's sklearn formulation, kept as the
+checker the tests compare those counters with.
 """
 import argparse
 import os
@@ -14,7 +16,7 @@ import torch
 import yaml
 from torch.utils.data import DataLoader
 
-from .. import contact_cnn, contact_dataset, compute_accuracy
+from .. import contact_cnn, contact_dataset, compute_accuracy, evaluate
 from .inference_one_seq import load_checkpoint
 
 
@@ -52,8 +54,7 @@ def main(argv=None):
     model = contact_cnn()
     model.load_state_dict(load_checkpoint(config["model_load_path"], map_location=device)["model_state_dict"])
     model = model.eval().to(device)
-    acc, acc_per_leg, bin_pred_arr, bin_gt_arr, pred_arr, gt_arr = compute_accuracy(loader, model)
-    m = compute_metrics(bin_pred_arr, bin_gt_arr, pred_arr, gt_arr)
+    acc, acc_per_leg, m = evaluate(loader, model)
     print("Test accuracy in terms of class is: %.4f" % acc)
     for leg in range(4):
         print("Accuracy of leg %d is: %.4f" % (leg, acc_per_leg[leg]))

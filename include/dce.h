@@ -165,11 +165,17 @@ DCE_API int dce_decimal2binary(const int64_t *cls_dev, int64_t n, uint8_t *bits_
 DCE_API int dce_ingest_f64(const double *src_dev, float *dst_dev, int64_t n, void *stream);
 
 /*
- * Fused accuracy counters of `inference_and_compute_acc` / `compute_accuracy`
- * (src/inference_one_seq.py:33-57, src/test.py:72-107): given predicted
- * classes and labels, accumulate counts_dev[0] += #(pred == label),
- * counts_dev[1..4] += per-leg bit agreement.  counts_dev is int64[5].
+ * Fused evaluation counters of `inference_and_compute_acc` / `compute_accuracy` and of test.py's metrics
+ * (src/inference_one_seq.py:33-57, src/test.py:19-107): given predicted classes and labels, ACCUMULATE into
+ * counts_dev (int64[DCE_NUM_COUNTS], zeroed by the caller):
+ *   [0]                      #(pred == label)
+ *   [1 + leg]                per-leg contact-bit agreement, leg 0..3 (RF, LF, RH, LH)
+ *   [5 + 4 leg + 2 gt + pr]  the four 2x2 per-leg confusion matrices, rows = ground-truth bit, columns = predicted
+ *                            bit — sklearn's confusion_matrix(gt, pred, labels=[0,1]) of src/test.py:19-27
+ *   [21 + 16 gt + pr]        the 16x16 class confusion matrix (precision_score / jaccard_score of src/test.py:50-70
+ *                            are functions of it)
  */
+#define DCE_NUM_COUNTS 277
 DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_dev, int64_t n,
                         int64_t *counts_dev, void *stream);
 
@@ -184,6 +190,8 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *   "latency_kernel" 1 (default): calls of <= 4 windows run the single cooperative latency kernel;
  *                  0: the per-layer kernels (tensor-core convolutions + fp32 GEMV Linear layers);
  *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel;
+ *   "sm_limit"     0 (default): use every SM; n > 0: the batch kernels launch at most n CTAs (what a MIG slice or a
+ *                  smaller sm_100 part gives them: several tiles per CTA in every layer);
  *   "block1_dbg" / "tapgemm_dbg"  bit masks of timing ablations inside the kernels (results invalid);
  *   "trace" 1: allocate and arm a per-role clock64 timeline of CTA 0 (libraries built with -DDCE_TRACE=1);
  *   "trace_layer"  which kernel records it: -1 block1 (default), 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2.

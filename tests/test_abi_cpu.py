@@ -87,3 +87,25 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     assert res.returncode == 0, res.stderr
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0 and "version 100" in run.stdout and "invalid argument" in run.stdout
+
+
+def test_torch_extension_registers_the_ops():
+    """contact_cnn.forward -> torch.ops.dce.forward -> dce_forward.  _dce_torch.so (TORCH_LIBRARY `dce`)
+    loads without a GPU, registers forward / stream / accuracy_counts, answers shape queries on the Meta backend
+    (fake-tensor tracing) and refuses CPU tensors (no CPU kernel exists: the product path has no fallback)."""
+    import pytest
+    import torch
+    from deep_contact_estimator_b200 import _lib, build
+    build.build_torch_extension()
+    ops = _lib.torch_ops()
+    assert ops is not None
+    x = torch.empty(7, 150, 54, device="meta")
+    ws = torch.empty(16, dtype=torch.uint8, device="meta")
+    lo, cl, bi = ops.forward(0, x, ws, 1, True, True, False)
+    assert lo.shape == (7, 16) and lo.dtype == torch.float32 and cl.shape == (7,) and cl.dtype == torch.int32 and bi.shape == (0, 4)
+    lo, cl, bi = ops.stream(0, torch.empty(1000, 54, device="meta"), 3, 500, ws, 1, False, True, True)
+    assert lo.shape == (0, 16) and cl.shape == (500,) and bi.shape == (500, 4) and bi.dtype == torch.uint8
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.forward(0, torch.zeros(2, 150, 54), torch.zeros(16, dtype=torch.uint8), 1, True, True, True)
+    schema = str(torch.ops.dce.forward.default._schema)
+    assert "Tensor x" in schema and "int handle" in schema

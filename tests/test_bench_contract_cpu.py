@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -16,7 +17,9 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "windows/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"].startswith("contact windows/sec") and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import make_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if make_ref.available() else "port")      # oracle/_ref when it is there
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0 and d["latency_b1"]["host_us_p50"] > 0
 

@@ -304,7 +304,18 @@ def test_decimal2binary_and_counts_kernels(dev, golden_dir):
     lab = torch.randint(0, 16, (100003,), generator=g)
     c = eng.accuracy_counts(cls.to(dev), lab.to(dev)).cpu().numpy()
     assert c[0] == int((cls == lab).sum())
-    assert np.array_equal(c[1:], (oracle.decimal2binary(cls) == oracle.decimal2binary(lab)).sum(0).numpy())
+    assert np.array_equal(c[1:5], (oracle.decimal2binary(cls) == oracle.decimal2binary(lab)).sum(0).numpy())
+    # the confusion counters (per-leg 2x2, 16x16 classes) against their host statement, and accumulation over two calls
+    assert np.array_equal(c, dce.counts_from_arrays(cls.numpy(), lab.numpy()))
+    from sklearn.metrics import confusion_matrix
+    m = dce.metrics_from_counts(c)
+    for leg, name in enumerate(("leg_rf", "leg_lf", "leg_rh", "leg_lh")):
+        want = confusion_matrix(oracle.decimal2binary(lab)[:, leg].numpy(), oracle.decimal2binary(cls)[:, leg].numpy(), labels=[0, 1])
+        assert np.array_equal(m["confusion_mat"][name], want)                 # src/test.py:23-26
+    acc = torch.zeros(277, dtype=torch.int64, device=dev)
+    eng.accuracy_counts(cls[:40000].to(dev), lab[:40000].to(dev), acc)
+    eng.accuracy_counts(cls[40000:].to(dev), lab[40000:].to(dev), acc)
+    assert np.array_equal(acc.cpu().numpy(), c)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -384,6 +395,26 @@ def test_random_shapes_property(dev, params0):
         assert np.array_equal(c2.cpu().numpy(), wc.numpy()[: x.shape[0]])
 
     check()
+
+
+def test_fewer_sms_than_tiles(dev, params0):
+    """A device (MIG slice, smaller part) with fewer SMs than a layer has tiles: every persistent kernel then walks
+    several tiles per CTA — including fc.0, whose two 256-column accumulators leave no second TMEM buffer (the issue
+    order that used to deadlock there).  Same bits as the full-width launch."""
+    eng = dce.ContactEngine(params0, dev, "bf16x3")
+    x = synth.make_windows(4096, seed=12).to(dev)
+    want = eng.classify(x)
+    torch.cuda.synchronize()
+    try:
+        for limit in (40, 7):
+            assert eng.set_option("sm_limit", limit) == 0
+            got = eng.classify(x if limit == 40 else x[:600].contiguous())
+            torch.cuda.synchronize()
+            k = 4096 if limit == 40 else 600
+            assert torch.equal(got[0], want[0][:k]) and torch.equal(got[1], want[1][:k]) and torch.equal(got[2], want[2][:k])
+    finally:
+        eng.set_option("sm_limit", 0)
+    eng.close()
 
 
 def test_fused_and_layerwise_kernels_agree(dev, params0):
@@ -545,3 +576,35 @@ def test_realtime_estimator_on_gpu(dev, params0):
     got = [est.push_row(log[t]) for t in range(log.shape[0])]
     assert all(g is None for g in got[:149])
     assert [g[0] for g in got[149:]] == wc.tolist() and [list(g[1]) for g in got[149:]] == wb.tolist()
+
+
+def test_torch_ops_binding_equals_ctypes_binding(dev, params0, monkeypatch):
+    """The two bindings of the C ABI — torch.ops.dce.* (csrc/dce_torch.cpp, what contact_cnn.forward uses) and plain
+    ctypes — enqueue the same kernels: identical bits, on the current stream, for views at odd offsets too."""
+    from deep_contact_estimator_b200 import _lib as L
+    ops = L.torch_ops()
+    assert ops is not None, "_dce_torch.so was not built (python -m deep_contact_estimator_b200.build)"
+    eng = engine(dev, "bf16x3")
+    x = synth.make_windows(300, seed=91).to(dev)
+    log = synth.make_sensor_log(1200, seed=92).to(dev)
+    a = eng.classify(x)
+    sa = eng.stream(log, 5, 800, want_logits=True)
+    odd = eng.stream(log[1:], 4, 800, want_logits=True)          # log[1:] starts 216 B in: 8-byte aligned only
+    assert torch.equal(odd[0], sa[0]) and torch.equal(odd[2], sa[2])
+    lo, cl, bi = ops.forward(eng._handle.value, x, eng._ws(300), 1, True, True, True)
+    assert torch.equal(lo, a[0]) and torch.equal(cl, a[1]) and torch.equal(bi, a[2])
+    with pytest.raises(RuntimeError):
+        ops.forward(eng._handle.value, x, torch.zeros(1024, dtype=torch.uint8, device=dev), 1, True, True, True)   # workspace too small
+    with pytest.raises(RuntimeError):
+        ops.stream(eng._handle.value, log, 1000, 500, eng._ws(500), 1, False, True, True)                      # range outside the log
+    monkeypatch.setattr(L, "_torch_ops", None)                   # DCE_BINDING=ctypes
+    b = eng.classify(x)
+    sb = eng.stream(log, 5, 800, want_logits=True)
+    for u, v in zip(a + sa, b + sb):
+        assert torch.equal(u, v)
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        monkeypatch.setattr(L, "_torch_ops", ops)
+        c = eng.classify(x)
+    s.synchronize()
+    assert torch.equal(c[0], a[0])

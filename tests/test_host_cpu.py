@@ -154,3 +154,38 @@ def test_module_copies_and_pickles_without_its_engine():
         assert clone._engine is None and clone._engine_key is None
         assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
     assert m._engine is not None
+
+
+def test_metrics_from_counts_match_the_reference_sklearn_formulation():
+    """every metric /root/reference/src/test.py:19-70 prints is a function of the counters
+    dce_accuracy_counts accumulates on the device (4 per-leg 2x2 confusion matrices, 16x16 class confusion matrix).
+    Checked against the reference's own sklearn formulation (scripts/test.py: compute_metrics) on skewed random
+    predictions, including classes that never occur / are never predicted (sklearn's zero-division rule)."""
+    import warnings
+    import numpy as np
+    import torch
+    import deep_contact_estimator_b200 as dce
+    from deep_contact_estimator_b200.scripts.test import compute_metrics
+    from oracle import contact_oracle as oracle
+    rng = np.random.default_rng(3)
+    for n, classes in ((5000, 16), (300, 5), (64, 16)):
+        gt = rng.integers(0, classes, n)
+        pred = np.where(rng.random(n) < 0.7, gt, rng.integers(0, 16, n))
+        if classes == 5:
+            pred[pred == 3] = 4                         # class 3 occurs but is never predicted
+        c = dce.counts_from_arrays(pred, gt)
+        assert c.shape == (277,) and c[0] == (pred == gt).sum() and c[21:].sum() == n and c[5:21].sum() == 4 * n
+        m = dce.metrics_from_counts(c)
+        bp, bg = oracle.decimal2binary_numpy(pred).astype(np.float64), oracle.decimal2binary_numpy(gt).astype(np.float64)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = compute_metrics(bp, bg, pred.astype(np.float64), gt.astype(np.float64))
+        for key in ("precision_of_class", "precision_of_all_legs", "jaccard_of_class", "jaccard_of_all_legs"):
+            assert abs(m[key] - want[key]) < 1e-12, key
+        assert np.allclose(m["precision_of_legs"], want["precision_of_legs"], atol=1e-12)
+        assert np.allclose(m["jaccard_of_legs"], want["jaccard_of_legs"], atol=1e-12)
+        for leg in ("leg_rf", "leg_lf", "leg_rh", "leg_lh", "total"):
+            assert np.array_equal(m["confusion_mat"][leg], want["confusion_mat"][leg])
+            assert np.isclose(m["fn_rate"][leg], want["fn_rate"][leg], equal_nan=True)
+            assert np.isclose(m["fp_rate"][leg], want["fp_rate"][leg], equal_nan=True)
+        assert np.allclose(c[1:5], (bp == bg).sum(0))
