@@ -6,12 +6,12 @@
 TEST / BENCH INFRASTRUCTURE ONLY (as the rest of ``oracle/``).  The reference is pure Python; its two modules on
 the hot path are byte-compiled from ``/root/reference`` by CPython's own compiler
 
-    /root/reference/src/contact_cnn.py        ->  oracle/_ref/contact_cnn.pyc      (contact_cnn, src/contact_cnn.py:7-66)
-    /root/reference/utils/data_handler.py     ->  oracle/_ref/data_handler.pyc     (contact_dataset, utils/data_handler.py:13-61)
+    /root/reference/src/contact_cnn.py        ->  oracle/_ref/contact_cnn.bc      (contact_cnn, src/contact_cnn.py:7-66)
+    /root/reference/utils/data_handler.py     ->  oracle/_ref/data_handler.bc     (contact_dataset, utils/data_handler.py:13-61)
 
 the way a C reference would be compiled into ``oracle/_ref/*.so``: no reference SOURCE enters the repo, the
-outputs are git-ignored and travel to the GPU box with the snapshot (same image, same interpreter, so the ``.pyc``
-loads there).  ``load()`` imports them back (sourceless loader).  Users:
+outputs are git-ignored and travel to the GPU box with the snapshot (same image, same interpreter, so the byte code
+loads there; the files are CPython ``.pyc`` images under another suffix, because snapshot tools skip ``*.pyc``).  ``load()`` imports them back (sourceless loader).  Users:
 
   * ``bench.py --impl reference`` and ``cpu_baseline``: time the reference module itself on the box's host cores
     (``kind: "reference"``); when ``oracle/_ref`` is absent they fall back to the oracle port (``kind: "port"``);
@@ -37,7 +37,7 @@ def make(quiet: bool = False) -> str:
         return "kept (no /root/reference here)" if available() else "absent (no /root/reference here)"
     os.makedirs(OUT, exist_ok=True)
     for name, rel in UNITS.items():
-        py_compile.compile(os.path.join(REF, rel), cfile=os.path.join(OUT, name + ".pyc"), dfile=rel, doraise=True)
+        py_compile.compile(os.path.join(REF, rel), cfile=os.path.join(OUT, name + ".bc"), dfile=rel, doraise=True)
     with open(os.path.join(OUT, "README"), "w") as f:
         f.write("byte-compiled from /root/reference by oracle/make_ref.py (python %d.%d); git-ignored, not source\n" % sys.version_info[:2])
     if not quiet:
@@ -58,7 +58,7 @@ def load():
         raise FileNotFoundError("oracle/_ref is empty: run `python oracle/make_ref.py` where /root/reference exists")
     for name in UNITS:
         if name not in _mods:
-            path = os.path.join(OUT, name + ".pyc")
+            path = os.path.join(OUT, name + ".bc")
             loader = importlib.machinery.SourcelessFileLoader("dce_reference_" + name, path)
             spec = importlib.util.spec_from_loader(loader.name, loader)
             mod = importlib.util.module_from_spec(spec)

@@ -590,7 +590,10 @@ def test_torch_ops_binding_equals_ctypes_binding(dev, params0, monkeypatch):
     a = eng.classify(x)
     sa = eng.stream(log, 5, 800, want_logits=True)
     odd = eng.stream(log[1:], 4, 800, want_logits=True)          # log[1:] starts 216 B in: 8-byte aligned only
-    assert torch.equal(odd[0], sa[0]) and torch.equal(odd[2], sa[2])
+    # same windows through a shifted view: the statistics tiles are aligned to the rows of the log a call is given, so
+    # logits agree to rounding, classes and bits exactly
+    assert torch.equal(odd[1], sa[1]) and torch.equal(odd[2], sa[2])
+    assert oracle.normwise_rel_err(odd[0].cpu().numpy(), sa[0].cpu().numpy()) <= 1e-5
     lo, cl, bi = ops.forward(eng._handle.value, x, eng._ws(300), 1, True, True, True)
     assert torch.equal(lo, a[0]) and torch.equal(cl, a[1]) and torch.equal(bi, a[2])
     with pytest.raises(RuntimeError):
