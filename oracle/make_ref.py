@@ -46,14 +46,14 @@ def make(quiet: bool = False) -> str:
 
 
 def available() -> bool:
-    return all(os.path.exists(os.path.join(OUT, n + ".pyc")) for n in UNITS)
+    return all(os.path.exists(os.path.join(OUT, n + ".bc")) for n in UNITS)
 
 
 _mods = {}
 
 
 def load():
-    """-> (contact_cnn class, contact_dataset class) of the REFERENCE, from oracle/_ref/*.pyc; raises if absent."""
+    """-> (contact_cnn class, contact_dataset class) of the REFERENCE, from oracle/_ref/*.bc; raises if absent."""
     if not available():
         raise FileNotFoundError("oracle/_ref is empty: run `python oracle/make_ref.py` where /root/reference exists")
     for name in UNITS:
