@@ -309,6 +309,28 @@ int dce_stream(const dce_weights* w, const float* data_dev, int64_t T,
     return rc;
 }
 
+int dce_latency_server_start(const dce_weights* w, const float* x_host, int n, float* logits_host, int32_t* cls_host,
+                             uint8_t* bits_host, dce_latency_ctrl* ctrl, void* workspace_dev, size_t workspace_bytes,
+                             double idle_timeout_s, void* stream) {
+    int rc = check_common(w, workspace_dev, workspace_bytes, n, DCE_PREC_BF16X3);
+    if (rc != DCE_OK) return rc;
+    if (n < 1 || n > dce::lat::kMaxB || !x_host || !ctrl || !(idle_timeout_s > 0.0)) return DCE_EINVAL;
+    if ((uintptr_t)x_host % 16 || (uintptr_t)ctrl % 128 || (logits_host && (uintptr_t)logits_host % 16) ||
+        (bits_host && (uintptr_t)bits_host % 4) || (cls_host && (uintptr_t)cls_host % 4)) return DCE_EALIGN;
+    ctrl->seq_in = 0; ctrl->seq_out = 0; ctrl->quit = 0; ctrl->alive = 0;
+    const Fp32Layout& L = w->f32;
+    dce::lat::Weights wt;
+    wt.w1 = at<float>(w, L.w1); wt.w2 = at<float>(w, L.w2); wt.w3 = at<float>(w, L.w3); wt.w4q = at<float>(w, L.w4q);
+    wt.f1s = at<float>(w, L.f1s); wt.f2s = at<float>(w, L.f2s); wt.f3t = at<float>(w, L.f3t);
+    for (int i = 0; i < 7; ++i) wt.b[i] = at<float>(w, L.b[i]);
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    rc = dce::lat::run(wt, w->sm_count, x_host, false, 0, n, logits_host, cls_host, bits_host, (char*)workspace_dev, ctx, 1, 1,
+                       reinterpret_cast<volatile unsigned*>(ctrl), (unsigned long long)(idle_timeout_s * 1e9));
+    g_launches = ctx.launches;
+    if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
+    return rc;
+}
+
 static int profile_any(const dce_weights* w, const float* src, bool is_stream, int64_t T, int64_t first, int64_t n,
                        float* logits_dev, int32_t* cls_dev, uint8_t* bits_dev, void* workspace_dev, size_t workspace_bytes,
                        int precision, void* stream, int max_kernels, float* ms_out, const char** names_out, int* n_out) {
@@ -352,6 +374,9 @@ int dce_weights_set_option(dce_weights* w, const char* key, int value) {
     if (!strcmp(key, "fuse_block1")) { o.fuse_block1 = value; return DCE_OK; }
     if (!strcmp(key, "fuse_block2")) { o.fuse_block2 = value; return DCE_OK; }
     if (!strcmp(key, "fuse_fc3")) { o.fuse_fc3 = value; return DCE_OK; }
+    if (!strcmp(key, "fc_pair")) { o.fc_pair = value; return DCE_OK; }
+    if (!strcmp(key, "block2_dbg")) { o.block2_dbg = value; return DCE_OK; }
+    if (!strcmp(key, "fc2_ksa8")) { o.fc2_ksa8 = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { o.latency_kernel = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { o.latency_coop = value; return DCE_OK; }
     if (!strcmp(key, "latency_tma_in")) { o.latency_tma_in = value; return DCE_OK; }

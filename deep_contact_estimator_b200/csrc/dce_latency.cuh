@@ -72,7 +72,13 @@ struct Params {
     float *p1, *a4, *h1, *part;
     unsigned* sync;
     float* logits; int32_t* cls; uint8_t* bits;
+    // server mode (latency_kernel<true>): the doorbell block in PINNED HOST memory (dce_latency_ctrl, include/dce.h) and
+    // how long the kernel waits for a doorbell before it retires on its own
+    volatile unsigned* ctrl; unsigned long long idle_ns;
 };
+constexpr int kCtrlSeqIn = 0, kCtrlQuit = 1, kCtrlSeqOut = 16, kCtrlCls0 = 17, kCtrlBits0 = 18, kCtrlDeviceNs = 19, kCtrlAlive = 20;   // 32-bit word indices of dce_latency_ctrl
+constexpr unsigned kGoQuit = 0xffffffffu;
+constexpr int kSyncGo = 5;                                                         // workspace header word: the broadcast doorbell
 
 // ---- K0 additions: contiguous per-CTA slices, so a slice is a handful of bulk copies -----------------
 // w4q[q][k = tap*128 + cin][32]  from wp4[tap][cin][cout]
@@ -110,8 +116,10 @@ __global__ void pack_f2s_kernel(const float* __restrict__ f2p, float* __restrict
 // `after_arrive` runs in thread 0 between its arrival and its wait: the place to issue the NEXT phase's weight
 // prefetch.  Issued before the arrival, the bulk copies (up to 192 KB per CTA) sat in front of the fence and the
 // arrival in the memory system and made this barrier 1.5 us longer than the others.
+// `target` = arrivals the counter must have seen (k * G; in server mode the counter runs on over the steps and the
+// comparison is modulo 2^32).
 template <class F>
-__device__ __forceinline__ void grid_sync(unsigned* sync, unsigned k, unsigned G, F after_arrive) {
+__device__ __forceinline__ void grid_sync(unsigned* sync, unsigned target, F after_arrive) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -120,7 +128,7 @@ __device__ __forceinline__ void grid_sync(unsigned* sync, unsigned k, unsigned G
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
-        } while (v < k * G);
+        } while ((int)(v - target) < 0);
         __threadfence();
     }
     __syncthreads();
@@ -206,6 +214,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 #define LAT_TRACE(ev) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
     reinterpret_cast<long long*>(p.sync)[8 + (blockIdx.x ? 12 : 0) + (ev)] = clock64(); } while (0)
 
+// SERVER = false: one call = one launch (dce_forward / dce_stream with <= 4 windows).
+// SERVER = true : the control-loop form (dce_latency_server_start): the kernel stays resident and runs one step per
+//   DOORBELL — the host writes the new window(s) into pinned memory and increments ctrl->seq_in; CTA 0 polls that word
+//   over PCIe and re-publishes it in device memory for the other CTAs; the last CTA writes class, bits (and logits)
+//   into pinned host memory and then ctrl->seq_out.  No launch, no stream synchronisation, no copy engine in the
+//   loop; the next step's convolution weights are requested BEFORE the wait for the doorbell.  The kernel retires by
+//   itself when ctrl->quit is set or no doorbell arrives for idle_ns (so a forgotten server cannot hold the GPU).
+template <bool SERVER>
 __global__ void __launch_bounds__(kThreads, 1)
 latency_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -236,9 +252,15 @@ latency_kernel(const Params p) {
     if (tid == 0) {
         for (int i = 0; i < kNumBars; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_barrier_init();
+        if (SERVER && cta == 0) { p.ctrl[kCtrlAlive] = 1u; __threadfence_system(); }
     }
     __syncthreads();
     LAT_TRACE(0);
+    uint32_t xphase = 0;                              // bar_x is used once per phase-A item, over all steps
+    unsigned seq_done = 0;                            // server: the last step served (the host starts at 0)
+    for (unsigned iter = 0;; ++iter) {
+    const uint32_t ph = SERVER ? (iter & 1u) : 0u;    // parity of the once-per-step weight barriers
+    const unsigned bar0 = SERVER ? iter * 3u * (unsigned)G : 0u;
     // batch mode: the 6 input rows of an item are one contiguous, 16-byte aligned span of x (rows are 216 B, the
     // span starts on an even row): ONE bulk copy straight into xin — x may be pinned HOST memory (LatencyRunner),
     // where one large read beats 324 scalar loads over PCIe.  Rows outside the window are zero-filled by hand.
@@ -250,7 +272,7 @@ latency_kernel(const Params p) {
         ptx::bulk_g2s(xin + (lo - (2 * tp - 2)) * 54, p.x + (size_t)b * 8100 + lo * 54, (uint32_t)(hi - lo) * 216u, bar_x);
     };
     if (tid == 0) {
-        if (a_cta && tma_in) issue_x(cta);
+        if (!SERVER && a_cta && tma_in) issue_x(cta);
         if (a_cta) {
             ptx::mbar_arrive_expect_tx(bar_w1, kW1Bytes);
             ptx::bulk_g2s(w1s, p.w1, kW1Bytes, bar_w1);
@@ -267,6 +289,55 @@ latency_kernel(const Params p) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     }
 
+    if (SERVER) {
+        // ---- wait for the doorbell (the convolution weights of this step are already on their way) ----
+        unsigned* go_s = reinterpret_cast<unsigned*>(last_flag) + 1;      // [0] the doorbell value, [1] input copy already issued
+        if (tid == 0) {
+            unsigned go, x_issued = 0u;
+            if (cta == 0) {
+                // CTA 0 alone decides: it polls the host word — one 8-byte read of {seq_in, quit} over PCIe per probe —
+                // and publishes what it saw (a step number, or "retire") in device memory for everybody else
+                unsigned long long t0, t1, w;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                unsigned sq, quit, spins = 0;
+                do {
+                    w = *reinterpret_cast<const volatile unsigned long long*>(p.ctrl);
+                    sq = (unsigned)w;
+                    quit = (unsigned)(w >> 32);
+                    if ((++spins & 255u) == 0u) {
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > p.idle_ns) quit = 1u;
+                    }
+                } while (sq == seq_done && !quit);
+                go = quit ? kGoQuit : sq;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sync + kSyncGo), "r"(go) : "memory");
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                *reinterpret_cast<unsigned long long*>(p.sync + 6) = t1;      // when this step's doorbell was seen (device header)
+            } else {
+                // everybody else waits for CTA 0's word in device memory.  (Measured: letting the 74 other phase-A CTAs poll
+                // the host word too, to start their input copies one hop earlier, saves 2 us on the device and costs 190 us
+                // on the host — the CPU's store to a line 75 SMs keep reading over PCIe takes that long to win ownership.)
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(go) : "l"(p.sync + kSyncGo) : "memory");
+                } while (go == seq_done);
+            }
+            go_s[0] = go; go_s[1] = x_issued;
+        }
+        __syncthreads();
+        const unsigned go = go_s[0];
+        if (go == kGoQuit) {                          // retire: nothing may be in flight into shared memory when the CTA exits
+            if (tid == 0) {
+                if (a_cta) { ptx::mbar_wait(bar_w1, ph); ptx::mbar_wait(bar_w2, ph); }
+                ptx::mbar_wait(bar_w3, ph);
+                if (go_s[1]) ptx::mbar_wait(bar_x, xphase);
+            }
+            __syncthreads();
+            break;
+        }
+        seq_done = go;
+        if (tid == 0 && a_cta && tma_in && !go_s[1]) issue_x(cta);
+    }
+
     auto issue_stage = [&](int g) {                   // thread 0: stage g (= window g/10, k-rows (g%10)*512 ..) -> ring slot g%5
         const int s = g % kStages, slot = g % kRing;
         const uint32_t bytes = s < kStages - 1 ? kStageBytes : (4736 - (kStages - 1) * kStageRows) * 64;
@@ -277,7 +348,6 @@ latency_kernel(const Params p) {
     // ================= phase A: ingest (+ z-score) -> conv1 -> conv2 -> pool =================
     {
         int stat_b = -1;
-        uint32_t xphase = 0;
         for (int it = cta; it < nA; it += G) {
             const int b = it / 75, tp = it - b * 75;
             const float* xw = p.stream ? p.x + (size_t)(p.first + b) * 54 : p.x + (size_t)b * 8100;
@@ -302,7 +372,7 @@ latency_kernel(const Params p) {
                 }
             }
             __syncthreads();
-            ptx::mbar_wait(bar_w1, 0);
+            ptx::mbar_wait(bar_w1, ph);
             conv_partial<54, 64, 4>(xin, w1s, red);                      // conv1 rows 2tp-1 .. 2tp+2
             __syncthreads();
             if (tid < 256) {
@@ -314,7 +384,7 @@ latency_kernel(const Params p) {
                 mid[r * 64 + o] = (row >= 0 && row < 150) ? s : 0.f;     // conv2's zero padding
             }
             __syncthreads();
-            ptx::mbar_wait(bar_w2, 0);
+            ptx::mbar_wait(bar_w2, ph);
             conv_partial<64, 64, 2>(mid, w2s, red);                      // conv2 rows 2tp, 2tp+1
             __syncthreads();
             if (tid < 64) {
@@ -329,8 +399,8 @@ latency_kernel(const Params p) {
     }
     LAT_TRACE(1);
     const int q = cta & 3;
-    grid_sync(p.sync, 1u, (unsigned)G, [&]() {        // [W1 | W2] is free now: fetch this CTA's quarter of conv4
-        if (a_cta) { ptx::mbar_wait(bar_w1, 0); ptx::mbar_wait(bar_w2, 0); }
+    grid_sync(p.sync, bar0 + 1u * (unsigned)G, [&]() {        // [W1 | W2] is free now: fetch this CTA's quarter of conv4
+        if (a_cta) { ptx::mbar_wait(bar_w1, ph); ptx::mbar_wait(bar_w2, ph); }
         ptx::mbar_arrive_expect_tx(bar_w4, kW4qBytes);
         ptx::bulk_g2s(w4s, p.w4q + (size_t)q * (kW4qBytes / 4), kW4qBytes / 2, bar_w4);
         ptx::bulk_g2s(w4s + kW4qBytes / 8, p.w4q + (size_t)q * (kW4qBytes / 4) + kW4qBytes / 8, kW4qBytes / 2, bar_w4);
@@ -347,7 +417,7 @@ latency_kernel(const Params p) {
                 xin[i] = (row >= 0 && row < 75) ? __ldcg(p.p1 + (size_t)(b * 75 + row) * 64 + c) : 0.f;
             }
             __syncthreads();
-            ptx::mbar_wait(bar_w3, 0);
+            ptx::mbar_wait(bar_w3, ph);
             conv_partial<64, 128, 4>(xin, w3s, red);                     // conv3 rows 2t-1 .. 2t+2, all 128 channels
             __syncthreads();
             {
@@ -359,7 +429,7 @@ latency_kernel(const Params p) {
                 mid[r * 128 + o] = (row >= 0 && row < 75) ? s : 0.f;      // conv4's zero padding
             }
             __syncthreads();
-            ptx::mbar_wait(bar_w4, 0);
+            ptx::mbar_wait(bar_w4, ph);
             conv_partial<128, 32, 2>(mid, w4s, red);                     // conv4 rows 2t, 2t+1, channels q*32 .. q*32+31
             __syncthreads();
             if (tid < 32) {
@@ -373,9 +443,9 @@ latency_kernel(const Params p) {
         }
     }
     LAT_TRACE(3);
-    grid_sync(p.sync, 2u, (unsigned)G, [&]() {        // conv weights are dead: start the fc.0 ring and the fc.3 slice
-        ptx::mbar_wait(bar_w3, 0);
-        ptx::mbar_wait(bar_w4, 0);
+    grid_sync(p.sync, bar0 + 2u * (unsigned)G, [&]() {        // conv weights are dead: start the fc.0 ring and the fc.3 slice
+        ptx::mbar_wait(bar_w3, ph);
+        ptx::mbar_wait(bar_w4, ph);
         if (fc_cta) {
             for (int g = 0; g < kRing && g < total_stages; ++g) issue_stage(g);
             ptx::mbar_arrive_expect_tx(bar_f2, kF2Bytes);
@@ -433,7 +503,7 @@ latency_kernel(const Params p) {
         }
     }
     LAT_TRACE(5);
-    grid_sync(p.sync, 3u, (unsigned)G, []() {});
+    grid_sync(p.sync, bar0 + 3u * (unsigned)G, []() {});
     LAT_TRACE(6);
 
     // ================= phase D: fc.3 + ReLU (outputs cta*4 .. cta*4+3) and this CTA's share of fc.6 =================
@@ -441,7 +511,7 @@ latency_kernel(const Params p) {
         float* w3sl = stat;                            // [4][16] fc.6 weights of this CTA's four fc.3 outputs
         float* h2s = stat + 64;                        // [B][4]
         if (tid < 64) w3sl[tid] = w3r;
-        ptx::mbar_wait(bar_f2, 0);
+        ptx::mbar_wait(bar_f2, ph);
         for (int b = 0; b < p.B; ++b) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -495,19 +565,48 @@ latency_kernel(const Params p) {
                     float y[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) y[j] = logit_s[j];
+                    if (SERVER && !p.logits && p.B == 1 && p.cls == reinterpret_cast<const int32_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlCls0) &&
+                        p.bits == reinterpret_cast<const uint8_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlBits0)) {
+                        // the caller's result words sit next to seq_out: class, bits, device time and the step number leave
+                        // as ONE aligned 16-byte store — one PCIe write, nothing to order, no system-scope fence
+                        int32_t c1; uint8_t b4[4];
+                        fp32::argmax_bits_store(y, 0, nullptr, &c1, b4);
+                        unsigned long long t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        const unsigned ns = (unsigned)(t1 - __ldcg(reinterpret_cast<const unsigned long long*>(p.sync + 6)));
+                        const unsigned bw = (unsigned)b4[0] | ((unsigned)b4[1] << 8) | ((unsigned)b4[2] << 16) | ((unsigned)b4[3] << 24);
+                        p.sync[2] = 0u;
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p.ctrl + kCtrlSeqOut), "r"(seq_done), "r"((unsigned)c1), "r"(bw), "r"(ns) : "memory");
+                        *last_flag = 2;                              // results delivered
+                    } else
                     fp32::argmax_bits_store(y, (int64_t)b, p.logits, p.cls, p.bits);
                 }
                 __syncthreads();
             }
-            if (tid == 0) p.sync[2] = 0u;
+            if (tid == 0 && *last_flag != 2) {
+                p.sync[2] = 0u;
+                if (SERVER) {                          // results are in host memory before the host sees the step number
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    p.ctrl[kCtrlDeviceNs] = (unsigned)(t1 - __ldcg(reinterpret_cast<const unsigned long long*>(p.sync + 6)));
+                    __threadfence_system();
+                    p.ctrl[kCtrlSeqOut] = seq_done;
+                }
+            }
             LAT_TRACE(8);
         }
     }
     LAT_TRACE(9);
+    if (!SERVER) break;
+    __syncthreads();                                  // every thread is done with this step's shared memory
+    }   // for (iter)
     // every CTA is past the last barrier's spin when it gets here: the last one out re-arms the counters
     if (tid == 0) {
         const unsigned old = atomicAdd(p.sync + 1, 1u);
-        if (old == (unsigned)G - 1u) { p.sync[0] = 0u; p.sync[1] = 0u; p.sync[3] = 0u; __threadfence(); }
+        if (old == (unsigned)G - 1u) {
+            p.sync[0] = 0u; p.sync[1] = 0u; p.sync[3] = 0u; p.sync[kSyncGo] = 0u; __threadfence();
+            if (SERVER) { p.ctrl[kCtrlAlive] = 0u; __threadfence_system(); }
+        }
     }
 }
 
@@ -517,13 +616,17 @@ struct Weights {                  // pointers into the packed buffer
 
 // -> DCE_EUNSUPPORTED when the device cannot co-schedule the grid (the caller then uses the per-layer kernels)
 // coop / tma_in: launch-attribute and input-staging ablations (dce_weights_set_option "latency_coop", "latency_tma_in")
+// ctrl != nullptr: start the resident server form instead (one launch serves steps until quit / idle timeout)
 inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mode, int64_t first, int n,
-               float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx, int coop = 1, int tma_in = 1) {
+               float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx, int coop = 1, int tma_in = 1,
+               volatile unsigned* ctrl = nullptr, unsigned long long idle_ns = 0) {
     const int grid = sm_count / 4 * 4;
     if (grid < kSlices || n < 1 || n > kMaxB) return DCE_EUNSUPPORTED;
+    if (ctrl && (stream_mode || !tma_in)) return DCE_EINVAL;      // the server re-reads host memory every step: bulk copies only (no cached loads)
     static DeviceOnce once;
     if (auto first_ = once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(latency_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(latency_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
     }
     const Workspace W = make_workspace(n);
@@ -535,13 +638,19 @@ inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mo
     p.h1 = reinterpret_cast<float*>(ws + W.h1); p.part = reinterpret_cast<float*>(ws + W.part);
     p.sync = reinterpret_cast<unsigned*>(ws);
     p.logits = logits; p.cls = cls; p.bits = bits;
+    p.ctrl = ctrl; p.idle_ns = idle_ns;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = ctx.stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;        // the launch fails instead of deadlocking if the grid cannot be co-resident
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
-    DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel, p); (void)le_; });
+    if (ctrl) {
+        if (!coop) return DCE_EINVAL;                 // the server spins on grid barriers for its whole life: co-residency must be guaranteed
+        DCE_KL(ctx, "latency_server", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<true>, p); (void)le_; });
+        return DCE_OK;
+    }
+    DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<false>, p); (void)le_; });
     return DCE_OK;
 }
 

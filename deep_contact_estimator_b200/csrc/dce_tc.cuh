@@ -75,7 +75,7 @@ struct Tape {
     size_t kch_stride, part_stride, bytes;
 };
 inline Tape make_tape(int64_t rows, int kch) {
-    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;   // even: MT = 2 tiles
+    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;   // even: MT = 2 tiles, CTA pairs
     t.cap = kGuard + t.m_tiles * 128 + 136; t.kch = kch;   // trailing guard: the fused kernels' 124-row tiles read up to 130 rows past a tile start
     t.kch_stride = (size_t)t.cap * 16; t.part_stride = t.kch_stride * kch; t.bytes = align_up(t.part_stride * 2, 256);
     return t;
@@ -649,15 +649,18 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 7;
+constexpr int kNumPacked = 10;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0 (layer-wise conv3: resident image)
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
-                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
-constexpr int kLayerConv3Ring = 6;
+                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+                                 {128, 1, 4, 148, 16, 1, 4736, 8}, // fc.0 in half blocks of 128 columns: one per CTA of a pair (dce_tc_pair.cuh)
+                                 {64, 1, 4, 64, 8, 2, 2048, 10},   // fc.3 in half blocks of 64 columns
+                                 {128, 1, 8, 32, 4, 2, 2048, 10}}; // fc.3 with 64 K-elements per stage
+constexpr int kLayerConv3Ring = 6, kLayerFc1Pair = 7, kLayerFc2Pair = 8, kLayerFc2K8 = 9;
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };

@@ -34,6 +34,8 @@ struct Block2Params {
     uint8_t* out; size_t out_part_stride, out_kch_stride; int out_rows_cap;
     int n_tiles;
     long long* trace;            // optional clock64 timeline of CTA 0 (DCE_TRACE builds)
+    int dbg;                     // timing ablations (results invalid): 1 = no weight copies once the ring is primed; 2 = no output stores;
+                                 // 4 = slabA is loaded for the first tile only
 };
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
@@ -91,8 +93,11 @@ block2_kernel(const Block2Params p) {
                 const uint32_t slot = it % kB2Ring, ph = (it / kB2Ring) & 1;
                 ptx::mbar_wait_relaxed(&wempty[slot], ph ^ 1);
                 if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx(&wfull[slot], kB2WBlock);
-                    ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
+                    if ((p.dbg & 1) && it >= kB2Ring) ptx::mbar_arrive(&wfull[slot]);
+                    else {
+                        ptx::mbar_arrive_expect_tx(&wfull[slot], kB2WBlock);
+                        ptx::bulk_g2s(ring + slot * kB2WBlock, w + (size_t)s * kB2WBlock, kB2WBlock, &wfull[slot]);
+                    }
                 }
                 __syncwarp();
             }
@@ -107,6 +112,11 @@ block2_kernel(const Block2Params p) {
         for (int k = 0; k < my_tiles; ++k) {
             const int b = (int)(blockIdx.x + k * gridDim.x) * kB2Rows;
             ptx::mbar_wait_relaxed(a_empty, (k & 1) ^ 1);                       // conv3(k-1) has drained slabA
+            if ((p.dbg & 4) && k > 0) {
+                if (ptx::elect_one()) ptx::mbar_arrive(a_full);
+                __syncwarp();
+                continue;
+            }
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(a_full, kB2SlabA);
                 const uint8_t* src = p.x2 + (size_t)(b - 3 + kGuard) * 16;
@@ -235,7 +245,7 @@ block2_kernel(const Block2Params p) {
             const uint32_t buf = k & 1, ph = (k >> 1) & 1;
             const int r = tile * kB2Rows - 2 + rit;            // conv4 output row (X3 row space)
             int w = 0, to = 0;
-            bool store = r >= 0 && r < NR && rit >= 2 && rit < 126;
+            bool store = r >= 0 && r < NR && rit >= 2 && rit < 126 && !(p.dbg & 2);
             if (store) { w = r / kRW2; to = (r - w * kRW2) >> 1; store = to < 37 && w < p.out_rows_cap; }
             if (warp == 0) B2_TRACE(k, 10);
             ptx::mbar_wait_relaxed(&d4_full[buf], ph);

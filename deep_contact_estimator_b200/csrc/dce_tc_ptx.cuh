@@ -127,16 +127,19 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
-// arrive on an mbarrier of another CTA of the cluster (address from mapa); release at cluster scope
+// arrive on an mbarrier of another CTA of the cluster (address from mapa).  Default semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): a `.release.cluster` arrive costs a cluster-scope fence (~1 us with traffic in flight),
+// and nothing a thread wrote needs releasing here — what the barrier orders was written by bulk TMA / read by tcgen05.ld
+// and is complete when the arriving thread has observed its own mbarrier / tcgen05.wait.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait for a phase completed (also) by arrivals from the peer CTA: acquire at cluster scope
+// wait for a phase completed (also) by arrivals from the peer CTA (plain form, as CUTLASS's ClusterBarrier::wait)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;

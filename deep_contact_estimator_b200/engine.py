@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 from typing import Mapping, Optional, Tuple
 
 import torch
@@ -364,9 +365,10 @@ class ContactEngine:
         return out_cls_host, out_bits_host
 
     # -- K3: control-loop runner -------------------------------------------------
-    def latency_runner(self, n: int = 1, want_logits: bool = False, use_graph: bool = False) -> "LatencyRunner":
+    def latency_runner(self, n: int = 1, want_logits: bool = False, use_graph: bool = False, persistent: bool = False,
+                       idle_timeout_s: float = 2.0) -> "LatencyRunner":
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
-        return LatencyRunner(self, n, want_logits, use_graph)
+        return LatencyRunner(self, n, want_logits, use_graph, persistent, idle_timeout_s)
 
     def set_option(self, key, value: int) -> int:
         """``dce_weights_set_option``: an ablation / debugging switch of THIS engine's handle (include/dce.h);
@@ -423,14 +425,25 @@ class LatencyRunner:
         run.x_host[0] = newest_window          # (150, 54) float32, z-scored (utils/data_handler.py:55-56)
         cls, bits = run.step()                 # pinned host tensors, valid until the next step()
 
+    ``persistent=True`` is the resident form (``dce_latency_server_start``, include/dce.h): ONE cooperative kernel
+    stays on the GPU and serves a step per doorbell — ``step()`` writes the window, increments a word in pinned
+    memory and spins on the answer word; no launch, no stream synchronisation, no CUDA call at all in the loop.
+    The server holds every SM while it lives; it retires on ``close()`` or after ``idle_timeout_s`` without a step
+    (the next ``step()`` starts it again), so other work on the device is delayed by at most that long.
+
     Replaces one iteration of the reference loop at its default batch_size 1
     (/root/reference/src/inference_one_seq.py:23-28, config/inference_one_seq_params.yaml:10).
     """
 
-    def __init__(self, eng: ContactEngine, n: int = 1, want_logits: bool = False, use_graph: bool = False):
+    _SEQ_IN, _QUIT, _SEQ_OUT, _CLS0, _BITS0, _DEVICE_NS, _ALIVE = 0, 1, 16, 17, 18, 19, 20     # 32-bit words of dce_latency_ctrl
+
+    def __init__(self, eng: ContactEngine, n: int = 1, want_logits: bool = False, use_graph: bool = False,
+                 persistent: bool = False, idle_timeout_s: float = 2.0):
         if not 1 <= n <= 4:
             raise ValueError("the latency path takes 1..4 windows per step")
-        self.eng, self.n, self.use_graph = eng, n, use_graph
+        if persistent and use_graph:
+            raise ValueError("persistent and use_graph exclude each other")
+        self.eng, self.n, self.use_graph, self.persistent, self.idle_timeout_s = eng, n, use_graph, persistent, float(idle_timeout_s)
         dev = eng.device
         self.x_host = torch.zeros((n, WINDOW, CHANNELS), dtype=torch.float32).pin_memory()
         self.cls_host = torch.zeros((n,), dtype=torch.int32).pin_memory()
@@ -472,6 +485,61 @@ class LatencyRunner:
                 with torch.cuda.graph(self.graph, stream=self.stream):
                     launch()
         self._ws = ws
+        self._ctrl = self._c = None
+        self.server_starts = 0
+        if persistent:
+            self._ctrl = torch.zeros(32, dtype=torch.int32).pin_memory()        # dce_latency_ctrl: 128 bytes, page aligned
+            self._c = self._ctrl.numpy().view("uint32")
+            if n == 1 and not want_logits:
+                # results inside the control block: class, bits and the step number arrive as one 16-byte store
+                self.cls_host = self._ctrl[self._CLS0:self._CLS0 + 1]
+                self.bits_host = self._ctrl[self._BITS0:self._BITS0 + 1].view(torch.uint8).reshape(1, 4)
+            start = eng.lib.dce_latency_server_start
+            sargs = (P(self.x_host), n, P(self.logits_host), P(self.cls_host), P(self.bits_host), P(self._ctrl), P(ws), ws.numel(),
+                     ctypes.c_double(self.idle_timeout_s), ctypes.c_void_p(self.stream.cuda_stream))
+
+            def start_server():
+                self.stream.synchronize()                            # a retired server has left the stream
+                with torch.cuda.device(index):
+                    _lib.check(start(eng._handle, *sargs), "dce_latency_server_start")
+                self._seq = 0
+                self.server_starts += 1
+                c, t0 = self._c, time.perf_counter()
+                while not c[self._ALIVE]:
+                    if time.perf_counter() - t0 > 10.0:
+                        raise RuntimeError("the latency server did not come up within 10 s (is the GPU busy with other kernels?)")
+            self._start_server = start_server
+            start_server()
+
+    def _step_persistent(self):
+        c = self._c
+        if not c[self._ALIVE]:                                       # retired after idle_timeout_s without a step
+            self._start_server()
+        self._seq += 1
+        seq = self._seq
+        c[self._SEQ_IN] = seq                                        # the doorbell (the window was written before it)
+        spins = 0
+        while c[self._SEQ_OUT] != seq:
+            spins += 1
+            if (spins & 1023) == 0 and not c[self._ALIVE]:           # it retired just as the doorbell rang: start over
+                if c[self._SEQ_OUT] == seq:
+                    break
+                self._start_server()
+                self._seq = seq = 1
+                c[self._SEQ_IN] = seq
+        return self.cls_host, self.bits_host
+
+    def close(self):
+        """Retire the resident server (persistent mode); idempotent."""
+        if self._c is not None and self._c[self._ALIVE]:
+            self._c[self._QUIT] = 1
+            self.stream.synchronize()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def enqueue(self):
         """Launch one step without waiting (``self.stream``)."""
@@ -485,6 +553,8 @@ class LatencyRunner:
         """Classify ``self.x_host`` (or ``window``, copied into it first); returns host ``(cls, bits)``."""
         if window is not None:
             self.x_host.copy_(window.reshape(self.x_host.shape))
+        if self.persistent:
+            return self._step_persistent()
         self.enqueue()
         self.stream.synchronize()
         return self.cls_host, self.bits_host

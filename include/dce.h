@@ -121,6 +121,46 @@ DCE_API int dce_forward(const dce_weights *w, const float *x_dev, int64_t B,
                 void *workspace_dev, size_t workspace_bytes, int precision, void *stream);
 
 /*
+ * K3 as a resident SERVER — the 1 kHz control loop (BASELINE configs[4]; one iteration of the reference loop at its
+ * default batch_size 1, src/inference_one_seq.py:23-28) without a launch, a stream synchronisation or a copy engine
+ * per step.  dce_latency_server_start() enqueues ONE cooperative kernel that stays resident on every SM and serves a
+ * step each time the host rings the doorbell:
+ *     write the n new windows to x_host;  ctrl->seq_in = ++seq;  spin until ctrl->seq_out == seq;
+ *     read cls_host / bits_host / logits_host                          (dce_latency_server_step() below does this)
+ * x_host [n][150][54] fp32, the three outputs and ctrl must be PINNED, device-mapped host memory (cudaHostAlloc);
+ * NULL outputs are skipped.  The kernel retires when ctrl->quit is set non-zero or when no doorbell has arrived for
+ * idle_timeout_s (ctrl->alive drops to 0; start it again for the next step), so a forgotten server cannot hold the
+ * GPU; while it runs, other kernels on the device find no free SM.  Results are bit-identical to dce_forward on the
+ * same windows.  workspace: as for dce_forward, for the server's exclusive use until it has retired.
+ */
+typedef struct dce_latency_ctrl {
+    volatile uint32_t seq_in;        /* host -> device: step number requested (start at 0, +1 per step)       */
+    volatile uint32_t quit;          /* host -> device: non-zero = retire                                      */
+    uint32_t reserved0[14];
+    volatile uint32_t seq_out;       /* device -> host: last step whose results are in the host buffers        */
+    volatile int32_t  cls0;          /* result words: pass cls_host = &ctrl->cls0, bits_host = ctrl->bits0 and      */
+    volatile uint8_t  bits0[4];      /*   logits_host = NULL (n = 1) and the results arrive with seq_out in ONE        */
+    volatile uint32_t device_ns;     /*   16-byte store (no system fence: ~1 us less); device_ns = doorbell seen -> results written */
+    volatile uint32_t alive;         /* device -> host: 1 while the server runs                                */
+    uint32_t reserved1[11];
+} dce_latency_ctrl;                  /* 128 bytes: one cache line per direction                                */
+
+DCE_API int dce_latency_server_start(const dce_weights *w, const float *x_host, int n,
+                             float *logits_host, int32_t *cls_host, uint8_t *bits_host,
+                             dce_latency_ctrl *ctrl, void *workspace_dev, size_t workspace_bytes,
+                             double idle_timeout_s, void *stream);
+
+/* One step of a running server (host side only; no CUDA call).  Returns 0, or -1 if the server is not alive. */
+static inline int dce_latency_server_step(dce_latency_ctrl *ctrl) {
+    const uint32_t seq = ctrl->seq_in + 1u;
+    if (!ctrl->alive) return -1;
+    __atomic_store_n(&ctrl->seq_in, seq, __ATOMIC_RELEASE);          /* the window is written before the doorbell */
+    while (__atomic_load_n(&ctrl->seq_out, __ATOMIC_ACQUIRE) != seq)
+        if (!ctrl->alive) return -1;
+    return 0;
+}
+
+/*
  * K2: the body of `inference(dataloader, model, device)`
  * (src/inference_one_seq.py:19-30) over a device-resident sensor log: for
  * window i in [first_window, first_window + n_windows): rows i..i+149 of
