@@ -6,7 +6,7 @@ the ``contact_cnn`` module surface, ``contact_dataset``, and the
 hand-written sm_100a kernels behind the C ABI in ``include/dce.h``.
 """
 from .synth import WINDOW, CHANNELS, CLASSES, PARAM_NAMES, PARAM_SHAPES
-from .engine import ContactEngine, LatencyRunner, default_precision
+from .engine import ContactEngine, LatencyRunner, RowRunner, default_precision
 from .contact_cnn import contact_cnn
 from .data_handler import contact_dataset
 from .inference import (inference, inference_and_compute_acc, compute_accuracy, decimal2binary, evaluate,
@@ -14,7 +14,7 @@ from .inference import (inference, inference_and_compute_acc, compute_accuracy, 
 from .realtime import RealtimeContactEstimator
 
 __all__ = [
-    "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "RealtimeContactEstimator", "inference", "inference_and_compute_acc",
+    "contact_cnn", "contact_dataset", "ContactEngine", "LatencyRunner", "RowRunner", "RealtimeContactEstimator", "inference", "inference_and_compute_acc",
     "compute_accuracy", "decimal2binary", "default_precision", "evaluate", "metrics_from_counts", "counts_from_arrays",
     "WINDOW", "CHANNELS", "CLASSES", "PARAM_NAMES", "PARAM_SHAPES",
 ]

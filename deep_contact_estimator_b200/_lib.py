@@ -55,6 +55,7 @@ _SIGNATURES = {
                                    c_int, c_void_p, c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int)]),
     "dce_latency_server_start": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                          ctypes.c_double, c_void_p]),
+    "dce_latency_row_server_start": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_double, c_void_p]),
     "dce_weights_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "dce_debug_read_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "dce_decimal2binary": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

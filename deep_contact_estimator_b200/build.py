@@ -75,7 +75,9 @@ def build_torch_extension(force: bool = False, verbose: bool = False) -> str:
         return TORCH_LIB_PATH
     import torch
     from torch.utils import cpp_extension
-    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    # the system g++, NOT $CXX: this image's $CXX (/opt/gcc/bin/g++) links libstdc++ statically, and an extension carrying
+    # its own copy of the C++ runtime crashes as soon as a c10::Error (TORCH_CHECK) unwinds through it
+    cxx = shutil.which("g++") or os.environ.get("CXX") or "g++"
     cuda_home = os.environ.get("CUDA_HOME") or os.path.dirname(os.path.dirname(_nvcc()))
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
@@ -86,6 +88,10 @@ def build_torch_extension(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    needed = subprocess.run(["readelf", "-d", TORCH_LIB_PATH], capture_output=True, text=True).stdout
+    if needed and "libstdc++.so" not in needed:
+        os.remove(TORCH_LIB_PATH)
+        raise RuntimeError(f"{cxx} linked libstdc++ statically into _dce_torch.so: exceptions could not cross it; use the system g++")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
     return TORCH_LIB_PATH

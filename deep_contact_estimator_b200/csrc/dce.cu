@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stddef.h>
 #include <new>
 
 #include "../../include/dce.h"
@@ -326,6 +327,30 @@ int dce_latency_server_start(const dce_weights* w, const float* x_host, int n, f
     Ctx ctx; ctx.stream = (cudaStream_t)stream;
     rc = dce::lat::run(wt, w->sm_count, x_host, false, 0, n, logits_host, cls_host, bits_host, (char*)workspace_dev, ctx, 1, 1,
                        reinterpret_cast<volatile unsigned*>(ctrl), (unsigned long long)(idle_timeout_s * 1e9));
+    g_launches = ctx.launches;
+    if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
+    return rc;
+}
+
+int dce_latency_row_server_start(const dce_weights* w, dce_latency_row_ctrl* ctrl, float* ring_dev, void* workspace_dev,
+                                 size_t workspace_bytes, double idle_timeout_s, void* stream) {
+    int rc = check_common(w, workspace_dev, workspace_bytes, 1, DCE_PREC_BF16X3);
+    if (rc != DCE_OK) return rc;
+    if (!ring_dev || !ctrl || !(idle_timeout_s > 0.0)) return DCE_EINVAL;
+    if ((uintptr_t)ring_dev % 16 || (uintptr_t)ctrl % 128) return DCE_EALIGN;
+    static_assert(sizeof(dce_latency_row_ctrl) == 512 && offsetof(dce_latency_row_ctrl, seq_out) == dce::lat::kRowSeqOut * 4 &&
+                  offsetof(dce_latency_row_ctrl, alive) == dce::lat::kRowAlive * 4, "include/dce.h and dce_latency.cuh agree on the layout");
+    static_assert(sizeof(dce_latency_ctrl) == 128 && offsetof(dce_latency_ctrl, seq_out) == dce::lat::kCtrlSeqOut * 4 &&
+                  offsetof(dce_latency_ctrl, alive) == dce::lat::kCtrlAlive * 4 && offsetof(dce_latency_ctrl, cls0) == dce::lat::kCtrlCls0 * 4, "layout");
+    memset((void*)ctrl, 0, sizeof(*ctrl));
+    const Fp32Layout& L = w->f32;
+    dce::lat::Weights wt;
+    wt.w1 = at<float>(w, L.w1); wt.w2 = at<float>(w, L.w2); wt.w3 = at<float>(w, L.w3); wt.w4q = at<float>(w, L.w4q);
+    wt.f1s = at<float>(w, L.f1s); wt.f2s = at<float>(w, L.f2s); wt.f3t = at<float>(w, L.f3t);
+    for (int i = 0; i < 7; ++i) wt.b[i] = at<float>(w, L.b[i]);
+    Ctx ctx; ctx.stream = (cudaStream_t)stream;
+    rc = dce::lat::run(wt, w->sm_count, ring_dev, true, 0, 1, nullptr, nullptr, nullptr, (char*)workspace_dev, ctx, 1, 1,
+                       reinterpret_cast<volatile unsigned*>(ctrl), (unsigned long long)(idle_timeout_s * 1e9), true);
     g_launches = ctx.launches;
     if (rc == DCE_ECUDA && ctx.err != cudaSuccess) g_last_cuda_error = (int)ctx.err;
     return rc;

@@ -78,7 +78,11 @@ struct Params {
 };
 constexpr int kCtrlSeqIn = 0, kCtrlQuit = 1, kCtrlSeqOut = 16, kCtrlCls0 = 17, kCtrlBits0 = 18, kCtrlDeviceNs = 19, kCtrlAlive = 20;   // 32-bit word indices of dce_latency_ctrl
 constexpr unsigned kGoQuit = 0xffffffffu;
-constexpr int kSyncGo = 5;                                                         // workspace header word: the broadcast doorbell
+constexpr int kSyncGo = 5, kSyncPos = 8;                                           // workspace header words: the broadcast doorbell, the ring slot
+// row server (latency_kernel<2>, dce_latency_row_ctrl): 19 chunks of 16 bytes {3 floats of the row, tag} .. {quit, pos, -, tag},
+// then the result block
+constexpr int kRowChunks = 19, kRowSeqOut = 80, kRowAlive = 84;
+constexpr int kRingRows = 2 * 150;
 
 // ---- K0 additions: contiguous per-CTA slices, so a slice is a handful of bulk copies -----------------
 // w4q[q][k = tap*128 + cin][32]  from wp4[tap][cin][cout]
@@ -173,7 +177,7 @@ __device__ __forceinline__ void window_stats(const float* __restrict__ xw, float
     for (int i = 0; i < 17; ++i) {
         const int row = s + 9 * i;
         const bool ok = act && row < 150;
-        xv[i] = ok ? __ldg(xw + row * 54 + c) : 0.f;
+        xv[i] = ok ? __ldcg(xw + row * 54 + c) : 0.f;      // L2: the row server re-reads a ring that changes between steps of ONE launch
         sum += xv[i];
     }
     if (act) part[s * 54 + c] = sum;
@@ -221,9 +225,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   into pinned host memory and then ctrl->seq_out.  No launch, no stream synchronisation, no copy engine in the
 //   loop; the next step's convolution weights are requested BEFORE the wait for the doorbell.  The kernel retires by
 //   itself when ctrl->quit is set or no doorbell arrives for idle_ns (so a forgotten server cannot hold the GPU).
-template <bool SERVER>
+// SERVER = 2 : the same with ONE NEW ROW per step instead of a whole window (dce_latency_row_server_start): the host
+//   writes the 54 floats of the newest sensor sample as 18 tagged 16-byte chunks (+ one chunk {quit, ring slot}); warp 0
+//   of CTA 0 polls all 19 chunks in parallel — doorbell and data arrive in the same PCIe round trip — stores the row
+//   into a 2 x 150-row ring in device memory and publishes the step; the window (the newest 150 rows, contiguous in
+//   the doubled ring) is z-scored on the device as in stream mode (utils/data_handler.py:55-56).  216 bytes cross
+//   PCIe per step instead of 32 400, and the host does no arithmetic at all.
+template <int SERVER>
 __global__ void __launch_bounds__(kThreads, 1)
 latency_kernel(const Params p) {
+    constexpr bool ROWS = SERVER == 2;
+    const volatile unsigned* res_block = p.ctrl + (ROWS ? kRowSeqOut : kCtrlSeqOut);
     extern __shared__ __align__(128) uint8_t smem[];
     float* w1s = reinterpret_cast<float*>(smem + oW1);
     float* w2s = reinterpret_cast<float*>(smem + oW2);
@@ -252,19 +264,20 @@ latency_kernel(const Params p) {
     if (tid == 0) {
         for (int i = 0; i < kNumBars; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_barrier_init();
-        if (SERVER && cta == 0) { p.ctrl[kCtrlAlive] = 1u; __threadfence_system(); }
+        if (SERVER && cta == 0) { p.ctrl[ROWS ? kRowAlive : kCtrlAlive] = 1u; __threadfence_system(); }
     }
     __syncthreads();
     LAT_TRACE(0);
     uint32_t xphase = 0;                              // bar_x is used once per phase-A item, over all steps
     unsigned seq_done = 0;                            // server: the last step served (the host starts at 0)
+    unsigned ring_pos = 0;                            // row server: ring slot of the newest row
     for (unsigned iter = 0;; ++iter) {
     const uint32_t ph = SERVER ? (iter & 1u) : 0u;    // parity of the once-per-step weight barriers
     const unsigned bar0 = SERVER ? iter * 3u * (unsigned)G : 0u;
     // batch mode: the 6 input rows of an item are one contiguous, 16-byte aligned span of x (rows are 216 B, the
     // span starts on an even row): ONE bulk copy straight into xin — x may be pinned HOST memory (LatencyRunner),
     // where one large read beats 324 scalar loads over PCIe.  Rows outside the window are zero-filled by hand.
-    const bool tma_in = !p.stream && p.tma_in;
+    const bool tma_in = !p.stream && p.tma_in && !ROWS;
     auto issue_x = [&](int it) {                      // thread 0
         const int b = it / 75, tp = it - b * 75;
         const int lo = (2 * tp - 2 > 0) ? 2 * tp - 2 : 0, hi = (2 * tp + 4 < 150) ? 2 * tp + 4 : 150;
@@ -289,7 +302,67 @@ latency_kernel(const Params p) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     }
 
-    if (SERVER) {
+    if (ROWS) {
+        // ---- wait for the next row (the convolution weights of this step are already on their way) ----
+        unsigned* go_s = reinterpret_cast<unsigned*>(last_flag) + 1;      // [0] the doorbell value, [1] the ring slot
+        if (warp == 0) {
+            unsigned go = 0u, pos = 0u;
+            if (cta == 0) {
+                const unsigned want = seq_done + 1u;
+                unsigned long long t0 = 0, t1;
+                if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                unsigned quit = 0u, spins = 0u;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                bool all;
+                do {
+                    if (lane < kRowChunks)
+                        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                     : "l"(p.ctrl + lane * 4) : "memory");
+                    all = __all_sync(0xffffffffu, lane >= kRowChunks || v.w == want);
+                    quit = __shfl_sync(0xffffffffu, v.x, kRowChunks - 1);
+                    if ((++spins & 255u) == 0u) {
+                        unsigned late = 0u;
+                        if (lane == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); late = (t1 - t0 > p.idle_ns) ? 1u : 0u; }
+                        quit |= __shfl_sync(0xffffffffu, late, 0);
+                    }
+                } while (!all && !quit);
+                if (!quit) {
+                    pos = __shfl_sync(0xffffffffu, v.y, kRowChunks - 1) % 150u;
+                    if (lane < kRowChunks - 1) {
+                        float* ring = const_cast<float*>(p.x);
+                        float* r0 = ring + (size_t)pos * 54 + lane * 3;
+                        r0[0] = __uint_as_float(v.x); r0[1] = __uint_as_float(v.y); r0[2] = __uint_as_float(v.z);
+                        r0[150 * 54] = __uint_as_float(v.x); r0[150 * 54 + 1] = __uint_as_float(v.y); r0[150 * 54 + 2] = __uint_as_float(v.z);
+                        __threadfence();
+                    }
+                    __syncwarp();
+                    go = want;
+                } else go = kGoQuit;
+                if (lane == 0) {
+                    p.sync[kSyncPos] = pos;
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sync + kSyncGo), "r"(go) : "memory");
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    *reinterpret_cast<unsigned long long*>(p.sync + 6) = t1;
+                }
+            } else if (lane == 0) {
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(go) : "l"(p.sync + kSyncGo) : "memory");
+                } while (go == seq_done);
+                pos = __ldcg(p.sync + kSyncPos);
+            }
+            if (lane == 0) { go_s[0] = go; go_s[1] = pos; }
+        }
+        __syncthreads();
+        const unsigned go = go_s[0];
+        if (go == kGoQuit) {
+            if (tid == 0) { if (a_cta) { ptx::mbar_wait(bar_w1, ph); ptx::mbar_wait(bar_w2, ph); } ptx::mbar_wait(bar_w3, ph); }
+            __syncthreads();
+            break;
+        }
+        seq_done = go;
+        ring_pos = go_s[1];
+    }
+    if (SERVER == 1) {
         // ---- wait for the doorbell (the convolution weights of this step are already on their way) ----
         unsigned* go_s = reinterpret_cast<unsigned*>(last_flag) + 1;      // [0] the doorbell value, [1] input copy already issued
         if (tid == 0) {
@@ -350,7 +423,8 @@ latency_kernel(const Params p) {
         int stat_b = -1;
         for (int it = cta; it < nA; it += G) {
             const int b = it / 75, tp = it - b * 75;
-            const float* xw = p.stream ? p.x + (size_t)(p.first + b) * 54 : p.x + (size_t)b * 8100;
+            const float* xw = ROWS ? p.x + (size_t)(ring_pos + 1u) * 54             // rows slot+1 .. slot+150 of the doubled ring: oldest .. newest
+                                   : p.stream ? p.x + (size_t)(p.first + b) * 54 : p.x + (size_t)b * 8100;
             if (p.stream && b != stat_b) { window_stats(xw, red, stat); stat_b = b; }
             if (tma_in) {
                 if (it != cta && tid == 0) issue_x(it);                  // (the first item's copy was issued in the prologue)
@@ -365,7 +439,7 @@ latency_kernel(const Params p) {
                     const int j = i / 54, c = i - j * 54, row = 2 * tp - 2 + j;
                     float v = 0.f;
                     if (row >= 0 && row < 150) {
-                        v = __ldg(xw + row * 54 + c);
+                        v = __ldcg(xw + row * 54 + c);
                         if (p.stream) v = (v - stat[c]) / stat[64 + c];
                     }
                     xin[i] = v;
@@ -565,8 +639,8 @@ latency_kernel(const Params p) {
                     float y[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) y[j] = logit_s[j];
-                    if (SERVER && !p.logits && p.B == 1 && p.cls == reinterpret_cast<const int32_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlCls0) &&
-                        p.bits == reinterpret_cast<const uint8_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlBits0)) {
+                    if (ROWS || (SERVER && !p.logits && p.B == 1 && p.cls == reinterpret_cast<const int32_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlCls0) &&
+                                 p.bits == reinterpret_cast<const uint8_t*>(const_cast<const unsigned*>(p.ctrl) + kCtrlBits0))) {
                         // the caller's result words sit next to seq_out: class, bits, device time and the step number leave
                         // as ONE aligned 16-byte store — one PCIe write, nothing to order, no system-scope fence
                         int32_t c1; uint8_t b4[4];
@@ -576,7 +650,7 @@ latency_kernel(const Params p) {
                         const unsigned ns = (unsigned)(t1 - __ldcg(reinterpret_cast<const unsigned long long*>(p.sync + 6)));
                         const unsigned bw = (unsigned)b4[0] | ((unsigned)b4[1] << 8) | ((unsigned)b4[2] << 16) | ((unsigned)b4[3] << 24);
                         p.sync[2] = 0u;
-                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p.ctrl + kCtrlSeqOut), "r"(seq_done), "r"((unsigned)c1), "r"(bw), "r"(ns) : "memory");
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(res_block), "r"(seq_done), "r"((unsigned)c1), "r"(bw), "r"(ns) : "memory");
                         *last_flag = 2;                              // results delivered
                     } else
                     fp32::argmax_bits_store(y, (int64_t)b, p.logits, p.cls, p.bits);
@@ -605,7 +679,8 @@ latency_kernel(const Params p) {
         const unsigned old = atomicAdd(p.sync + 1, 1u);
         if (old == (unsigned)G - 1u) {
             p.sync[0] = 0u; p.sync[1] = 0u; p.sync[3] = 0u; p.sync[kSyncGo] = 0u; __threadfence();
-            if (SERVER) { p.ctrl[kCtrlAlive] = 0u; __threadfence_system(); }
+            p.sync[kSyncPos] = 0u;
+            if (SERVER) { p.ctrl[ROWS ? kRowAlive : kCtrlAlive] = 0u; __threadfence_system(); }
         }
     }
 }
@@ -619,19 +694,21 @@ struct Weights {                  // pointers into the packed buffer
 // ctrl != nullptr: start the resident server form instead (one launch serves steps until quit / idle timeout)
 inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mode, int64_t first, int n,
                float* logits, int32_t* cls, uint8_t* bits, char* ws, Ctx& ctx, int coop = 1, int tma_in = 1,
-               volatile unsigned* ctrl = nullptr, unsigned long long idle_ns = 0) {
+               volatile unsigned* ctrl = nullptr, unsigned long long idle_ns = 0, bool rows = false) {
     const int grid = sm_count / 4 * 4;
     if (grid < kSlices || n < 1 || n > kMaxB) return DCE_EUNSUPPORTED;
-    if (ctrl && (stream_mode || !tma_in)) return DCE_EINVAL;      // the server re-reads host memory every step: bulk copies only (no cached loads)
+    if (ctrl && !rows && (stream_mode || !tma_in)) return DCE_EINVAL;      // the server re-reads host memory every step: bulk copies only (no cached loads)
+    if (rows && (!ctrl || n != 1)) return DCE_EINVAL;
     static DeviceOnce once;
     if (auto first_ = once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(latency_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(latency_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(latency_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(latency_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(latency_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
     }
     const Workspace W = make_workspace(n);
     Params p{};
-    p.x = src; p.stream = stream_mode ? 1 : 0; p.tma_in = tma_in; p.first = first; p.B = n;
+    p.x = src; p.stream = (stream_mode || rows) ? 1 : 0; p.tma_in = tma_in; p.first = first; p.B = n;
     p.w1 = wt.w1; p.w2 = wt.w2; p.w3 = wt.w3; p.w4q = wt.w4q; p.f1s = wt.f1s; p.f2s = wt.f2s; p.f3t = wt.f3t;
     p.b1 = wt.b[0]; p.b2 = wt.b[1]; p.b3 = wt.b[2]; p.b4 = wt.b[3]; p.bf1 = wt.b[4]; p.bf2 = wt.b[5]; p.bf3 = wt.b[6];
     p.p1 = reinterpret_cast<float*>(ws + W.p1); p.a4 = reinterpret_cast<float*>(ws + W.a4);
@@ -647,10 +724,11 @@ inline int run(const Weights& wt, int sm_count, const float* src, bool stream_mo
     cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
     if (ctrl) {
         if (!coop) return DCE_EINVAL;                 // the server spins on grid barriers for its whole life: co-residency must be guaranteed
-        DCE_KL(ctx, "latency_server", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<true>, p); (void)le_; });
+        if (rows) DCE_KL(ctx, "latency_row_server", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<2>, p); (void)le_; });
+        else DCE_KL(ctx, "latency_server", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<1>, p); (void)le_; });
         return DCE_OK;
     }
-    DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<false>, p); (void)le_; });
+    DCE_KL(ctx, "latency_fused", { cudaError_t le_ = cudaLaunchKernelEx(&cfg, latency_kernel<0>, p); (void)le_; });
     return DCE_OK;
 }
 

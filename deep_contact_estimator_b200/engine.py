@@ -370,6 +370,10 @@ class ContactEngine:
         """Batch-``n`` (<= 4) control-loop path: see :class:`LatencyRunner`."""
         return LatencyRunner(self, n, want_logits, use_graph, persistent, idle_timeout_s)
 
+    def row_runner(self, idle_timeout_s: float = 2.0) -> "RowRunner":
+        """The control loop fed one new 54-channel row per tick: see :class:`RowRunner`."""
+        return RowRunner(self, idle_timeout_s)
+
     def set_option(self, key, value: int) -> int:
         """``dce_weights_set_option``: an ablation / debugging switch of THIS engine's handle (include/dce.h);
         returns the ABI's code (0, or -1 for an unknown key)."""
@@ -558,3 +562,101 @@ class LatencyRunner:
         self.enqueue()
         self.stream.synchronize()
         return self.cls_host, self.bits_host
+
+
+class RowRunner:
+    """The 1 kHz control loop fed ONE NEW SENSOR ROW per tick (``dce_latency_row_server_start``, include/dce.h): the
+    resident kernel keeps the last 150 rows in a device ring, z-scores the newest window itself
+    (utils/data_handler.py:55-56) and classifies it.  ``push(row)`` writes 216 bytes + tags into pinned memory and
+    spins on the answer word: no CUDA call, no host arithmetic.
+
+        rr = engine.row_runner()
+        for row in sensor_rows:                # (54,) float32: [q, qd, acc, omega, p, v] (utils/mat2numpy.py:73)
+            cls, bits = rr.push(row)           # valid once 150 rows have been pushed (rr.ready)
+
+    The server holds every SM while it lives and retires after ``idle_timeout_s`` without a row (the next push
+    restarts it; the ring is kept), or on ``close()``.
+    """
+
+    _SEQ_OUT, _CLS0, _BITS0, _DEVICE_NS, _ALIVE = 80, 81, 82, 83, 84
+
+    def __init__(self, eng: ContactEngine, idle_timeout_s: float = 2.0):
+        import numpy as np
+        self.eng, self.idle_timeout_s = eng, float(idle_timeout_s)
+        dev = eng.device
+        self.stream = torch.cuda.Stream(dev)
+        self._ctrl = torch.zeros(128, dtype=torch.int32).pin_memory()          # dce_latency_row_ctrl: 512 bytes
+        self._c = self._ctrl.numpy().view("uint32")
+        self._chunks = self._c[:76].reshape(19, 4)
+        self._floats = self._chunks[:18, :3].view("float32")                   # (18, 3): the 54 floats of the row
+        self._tags = self._chunks[:, 3]
+        self.ring = torch.zeros((2 * WINDOW, CHANNELS), dtype=torch.float32, device=dev)
+        self._ws = torch.zeros(eng.lib.dce_workspace_bytes(1, _lib.PRECISIONS[eng.precision]), dtype=torch.uint8, device=dev)
+        self.rows_seen = 0
+        self.server_starts = 0
+        self._seq = 0
+        self._np = np
+        P = ContactEngine._p
+        start = eng.lib.dce_latency_row_server_start
+        args = (P(self._ctrl), P(self.ring), P(self._ws), self._ws.numel(), ctypes.c_double(self.idle_timeout_s),
+                ctypes.c_void_p(self.stream.cuda_stream))
+        index = dev.index
+
+        def start_server():
+            torch.cuda.synchronize(dev)                          # ring / workspace initialised; a retired server has left the stream
+            with torch.cuda.device(index):
+                _lib.check(start(eng._handle, *args), "dce_latency_row_server_start")
+            self._seq = 0
+            self.server_starts += 1
+            t0 = time.perf_counter()
+            while not self._c[self._ALIVE]:
+                if time.perf_counter() - t0 > 10.0:
+                    raise RuntimeError("the row server did not come up within 10 s (is the GPU busy with other kernels?)")
+        self._start_server = start_server
+        start_server()
+
+    @property
+    def ready(self) -> bool:
+        return self.rows_seen >= WINDOW
+
+    @property
+    def device_us(self) -> float:
+        """Device time of the last step: row seen -> results written (microseconds)."""
+        return float(self._c[self._DEVICE_NS]) * 1e-3
+
+    def push(self, row):
+        """Append one 54-vector (numpy array / sequence / CPU tensor) and classify the newest window:
+        ``(class 0..15, (RF, LF, RH, LH) contact bits)``; meaningful once ``ready``."""
+        c = self._c
+        if not c[self._ALIVE]:
+            self._start_server()
+        r = row.numpy() if torch.is_tensor(row) else self._np.asarray(row, dtype="float32")
+        slot = self.rows_seen % WINDOW
+        self.rows_seen += 1
+        self._seq += 1
+        seq = self._seq
+        self._floats[...] = r.reshape(18, 3)
+        self._chunks[18, 1] = slot
+        self._tags[...] = seq                                    # the doorbell: every chunk's tag, after its data
+        spins = 0
+        while c[self._SEQ_OUT] != seq:
+            spins += 1
+            if (spins & 1023) == 0 and not c[self._ALIVE]:       # it retired just as the row arrived: start over, same slot
+                if c[self._SEQ_OUT] == seq:
+                    break
+                self._start_server()
+                self._seq = seq = 1
+                self._tags[...] = seq
+        b = int(c[self._BITS0])
+        return int(c[self._CLS0]), (b & 1, (b >> 8) & 1, (b >> 16) & 1, (b >> 24) & 1)
+
+    def close(self):
+        if self._c is not None and self._c[self._ALIVE]:
+            self._chunks[18, 0] = 1                               # quit
+            self.stream.synchronize()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

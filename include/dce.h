@@ -161,6 +161,49 @@ static inline int dce_latency_server_step(dce_latency_ctrl *ctrl) {
 }
 
 /*
+ * The same server fed ONE NEW SENSOR ROW per step — what a 1 kHz estimator actually receives (README.md:67-83 of the
+ * reference: one leg_control_data + microstrain sample per tick).  The device keeps the last 150 rows in a ring
+ * (ring_dev: [300][54] fp32 DEVICE memory owned by the caller; row k lives at slots k % 150 and k % 150 + 150, so the
+ * newest window is always one contiguous slice) and z-scores the window itself exactly as stream mode does
+ * (utils/data_handler.py:55-56): 216 bytes cross PCIe per step instead of 32 400 and the host does no arithmetic.
+ * Protocol: the host writes the row as 18 chunks {3 floats, tag} and a 19th chunk {quit, slot, 0, tag}, every tag =
+ * the step number (from 1; floats before the tag of their chunk) — dce_latency_row_server_push() below; the device
+ * polls all chunks in one PCIe round trip, so doorbell and data arrive together.  Results come back in the control
+ * block (seq_out, cls0, bits0 in one 16-byte store).  Retirement as for dce_latency_server_start; the ring survives
+ * a restart (keep passing consecutive slots).
+ */
+typedef struct dce_latency_row_ctrl {
+    volatile uint32_t chunk[19][4];  /* [i < 18] = {row[3i], row[3i+1], row[3i+2] as float bits, tag}; [18] = {quit, slot, 0, tag} */
+    uint32_t reserved0[4];
+    volatile uint32_t seq_out;       /* offset 320: {seq_out, cls0, bits0, device_ns} arrive as one store          */
+    volatile int32_t  cls0;
+    volatile uint8_t  bits0[4];
+    volatile uint32_t device_ns;
+    volatile uint32_t alive;
+    uint32_t reserved1[43];
+} dce_latency_row_ctrl;              /* 512 bytes */
+
+DCE_API int dce_latency_row_server_start(const dce_weights *w, dce_latency_row_ctrl *ctrl, float *ring_dev,
+                                 void *workspace_dev, size_t workspace_bytes, double idle_timeout_s, void *stream);
+
+/* Push row `seq` (1, 2, ...) into ring slot `slot` (0..149, consecutive) and wait for its class / bits.  Host side only. */
+static inline int dce_latency_row_server_push(dce_latency_row_ctrl *ctrl, const float row[54], uint32_t slot, uint32_t seq) {
+    int i;
+    if (!ctrl->alive) return -1;
+    for (i = 0; i < 18; ++i) {
+        union { float f; uint32_t u; } a, b, c;
+        a.f = row[3 * i]; b.f = row[3 * i + 1]; c.f = row[3 * i + 2];
+        ctrl->chunk[i][0] = a.u; ctrl->chunk[i][1] = b.u; ctrl->chunk[i][2] = c.u;
+    }
+    ctrl->chunk[18][1] = slot;
+    __atomic_thread_fence(__ATOMIC_RELEASE);                          /* data before tags */
+    for (i = 0; i < 19; ++i) ctrl->chunk[i][3] = seq;
+    while (__atomic_load_n(&ctrl->seq_out, __ATOMIC_ACQUIRE) != seq)
+        if (!ctrl->alive) return -1;
+    return 0;
+}
+
+/*
  * K2: the body of `inference(dataloader, model, device)`
  * (src/inference_one_seq.py:19-30) over a device-resident sensor log: for
  * window i in [first_window, first_window + n_windows): rows i..i+149 of

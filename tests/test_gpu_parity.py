@@ -568,14 +568,73 @@ def test_classify_host_matches_classify(dev, params0):
 
 
 def test_realtime_estimator_on_gpu(dev, params0):
-    """RealtimeContactEstimator over the real LatencyRunner: contact bits per tick == the reference loop's."""
+    """RealtimeContactEstimator over the row server (ring + z-score + classification on the device): contact bits per
+    tick == the reference loop's."""
     from deep_contact_estimator_b200.realtime import RealtimeContactEstimator
     log = synth.make_sensor_log(150 + 20, seed=4)
     _, wc, wb = oracle.inference_stream(params0, log)
     est = RealtimeContactEstimator(engine=engine(dev, "bf16x3"))
-    got = [est.push_row(log[t]) for t in range(log.shape[0])]
+    try:
+        got = [est.push_row(log[t]) for t in range(log.shape[0])]
+    finally:
+        est.close()
     assert all(g is None for g in got[:149])
     assert [g[0] for g in got[149:]] == wc.tolist() and [list(g[1]) for g in got[149:]] == wb.tolist()
+
+
+def test_resident_latency_servers(dev, params0):
+    """BASELINE configs[4] without a launch per step: the resident window server (LatencyRunner(persistent=True):
+    doorbell in pinned memory, results + step number in one 16-byte store) and the row server (RowRunner: one new
+    54-float row per tick, ring and z-score on the device).  Window server: bit-identical to the launch-per-step kernel,
+    for n = 1 (results in the control block), n = 1 with logits and n = 3 (results in the caller's pinned arrays).
+    Row server: classes and bits of every window equal to the reference loop at batch_size 1
+    (src/inference_one_seq.py:19-30 over utils/data_handler.py:55-57).  Both retire on their own when idle, restart on
+    the next step, and leave the GPU to ordinary calls in between."""
+    import time
+    eng = dce.ContactEngine(params0, dev, "bf16x3")
+    xs = synth.make_windows(24, seed=14)
+    want_l, want_c, want_b = [t.cpu() for t in eng.classify(xs.to(dev))]
+    ref = eng.latency_runner(1, want_logits=True)
+    ref_logits = []
+    for j in range(24):                                        # (before any server is up: a resident server leaves no SM to a launch)
+        ref.step(xs[j])
+        ref_logits.append(ref.logits_host[0].clone())
+    for n, logits in ((1, False), (1, True), (3, False)):
+        run = eng.latency_runner(n, want_logits=logits, persistent=True, idle_timeout_s=0.3)
+        try:
+            for i in range(0, 24, n):
+                cls, bits = run.step(xs[i:i + n])
+                for j in range(n):
+                    assert int(cls[j]) == int(want_c[i + j]) and bits[j].tolist() == want_b[i + j].tolist()
+                    if logits:
+                        assert torch.equal(run.logits_host[j], ref_logits[i + j])       # same kernel body: same bits
+            assert run.server_starts == 1
+            time.sleep(0.6)                                    # idle: the server retires and frees the SMs ...
+            assert not run._c[run._ALIVE]
+            assert torch.equal(eng.classify(xs.to(dev))[1].cpu(), want_c)               # ... an ordinary call runs ...
+            cls, bits = run.step(xs[:n])                       # ... and the next step brings the server back
+            assert run.server_starts == 2 and int(cls[0]) == int(want_c[0])
+        finally:
+            run.close()
+        assert not run._c[run._ALIVE]
+    log = synth.make_sensor_log(150 + 64, seed=33)
+    _, wc, wb = oracle.inference_stream(params0, log)
+    rr = eng.row_runner(idle_timeout_s=0.3)
+    try:
+        got = []
+        for t in range(log.shape[0]):
+            out = rr.push(log[t])
+            if t == 170:
+                time.sleep(0.6)                                # retire mid-log: the ring survives the restart
+            if rr.ready:
+                got.append(out)
+        assert rr.server_starts == 2
+    finally:
+        rr.close()
+    assert [g[0] for g in got] == wc.tolist() and [list(g[1]) for g in got] == wb.tolist()
+    with pytest.raises(ValueError):
+        eng.latency_runner(1, persistent=True, use_graph=True)
+    eng.close()
 
 
 def test_torch_ops_binding_equals_ctypes_binding(dev, params0, monkeypatch):

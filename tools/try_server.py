@@ -72,3 +72,22 @@ run.step(xs[5])
 print("restarted:", run.server_starts, "result ok:", int(run.cls_host[0]) == want[5][0], flush=True)
 run.close()
 print("closed: alive =", int(run._c[run._ALIVE]), flush=True)
+
+# ---- row server: one new 54-float row per step, ring + z-score on the device ----
+from oracle import contact_oracle as oracle
+log = synth.make_sensor_log(150 + 400, seed=9)
+_, wc, wb = oracle.inference_stream(synth.make_params(0), log)
+rr = eng.row_runner(idle_timeout_s=0.5)
+rows = log.numpy()
+got, t, d = [], [], []
+for i in range(rows.shape[0]):
+    t0 = time.perf_counter(); out = rr.push(rows[i]); t.append((time.perf_counter() - t0) * 1e6); d.append(rr.device_us)
+    if rr.ready:
+        got.append(out)
+okr = [g[0] for g in got] == wc.tolist() and [list(g[1]) for g in got] == wb.tolist()
+print("row server: %d windows, classes + bits equal to the reference loop: %s; host p50 %.1f us p99 %.1f | device p50 %.1f us" %
+      (len(got), okr, np.percentile(t[150:], 50), np.percentile(t[150:], 99), np.percentile(d[150:], 50)), flush=True)
+time.sleep(0.8)
+out = rr.push(rows[0])                       # restarted server, ring kept
+print("row server after idle retirement: starts", rr.server_starts, flush=True)
+rr.close()
