@@ -649,18 +649,15 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 10;
+constexpr int kNumPacked = 7;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0 (layer-wise conv3: resident image)
                                  {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
                                  {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
                                  {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
-                                 {128, 3, 2, 4, 1, 0, 64, 4},      // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
-                                 {128, 1, 4, 148, 16, 1, 4736, 8}, // fc.0 in half blocks of 128 columns: one per CTA of a pair (dce_tc_pair.cuh)
-                                 {64, 1, 4, 64, 8, 2, 2048, 10},   // fc.3 in half blocks of 64 columns
-                                 {128, 1, 8, 32, 4, 2, 2048, 10}}; // fc.3 with 64 K-elements per stage
-constexpr int kLayerConv3Ring = 6, kLayerFc1Pair = 7, kLayerFc2Pair = 8, kLayerFc2K8 = 9;
+                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+constexpr int kLayerConv3Ring = 6;
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };

@@ -3,7 +3,6 @@
 #include "dce_tc.cuh"
 #include "dce_tc_block1.cuh"
 #include "dce_tc_block2.cuh"
-#include "dce_tc_pair.cuh"
 #include "dce_small.cuh"
 
 namespace dce {
@@ -15,13 +14,11 @@ struct Options {
     int fuse_block1 = 1;         // 0: ingest, conv1, conv2 as separate launches (activations round-trip through HBM)
     int fuse_block2 = 1;         // 0: conv3, conv4 as separate launches
     int fuse_fc3 = 1;            // 0: fc.3 writes H2, a separate kernel does fc.6 + argmax + bits
-    int fc_pair = 0;             // 1: fc.0 / fc.3 on CTA pairs (cta_group::2, dce_tc_pair.cuh); 0: one CTA per tile (tapgemm_kernel)
     int latency_kernel = 1;      // 0: calls of <= 4 windows take the per-layer kernels
     int latency_coop = 1, latency_tma_in = 1;
     int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
     int tapgemm_dbg = 0;
     int block2_dbg = 0;
-    int fc2_ksa8 = 0;            // experiment: fc.3 with 64 K-elements per stage (12 MMAs per issuer visit instead of 6)
     int sm_limit = 0;            // > 0: the batch kernels use at most this many CTAs (what a MIG slice / smaller part would give them)
     int trace_layer = -1;        // which kernel records into `trace`: -1 block1, 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2
     long long* trace = nullptr;  // device buffer [60 tiles][16 events] of clock64 samples of CTA 0 (DCE_TRACE builds)
@@ -188,10 +185,6 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         p.N = 2048; p.rw = 1; p.tv = 1;
         p.dbg = opt.tapgemm_dbg;
         p.trace = (opt.trace_layer == 4) ? opt.trace : nullptr;
-        if (opt.fc_pair) {
-            p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerFc1Pair]);
-            rc = launch_fcpair<256, 4, 4, EPI_FC_TAPE, 2>(ctx, "tc_fc1_pair", sm_count, p);
-        } else
         rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
         if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
@@ -203,13 +196,6 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         if (opt.fuse_fc3) {
             // ---- fc.3 + ReLU with fc.6 folded into the epilogue (a11, a12): H2 stays in registers; 8 logit shares per window
             p.w3t = bp.w3;
-            if (opt.fc_pair) {
-                p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerFc2Pair]);
-                rc = launch_fcpair<128, 4, 8, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3_pair", sm_count, p);
-            } else if (opt.fc2_ksa8) {
-                p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerFc2K8]); p.stages = kLayers[kLayerFc2K8].stages;
-                rc = launch_layer<128, 1, 8, 3, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3_k8", sm_count, p);
-            } else
             rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
             if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,
