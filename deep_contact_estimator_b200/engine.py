@@ -197,8 +197,17 @@ class ContactEngine:
         return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
 
     # -- host-buffer entry point (what a user with numpy / pinned data calls) ----
+    def classify_host_async(self, x_host: torch.Tensor, out_bits_host: torch.Tensor, out_cls_host: torch.Tensor,
+                            chunk: int = 1024) -> "HostBatch":
+        """``classify_host`` without the final wait: enqueues the chunked upload, the kernels and the device->host read
+        of the results and returns a :class:`HostBatch` whose ``wait()`` blocks until ``out_cls_host`` / ``out_bits_host``
+        (pinned, caller-owned, one pair per batch in flight) hold the answer.  Keeping two batches in flight lets the
+        upload of batch i+1 run under the kernel tail of batch i (the ~0.25 ms after the last chunk has landed), which a
+        call that waits for its own result cannot hide.  Inputs must stay untouched until ``wait()`` returns."""
+        return self.classify_host(x_host, out_bits_host, out_cls_host, chunk=chunk, _async=True)
+
     def classify_host(self, x_host: torch.Tensor, out_bits_host: Optional[torch.Tensor] = None,
-                      out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024, zero_copy: bool = False):
+                      out_cls_host: Optional[torch.Tensor] = None, chunk: int = 1024, zero_copy: bool = False, _async: bool = False):
         """``x_host``: ``(B,150,54)`` fp32 on the HOST (pinned for full speed).
         Copies chunk by chunk on a side stream so the host->device transfer of
         chunk i+1 overlaps the kernels of chunk i; returns host ``(cls, bits)``
@@ -244,13 +253,19 @@ class ContactEngine:
             compute = torch.cuda.current_stream(self.device)
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
+            fresh = False
             if getattr(self, "_stage", None) is None:
                 self._stage = [torch.empty((chunk, WINDOW, CHANNELS), dtype=torch.float32, device=self.device) for _ in range(2)]
                 self._stage_free = [torch.cuda.Event() for _ in range(2)]
+                fresh = True
             if self._stage[0].shape[0] != chunk:
                 self._stage = [torch.empty((chunk, WINDOW, CHANNELS), dtype=torch.float32, device=self.device) for _ in range(2)]
+                fresh = True
             copy = self._copy_stream
-            copy.wait_stream(compute)
+            if fresh:
+                copy.wait_stream(compute)      # new staging memory may have been handed back by work still queued on `compute`
+            # (otherwise the copy stream does NOT wait for earlier compute work: the per-buffer `_stage_free` events below are the
+            # only dependency, so the upload of this batch runs under the kernel tail of the previous one)
             bits_dev = torch.empty((n, 4), dtype=torch.uint8, device=self.device)
             cls_dev = torch.empty((n,), dtype=torch.int32, device=self.device)
             ws = self._ws(min(n, chunk))
@@ -271,8 +286,14 @@ class ContactEngine:
                 self._stage_free[i & 1].record(compute)
             out_bits_host.copy_(bits_dev, non_blocking=True)
             out_cls_host.copy_(cls_dev, non_blocking=True)
+            self.last_launches = launches
+            if _async:
+                if not (out_bits_host.is_pinned() and out_cls_host.is_pinned()):
+                    raise ValueError("classify_host_async needs pinned output tensors (the device->host read must not block)")
+                done = torch.cuda.Event()
+                done.record(compute)
+                return HostBatch(done, out_cls_host, out_bits_host, (bits_dev, cls_dev))
             compute.synchronize()
-        self.last_launches = launches
         return out_cls_host, out_bits_host
 
     # -- K2 -------------------------------------------------------------------
@@ -415,6 +436,18 @@ class ContactEngine:
                                               ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "dce_accuracy_counts")
         return counts
+
+
+class HostBatch:
+    """A batch in flight (``ContactEngine.classify_host_async``): ``wait()`` -> host ``(cls, bits)``."""
+
+    def __init__(self, done, cls_host, bits_host, keep):
+        self._done, self.cls_host, self.bits_host, self._keep = done, cls_host, bits_host, keep
+
+    def wait(self):
+        self._done.synchronize()
+        self._keep = None
+        return self.cls_host, self.bits_host
 
 
 class LatencyRunner:

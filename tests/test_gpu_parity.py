@@ -557,6 +557,21 @@ def test_classify_host_matches_classify(dev, params0):
     assert hc2 is out_c and hb2 is out_b and torch.equal(out_c, cl.cpu()) and torch.equal(out_b, bi.cpu())
     want = oracle_logits(params0, x[:64]).argmax(1)
     assert np.array_equal(hc.numpy()[:64], want)
+    # two batches in flight (classify_host_async): each lands in its own pinned outputs, same bits as the blocking call
+    xb = [x.pin_memory(), synth.make_windows(2500, seed=32).pin_memory()]
+    outs = [(torch.empty((2500, 4), dtype=torch.uint8).pin_memory(), torch.empty((2500,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    wants = [eng.classify(b.to(dev), want_logits=False) for b in xb]
+    pending = None
+    for rep in range(6):
+        h = eng.classify_host_async(xb[rep & 1], *outs[rep & 1], chunk=1024)
+        if pending is not None:
+            c, b = pending.wait()
+            assert torch.equal(c, wants[(rep - 1) & 1][1].cpu()) and torch.equal(b, wants[(rep - 1) & 1][2].cpu())
+        pending = h
+    c, b = pending.wait()
+    assert torch.equal(c, wants[1][1].cpu()) and torch.equal(b, wants[1][2].cpu())
+    with pytest.raises(ValueError):
+        eng.classify_host_async(xb[0], torch.empty((2500, 4), dtype=torch.uint8), torch.empty((2500,), dtype=torch.int32))   # pageable outputs
     e_c, e_b = eng.classify_host(torch.empty(0, 150, 54))
     assert e_c.shape == (0,) and e_b.shape == (0, 4)
     with pytest.raises(ValueError):
