@@ -485,6 +485,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the latency_b1 leg (profiler runs: its resident servers wait for host doorbells)")
     ap.add_argument("--stream-steps", type=int, default=2_000_000, help="rows of the synthetic log of the `stream` leg per GPU (0: skip)")
     ap.add_argument("--big-batch", type=int, default=32768, help="windows per GPU of the one-call big-batch leg, BASELINE configs[3] (0: skip)")
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
@@ -634,7 +635,7 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
 
-    latency = gpu_latency_b1(eng, dev)
+    latency = None if args.no_latency else gpu_latency_b1(eng, dev)
     eager = torch_eager_gpu(dev, xs[0], eng.classify(xs[0], want_logits=True)[0])
     peaks, peak_src = load_peaks()
     dom = max(per_kernel_ms, key=per_kernel_ms.get) if per_kernel_ms else None

@@ -129,11 +129,14 @@ struct TapGemmCfg {
     static constexpr int B_BYTES = 2 * B_PART;
     static constexpr int STAGE_BYTES = A_BYTES + (WST ? 0 : B_BYTES);
     static constexpr int WRES_BYTES = WST * B_BYTES;
-    static constexpr int NBUF = (2 * MT * BN <= 512) ? 2 : 1;   // accumulator buffers (epilogue / MMA overlap)
-    static constexpr int TMEM_COLS = NBUF * MT * BN;
+    // BN = 240 (fc.0: 2048 = 8 x 240 + 128 output features -> 9 n-tiles x 16 M-tile pairs = 144 tiles for 148 SMs instead of
+    // 128): the MMA is N = 240, the accumulator keeps a 256-column pitch, and the epilogue masks the columns that do not exist
+    static constexpr int ACC_COLS = (BN == 240) ? 256 : BN;
+    static constexpr int NBUF = (2 * MT * ACC_COLS <= 512) ? 2 : 1;   // accumulator buffers (epilogue / MMA overlap)
+    static constexpr int TMEM_COLS = NBUF * MT * ACC_COLS;
     static constexpr int BAR_BYTES = (2 * NSTAGE + 5) * 8 + 8;
     static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = RING_BYTES + WRES_BYTES + BAR_BYTES + kEpiWarps * (BN / 2) * 4;
+    static constexpr int SMEM_BYTES = RING_BYTES + WRES_BYTES + BAR_BYTES + kEpiWarps * (ACC_COLS / 2) * 4;
     static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
     static_assert(STAGE_BYTES % 16 == 0, "bulk copies are 16-byte granular");
@@ -160,8 +163,10 @@ tapgemm_kernel(const TapGemmParams p) {
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     float* s_bias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::WRES_BYTES + Cfg::BAR_BYTES);   // [8 warps][BN/2]
-    float4* s_w3 = reinterpret_cast<float4*>(s_bias + kEpiWarps * (BN / 2));    // EPI_FC_LOGITS: [BN columns][16] fc.6 weights of this n-tile
+    float4* s_w3 = reinterpret_cast<float4*>(s_bias + kEpiWarps * (Cfg::ACC_COLS / 2));    // EPI_FC_LOGITS: [BN columns][16] fc.6 weights of this n-tile
     static_assert(EPI != EPI_FC_LOGITS || MT == 1, "the logit-share epilogue keeps one row per thread");
+    static_assert(BN != 240 || EPI == EPI_FC_TAPE, "the masked 240-column tile is fc.0's");
+    constexpr int ACC = Cfg::ACC_COLS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
@@ -255,7 +260,7 @@ tapgemm_kernel(const TapGemmParams p) {
             for (int tcount = 0; tcount < my_tiles; ++tcount) {
                 const uint32_t buf = tcount % NBUF;
                 if (mt == 0) TG_TRACE(tcount, 2);
-                const uint32_t d = tmem_base + buf * (MT * BN) + mt * BN;
+                const uint32_t d = tmem_base + buf * (MT * ACC) + mt * ACC;
                 // A single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM): the epilogue that frees it cannot start
                 // before this issuer's own `tfull` commit of the previous tile, so the buffer is awaited here, at the top of
                 // the tile, not by the mid-stage probe below (which would wait for it BEFORE that commit: a deadlock found
@@ -305,7 +310,7 @@ tapgemm_kernel(const TapGemmParams p) {
     } else {
         // ===== epilogue: TMEM -> registers -> bias / ReLU / pool -> bf16 hi/lo -> next layer's tape =====
         // warp e: TMEM lane quadrant q = e % 4 (hardware restriction), column half h = e / 4.
-        constexpr int HALF = BN / 2;
+        constexpr int HALF = ACC / 2;
         const int q = warp & 3, h = warp >> 2;
         const int row_in_tile = q * 32 + lane;
         float* my_bias = s_bias + warp * HALF;               // warp-private copy of this warp's bias slice
@@ -317,7 +322,7 @@ tapgemm_kernel(const TapGemmParams p) {
             const int n0 = n * BN + h * HALF;                // first output feature this warp owns
             if (n != last_n) {                               // stage this warp's bias slice (warp-private copy)
                 __syncwarp();
-                for (int i = lane; i < HALF; i += 32) my_bias[i] = __ldg(p.bias + n0 + i);
+                for (int i = lane; i < HALF; i += 32) my_bias[i] = (h * HALF + i < BN && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
                 if (EPI == EPI_FC_LOGITS) {
                     // fc.6 rows n*BN .. n*BN+BN-1, staged once by the eight epilogue warps together (they walk the same
                     // tile sequence, so they meet at this named barrier the same number of times)
@@ -363,8 +368,8 @@ tapgemm_kernel(const TapGemmParams p) {
             }
             constexpr int CPM = HALF / 32;                   // 32-column chunks per M-tile for this warp
             constexpr int NCH = MT * CPM;
-            const uint32_t taddr0 = tmem_base + buf * (MT * BN) + h * HALF + ((uint32_t)(q * 32) << 16);
-            auto chunk_addr = [&](int ci) { return taddr0 + (ci / CPM) * BN + (ci % CPM) * 32; };
+            const uint32_t taddr0 = tmem_base + buf * (MT * ACC) + h * HALF + ((uint32_t)(q * 32) << 16);
+            auto chunk_addr = [&](int ci) { return taddr0 + (ci / CPM) * ACC + (ci % CPM) * 32; };
 
             float lg[16];                                    // EPI_FC_LOGITS: this thread's share of its row's 16 logits
 #pragma unroll
@@ -422,6 +427,7 @@ tapgemm_kernel(const TapGemmParams p) {
                     uint4 hi, lo;
                     split8(y + qd * 8, hi, lo);
                     const int kch = (n0 + c0) / 8 + qd;
+                    if (BN == 240 && (h * HALF + c0 + qd * 8 >= BN || n0 + c0 + qd * 8 >= p.N)) continue;   // columns of the pitch / of the last n-tile that do not exist
                     if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
                         uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off[mt];
                         *reinterpret_cast<uint4*>(dst) = hi;
@@ -481,7 +487,7 @@ tapgemm_kernel(const TapGemmParams p) {
 // kind 2: fc.3  W[n][k]
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
-                              int BN, int TAPS, int KSA, int kind, int cin) {
+                              int BN, int TAPS, int KSA, int kind, int cin, int nout) {
     const size_t per_part = (size_t)TAPS * KSA * BN * 8;            // elements in one part of one block
     const size_t total = (size_t)n_tiles * stages * per_part;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -495,7 +501,8 @@ __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__
         const int n = nt * BN + nn;
         const int c = (s * KSA + j) * 8 + e;
         float v;
-        if (kind == 0) v = (c < cin) ? W[((size_t)n * cin + c) * 3 + tap] : 0.f;
+        if (n >= nout) v = 0.f;                      // padding columns of a ragged last n-tile
+        else if (kind == 0) v = (c < cin) ? W[((size_t)n * cin + c) * 3 + tap] : 0.f;
         else if (kind == 1) { const int t = c / 128, ch = c % 128; v = W[(size_t)n * 4736 + ch * 37 + t]; }
         else v = W[(size_t)n * cin + c];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -647,16 +654,16 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 // host side: packed layout, workspace, launch sequence
 // ---------------------------------------------------------------------------------------------
-struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src; };
+struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src, nout; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
 constexpr int kNumPacked = 7;
-constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0},       // block1.0
-                                 {64, 3, 4, 2, 1, 0, 64, 2},       // block1.2
-                                 {128, 3, 4, 2, 1, 0, 64, 4},      // block2.0 (layer-wise conv3: resident image)
-                                 {128, 3, 2, 8, 1, 0, 128, 6},     // block2.2
-                                 {256, 1, 4, 148, 8, 1, 4736, 8},  // fc.0
-                                 {128, 1, 4, 64, 4, 2, 2048, 10},  // fc.3
-                                 {128, 3, 2, 4, 1, 0, 64, 4}};     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0, 64},       // block1.0
+                                 {64, 3, 4, 2, 1, 0, 64, 2, 64},       // block1.2
+                                 {128, 3, 4, 2, 1, 0, 64, 4, 128},     // block2.0 (layer-wise conv3: resident image)
+                                 {128, 3, 2, 8, 1, 0, 128, 6, 128},    // block2.2
+                                 {240, 1, 4, 148, 9, 1, 4736, 8, 2048},  // fc.0: 8 n-tiles of 240 + one of 128 (zero-padded to 240)
+                                 {128, 1, 4, 64, 4, 2, 2048, 10, 512}, // fc.3
+                                 {128, 3, 2, 4, 1, 0, 64, 4, 128}};    // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
 constexpr int kLayerConv3Ring = 6;
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
@@ -674,7 +681,7 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
         const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
         DCE_KL(ctx, "tc_pack_b", pack_b_kernel<<<blocks, 256, 0, ctx.stream>>>(
-            params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin));
+            params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin, c.nout));
     }
     return DCE_OK;
 }

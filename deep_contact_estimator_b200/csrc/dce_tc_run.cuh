@@ -185,7 +185,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         p.N = 2048; p.rw = 1; p.tv = 1;
         p.dbg = opt.tapgemm_dbg;
         p.trace = (opt.trace_layer == 4) ? opt.trace : nullptr;
-        rc = launch_layer<256, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
+        rc = launch_layer<240, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
         if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
         p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small-shape run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
-   compute-sanitizer --tool memcheck python tools/sanitize.py [--experimental]"""
+   compute-sanitizer --tool memcheck python tools/sanitize.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,4 +26,19 @@ for precision in ("bf16x3", "fp32"):
         lo, cl, bi = eng.classify(x.to(dev)); torch.cuda.synchronize()
         assert np.array_equal(cl.cpu().numpy(), oracle.forward_torch(params, x).detach().numpy().argmax(1)), key
         eng.set_option(key, 1)
+# the resident servers (a few steps each; generous idle timeout: the sanitizer slows the kernels down a lot)
+eng = dce.ContactEngine(params, dev, "bf16x3")
+xs = synth.make_windows(6, seed=3)
+want = oracle.forward_torch(params, xs).detach().numpy().argmax(1)
+run = eng.latency_runner(1, persistent=True, idle_timeout_s=30.0)
+for i in range(6):
+    cls, bits = run.step(xs[i])
+    assert int(cls[0]) == int(want[i]), ("window server", i)
+run.close()
+log = synth.make_sensor_log(150 + 4, seed=2)
+_, wc, wb = oracle.inference_stream(params, log)
+rr = eng.row_runner(idle_timeout_s=30.0)
+got = [rr.push(log[t]) for t in range(log.shape[0])][149:]
+rr.close()
+assert [g[0] for g in got] == wc.tolist(), "row server"
 print("sanitize run ok")
