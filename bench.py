@@ -485,6 +485,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--precision", default=None, choices=[None, "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="only the device-resident `value` loop and the per-kernel times (the ncu launch list of THIS command is "
+                         "the step's five kernels and nothing else); prints the same line with the other legs null")
     ap.add_argument("--no-latency", action="store_true", help="skip the latency_b1 leg (profiler runs: its resident servers wait for host doorbells)")
     ap.add_argument("--stream-steps", type=int, default=2_000_000, help="rows of the synthetic log of the `stream` leg per GPU (0: skip)")
     ap.add_argument("--big-batch", type=int, default=32768, help="windows per GPU of the one-call big-batch leg, BASELINE configs[3] (0: skip)")
@@ -577,6 +580,20 @@ def main():
     # ---- per-kernel durations for the roofline (CUDA events around every launch) ----
     prof_runs = [eng.profile_forward(xs[i % NBUF]) for i in range(min(args.steps, 50))]
     per_kernel_ms, per_kernel_launches = dominant_kernel(prof_runs)
+
+    if args.kernel_only:
+        if rank == 0:
+            step_kernel_ms = sum(per_kernel_ms.values())
+            print(json.dumps({"metric": "contact windows/sec at batch=4096", "value": value, "unit": "windows/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3_f32acc" if precision == "bf16x3" else "f32",
+                              "data": "synthetic", "config": {"workload": workload_name(B), "precision": precision, "kernel_only": True},
+                              "e2e": None, "gpu_launches": launches, "clocks": clocks,
+                              "kernels_ms_per_step": {k: round(v, 4) for k, v in per_kernel_ms.items()},
+                              "kernel_share_of_step": {k: round(v / step_kernel_ms, 4) for k, v in per_kernel_ms.items()}}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---- end to end from pinned host memory (`e2e`) --------------------------------
     for i in range(2):

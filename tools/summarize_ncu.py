@@ -18,7 +18,8 @@ def short(name):
         re.search(r"tapgemm_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", name)
     if m:
         return "tapgemm<BN=%s,TAPS=%s,KSA=%s,NSTAGE=%s,EPI=%s>" % m.groups()
-    return re.sub(r"\(.*", "", name).replace("void ", "").replace("dce::", "")
+    name = name[:name.rfind("(")] if "(" in name else name
+    return name.replace("void ", "").replace("dce::", "").replace("(int)", "").replace("(bool)", "")
 
 
 def main():
