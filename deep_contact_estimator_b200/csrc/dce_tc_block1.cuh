@@ -138,7 +138,15 @@ block1_kernel(const Block1Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();      // the X2 tape we overwrite may still be read by the previous step's conv3; the stream-mode stats come from the kernel before us
+    // The X2 tape we overwrite may still be read by the previous step's block2, and the stream-mode statistics come from the
+    // kernel before us: converters, epilogues and issuers wait.  The conv weights (warp 12) and the raw input rows (loader,
+    // warp 13) are written by no kernel of the step: both are requested while the previous kernel drains.
+    if (warp == 12 && ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
+        ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
+        ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
+    }
+    if (warp != 13) pdl_wait();
 
     if (warp < 4) {
         // ===== converters: fp32 rows -> slab0[buf] =====
@@ -287,12 +295,6 @@ block1_kernel(const Block1Params p) {
         // Two issuers so that one's serial code between tiles (mbarrier probes, fences, descriptors: ~500 cycles, more
         // than the tensor pipe's short queue covers) is filled by the other's MMAs; each accumulator keeps one issuer.
         {
-            if (warp == 12 && ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
-                ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
-                ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
-            }
-            __syncwarp();
             ptx::mbar_wait(wbar, 0);
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64);
             const uint32_t w1a = ptx::smem_u32(w1s), w2a = ptx::smem_u32(w2s);

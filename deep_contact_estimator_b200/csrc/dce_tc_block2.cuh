@@ -83,7 +83,9 @@ block2_kernel(const Block2Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
+    // everything the previous kernel wrote (the X2 tape) is visible after this; the weight producer reads only the packed
+    // weights, which no kernel of the step writes: it fills the ring while the previous kernel drains
+    if (warp != 9) pdl_wait();
 
     if (warp == 9) {
         // ===== weight producer: blocks in the order the issuer consumes them: c3(0); then c3(k+1), c4(k) =====

@@ -353,6 +353,28 @@ def test_two_gpu_shards_equal_single(dev):
     assert torch.equal(torch.cat(parts), single)
 
 
+def test_runner_on_second_gpu_while_first_is_current(dev, params0):
+    """The C ABI launches on the calling thread's CURRENT device (include/dce.h): a LatencyRunner / engine on cuda:1 must
+    make it current itself, whatever the caller has selected."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d1 = torch.device("cuda", 1)
+    x = synth.make_windows(6, seed=19)
+    want = oracle_logits(params0, x).argmax(1)
+    eng1 = dce.ContactEngine(params0, d1, "bf16x3")
+    torch.cuda.set_device(0)
+    run = eng1.latency_runner(1)
+    for i in range(6):
+        cls, _ = run.step(x[i])
+        assert int(cls[0]) == int(want[i])
+    srv = eng1.latency_runner(1, persistent=True, idle_timeout_s=0.3)
+    cls, _ = srv.step(x[2])
+    srv.close()
+    assert int(cls[0]) == int(want[2]) and torch.cuda.current_device() == 0
+    assert np.array_equal(eng1.classify(x.to(d1))[1].cpu().numpy(), want)
+    eng1.close()
+
+
 def test_entrypoint_script_on_gpu(dev, tmp_path):
     """scripts/inference_one_seq.main() end to end on the GPU: yaml config -> dataset on device ->
     checkpoint -> one dce_stream call -> .mat and LCM log on disk."""
