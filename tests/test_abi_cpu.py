@@ -109,3 +109,38 @@ def test_torch_extension_registers_the_ops():
         ops.forward(0, torch.zeros(2, 150, 54), torch.zeros(16, dtype=torch.uint8), 1, True, True, True)
     schema = str(torch.ops.dce.forward.default._schema)
     assert "Tensor x" in schema and "int handle" in schema
+
+
+def test_server_control_blocks_match_the_python_runners(tmp_path):
+    """The resident servers talk through plain structs in pinned memory (dce_latency_ctrl, dce_latency_row_ctrl): the word
+    indices the Python runners poke must be the header's offsets (the CUDA side static_asserts the same against its own
+    constants, csrc/dce.cu)."""
+    import shutil
+    import subprocess
+    from deep_contact_estimator_b200.engine import LatencyRunner, RowRunner
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "dce.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dce_latency_ctrl), offsetof(dce_latency_ctrl, seq_in) / 4, offsetof(dce_latency_ctrl, quit) / 4,
+           offsetof(dce_latency_ctrl, seq_out) / 4, offsetof(dce_latency_ctrl, cls0) / 4, offsetof(dce_latency_ctrl, bits0) / 4,
+           offsetof(dce_latency_ctrl, device_ns) / 4, offsetof(dce_latency_ctrl, alive) / 4);
+    printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dce_latency_row_ctrl), offsetof(dce_latency_row_ctrl, chunk) / 4,
+           offsetof(dce_latency_row_ctrl, seq_out) / 4, offsetof(dce_latency_row_ctrl, cls0) / 4, offsetof(dce_latency_row_ctrl, bits0) / 4,
+           offsetof(dce_latency_row_ctrl, device_ns) / 4, offsetof(dce_latency_row_ctrl, alive) / 4);
+    return 0;
+}
+''')
+    exe = str(tmp_path / "layout")
+    res = subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    a, b = [list(map(int, line.split())) for line in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines()]
+    L = LatencyRunner
+    assert a == [128, L._SEQ_IN, L._QUIT, L._SEQ_OUT, L._CLS0, L._BITS0, L._DEVICE_NS, L._ALIVE]
+    R = RowRunner
+    assert b == [512, 0, R._SEQ_OUT, R._CLS0, R._BITS0, R._DEVICE_NS, R._ALIVE]
