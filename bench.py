@@ -265,7 +265,7 @@ def c_caller_latency():
         out = subprocess.run([exe, "--gpu", "1000"], capture_output=True, text=True, timeout=120).stdout
         import re
         res = {}
-        for key, label in (("launch_per_step", "launch per step"), ("window_server", "resident server")):
+        for key, label in (("launch_per_step", "launch per step"), ("window_server", "resident server"), ("row_server", "row server")):
             m = re.search(label + r"\s*: host p50 ([0-9.]+) us\s+p99 ([0-9.]+) us", out)
             if m:
                 res[key] = {"host_us_p50": float(m.group(1)), "host_us_p99": float(m.group(2))}

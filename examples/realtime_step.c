@@ -143,6 +143,32 @@ static int run_gpu(int steps) {
     printf("C caller, resident server : host p50 %.1f us  p99 %.1f us  device %.1f us  classes equal to the launch-per-step form: %s\n",
            t[steps / 2], t[steps * 99 / 100], sv.ctrl->device_ns * 1e-3, same ? "yes" : "NO");
     dce_realtime_server_close(&sv);
+    {   /* row server: one new 54-float sensor row per step; ring + z-score + classification on the device */
+        dce_latency_row_ctrl *rc_ = NULL;
+        float *ring = NULL, row[DCE_CHANNELS];
+        if (cudaHostAlloc((void **)&rc_, sizeof *rc_, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc((void **)&ring, 2 * DCE_WINDOW * DCE_CHANNELS * sizeof(float)) != cudaSuccess ||
+            cudaMemset(ring, 0, 2 * DCE_WINDOW * DCE_CHANNELS * sizeof(float)) != cudaSuccess) return 2;
+        if ((rc = dce_latency_row_server_start(rt.w, rc_, ring, rt.workspace, rt.workspace_bytes, 2.0, rt.stream)) != DCE_OK) {
+            printf("row server: %s\n", dce_strerror(rc)); return 2;
+        }
+        while (!rc_->alive) { }
+        lcg_state = 4242u;
+        for (i = 0; i < steps + DCE_WINDOW; ++i) {
+            int k = i - DCE_WINDOW, j;
+            for (j = 0; j < DCE_CHANNELS; ++j) row[j] = 3.4f * lcg_uniform() + 0.1f * (float)j;
+            double t0 = now_us();
+            if (dce_latency_row_server_push(rc_, row, (uint32_t)(i % DCE_WINDOW), (uint32_t)(i + 1)) != 0) { printf("row server retired\n"); return 2; }
+            if (k >= 0) t[k] = now_us() - t0;
+        }
+        qsort(t, (size_t)steps, sizeof(double), cmp_double);
+        printf("C caller, row server      : host p50 %.1f us  p99 %.1f us  device %.1f us  (last class %d)\n",
+               t[steps / 2], t[steps * 99 / 100], rc_->device_ns * 1e-3, (int)rc_->cls0);
+        rc_->chunk[18][0] = 1;                             /* quit */
+        cudaStreamSynchronize(rt.stream);
+        cudaFreeHost((void *)rc_);
+        cudaFree(ring);
+    }
     dce_realtime_close(&rt);
     free(t); free(want);
     return same ? 0 : 3;
