@@ -87,7 +87,14 @@ for i in range(rows.shape[0]):
 okr = [g[0] for g in got] == wc.tolist() and [list(g[1]) for g in got] == wb.tolist()
 print("row server: %d windows, classes + bits equal to the reference loop: %s; host p50 %.1f us p99 %.1f | device p50 %.1f us" %
       (len(got), okr, np.percentile(t[150:], 50), np.percentile(t[150:], 99), np.percentile(d[150:], 50)), flush=True)
-time.sleep(0.8)
+rr.close()
+# clock64 timeline of the last step (first and last CTA; written behind the barrier counters of the workspace header)
+tr = rr._ws[64:64 + 24 * 8].view(torch.int64).cpu().numpy().reshape(2, 12)
+NAMES = ["A done", "bar1", "B done", "bar2", "C done", "bar3", "D done", "E done (last CTA only)", "exit"]
+for which, row in zip(("cta 0", "last cta"), tr):
+    d = (row[1:10] - row[10]) / 1.965e3
+    print(f"row server, {which}: us since 'row seen' (at 1.965 GHz): " + "  ".join(f"{n} {v:.2f}" for n, v in zip(NAMES, d)), flush=True)
+time.sleep(0.3)
 out = rr.push(rows[0])                       # restarted server, ring kept
-print("row server after idle retirement: starts", rr.server_starts, flush=True)
+print("row server after close + push: starts", rr.server_starts, flush=True)
 rr.close()
