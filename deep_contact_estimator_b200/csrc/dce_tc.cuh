@@ -183,24 +183,7 @@ tapgemm_kernel(const TapGemmParams p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // Everything the previous kernel wrote (the activation tape) is visible after pdl_wait().  The weight blocks are written
-    // by no kernel of the step: the producer warp that owns them requests those of the first NSTAGE stages before it waits,
-    // i.e. while the previous kernel drains (a resident CTA otherwise pays one L2 round trip after the wait).
-    constexpr int kNA = MT * 2 * KSA;
-    constexpr int kWeightWarp = kProducerWarp0 + kNA % kProdWarps;
-    int early_b = 0;                                            // stages of this CTA's first tile whose B block is already on its way
-    if (!WST && warp == kWeightWarp && (int)blockIdx.x < total_tiles) {
-        early_b = p.stages < NSTAGE ? p.stages : NSTAGE;
-        if (ptx::elect_one()) {
-            const uint8_t* wsrc = p.w_packed + (size_t)((int)blockIdx.x % p.n_tiles) * p.stages * Cfg::B_BYTES;
-            for (int s = 0; s < early_b; ++s) {
-                ptx::mbar_expect_tx(&full[s], Cfg::B_BYTES);
-                ptx::bulk_g2s(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, wsrc + (size_t)s * Cfg::B_BYTES, Cfg::B_BYTES, &full[s]);
-            }
-        }
-        __syncwarp();
-    }
-    pdl_wait();
+    pdl_wait();                                                 // everything the previous kernel wrote is visible from here on
 
     if (warp >= kProducerWarp0) {
         // ===== TMA producers (warp-uniform loops; one elected lane per warp issues) =====
@@ -235,13 +218,11 @@ tapgemm_kernel(const TapGemmParams p) {
                         __syncwarp();
                         continue;
                     }
-                    const bool b_done = (int)it < early_b;      // this warp requested the stage's B block before pdl_wait
                     if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(&full[slot], b_done ? my_bytes - Cfg::B_BYTES : my_bytes);
+                        ptx::mbar_arrive_expect_tx(&full[slot], my_bytes);
 #pragma unroll
                         for (int c0 = 0; c0 <= NA; c0 += kProdWarps) {
                             const int c = c0 + pw;
-                            if (c == NA && b_done) continue;
                             if (c < NA) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
                                 ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,

@@ -47,7 +47,7 @@ struct Block1Params {
     int dbg;                     // timing ablations only (results invalid when non-zero)
     long long* trace;            // optional: CTA 0 records clock64() per role per tile ([tile][16])
 };
-#define B1_TRACE(k, ev) do { if (p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
+#define B1_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ int pos_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-role clock64 timeline of CTA 0 of the fused block1 kernel (cycles relative to the first event)."""
+"""Per-role clock64 timeline of CTA 0 of the fused block1 kernel (cycles relative to the first event).
+Needs a trace build: DCE_TRACE=1 python -m deep_contact_estimator_b200.build --force"""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
