@@ -668,17 +668,20 @@ class RowRunner:
         self.rows_seen += 1
         self._seq += 1
         seq = self._seq
-        self._floats[...] = r.reshape(18, 3)
+        r = r.reshape(18, 3)
+        self._floats[...] = r
         self._chunks[18, 1] = slot
         self._tags[...] = seq                                    # the doorbell: every chunk's tag, after its data
         spins = 0
         while c[self._SEQ_OUT] != seq:
             spins += 1
-            if (spins & 1023) == 0 and not c[self._ALIVE]:       # it retired just as the row arrived: start over, same slot
+            if (spins & 1023) == 0 and not c[self._ALIVE]:       # it retired just as the row arrived: start over, same row, same slot
                 if c[self._SEQ_OUT] == seq:
                     break
-                self._start_server()
+                self._start_server()                             # (clears the control block; the ring in device memory is kept)
                 self._seq = seq = 1
+                self._floats[...] = r
+                self._chunks[18, 1] = slot
                 self._tags[...] = seq
         b = int(c[self._BITS0])
         return int(c[self._CLS0]), (b & 1, (b >> 8) & 1, (b >> 16) & 1, (b >> 24) & 1)
