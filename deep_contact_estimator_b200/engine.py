@@ -438,6 +438,19 @@ class ContactEngine:
         return counts
 
 
+_resident = {}          # device index -> the runner whose resident server was started last (one server holds every SM)
+
+
+def _claim_device(eng, runner):
+    """A resident server occupies the whole GPU: refuse to start a second one while another runner's is alive (it could
+    only wait for the first to idle out)."""
+    idx = eng.device.index
+    other = _resident.get(idx)
+    if other is not None and other is not runner and other._c is not None and other._c[other._ALIVE]:
+        raise RuntimeError(f"cuda:{idx} already runs a resident latency server ({type(other).__name__}); close() it first")
+    _resident[idx] = runner
+
+
 class HostBatch:
     """A batch in flight (``ContactEngine.classify_host_async``): ``wait()`` -> host ``(cls, bits)``."""
 
@@ -536,6 +549,7 @@ class LatencyRunner:
                      ctypes.c_double(self.idle_timeout_s), ctypes.c_void_p(self.stream.cuda_stream))
 
             def start_server():
+                _claim_device(eng, self)
                 self.stream.synchronize()                            # a retired server has left the stream
                 with torch.cuda.device(index):
                     _lib.check(start(eng._handle, *sargs), "dce_latency_server_start")
@@ -636,6 +650,7 @@ class RowRunner:
         index = dev.index
 
         def start_server():
+            _claim_device(eng, self)
             torch.cuda.synchronize(dev)                          # ring / workspace initialised; a retired server has left the stream
             with torch.cuda.device(index):
                 _lib.check(start(eng._handle, *args), "dce_latency_row_server_start")

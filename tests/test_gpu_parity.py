@@ -671,6 +671,12 @@ def test_resident_latency_servers(dev, params0):
     assert [g[0] for g in got] == wc.tolist() and [list(g[1]) for g in got] == wb.tolist()
     with pytest.raises(ValueError):
         eng.latency_runner(1, persistent=True, use_graph=True)
+    a = eng.latency_runner(1, persistent=True, idle_timeout_s=5.0)
+    try:
+        with pytest.raises(RuntimeError, match="already runs a resident"):     # one server holds every SM: no second one beside it
+            eng.row_runner()
+    finally:
+        a.close()
     eng.close()
 
 
