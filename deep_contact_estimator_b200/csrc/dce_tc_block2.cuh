@@ -35,7 +35,7 @@ struct Block2Params {
     int n_tiles;
     long long* trace;            // optional clock64 timeline of CTA 0 (DCE_TRACE builds)
     int dbg;                     // timing ablations (results invalid): 1 = no weight copies once the ring is primed; 2 = no output stores;
-                                 // 4 = slabA is loaded for the first tile only
+                                 // 4 = slabA is loaded for the first tile only; 16 = epilogue 2 stops after its TMEM load; 32 = epilogue 1 writes nothing
 };
 
 #define B2_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
@@ -217,6 +217,7 @@ block2_kernel(const Block2Params p) {
             if (warp == 0) B2_TRACE(k, 7);
             ptx::mbar_wait(x3_empty, (k & 1) ^ 1);             // conv4 of the previous tile has finished reading slabB (critical path: tight poll)
             if (warp == 0) B2_TRACE(k, 8);
+            if (p.dbg & 32) { ptx::mbar_arrive(x3_full); return; }   // ablation: epilogue 1 writes nothing
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const uint32_t (&v)[32] = c ? vb : va;
@@ -261,6 +262,7 @@ block2_kernel(const Block2Params p) {
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&d4_empty[buf]);
+            if (p.dbg & 16) return;                            // ablation: epilogue 2 ends with the TMEM load
             uint8_t* base = p.out + (size_t)(to * 16) * p.out_kch_stride + (size_t)(w + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {

@@ -275,7 +275,8 @@ DCE_API int dce_accuracy_counts(const int32_t *cls_dev, const int64_t *labels_de
  *   "latency_coop" / "latency_tma_in"  launch attribute / input staging ablations of that kernel;
  *   "sm_limit"     0 (default): use every SM; n > 0: the batch kernels launch at most n CTAs (what a MIG slice or a
  *                  smaller sm_100 part gives them: several tiles per CTA in every layer);
- *   "block1_dbg" / "block2_dbg" / "tapgemm_dbg"  bit masks of timing ablations inside the kernels (results invalid);
+ *   "block1_dbg" / "block2_dbg" / "tapgemm_dbg"  bit masks of timing ablations inside the kernels (results invalid; the
+ *                  bits are listed next to the parameter structs in csrc/);
  *   "trace" 1: allocate and arm a per-role clock64 timeline of CTA 0 (libraries built with -DDCE_TRACE=1);
  *   "trace_layer"  which kernel records it: -1 block1 (default), 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2.
  * Returns DCE_EINVAL for an unknown key.
