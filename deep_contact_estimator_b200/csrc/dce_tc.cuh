@@ -486,8 +486,11 @@ tapgemm_kernel(const TapGemmParams p) {
 // kind 1: fc.0  W[n][c*37 + t]    K index k' = t*128 + c      (src/contact_cnn.py:64)
 // kind 2: fc.3  W[n][k]
 // ---------------------------------------------------------------------------------------------
+// stack = 1: the block holds, per (tap, kchunk), [W_hi (BN rows) ; W_lo (BN rows)] as ONE K-major operand of 2*BN rows
+// (an N = 2*BN MMA against A_hi yields a_hi*w_hi and a_hi*w_lo side by side; dce_tc_block2s.cuh) instead of a hi image
+// followed by a lo image.
 __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int n_tiles, int stages,
-                              int BN, int TAPS, int KSA, int kind, int cin, int nout) {
+                              int BN, int TAPS, int KSA, int kind, int cin, int nout, int stack) {
     const size_t per_part = (size_t)TAPS * KSA * BN * 8;            // elements in one part of one block
     const size_t total = (size_t)n_tiles * stages * per_part;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -508,6 +511,12 @@ __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
         const size_t blk = ((size_t)nt * stages + s) * (2 * per_part * 2);      // bytes
+        if (stack) {
+            const size_t within = ((((size_t)tap * KSA + j) * 2 * BN + nn) * 8 + e) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
+            *reinterpret_cast<__nv_bfloat16*>(out + blk + within + (size_t)BN * 16) = l;
+            continue;
+        }
         const size_t within = ((((size_t)tap * KSA + j) * BN + nn) * 8 + e) * 2;
         *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
         *reinterpret_cast<__nv_bfloat16*>(out + blk + per_part * 2 + within) = l;
@@ -654,17 +663,21 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 // host side: packed layout, workspace, launch sequence
 // ---------------------------------------------------------------------------------------------
-struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src, nout; };
+struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src, nout, stack; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 7;
+constexpr int kNumPacked = 11;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0, 64},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2, 64},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4, 128},     // block2.0 (layer-wise conv3: resident image)
                                  {128, 3, 2, 8, 1, 0, 128, 6, 128},    // block2.2
                                  {240, 1, 4, 148, 9, 1, 4736, 8, 2048},  // fc.0: 8 n-tiles of 240 + one of 128 (zero-padded to 240)
                                  {128, 1, 4, 64, 4, 2, 2048, 10, 512}, // fc.3
-                                 {128, 3, 2, 4, 1, 0, 64, 4, 128}};    // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
-constexpr int kLayerConv3Ring = 6;
+                                 {128, 3, 2, 4, 1, 0, 64, 4, 128},     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
+                                 {128, 3, 2, 4, 1, 0, 64, 4, 128, 1},  // block2.0, ring blocks with the stacked [W_hi ; W_lo] operand (block2s_kernel)
+                                 {128, 3, 2, 8, 1, 0, 128, 6, 128, 1},   // block2.2, stacked
+                                 {64, 3, 8, 1, 1, 0, 54, 0, 64, 1},      // block1.0, stacked [tap][kchunk][W_hi 64 rows | W_lo 64 rows] (block1s_kernel)
+                                 {64, 3, 8, 1, 1, 0, 64, 2, 64, 1}};     // block1.2, stacked
+constexpr int kLayerConv3Ring = 6, kLayerConv3Stack = 7, kLayerConv4Stack = 8, kLayerConv1Stack = 9, kLayerConv2Stack = 10;
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
@@ -681,7 +694,7 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
         const size_t total = (size_t)c.n_tiles * c.stages * c.TAPS * c.KSA * c.BN * 8;
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
         DCE_KL(ctx, "tc_pack_b", pack_b_kernel<<<blocks, 256, 0, ctx.stream>>>(
-            params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin, c.nout));
+            params[c.src], reinterpret_cast<uint8_t*>(buf + L.w[i]), c.n_tiles, c.stages, c.BN, c.TAPS, c.KSA, c.kind, c.cin, c.nout, c.stack));
     }
     return DCE_OK;
 }

@@ -2,7 +2,9 @@
 #pragma once
 #include "dce_tc.cuh"
 #include "dce_tc_block1.cuh"
+#include "dce_tc_block1s.cuh"
 #include "dce_tc_block2.cuh"
+#include "dce_tc_block2s.cuh"
 #include "dce_small.cuh"
 
 namespace dce {
@@ -19,6 +21,8 @@ struct Options {
     int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
     int tapgemm_dbg = 0;
     int block2_dbg = 0;
+    int block1_stack = 1;        // 1: block1s_kernel (stacked operand, two slab1 buffers); 0: block1_kernel
+    int block2_stack = 1;        // 1: block2s_kernel (stacked [W_hi ; W_lo] operand: N = 256 + N = 128 MMAs); 0: block2_kernel (three N = 128 MMAs)
     int sm_limit = 0;            // > 0: the batch kernels use at most this many CTAs (what a MIG slice / smaller part would give them)
     int trace_layer = -1;        // which kernel records into `trace`: -1 block1, 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2
     long long* trace = nullptr;  // device buffer [60 tiles][16 events] of clock64 samples of CTA 0 (DCE_TRACE builds)
@@ -76,6 +80,8 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             if (auto first_ = attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1sSmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1sSmemBytes);
                 if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
@@ -87,6 +93,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = opt.block1_dbg; b.trace = (opt.trace_layer < 0) ? opt.trace : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
+            if (opt.block1_stack) {
+                b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv1Stack]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv2Stack]);
+                if (stream_mode)
+                    DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1s_kernel<true>, dim3(grid), dim3(kB1Threads), kB1sSmemBytes, s, b); (void)le_; });
+                else
+                    DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1s_kernel<false>, dim3(grid), dim3(kB1Threads), kB1sSmemBytes, s, b); (void)le_; });
+            } else
             if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
@@ -121,6 +134,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             static DeviceOnce b2_once;
             if (auto first_ = b2_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block2Params b{};
@@ -132,6 +146,10 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             b.trace = (opt.trace_layer == 6) ? opt.trace : nullptr;
             b.dbg = opt.block2_dbg;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
+            if (opt.block2_stack) {
+                b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv3Stack]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv4Stack]);
+                DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2s_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
+            } else
             DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
         } else {
         p = TapGemmParams{};

@@ -15,9 +15,9 @@ eng.classify(x); torch.cuda.synchronize()
 buf = eng.read_trace(60 * 16)
 t = np.array(buf, dtype=np.int64).reshape(60, 16)
 t0 = t[t > 0].min()
-names = ["cv:start", "cv:x0empty", "cv:landed", "cv:done", "mma:c1", "mma:c2", "e1:start", "e1:d1full", "e1:ld_done", "e1:x1empty", "e1:done", "e2:start", "e2:d2full", "e2:done"]
+names = ["cv:start", "cv:x0empty", "cv:landed", "cv:done", "mma:c1", "mma:c2", "e1:start", "e1:d1full", "e1:ld_done", "e1:x1empty", "e1:done", "e2:start", "e2:d2full", "e2:done", "-", "cv:read"]
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for k in range(2, 12):
-    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(14)))
+    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(16)))
 d = np.diff(t[5:30, 5])
 print("period between successive conv2 issues (cycles):", d.mean(), d.min(), d.max())

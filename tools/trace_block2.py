@@ -14,7 +14,7 @@ eng.classify(x); torch.cuda.synchronize()
 buf = eng.read_trace(60 * 16)
 t = np.array(buf, dtype=np.int64).reshape(60, 16)
 t0 = t[t > 0].min()
-names = ["c3:pre", "c3:go", "c4:pre", "c4:go", "c4:issued", "e1:start", "e1:d3full", "e1:ld", "e1:x3empty", "e1:done", "e2:start", "e2:d4full", "e2:done"]
+names = ["c3:pre", "c3:go", "c4:pre", "c4:go", "c4:issued", "e1:start", "e1:d3full", "e1:ld", "e1:x3empty", "e1:done", "e2:start", "e2:d4full", "e2:done", "e2:ld", "e2:pooled", "e2:cvt0"]
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for k in range(3, 11):
-    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(13)))
+    print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(len(names))))
