@@ -69,7 +69,7 @@ constexpr int64_t kChunkFp32 = 4096;   // windows per internal pass (bounds the 
 
 struct Fp32Workspace { size_t act4, h1, h2, end; };
 Fp32Workspace fp32_workspace(int64_t n) {
-    Fp32Workspace W; size_t o = 256;      // [0,256): the latency kernel's barrier counters (dce_latency.cuh)
+    Fp32Workspace W; size_t o = 512;      // [0,256): the latency kernel's barrier counters (dce_latency.cuh); [256,512): fc.3 tickets (dce_tc.cuh)
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.act4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.h2 = take((size_t)n * 512 * 4);
     W.end = o; return W;
@@ -229,7 +229,7 @@ void* dce_weights_packed_ptr(dce_weights* w) { return w ? (void*)w->buf : nullpt
 int dce_weights_adopt(dce_weights* w) { if (!w) return DCE_EINVAL; w->packed = true; return DCE_OK; }
 
 size_t dce_workspace_bytes(int64_t max_windows, int precision) {
-    if (max_windows <= 0) return 256;
+    if (max_windows <= 0) return 512;
     size_t need = 0;
     if (precision == DCE_PREC_FP32) {
         const int64_t n = max_windows < kChunkFp32 ? max_windows : kChunkFp32;
@@ -401,6 +401,7 @@ int dce_weights_set_option(dce_weights* w, const char* key, int value) {
     if (!strcmp(key, "fuse_fc3")) { o.fuse_fc3 = value; return DCE_OK; }
     if (!strcmp(key, "block2_dbg")) { o.block2_dbg = value; return DCE_OK; }
     if (!strcmp(key, "block2_stack")) { o.block2_stack = value; return DCE_OK; }
+    if (!strcmp(key, "fuse_argmax")) { o.fuse_argmax = value; return DCE_OK; }
     if (!strcmp(key, "block1_stack")) { o.block1_stack = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { o.latency_kernel = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { o.latency_coop = value; return DCE_OK; }

@@ -57,7 +57,7 @@ static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
 // leaves them zero) and a small clock64 trace, then P1, A4, H1 and the per-CTA logit shares (fp32)
 struct Workspace { size_t p1, a4, h1, part, end; };
 inline Workspace make_workspace(int n) {
-    Workspace W; size_t o = 256;
+    Workspace W; size_t o = 512;                                    // [256,512): fc.3 tickets of the batch path (dce_tc.cuh)
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.p1 = take((size_t)n * 75 * 64 * 4); W.a4 = take((size_t)n * 4736 * 4); W.h1 = take((size_t)n * 2048 * 4); W.part = take((size_t)n * kSlices * 16 * 4);
     W.end = o;

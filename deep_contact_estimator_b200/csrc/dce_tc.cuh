@@ -62,6 +62,11 @@ struct TapGemmParams {
     int out_rows_cap;            // rows the output tape can hold (excluding guards)
     float* out_f32;              // EPI_FC_F32: [n_valid][N];  EPI_FC_LOGITS: logit shares [2 * n_tiles][n_valid][16]
     const float* w3t;            // EPI_FC_LOGITS: the NEXT Linear layer's weight, k-major [N][16] (fc.6)
+    // EPI_FC_LOGITS with tickets != nullptr: the CTA that completes an M-tile's last n-tile (atomic ticket per M-tile) adds the
+    // logit shares in their fixed order + bias, takes the argmax and writes logits / class / contact bits: no extra launch
+    unsigned* tickets;           // [m_tiles], zero once; counts on modulo n_tiles across calls
+    const float* b3;             // fc.6 bias [16]
+    float* logits; int32_t* cls; uint8_t* bits;      // outputs of this chunk (may be null)
     int N;                       // total output features
     int rw, tv;                  // rows per window / valid rows per window of the INPUT tape (conv modes)
     int n_valid;                 // EPI_FC_F32: valid rows
@@ -468,6 +473,37 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[j] = make_float4(lg[4 * j], lg[4 * j + 1], lg[4 * j + 2], lg[4 * j + 3]);
             }
+            if (EPI == EPI_FC_LOGITS && p.tickets) {
+                // last CTA of this M-tile reduces: shares -> logits -> argmax -> contact bits (src/inference_one_seq.py:26-27,59-62)
+                __threadfence();                                     // this thread's shares are visible before the ticket
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (warp == 0 && lane == 0) {
+                    const unsigned old = atomicAdd(p.tickets + m0, 1u);
+                    *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = (old % (unsigned)p.n_tiles == (unsigned)p.n_tiles - 1) ? 1u : 0u;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (*reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) && warp < 4) {
+                    __threadfence();                                 // acquire side: the other CTAs' shares
+                    const int64_t w = 128 * (int64_t)m0 + warp * 32 + lane;
+                    if (w < p.n_valid) {
+                        float sacc[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sacc[j] = 0.f;
+                        for (int sidx = 0; sidx < 2 * p.n_tiles; ++sidx) {
+                            const float4* src = reinterpret_cast<const float4*>(p.out_f32 + ((size_t)sidx * p.n_valid + w) * 16);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 v = __ldcg(src + j);
+                                sacc[4 * j] += v.x; sacc[4 * j + 1] += v.y; sacc[4 * j + 2] += v.z; sacc[4 * j + 3] += v.w;
+                            }
+                        }
+                        float yl[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) yl[j] = __ldg(p.b3 + j) + sacc[j];
+                        fp32::argmax_bits_store(yl, w, p.logits, p.cls, p.bits);
+                    }
+                }
+            }
             if (warp == 0) TG_TRACE(tcount, 8);
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -701,10 +737,12 @@ inline int pack(char* buf, const PackedLayout& L, const float* const* params, Ct
 
 struct Workspace {
     Tape x0, x1, x2, x3, x4, h1;
-    size_t o_x0, o_x1, o_x2, o_x3, o_x4, o_h1, o_h2, o_mean, o_sdev, end;
+    size_t o_x0, o_x1, o_x2, o_x3, o_x4, o_h1, o_h2, o_tickets, o_mean, o_sdev, end;
 };
 inline Workspace make_workspace(int64_t n) {
-    Workspace W; size_t o = 256;          // [0,256): the latency kernel's barrier counters (dce_latency.cuh)
+    Workspace W; size_t o = 512;          // [0,256): the latency kernel's barrier counters (dce_latency.cuh); [256,512): fc.3's per-M-tile
+                                          // tickets (at a fixed place: every other offset depends on the chunk size).  Zero once.
+    W.o_tickets = 256;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.x0 = make_tape(n * kRW1, 8);   W.o_x0 = take(W.x0.bytes);
     W.x1 = make_tape(n * kRW1, 8);   W.o_x1 = take(W.x1.bytes);

@@ -16,6 +16,7 @@ struct Options {
     int fuse_block1 = 1;         // 0: ingest, conv1, conv2 as separate launches (activations round-trip through HBM)
     int fuse_block2 = 1;         // 0: conv3, conv4 as separate launches
     int fuse_fc3 = 1;            // 0: fc.3 writes H2, a separate kernel does fc.6 + argmax + bits
+    int fuse_argmax = 1;         // 0: a separate kernel adds fc.3's logit shares and takes the argmax
     int latency_kernel = 1;      // 0: calls of <= 4 windows take the per-layer kernels
     int latency_coop = 1, latency_tma_in = 1;
     int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
@@ -214,6 +215,14 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         if (opt.fuse_fc3) {
             // ---- fc.3 + ReLU with fc.6 folded into the epilogue (a11, a12): H2 stays in registers; 8 logit shares per window
             p.w3t = bp.w3;
+            if (opt.fuse_argmax) {
+                // ---- ... and the share reduction, argmax and contact bits (a12-a14) folded into the same launch: the CTA
+                // that finishes an M-tile's last n-tile does them
+                p.tickets = reinterpret_cast<unsigned*>(ws + W.o_tickets); p.b3 = bp.b[6];
+                p.logits = logits ? logits + c0 * 16 : nullptr; p.cls = cls ? cls + c0 : nullptr; p.bits = bits ? bits + c0 * 4 : nullptr;
+                if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3_argmax", sm_count, p)) != DCE_OK) return rc;
+                continue;
+            }
             rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
             if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,

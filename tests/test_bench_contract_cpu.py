@@ -39,7 +39,7 @@ def test_kernel_flops_cover_the_whole_path():
     for the layer-wise ablation alike."""
     sys.path.insert(0, ROOT)
     import bench
-    default = ["tc_block1", "tc_block2", "tc_fc1", "tc_fc2_fc3", "logits_argmax_bits"]
+    default = ["tc_block1", "tc_block2", "tc_fc1", "tc_fc2_fc3_argmax"]
     layerwise = ["tc_ingest", "tc_conv1", "tc_conv2_pool", "tc_conv3", "tc_conv4_pool", "tc_fc1", "tc_fc2", "fc3_argmax_bits"]
     for names in (default, layerwise):
         assert sum(bench.kernel_flops(n) for n in names) == bench.FLOP_PER_WINDOW, names
