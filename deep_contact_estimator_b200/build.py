@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdce_b200.so")
 SOURCES = ["dce.cu"]
-HEADERS = ["dce_common.cuh", "dce_fp32.cuh", "dce_tc.cuh", "dce_tc_ptx.cuh", "dce_tc_block1.cuh", "dce_tc_block2.cuh", "dce_tc_block2s.cuh", "dce_tc_block1s.cuh", "dce_tc_run.cuh", "dce_small.cuh", "dce_latency.cuh", os.path.join("..", "..", "include", "dce.h")]
+HEADERS = ["dce_common.cuh", "dce_fp32.cuh", "dce_tc.cuh", "dce_tc_ptx.cuh", "dce_tc_block1.cuh", "dce_tc_block2.cuh", "dce_tc_run.cuh", "dce_small.cuh", "dce_latency.cuh", os.path.join("..", "..", "include", "dce.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -400,9 +400,7 @@ int dce_weights_set_option(dce_weights* w, const char* key, int value) {
     if (!strcmp(key, "fuse_block2")) { o.fuse_block2 = value; return DCE_OK; }
     if (!strcmp(key, "fuse_fc3")) { o.fuse_fc3 = value; return DCE_OK; }
     if (!strcmp(key, "block2_dbg")) { o.block2_dbg = value; return DCE_OK; }
-    if (!strcmp(key, "block2_stack")) { o.block2_stack = value; return DCE_OK; }
     if (!strcmp(key, "fuse_argmax")) { o.fuse_argmax = value; return DCE_OK; }
-    if (!strcmp(key, "block1_stack")) { o.block1_stack = value; return DCE_OK; }
     if (!strcmp(key, "latency_kernel")) { o.latency_kernel = value; return DCE_OK; }
     if (!strcmp(key, "latency_coop")) { o.latency_coop = value; return DCE_OK; }
     if (!strcmp(key, "latency_tma_in")) { o.latency_tma_in = value; return DCE_OK; }

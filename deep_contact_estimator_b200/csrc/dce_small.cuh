@@ -16,7 +16,7 @@ namespace small {
 constexpr int kMaxB = 4;
 
 // y[b][n0 .. n0+NPC) = relu(sum_k x[b][k] * w[k][n] + bias[n]);  NPC outputs per CTA, 256 threads
-// X_TAPE: x comes from the bf16 hi/lo fc.0 operand tape ([part][kch][row][8], row b at index b + 8)
+// X_TAPE: x comes from the bf16 hi/lo fc.0 operand ([part][row][K], row-major)
 template <int K, int N, int NPC, bool X_TAPE>
 __global__ void __launch_bounds__(256)
 gemv_bias_relu_kernel(const void* __restrict__ xin, size_t part_stride, size_t kch_stride, int B,
@@ -29,7 +29,7 @@ gemv_bias_relu_kernel(const void* __restrict__ xin, size_t part_stride, size_t k
         const uint8_t* tape = static_cast<const uint8_t*>(xin);
         for (int i = tid; i < B * (K / 8); i += 256) {
             const int b = i / (K / 8), kch = i % (K / 8);
-            const uint8_t* src = tape + (size_t)kch * kch_stride + (size_t)(b + 8) * 16;
+            const uint8_t* src = tape + (size_t)kch * kch_stride + (size_t)b * (K * 2);      // row-major [row][K] bf16, kch_stride = 16
             const uint4 hi = *reinterpret_cast<const uint4*>(src);
             const uint4 lo = *reinterpret_cast<const uint4*>(src + part_stride);
             const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};

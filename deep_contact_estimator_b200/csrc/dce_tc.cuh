@@ -50,6 +50,7 @@ constexpr int64_t kChunk = 4096;     // windows per internal pass
 enum Epi { EPI_TAPE = 0, EPI_POOL_TAPE = 1, EPI_POOL_FC = 2, EPI_FC_TAPE = 3, EPI_FC_F32 = 4, EPI_FC_LOGITS = 5 };
 
 struct TapGemmParams {
+    CUtensorMap a_map;           // AT = 1 (fc.0): the A operand as a row-major tensor {K elements, rows, hi | lo}; box {32, 128, 1}, 64-byte swizzle
     const uint8_t* a_tape;       // part 0 (hi); lo at + a_part_stride
     size_t a_part_stride;
     size_t a_kch_stride;         // bytes between consecutive kchunks = row capacity * 16
@@ -83,6 +84,15 @@ inline Tape make_tape(int64_t rows, int kch) {
     Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;   // even: MT = 2 tiles, CTA pairs
     t.cap = kGuard + t.m_tiles * 128 + 136; t.kch = kch;   // trailing guard: the fused kernels' 124-row tiles read up to 130 rows past a tile start
     t.kch_stride = (size_t)t.cap * 16; t.part_stride = t.kch_stride * kch; t.bytes = align_up(t.part_stride * 2, 256);
+    return t;
+}
+
+// The fc.0 operand (X4) is row-major instead: [part][row = window][K = 4736] bf16, no guard rows.  block2 writes it in whole
+// lines (a pooled row is 256 contiguous bytes), fc.0 reads it through a tensor map (boxes of 128 rows x 64 B).
+inline Tape make_rowmajor(int64_t rows, int kch) {
+    Tape t; t.rows = (int)rows; t.m_tiles = (int)((rows + 127) / 128); t.m_tiles += t.m_tiles & 1;
+    t.cap = t.m_tiles * 128; t.kch = kch;
+    t.kch_stride = 16; t.part_stride = (size_t)t.cap * kch * 16; t.bytes = align_up(t.part_stride * 2, 256);
     return t;
 }
 
@@ -124,9 +134,11 @@ __host__ __device__ constexpr int tapgemm_threads(int MT) { return (kEpiWarps + 
 // WST > 0: the layer has WST k-stages and a single n-tile, and its whole weight image (WST * B_BYTES)
 // stays resident in shared memory for the life of the CTA (conv3: 96 KB) — otherwise all 148 CTAs
 // re-stream the same few weight blocks from the same L2 lines for every tile, which hot-spots L2.
-template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1, int WST = 0>
+// AT = 1: the A operand is row-major in global memory ([part][row][K] bf16: what block2 can write in whole lines) and
+// arrives by tensor-map TMA, one box of 128 rows x 64 B (KSA = 4 kchunks) per M-tile and part, in the 64-byte swizzle.
+template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1, int WST = 0, int AT = 0>
 struct TapGemmCfg {
-    static constexpr int A_PART = KSA * kSlabBytes;
+    static constexpr int A_PART = AT ? 128 * KSA * 16 : KSA * kSlabBytes;
     static constexpr int A_TILE = 2 * A_PART;                 // hi + lo slabs of one M-tile
     static constexpr int A_BYTES = MT * A_TILE;
     static constexpr int B_TAPCH = BN * 16;
@@ -143,6 +155,7 @@ struct TapGemmCfg {
     static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_BYTES = RING_BYTES + WRES_BYTES + BAR_BYTES + kEpiWarps * (ACC_COLS / 2) * 4;
     static_assert(KSA % 2 == 0, "an MMA consumes two kchunks");
+    static_assert(!AT || (KSA == 4 && TAPS == 1 && WST == 0 && STAGE_BYTES % 1024 == 0), "tensor-map A operand: Linear layers, 64-byte rows, swizzle atoms stay aligned");
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
     static_assert(STAGE_BYTES % 16 == 0, "bulk copies are 16-byte granular");
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
@@ -153,13 +166,13 @@ struct TapGemmCfg {
 #endif
 #define TG_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0>
 __global__ void __launch_bounds__(tapgemm_threads(MT), 1)
-tapgemm_kernel(const TapGemmParams p) {
+tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     constexpr int kProducerWarp0 = kEpiWarps + MT;
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT>;
     constexpr int NBUF = Cfg::NBUF;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wres = smem + Cfg::RING_BYTES;                       // resident weight image (WST > 0)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::WRES_BYTES);
     uint64_t* empty = full + NSTAGE;
@@ -194,10 +207,12 @@ tapgemm_kernel(const TapGemmParams p) {
         // ===== TMA producers (warp-uniform loops; one elected lane per warp issues) =====
         // copy c of a stage: c < NA -> A slab (mt, part, j) of 2080 B; c == NA -> the B block.  Warp pw issues c = pw, pw+4, ...
         {
-            constexpr int NA = MT * 2 * KSA;
+            constexpr int NA = AT ? MT * 2 : MT * 2 * KSA;       // AT: one tensor-map box per (M-tile, part)
+            constexpr uint32_t kACopy = AT ? Cfg::A_PART : kSlabBytes;
             const int pw = warp - kProducerWarp0;
             uint32_t my_bytes = 0;
-            for (int c = pw; c <= NA; c += kProdWarps) my_bytes += (c < NA) ? kSlabBytes : (WST ? 0 : Cfg::B_BYTES);
+            for (int c = pw; c <= NA; c += kProdWarps) my_bytes += (c < NA) ? kACopy : (WST ? 0 : Cfg::B_BYTES);
+            if (AT && pw == 0 && ptx::elect_one()) ptx::tma_prefetch_desc(&p.a_map);
             if (WST && pw == 0) {                              // one-time load of the whole weight image
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(wbar, Cfg::WRES_BYTES);
@@ -228,7 +243,11 @@ tapgemm_kernel(const TapGemmParams p) {
 #pragma unroll
                         for (int c0 = 0; c0 <= NA; c0 += kProdWarps) {
                             const int c = c0 + pw;
-                            if (c < NA) {
+                            if (AT && c < NA) {
+                                const int mt = c >> 1, part = c & 1;
+                                ptx::tma_load_3d(st + mt * Cfg::A_TILE + part * Cfg::A_PART, &p.a_map, s * (KSA * 8),
+                                                 128 * (((p.dbg & 1) ? 0 : m) + mt), part, &full[slot]);
+                            } else if (c < NA) {
                                 const int mt = c / (2 * KSA), part = (c / KSA) & 1, j = c % KSA;
                                 ptx::bulk_g2s(st + mt * Cfg::A_TILE + part * Cfg::A_PART + j * kSlabBytes,
                                               a_row + (size_t)mt * 2048 + part * p.a_part_stride + (size_t)(s * KSA + j) * p.a_kch_stride,
@@ -286,9 +305,9 @@ tapgemm_kernel(const TapGemmParams p) {
                             const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
                             const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
                             const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                            const uint32_t a_hi = a0 + (2 * kk) * kSlabBytes + arow * 16;
-                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
+                            const uint32_t a_hi = AT ? a0 + kk * 32 : a0 + (2 * kk) * kSlabBytes + arow * 16;
+                            const uint64_t da_hi = AT ? ptx::make_smem_desc_sw64(a_hi) : ptx::make_smem_desc(a_hi, kSlabBytes, 128);
+                            const uint64_t da_lo = AT ? ptx::make_smem_desc_sw64(a_hi + Cfg::A_PART) : ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
                             if (leader) {
                                 ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, first);      // small terms first
                                 ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
@@ -366,7 +385,7 @@ tapgemm_kernel(const TapGemmParams p) {
                     const int w = row / p.rw, t = row % p.rw;
                     const int to = t >> 1;
                     valid[mt] = to < (p.tv >> 1);
-                    out_off[mt] = (valid[mt] && w < p.out_rows_cap) ? (size_t)(to * (BN / 8)) * p.out_kch_stride + (size_t)(w + kGuard) * 16 : (size_t)-1;
+                    out_off[mt] = (valid[mt] && w < p.out_rows_cap) ? ((size_t)w * 4736 + (size_t)to * BN) * 2 : (size_t)-1;   // row-major [window][t * 128 + c]
                 } else if (EPI == EPI_FC_TAPE) {
                     out_off[mt] = (size_t)(row + kGuard) * 16;
                 }
@@ -444,7 +463,7 @@ tapgemm_kernel(const TapGemmParams p) {
                     } else {
                         // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
                         if (out_off[mt] != (size_t)-1) {
-                            uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off[mt] + ((lane & 1) ? p.out_part_stride : 0);
+                            uint8_t* dst = p.out + (EPI == EPI_POOL_FC ? (size_t)kch * 16 : (size_t)kch * p.out_kch_stride) + out_off[mt] + ((lane & 1) ? p.out_part_stride : 0);
                             *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
                             if (EPI == EPI_POOL_TAPE && zero_prev[mt]) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
                         }
@@ -701,19 +720,18 @@ window_stats_kernel(const float* __restrict__ x, int64_t first, int n_windows, i
 // ---------------------------------------------------------------------------------------------
 struct LayerCfg { int BN, TAPS, KSA, stages, n_tiles, kind, cin, src, nout, stack; };
 //                                   BN  TAPS KSA stages n_tiles kind cin   state_dict index of the weight
-constexpr int kNumPacked = 11;
+constexpr int kNumPacked = 10;
 constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0, 64},       // block1.0
                                  {64, 3, 4, 2, 1, 0, 64, 2, 64},       // block1.2
                                  {128, 3, 4, 2, 1, 0, 64, 4, 128},     // block2.0 (layer-wise conv3: resident image)
                                  {128, 3, 2, 8, 1, 0, 128, 6, 128},    // block2.2
                                  {240, 1, 4, 148, 9, 1, 4736, 8, 2048},  // fc.0: 8 n-tiles of 240 + one of 128 (zero-padded to 240)
                                  {128, 1, 4, 64, 4, 2, 2048, 10, 512}, // fc.3
-                                 {128, 3, 2, 4, 1, 0, 64, 4, 128},     // block2.0 again, in 24 KB blocks for the fused block2 kernel's weight ring
-                                 {128, 3, 2, 4, 1, 0, 64, 4, 128, 1},  // block2.0, ring blocks with the stacked [W_hi ; W_lo] operand (block2s_kernel)
+                                 {128, 3, 2, 4, 1, 0, 64, 4, 128, 1},  // block2.0 in 24 KB ring blocks with the stacked [W_hi ; W_lo] operand (block2_kernel)
                                  {128, 3, 2, 8, 1, 0, 128, 6, 128, 1},   // block2.2, stacked
-                                 {64, 3, 8, 1, 1, 0, 54, 0, 64, 1},      // block1.0, stacked [tap][kchunk][W_hi 64 rows | W_lo 64 rows] (block1s_kernel)
+                                 {64, 3, 8, 1, 1, 0, 54, 0, 64, 1},      // block1.0, stacked [tap][kchunk][W_hi 64 rows | W_lo 64 rows] (block1_kernel)
                                  {64, 3, 8, 1, 1, 0, 64, 2, 64, 1}};     // block1.2, stacked
-constexpr int kLayerConv3Ring = 6, kLayerConv3Stack = 7, kLayerConv4Stack = 8, kLayerConv1Stack = 9, kLayerConv2Stack = 10;
+constexpr int kLayerConv3Stack = 6, kLayerConv4Stack = 7, kLayerConv1Stack = 8, kLayerConv2Stack = 9;     // images of the fused kernels
 inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
@@ -748,7 +766,7 @@ inline Workspace make_workspace(int64_t n) {
     W.x1 = make_tape(n * kRW1, 8);   W.o_x1 = take(W.x1.bytes);
     W.x2 = make_tape(n * kRW2, 8);   W.o_x2 = take(W.x2.bytes);
     W.x3 = make_tape(n * kRW2, 16);  W.o_x3 = take(W.x3.bytes);
-    W.x4 = make_tape(n, 592);        W.o_x4 = take(W.x4.bytes);
+    W.x4 = make_rowmajor(n, 592);    W.o_x4 = take(W.x4.bytes);
     W.h1 = make_tape(n, 256);        W.o_h1 = take(W.h1.bytes);
     W.o_h2 = take((size_t)n * 512 * 4);
     W.o_mean = take((size_t)n * 64 * 4);
@@ -760,10 +778,10 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, AT>;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
     static_assert(kSmem <= 232448, "exceeds 227 KB");

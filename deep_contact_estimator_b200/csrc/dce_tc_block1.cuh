@@ -2,14 +2,24 @@
 // -> MaxPool1d(2,2), one persistent kernel; activations between the two convolutions never
 // leave the SM.   /root/reference/src/contact_cnn.py:10-26, utils/data_handler.py:55-56
 //
+// Arithmetic per K-step (stacked B operand): every (tap, kchunk) of a weight image holds [W_hi (64 rows) ; W_lo (64 rows)]
+// as ONE K-major operand, so
+//      MMA 1 (N = 128):  A_hi x [W_hi ; W_lo]  -> D[:, 0:64] += a_hi w_hi,  D[:, 64:128] += a_hi w_lo
+//      MMA 2 (N =  64):  A_lo x  W_hi          -> D[:, 0:64] += a_lo w_hi
+// i.e. 14 KB instead of 18 KB of shared-memory operand reads per K-step (these small-N MMAs are bound by the 128 B/clk
+// operand fetch, not by the tensor pipe: 64 + 48 cycles instead of 3 x 48); the epilogues add the two accumulator halves.
+//
 // Tiling ("recompute nothing, shrink the valid range"): a tile produces 124 rows of conv2
 // output.  With b = 124*i:
 //      slab0 row s  <->  X0 row b-3+s   (s = 0..129)   fp32 input -> bf16 hi/lo, written by converter warps
 //      conv1 MMA row k  <->  X1 row b-2+k  (k = 0..127), reads slab0 rows k..k+2; result -> slab1 row k+1
 //      conv2 MMA row j  <->  out row b-2+j (j = 0..127), reads slab1 rows j..j+2; rows j in [2,126) are exact
 // so each tile is two 128-row UMMA passes for 124 useful rows (96.9 %), pool pairs (j, j+1) with j
-// even sit in adjacent lanes, and both conv weight images (2 x 48 KB bf16 hi/lo) stay resident in
-// shared memory for the life of the CTA.
+// even sit in adjacent lanes (the two lanes of a pair split the pooled columns between them), and both conv weight
+// images (2 x 48 KB bf16 hi/lo) stay resident in shared memory for the life of the CTA.  slab0 and slab1 have two
+// buffers each; the room for the second slab1 comes from dropping the all-zero kchunk 7 (channels 56..63 do not exist)
+// of the slab0 images: the K = 16 MMA that covers kchunks 6 and 7 takes its second kchunk from ONE shared zero chunk
+// through its leading-dimension offset.
 //
 // Warp roles (15 warps, 1 CTA/SM):
 //   warps 0-3  : converters   staged fp32 rows -> (z-score) -> bf16 hi/lo, in place in slab0[buf] (UMMA K-major layout)
@@ -28,8 +38,10 @@ namespace tc {
 constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
 constexpr int kB1Threads = 15 * 32;
 constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
-constexpr int kB1WBytes = 49152;                   // one conv weight image: [stage 2][part 2][tap 3][j 4][64][8] bf16
-constexpr int kB1SmemBytes = 2 * kB1WBytes + 3 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
+constexpr int kB1WBytes = 49152;                   // one conv weight image: [tap 3][kchunk 8][W_hi 64 rows | W_lo 64 rows][8] bf16
+constexpr int kB1Slab0 = 2 * 7 * kSlabBytes;        // slab0 buffer: [part][7 kchunks][130 rows][16 B] = 29120 (also stages the raw fp32 rows: <= 28128 B)
+constexpr int kB1SmemBytes = 2 * kB1WBytes + 2 * kB1Slab0 + kSlabBytes + 2 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
+static_assert(kB1SmemBytes <= 232448, "exceeds 227 KB");
 
 struct Block1Params {
     const float* x;              // batch: [W][150][54]; stream: [T][54]
@@ -92,23 +104,24 @@ __device__ __forceinline__ TileSegs tile_segs(const Block1Params& p, int r0) {
 template <bool STREAM>
 __global__ void __launch_bounds__(kB1Threads, 1)
 block1_kernel(const Block1Params p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w1s = smem;
     uint8_t* w2s = smem + kB1WBytes;
-    uint8_t* slab0 = smem + 2 * kB1WBytes;                  // two buffers
-    uint8_t* slab1 = slab0 + 2 * kB1SlabBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + kB1SlabBytes);
+    uint8_t* slab0 = smem + 2 * kB1WBytes;                  // two buffers of 7 kchunks x hi/lo
+    uint8_t* zchunk = slab0 + 2 * kB1Slab0;                // one all-zero kchunk: "kchunk 7" of every slab0 image
+    uint8_t* slab1 = zchunk + kSlabBytes;                   // two buffers of 8 kchunks x hi/lo
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab1 + 2 * kB1SlabBytes);
     uint64_t* x0_full = bars;        // [2] 128 converter threads arrive
     uint64_t* x0_empty = bars + 2;   // [2] tcgen05.commit
     uint64_t* d1_full = bars + 4;    // [2] commit
     uint64_t* d1_empty = bars + 6;   // [2] 8 epilogue warps arrive
     uint64_t* d2_full = bars + 8;    // [2] commit
     uint64_t* d2_empty = bars + 10;  // [2] 8 epilogue warps arrive
-    uint64_t* x1_full = bars + 12;   // 256 epilogue threads arrive
-    uint64_t* x1_empty = bars + 13;  // commit
-    uint64_t* wbar = bars + 14;      // weights landed
-    uint64_t* raw_full = bars + 15;  // [2] raw fp32 rows of a tile landed (bulk TMA, bytes)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* x1_full = bars + 12;   // [2] 256 epilogue threads arrive
+    uint64_t* x1_empty = bars + 14;  // [2] commit
+    uint64_t* wbar = bars + 16;      // weights landed
+    uint64_t* raw_full = bars + 17;  // [2] raw fp32 rows of a tile landed (bulk TMA, bytes)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // b1[64], b2[64]
     float* s_nrm = s_bias + 128;     // stream mode: [2 windows][mean 64 | 1/std 64] of the tile being converted
 
@@ -122,15 +135,16 @@ block1_kernel(const Block1Params p) {
             ptx::mbar_init(&d1_full[i], 1);   ptx::mbar_init(&d1_empty[i], 8);
             ptx::mbar_init(&d2_full[i], 1);   ptx::mbar_init(&d2_empty[i], 8);
         }
-        ptx::mbar_init(x1_full, 256); ptx::mbar_init(x1_empty, 1); ptx::mbar_init(wbar, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&x1_full[i], 256); ptx::mbar_init(&x1_empty[i], 1); }
+        ptx::mbar_init(wbar, 1);
         ptx::mbar_init(&raw_full[0], 1); ptx::mbar_init(&raw_full[1], 1);
         ptx::fence_barrier_init();
     }
     pdl_launch_dependents();
-    if (warp == 12) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
-    // zero the activation slabs once: kchunk 7 of slab0 (channels 56..63 do not exist) and the
-    // never-written halo rows of slab1 must not hold NaN bit patterns
-    for (int i = threadIdx.x; i < 3 * kB1SlabBytes / 16; i += kB1Threads)
+    if (warp == 12) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    // zero the activation slabs once: the shared zero kchunk and the never-written halo rows of slab1 must not hold
+    // NaN bit patterns
+    for (int i = threadIdx.x; i < (2 * kB1Slab0 + kSlabBytes + 2 * kB1SlabBytes) / 16; i += kB1Threads)
         reinterpret_cast<uint4*>(slab0)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 128) s_bias[threadIdx.x] = __ldg((threadIdx.x < 64 ? p.b1 : p.b2 - 64) + threadIdx.x);
     ptx::fence_proxy_async_smem();
@@ -178,9 +192,9 @@ block1_kernel(const Block1Params p) {
             if (warp == 0) B1_TRACE(k, 2);
             auto row_ptr = [&](int srow) -> const uint8_t* {                         // where slab row srow's raw data sits
                 const int j = (sg.n[1] > 0 && srow >= sg.s_lo[1]) ? 1 : 0;
-                return slab0 + buf * kB1SlabBytes + sg.off[j] + (srow - sg.s_lo[j]) * 216;
+                return slab0 + buf * kB1Slab0 + sg.off[j] + (srow - sg.s_lo[j]) * 216;
             };
-            uint8_t* dst0 = slab0 + buf * kB1SlabBytes;
+            uint8_t* dst0 = slab0 + buf * kB1Slab0;
             float2 f[27];
             int w0 = 0;
             const bool v0 = row_window(r0 + tid, w0);
@@ -220,6 +234,7 @@ block1_kernel(const Block1Params p) {
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");                           // all raw reads done: overwrite in place
+            if (warp == 0) B1_TRACE(k, 15);
 #pragma unroll
             for (int kch = 0; kch < 7; ++kch) {
                 float y[8];
@@ -233,10 +248,8 @@ block1_kernel(const Block1Params p) {
                 split8(y, hi, lo);
                 uint8_t* d = dst0 + kch * kSlabBytes + tid * 16;
                 *reinterpret_cast<uint4*>(d) = hi;
-                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+                *reinterpret_cast<uint4*>(d + 7 * kSlabBytes) = lo;
             }
-            // channels 56..63 do not exist: the hi image of kchunk 7 was clobbered by the raw rows
-            *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + tid * 16) = make_uint4(0, 0, 0, 0);
             if (tid < 14) {
                 float y[8];
 #pragma unroll
@@ -245,15 +258,15 @@ block1_kernel(const Block1Params p) {
                 split8(y, hi, lo);
                 uint8_t* d = dst0 + kch1 * kSlabBytes + s1 * 16;
                 *reinterpret_cast<uint4*>(d) = hi;
-                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+                *reinterpret_cast<uint4*>(d + 7 * kSlabBytes) = lo;
             }
-            if (tid < 2) *reinterpret_cast<uint4*>(dst0 + 7 * kSlabBytes + (128 + tid) * 16) = make_uint4(0, 0, 0, 0);
             ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
             ptx::mbar_arrive(&x0_full[buf]);
             if (warp == 0) B1_TRACE(k, 3);
         }
     } else if (warp == 13) {
         // ===== loader: raw fp32 rows of tile k -> slab0[k & 1] by bulk TMA, as soon as conv1(k-2) has drained it =====
+        const uint64_t pol_once = ptx::policy_evict_first();     // the input windows are read exactly once: first out of the L2
         for (int k = 0; k < my_tiles; ++k) {
             const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
             const uint32_t buf = k & 1;
@@ -261,7 +274,7 @@ block1_kernel(const Block1Params p) {
             ptx::mbar_wait_relaxed(&x0_empty[buf], ((k >> 1) & 1) ^ 1, 256);
             if (ptx::elect_one()) {
                 B1_TRACE(k, 14);
-                uint8_t* stage = slab0 + buf * kB1SlabBytes;
+                uint8_t* stage = slab0 + buf * kB1Slab0;
                 uint32_t total = 0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -275,7 +288,10 @@ block1_kernel(const Block1Params p) {
                     ptx::mbar_arrive_expect_tx(&raw_full[buf], total);
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
-                        if (sg.bytes[j] > 0) ptx::bulk_g2s(stage + sg.dst_al[j], sg.src_al[j], sg.bytes[j], &raw_full[buf]);
+                        if (sg.bytes[j] > 0) {
+                            if (p.dbg & 16) ptx::bulk_g2s(stage + sg.dst_al[j], sg.src_al[j], sg.bytes[j], &raw_full[buf]);
+                            else ptx::bulk_g2s_hint(stage + sg.dst_al[j], sg.src_al[j], sg.bytes[j], &raw_full[buf], pol_once);
+                        }
                 } else {
                     ptx::mbar_arrive(&raw_full[buf]);
                 }
@@ -285,7 +301,10 @@ block1_kernel(const Block1Params p) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
                         if (nx.bytes[j] > 0)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.src_al[j]), "r"(nx.bytes[j]) : "memory");
+                        {
+                            if (p.dbg & 16) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.src_al[j]), "r"(nx.bytes[j]) : "memory");
+                            else ptx::bulk_prefetch_l2_hint(nx.src_al[j], nx.bytes[j], pol_once);
+                        }
                 }
             }
             __syncwarp();
@@ -296,26 +315,28 @@ block1_kernel(const Block1Params p) {
         // than the tensor pipe's short queue covers) is filled by the other's MMAs; each accumulator keeps one issuer.
         {
             ptx::mbar_wait(wbar, 0);
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64);
+            constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc64 = ptx::make_idesc_bf16_f32(128, 64);
             const uint32_t w1a = ptx::smem_u32(w1s), w2a = ptx::smem_u32(w2s);
-            const uint32_t s0a = ptx::smem_u32(slab0), s1a = ptx::smem_u32(slab1);
+            const uint32_t s0a = ptx::smem_u32(slab0), s1a = ptx::smem_u32(slab1), za = ptx::smem_u32(zchunk);
 
-            // 36 MMAs: 3 taps x 4 kchunk pairs x (hi*lo, lo*hi, hi*hi); then the two completion commits
-            auto conv_mmas = [&](uint32_t a_base, uint32_t w_base, uint32_t d, uint64_t* bar_a, uint64_t* bar_b) {
+            // 24 MMAs: 3 taps x 4 kchunk pairs x (A_hi x [W_hi ; W_lo] at N = 128, A_lo x W_hi at N = 64); then the two
+            // completion commits.  KCH = kchunks per part of the A image; with KCH = 7 the pair (6, 7) takes kchunk 7
+            // from the shared zero chunk through its leading-dimension offset.
+            auto conv_mmas = [&](uint32_t a_base, int kch, uint32_t w_base, uint32_t d, uint64_t* bar_a, uint64_t* bar_b) {
                 if (ptx::elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint32_t a_hi = a_base + (2 * kk) * kSlabBytes + tap * 16;
-                            const uint32_t b_hi = w_base + (kk >> 1) * 24576 + (tap * 4 + (2 * kk & 3)) * 1024;
-                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                            const uint64_t da_lo = ptx::make_smem_desc(a_hi + 8 * kSlabBytes, kSlabBytes, 128);
-                            const uint64_t db_hi = ptx::make_smem_desc(b_hi, 1024, 128);
-                            const uint64_t db_lo = ptx::make_smem_desc(b_hi + 12288, 1024, 128);
-                            ptx::umma_bf16_ss(d, da_hi, db_lo, idesc, (tap | kk) ? 1u : 0u);
-                            ptx::umma_bf16_ss(d, da_lo, db_hi, idesc, 1u);
-                            ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
+                            const uint32_t a_lo = a_hi + (uint32_t)kch * kSlabBytes;
+                            const bool zpair = (kch == 7 && kk == 3);
+                            const uint64_t da_hi = ptx::make_smem_desc(a_hi, zpair ? (za + tap * 16 - a_hi) : (uint32_t)kSlabBytes, 128);
+                            const uint64_t da_lo = ptx::make_smem_desc(a_lo, zpair ? (za + tap * 16 - a_lo) : (uint32_t)kSlabBytes, 128);
+                            const uint64_t db = ptx::make_smem_desc(w_base + (tap * 8 + 2 * kk) * 2048, 2048, 128);
+                            ptx::umma_bf16_ss(d, da_hi, db, idesc128, (tap | kk) ? 1u : 0u);
+                            ptx::umma_bf16_ss(d, da_lo, db, idesc64, 1u);
                         }
                     }
                     ptx::umma_commit(bar_a);
@@ -329,15 +350,15 @@ block1_kernel(const Block1Params p) {
                 ptx::mbar_wait(&d1_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
                 B1_TRACE(k, 4);
-                conv_mmas(s0a + buf * kB1SlabBytes, w1a, tmem_base + buf * 64, &x0_empty[buf], &d1_full[buf]);
+                conv_mmas(s0a + buf * kB1Slab0, 7, w1a, tmem_base + buf * 128, &x0_empty[buf], &d1_full[buf]);
             };
             auto issue_c2 = [&](int k) {
                 const uint32_t buf = k & 1, ph = (k >> 1) & 1;
-                ptx::mbar_wait(x1_full, k & 1);
+                ptx::mbar_wait(&x1_full[buf], ph);
                 ptx::mbar_wait(&d2_empty[buf], ph ^ 1);
                 ptx::tc_fence_after_sync();
                 B1_TRACE(k, 5);
-                conv_mmas(s1a, w2a, tmem_base + 128 + buf * 64, x1_empty, &d2_full[buf]);
+                conv_mmas(s1a + buf * kB1SlabBytes, 8, w2a, tmem_base + 256 + buf * 128, &x1_empty[buf], &d2_full[buf]);
             };
             if (warp == 12) { for (int k = 0; k < my_tiles; ++k) issue_c1(k); }
             else            { for (int k = 0; k < my_tiles; ++k) issue_c2(k); }
@@ -346,8 +367,10 @@ block1_kernel(const Block1Params p) {
         // ===== epilogue warps 4..11 =====
         const int q = warp & 3, h = (warp - 4) >> 2;          // TMEM lane quadrant, column half
         const int rit = q * 32 + lane;                        // MMA row this thread owns
+        const int odd = lane & 1;
         const float* bias1 = s_bias + h * 32;
-        const float* bias2 = s_bias + 64 + h * 32;
+        const float* bias2 = s_bias + 64 + h * 32 + odd * 16;
+        const uint32_t tq = tmem_base + h * 32 + ((uint32_t)(q * 32) << 16);
 
         auto epi1 = [&](int k) {
             const int tile = blockIdx.x + k * gridDim.x;
@@ -358,35 +381,39 @@ block1_kernel(const Block1Params p) {
             ptx::mbar_wait_relaxed(&d1_full[buf], ph);
             if (warp == 4) B1_TRACE(k, 7);
             ptx::tc_fence_after_sync();
-            uint32_t v[32];
-            ptx::tmem_ld32(tmem_base + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
+            uint32_t v[32], u[32];
+            ptx::tmem_ld32(tq + buf * 128, v);                // a_hi w_hi + a_lo w_hi
+            ptx::tmem_ld32(tq + buf * 128 + 64, u);           // a_hi w_lo
             ptx::tmem_ld_wait();
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);  // accumulator is in registers now
-            float y[32];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias1 + i);
-                y[i] = valid ? relu_nan(__uint_as_float(v[i]) + b4.x) : 0.f;
-                y[i + 1] = valid ? relu_nan(__uint_as_float(v[i + 1]) + b4.y) : 0.f;
-                y[i + 2] = valid ? relu_nan(__uint_as_float(v[i + 2]) + b4.z) : 0.f;
-                y[i + 3] = valid ? relu_nan(__uint_as_float(v[i + 3]) + b4.w) : 0.f;
-            }
-            if (warp == 4) B1_TRACE(k, 8);
-            ptx::mbar_wait_relaxed(x1_empty, (k & 1) ^ 1);    // conv2 of the previous tile has finished reading slab1
-            if (warp == 4) B1_TRACE(k, 9);
-            if (p.dbg & 2) { ptx::mbar_arrive(x1_full); return; }
+            uint4 hi[4], lo[4];
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
-                uint4 hi, lo;
-                split8(y + qd * 8, hi, lo);
-                uint8_t* d = slab1 + (h * 4 + qd) * kSlabBytes + (rit + 1) * 16;
-                *reinterpret_cast<uint4*>(d) = hi;
-                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo;
+                float y[8];
+                const float4 b0 = *reinterpret_cast<const float4*>(bias1 + qd * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias1 + qd * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float sum = __uint_as_float(v[qd * 8 + i]) + __uint_as_float(u[qd * 8 + i]);
+                    y[i] = valid ? relu_nan(sum + bb[i]) : 0.f;
+                }
+                split8(y, hi[qd], lo[qd]);
+            }
+            if (warp == 4) B1_TRACE(k, 8);
+            ptx::mbar_wait_relaxed(&x1_empty[buf], ph ^ 1);   // conv2 of tile k-2 has finished reading this slab1 buffer
+            if (warp == 4) B1_TRACE(k, 9);
+            if (p.dbg & 2) { ptx::mbar_arrive(&x1_full[buf]); return; }
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                uint8_t* d = slab1 + buf * kB1SlabBytes + (h * 4 + qd) * kSlabBytes + (rit + 1) * 16;
+                *reinterpret_cast<uint4*>(d) = hi[qd];
+                *reinterpret_cast<uint4*>(d + 8 * kSlabBytes) = lo[qd];
             }
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(x1_full);
+            ptx::mbar_arrive(&x1_full[buf]);
             if (warp == 4) B1_TRACE(k, 10);
         };
         auto epi2 = [&](int k) {
@@ -400,34 +427,40 @@ block1_kernel(const Block1Params p) {
             ptx::mbar_wait_relaxed(&d2_full[buf], ph);
             if (warp == 4) B1_TRACE(k, 12);
             ptx::tc_fence_after_sync();
-            uint32_t v[32];
-            ptx::tmem_ld32(tmem_base + 128 + buf * 64 + h * 32 + ((uint32_t)(q * 32) << 16), v);
+            uint32_t v[32], u[32];
+            ptx::tmem_ld32(tq + 256 + buf * 128, v);
+            ptx::tmem_ld32(tq + 256 + buf * 128 + 64, u);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&d2_empty[buf]);
             if (p.dbg & 8) return;
-            float y[32];
+            // MaxPool1d(2,2) first (bias and ReLU commute with max): the two lanes of a pool pair exchange halves, the even
+            // lane finishes columns [0,16) of this warp's 32, the odd lane [16,32)
+            float y[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias2 + i);
-                y[i] = relu_nan(__uint_as_float(v[i]) + b4.x);
-                y[i + 1] = relu_nan(__uint_as_float(v[i + 1]) + b4.y);
-                y[i + 2] = relu_nan(__uint_as_float(v[i + 2]) + b4.z);
-                y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
+            for (int i = 0; i < 16; ++i) {
+                const float s0 = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                const float s1 = __uint_as_float(v[16 + i]) + __uint_as_float(u[16 + i]);
+                const float give = odd ? s0 : s1, keep = odd ? s1 : s0;
+                y[i] = max_nan(keep, __shfl_xor_sync(0xffffffffu, give, 1));
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float m = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // MaxPool1d(2,2)
-                y[i] = valid ? m : 0.f;
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias2 + i);
+                y[i] = valid ? relu_nan(y[i] + b4.x) : 0.f;
+                y[i + 1] = valid ? relu_nan(y[i + 1] + b4.y) : 0.f;
+                y[i + 2] = valid ? relu_nan(y[i + 2] + b4.z) : 0.f;
+                y[i + 3] = valid ? relu_nan(y[i + 3] + b4.w) : 0.f;
             }
             if (store && !(p.dbg & 1)) {
-                uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + ((lane & 1) ? p.out_part_stride : 0);
+                uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + (size_t)(h * 4 + odd * 2) * p.out_kch_stride;
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
+                for (int qd = 0; qd < 2; ++qd) {
                     uint4 hi, lo;
                     split8(y + qd * 8, hi, lo);
-                    *reinterpret_cast<uint4*>(base + (size_t)(h * 4 + qd) * p.out_kch_stride) = (lane & 1) ? lo : hi;
+                    *reinterpret_cast<uint4*>(base + (size_t)qd * p.out_kch_stride) = hi;
+                    *reinterpret_cast<uint4*>(base + (size_t)qd * p.out_kch_stride + p.out_part_stride) = lo;
                 }
             }
             if (warp == 4) B1_TRACE(k, 13);
@@ -441,7 +474,7 @@ block1_kernel(const Block1Params p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 12) ptx::tmem_dealloc(tmem_base, 256);
+    if (warp == 12) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace tc

@@ -4,6 +4,7 @@
 // tcgen05.ld (LDTM).  One thread issues MMAs on behalf of the CTA; accumulators
 // live in TMEM, not registers.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -61,6 +62,52 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 eviction-priority hints for data that is read exactly once (the raw input windows): they should not push the
+// activation tapes the next kernel is about to re-read out of the L2
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2_hint(const void* src_gmem, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src_gmem), "r"(bytes), "l"(policy) : "memory");
+}
+
+// ---- bulk copy shared -> global (1-D, contiguous; completion by bulk group) ----
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- tensor-map TMA load: a 3-D box global -> shared (UTMALDG), completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// host: cuTensorMapEncodeTiled through the runtime (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // Whole warp executes alloc/dealloc (.sync.aligned). ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -87,6 +134,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;      // bits [32,46) stride-dimension byte offset >> 4
     d |= (uint64_t)1 << 46;                                // bits [46,48) descriptor version = 1 (sm_100)
     // bits [49,52) base offset = 0, bit 52 lbo mode = 0, bits [61,64) layout type = 0 (no swizzle)
+    return d;
+}
+
+// K-major operand in the 64-byte swizzle (what a tensor-map TMA load with CU_TENSOR_MAP_SWIZZLE_64B and a 64-byte inner
+// box leaves in shared memory): a row is 64 B = 32 bf16 of K, an atom is 8 rows = 512 B whose 16-byte chunks are XORed
+// with bits 1..2 of the row; SBO = 512 B between 8-row groups, the leading-dimension field is not used.  An MMA's K = 16
+// slice k of the row starts 32 k bytes into the row (the hardware applies the swizzle to the address it computes).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                                // LBO (unused for swizzled K-major): 1
+    d |= (uint64_t)(512 >> 4) << 32;                       // SBO
+    d |= (uint64_t)1 << 46;                                // descriptor version 1 (sm_100)
+    d |= (uint64_t)4 << 61;                                // layout type: SWIZZLE_64B
     return d;
 }
 

@@ -2,9 +2,7 @@
 #pragma once
 #include "dce_tc.cuh"
 #include "dce_tc_block1.cuh"
-#include "dce_tc_block1s.cuh"
 #include "dce_tc_block2.cuh"
-#include "dce_tc_block2s.cuh"
 #include "dce_small.cuh"
 
 namespace dce {
@@ -22,8 +20,6 @@ struct Options {
     int block1_dbg = 0;          // timing ablations inside block1_kernel (results invalid)
     int tapgemm_dbg = 0;
     int block2_dbg = 0;
-    int block1_stack = 1;        // 1: block1s_kernel (stacked operand, two slab1 buffers); 0: block1_kernel
-    int block2_stack = 1;        // 1: block2s_kernel (stacked [W_hi ; W_lo] operand: N = 256 + N = 128 MMAs); 0: block2_kernel (three N = 128 MMAs)
     int sm_limit = 0;            // > 0: the batch kernels use at most this many CTAs (what a MIG slice / smaller part would give them)
     int trace_layer = -1;        // which kernel records into `trace`: -1 block1, 2..5 conv3 / conv4 / fc.0 / fc.3, 6 block2
     long long* trace = nullptr;  // device buffer [60 tiles][16 events] of clock64 samples of CTA 0 (DCE_TRACE builds)
@@ -81,26 +77,17 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             if (auto first_ = attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1sSmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block1s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1sSmemBytes);
                 if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block1Params b{};
             b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m; b.total_rows = total_rows;
             b.mean = mean; b.rstd = sdev;   // window_stats_kernel<true> writes 1/std
-            b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[0]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[1]);
+            b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv1Stack]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv2Stack]);
             b.b1 = bp.b[0]; b.b2 = bp.b[1];
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = opt.block1_dbg; b.trace = (opt.trace_layer < 0) ? opt.trace : nullptr;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (opt.block1_stack) {
-                b.w1 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv1Stack]); b.w2 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv2Stack]);
-                if (stream_mode)
-                    DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1s_kernel<true>, dim3(grid), dim3(kB1Threads), kB1sSmemBytes, s, b); (void)le_; });
-                else
-                    DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1s_kernel<false>, dim3(grid), dim3(kB1Threads), kB1sSmemBytes, s, b); (void)le_; });
-            } else
             if (stream_mode)
                 DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
@@ -135,22 +122,17 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             static DeviceOnce b2_once;
             if (auto first_ = b2_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(block2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
                 if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
             }
             Block2Params b{};
             b.x2 = x2; b.x2_part_stride = W.x2.part_stride; b.x2_kch_stride = W.x2.kch_stride; b.n_windows = m;
-            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv3Ring]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[3]);
+            b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv3Stack]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv4Stack]);
             b.b3 = bp.b[2]; b.b4 = bp.b[3];
-            b.out = x4; b.out_part_stride = W.x4.part_stride; b.out_kch_stride = W.x4.kch_stride; b.out_rows_cap = W.x4.m_tiles * 128;
+            b.out = x4; b.out_part_stride = W.x4.part_stride; b.out_rows_cap = W.x4.cap;
             b.n_tiles = (m * kRW2 + kB2Rows - 1) / kB2Rows;
             b.trace = (opt.trace_layer == 6) ? opt.trace : nullptr;
             b.dbg = opt.block2_dbg;
             const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
-            if (opt.block2_stack) {
-                b.w3 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv3Stack]); b.w4 = reinterpret_cast<const uint8_t*>(buf + L.w[kLayerConv4Stack]);
-                DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2s_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
-            } else
             DCE_KL(ctx, "tc_block2", { cudaError_t le_ = launch_pdl(block2_kernel, dim3(grid), dim3(kB2Threads), kB2SmemBytes, s, b); (void)le_; });
         } else {
         p = TapGemmParams{};
@@ -171,7 +153,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         p.a_tape = x3; p.a_part_stride = W.x3.part_stride; p.a_kch_stride = W.x3.kch_stride;
         p.w_packed = reinterpret_cast<const uint8_t*>(buf + L.w[3]); p.bias = bp.b[3];
         p.m_tiles = W.x3.m_tiles; p.stages = kLayers[3].stages;
-        p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.m_tiles * 128;
+        p.out = x4; p.out_part_stride = W.x4.part_stride; p.out_kch_stride = W.x4.kch_stride; p.out_rows_cap = W.x4.cap;
         p.trace = (opt.trace_layer == 3) ? opt.trace : nullptr;
         if (tiny) p.m_tiles = (m * kRW2 + 127) / 128;
         rc = tiny ? launch_layer<128, 3, 2, 6, EPI_POOL_FC, 1>(ctx, "tc_conv4_pool", sm_count, p)
@@ -204,7 +186,17 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         p.N = 2048; p.rw = 1; p.tv = 1;
         p.dbg = opt.tapgemm_dbg;
         p.trace = (opt.trace_layer == 4) ? opt.trace : nullptr;
-        rc = launch_layer<240, 1, 4, 3, EPI_FC_TAPE, 2>(ctx, "tc_fc1", sm_count, p);
+        {   // the row-major operand [part][window][4736] as a 3-D tensor; a box is 128 windows x 32 K-elements (64 B) of one part
+            ptx::EncodeTiledFn enc = ptx::encode_tiled_fn();
+            if (!enc) return DCE_EUNSUPPORTED;
+            const cuuint64_t dims[3] = {4736, (cuuint64_t)W.x4.cap, 2};
+            const cuuint64_t strides[2] = {4736 * 2, (cuuint64_t)W.x4.part_stride};
+            const cuuint32_t box[3] = {32, 128, 1}, es[3] = {1, 1, 1};
+            if (enc(&p.a_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x4, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return DCE_EINVAL;
+        }
+        rc = launch_layer<240, 1, 4, 3, EPI_FC_TAPE, 2, 0, 1>(ctx, "tc_fc1", sm_count, p);
         if (rc != DCE_OK) return rc;
         // ---- fc.3 + ReLU (a11): H1 -> H2 fp32
         p.a_tape = h1; p.a_part_stride = W.h1.part_stride; p.a_kch_stride = W.h1.kch_stride;

@@ -23,7 +23,7 @@ sets = [{}] + [s for s in sets if s]
 eng = dce.ContactEngine(synth.make_params(0), dev, "bf16x3")
 
 
-DEFAULTS = {"fuse_argmax": 1, "block1_stack": 1, "block2_stack": 1, "fuse_block1": 1, "fuse_block2": 1, "fuse_fc3": 1, "latency_kernel": 1, "latency_coop": 1, "latency_tma_in": 1}
+DEFAULTS = {"fuse_argmax": 1, "fuse_block1": 1, "fuse_block2": 1, "fuse_fc3": 1, "latency_kernel": 1, "latency_coop": 1, "latency_tma_in": 1}
 
 
 def apply(opts):
