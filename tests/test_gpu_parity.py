@@ -419,6 +419,34 @@ def test_random_shapes_property(dev, params0):
     check()
 
 
+def test_one_workspace_any_mix_of_call_sizes(dev, params0):
+    """The workspace header carries state from call to call (the latency kernel's barrier counters, the per-tile tickets
+    with which the batch path's last kernel elects the CTA that reduces the logit shares, counting on modulo 4) and every
+    other offset depends on the chunk size: a sequence of calls of very different sizes — batch, latency mode, stream,
+    a tail chunk that gives up 64 windows — on ONE engine must give what a fresh engine gives for each of them."""
+    eng = dce.ContactEngine(params0, dev, "bf16x3")
+    log = synth.make_sensor_log(150 + 700, seed=31).to(dev)
+    sizes = [4096, 3, 300, 4097, 1, 129, 4096 + 2, 2, 640, 4096]
+    for i, b in enumerate(sizes):
+        x = synth.make_windows(b, seed=200 + i).to(dev)
+        got = eng.classify(x)
+        fresh = dce.ContactEngine(params0, dev, "bf16x3")
+        want = fresh.classify(x)
+        torch.cuda.synchronize()
+        assert all(torch.equal(g, w) for g, w in zip(got, want)), (i, b)
+        if i % 3 == 1:
+            gs = eng.stream(log, 5, 600 + i, want_logits=True)
+            ws_ = fresh.stream(log, 5, 600 + i, want_logits=True)
+            torch.cuda.synchronize()
+            assert all(torch.equal(g, w) for g, w in zip(gs, ws_)), (i, "stream")
+        fresh.close()
+    with torch.no_grad():
+        x = synth.make_windows(4096, seed=209)
+        want_cls = oracle.forward_torch(params0, x).argmax(1)
+    assert torch.equal(eng.classify(x.to(dev))[1].cpu().long(), want_cls)
+    eng.close()
+
+
 def test_fewer_sms_than_tiles(dev, params0):
     """A device (MIG slice, smaller part) with fewer SMs than a layer has tiles: every persistent kernel then walks
     several tiles per CTA — including fc.0, whose two 256-column accumulators leave no second TMEM buffer (the issue
@@ -446,7 +474,7 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
     x = synth.make_windows(300, seed=77).to(dev)
     ref_logits, ref_cls, _ = eng.classify(x)
     try:
-        for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3"):
+        for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3", b"fuse_argmax"):
             assert eng.set_option(key, 0) == 0
             lo, cl, _ = eng.classify(x)
             assert torch.equal(cl, ref_cls)
@@ -454,7 +482,7 @@ def test_fused_and_layerwise_kernels_agree(dev, params0):
             assert eng.set_option(key, 1) == 0
         assert eng.set_option(b"no_such_option", 1) == -1
     finally:
-        eng.set_option(b"fuse_block1", 1); eng.set_option(b"fuse_block2", 1); eng.set_option(b"fuse_fc3", 1)
+        eng.set_option(b"fuse_block1", 1); eng.set_option(b"fuse_block2", 1); eng.set_option(b"fuse_fc3", 1); eng.set_option(b"fuse_argmax", 1)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -29,16 +29,26 @@ def tape(rows, kch):
     return dict(rows=rows, m_tiles=m_tiles, cap=cap, kch=kch, bytes=align(cap * 16 * kch * 2))
 
 
+def rowmajor(rows, kch):            # the fc.0 operand: [part][row][kch * 8] bf16, no guard rows (make_rowmajor, dce_tc.cuh)
+    m_tiles = (rows + 127) // 128
+    m_tiles += m_tiles & 1
+    cap = m_tiles * 128
+    return dict(rows=rows, m_tiles=m_tiles, cap=cap, kch=kch, bytes=align(cap * 16 * kch * 2), rowmajor=True)
+
+
 def workspace(n):
-    o, W = 256, {}                  # [0, 256): the latency kernel's barrier counters (make_workspace, dce_tc.cuh)
+    o, W = 512, {}                  # [0, 256): the latency kernel's barrier counters, [256, 512): fc.3 tickets (make_workspace, dce_tc.cuh)
     for name, t in (("x0", tape(n * 152, 8)), ("x1", tape(n * 152, 8)), ("x2", tape(n * 76, 8)),
-                    ("x3", tape(n * 76, 16)), ("x4", tape(n, 592)), ("h1", tape(n, 256))):
+                    ("x3", tape(n * 76, 16)), ("x4", rowmajor(n, 592)), ("h1", tape(n, 256))):
         t["off"] = o; W[name] = t; o = align(o + t["bytes"])
     W["h2"] = dict(off=o); o = align(o + n * 512 * 4)
     return W
 
 
 def decode(ws, t):
+    if t.get("rowmajor"):
+        raw = ws[t["off"]: t["off"] + t["cap"] * 16 * t["kch"] * 2].view(torch.bfloat16).view(2, t["cap"], t["kch"] * 8).float()
+        return (raw[0] + raw[1])[:t["rows"]].cpu()
     raw = ws[t["off"]: t["off"] + t["cap"] * 16 * t["kch"] * 2].view(torch.bfloat16).view(2, t["kch"], t["cap"], 8).float()
     v = raw[0] + raw[1]                                         # [kch][cap][8]
     return v.permute(1, 0, 2).reshape(t["cap"], t["kch"] * 8)[GUARD:GUARD + t["rows"]].cpu()

@@ -20,7 +20,7 @@ for precision in ("bf16x3", "fp32"):
     _, cl, bi = eng.stream(log.to(dev)); torch.cuda.synchronize()
     _, wc, wb = oracle.inference_stream(params, log)
     assert np.array_equal(bi.cpu().numpy(), wb.numpy()), precision
-    for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3", b"latency_kernel"):
+    for key in (b"fuse_block1", b"fuse_block2", b"fuse_fc3", b"fuse_argmax", b"latency_kernel"):
         eng.set_option(key, 0)
         x = synth.make_windows(37 if key != b"latency_kernel" else 3, seed=37)
         lo, cl, bi = eng.classify(x.to(dev)); torch.cuda.synchronize()
