@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true",
                     help="only the device-resident `value` loop and the per-kernel times (the ncu launch list of THIS command is "
-                         "the step's five kernels and nothing else); prints the same line with the other legs null")
+                         "the step's four kernels and nothing else); prints the same line with the other legs null")
     ap.add_argument("--no-latency", action="store_true", help="skip the latency_b1 leg (profiler runs: its resident servers wait for host doorbells)")
     ap.add_argument("--stream-steps", type=int, default=2_000_000, help="rows of the synthetic log of the `stream` leg per GPU (0: skip)")
     ap.add_argument("--big-batch", type=int, default=32768, help="windows per GPU of the one-call big-batch leg, BASELINE configs[3] (0: skip)")
