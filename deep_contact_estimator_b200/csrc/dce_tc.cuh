@@ -65,7 +65,7 @@ struct TapGemmParams {
     const float* w3t;            // EPI_FC_LOGITS: the NEXT Linear layer's weight, k-major [N][16] (fc.6)
     // EPI_FC_LOGITS with tickets != nullptr: the CTA that completes an M-tile's last n-tile (atomic ticket per M-tile) adds the
     // logit shares in their fixed order + bias, takes the argmax and writes logits / class / contact bits: no extra launch
-    unsigned* tickets;           // [m_tiles], zero once; counts on modulo n_tiles across calls
+    unsigned* tickets;           // [m_tiles], zero before the call and after it
     const float* b3;             // fc.6 bias [16]
     float* logits; int32_t* cls; uint8_t* bits;      // outputs of this chunk (may be null)
     int N;                       // total output features
@@ -498,7 +498,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (warp == 0 && lane == 0) {
                     const unsigned old = atomicAdd(p.tickets + m0, 1u);
-                    *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = (old % (unsigned)p.n_tiles == (unsigned)p.n_tiles - 1) ? 1u : 0u;
+                    const bool last = (old == (unsigned)p.n_tiles - 1);
+                    if (last) p.tickets[m0] = 0;                      // every arrival is in: the call leaves its tickets at zero
+                    *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = last ? 1u : 0u;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (*reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) && warp < 4) {
@@ -759,7 +761,7 @@ struct Workspace {
 };
 inline Workspace make_workspace(int64_t n) {
     Workspace W; size_t o = 512;          // [0,256): the latency kernel's barrier counters (dce_latency.cuh); [256,512): fc.3's per-M-tile
-                                          // tickets (at a fixed place: every other offset depends on the chunk size).  Zero once.
+                                          // tickets (at a fixed place: every other offset depends on the chunk size).  Zero once; every call leaves them at zero.
     W.o_tickets = 256;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     W.x0 = make_tape(n * kRW1, 8);   W.o_x0 = take(W.x0.bytes);

@@ -98,10 +98,9 @@ DCE_API int    dce_weights_adopt(dce_weights *w);
  * `max_windows` windows per call (the library chunks internally, so this
  * saturates at a fixed size). 256-byte aligned device memory, ZERO-FILLED
  * ONCE after allocation (cudaMemset): its first 256 bytes hold the grid-barrier
- * counters of the latency kernel, which every call leaves at zero, the next 256
- * the per-tile tickets of the batch path's last kernel (they count on modulo 4
- * from call to call), and tape padding rows must start finite.  One workspace
- * serves one call at a time. */
+ * counters of the latency kernel, the next 256 the per-tile tickets of the batch
+ * path's last kernel (every call leaves both at zero), and tape padding rows
+ * must start finite.  One workspace serves one call at a time. */
 DCE_API size_t dce_workspace_bytes(int64_t max_windows, int precision);
 
 /*

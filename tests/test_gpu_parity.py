@@ -421,7 +421,7 @@ def test_random_shapes_property(dev, params0):
 
 def test_one_workspace_any_mix_of_call_sizes(dev, params0):
     """The workspace header carries state from call to call (the latency kernel's barrier counters, the per-tile tickets
-    with which the batch path's last kernel elects the CTA that reduces the logit shares, counting on modulo 4) and every
+    with which the batch path's last kernel elects the CTA that reduces the logit shares) and every
     other offset depends on the chunk size: a sequence of calls of very different sizes — batch, latency mode, stream,
     a tail chunk that gives up 64 windows — on ONE engine must give what a fresh engine gives for each of them."""
     eng = dce.ContactEngine(params0, dev, "bf16x3")
