@@ -568,6 +568,15 @@ __global__ void pack_b_kernel(const float* __restrict__ W, uint8_t* __restrict__
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
         const size_t blk = ((size_t)nt * stages + s) * (2 * per_part * 2);      // bytes
+        if (stack == 2) {
+            // CTA-pair images (block1_kernel, BN = 64): [rank 2][tap][kchunk][96 rows][8].  Rows 0..63: rank 0 W_hi, rank 1 W_lo (each CTA's
+            // half of the stacked N = 128 operand); rows 64..95: W_hi rows 32 r .. 32 r + 31 (its half of the N = 64 operand)
+            const size_t rank_bytes = (size_t)TAPS * KSA * 96 * 16, cell = (((size_t)tap * KSA + j) * 96) * 16 + e * 2;
+            *reinterpret_cast<__nv_bfloat16*>(out + blk + cell + (size_t)nn * 16) = h;
+            *reinterpret_cast<__nv_bfloat16*>(out + blk + rank_bytes + cell + (size_t)nn * 16) = l;
+            *reinterpret_cast<__nv_bfloat16*>(out + blk + (nn >> 5) * rank_bytes + cell + (size_t)(64 + (nn & 31)) * 16) = h;
+            continue;
+        }
         if (stack) {
             const size_t within = ((((size_t)tap * KSA + j) * 2 * BN + nn) * 8 + e) * 2;
             *reinterpret_cast<__nv_bfloat16*>(out + blk + within) = h;
@@ -731,10 +740,13 @@ constexpr LayerCfg kLayers[kNumPacked] = {{64, 3, 4, 2, 1, 0, 54, 0, 64},       
                                  {128, 1, 4, 64, 4, 2, 2048, 10, 512}, // fc.3
                                  {128, 3, 2, 4, 1, 0, 64, 4, 128, 1},  // block2.0 in 24 KB ring blocks with the stacked [W_hi ; W_lo] operand (block2_kernel)
                                  {128, 3, 2, 8, 1, 0, 128, 6, 128, 1},   // block2.2, stacked
-                                 {64, 3, 8, 1, 1, 0, 54, 0, 64, 1},      // block1.0, stacked [tap][kchunk][W_hi 64 rows | W_lo 64 rows] (block1_kernel)
-                                 {64, 3, 8, 1, 1, 0, 64, 2, 64, 1}};     // block1.2, stacked
+                                 {64, 3, 8, 1, 1, 0, 54, 0, 64, 2},      // block1.0, stacked, one image per CTA of a pair (block1_kernel)
+                                 {64, 3, 8, 1, 1, 0, 64, 2, 64, 2}};     // block1.2, the same
 constexpr int kLayerConv3Stack = 6, kLayerConv4Stack = 7, kLayerConv1Stack = 8, kLayerConv2Stack = 9;     // images of the fused kernels
-inline size_t layer_packed_bytes(const LayerCfg& c) { return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16; }
+inline size_t layer_packed_bytes(const LayerCfg& c) {
+    if (c.stack == 2) return (size_t)2 * c.TAPS * c.KSA * 96 * 16;          // two CTA-pair images
+    return (size_t)c.n_tiles * c.stages * 2 * c.TAPS * c.KSA * c.BN * 16;
+}
 
 struct PackedLayout { size_t w[kNumPacked]; size_t begin, end; };
 inline PackedLayout make_packed_layout(size_t base) {

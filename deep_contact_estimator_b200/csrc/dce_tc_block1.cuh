@@ -21,7 +21,15 @@
 // of the slab0 images: the K = 16 MMA that covers kchunks 6 and 7 takes its second kchunk from ONE shared zero chunk
 // through its leading-dimension offset.
 //
-// Warp roles (15 warps, 1 CTA/SM):
+// CTA pairs (tcgen05.mma.cta_group::2): the two CTAs of a cluster, on the two SMs of a TPC, work on two consecutive tiles
+// in lockstep.  One M = 256 MMA covers both: each CTA supplies its own 128 rows of A and only HALF of the B operand (MMA 1:
+// rank 0 holds W_hi, rank 1 W_lo; MMA 2: each holds 32 of W_hi's 64 rows) from the same shared-memory offsets, and gets its
+// own 128 x N slice of D in its own TMEM.  Per SM and K-step the operand fetch drops from 14 to 11 KB and a CTA keeps
+// 2 x 36 KB of weights instead of 2 x 48, which is what makes room for the output staging tile below.  Only the leader CTA
+// (rank 0) issues MMAs; the peer's two issuer warps relay "my operand slab is written and my accumulator is free" to the
+// leader with one remote mbarrier arrive per tile and convolution; tcgen05.commit is multicast to the barriers of both.
+//
+// Warp roles (16 warps, 1 CTA/SM):
 //   warps 0-3  : converters   staged fp32 rows -> (z-score) -> bf16 hi/lo, in place in slab0[buf] (UMMA K-major layout)
 //   warps 4-11 : epilogue     epi1: TMEM D1 -> bias/ReLU/guard -> bf16 hi/lo -> slab1 (smem, feeds conv2)
 //                             epi2: TMEM D2 -> bias/ReLU/pool/guard -> bf16 hi/lo -> X2 tape (global)
@@ -29,6 +37,12 @@
 //   warp 12    : conv1 MMA issuer (+ weights via bulk TMA once)
 //   warp 14    : conv2 MMA issuer — separate issuers, so the tensor pipe always has the other conv's MMAs queued
 //                             while one issuer is between tiles or waiting for epi1 to fill slab1
+//   warp 15    : store warp   epi2 leaves the tile's 62 pooled rows in a staging tile in the tape's own [part][kchunk][row]
+//                             order: 16 contiguous runs of 992 B, which this warp hands to the copy engine (cp.async.bulk
+//                             shared -> global) while the epilogue warps go on.  (Staging them in the slab1 buffer conv2 has
+//                             just drained put the copies on epi1's path two tiles later: no gain.)  Issued as
+//                             st.global from the epilogue warps the same bytes cost 12 % of the kernel (ablation
+//                             block1_dbg=1): the epilogue warps are the kernel's critical resource
 #pragma once
 #include "dce_tc.cuh"
 
@@ -36,11 +50,14 @@ namespace dce {
 namespace tc {
 
 constexpr int kB1Rows = 124;                       // useful conv2 rows per tile
-constexpr int kB1Threads = 15 * 32;
+constexpr int kB1Threads = 16 * 32;
 constexpr int kB1SlabBytes = 2 * 8 * kSlabBytes;   // [part][8 kchunks][130 rows][16 B] = 33280
-constexpr int kB1WBytes = 49152;                   // one conv weight image: [tap 3][kchunk 8][W_hi 64 rows | W_lo 64 rows][8] bf16
+constexpr int kB1WRows = 96;                       // per (tap, kchunk) and CTA: 64 rows for MMA 1 (rank 0: W_hi, rank 1: W_lo) + 32 for MMA 2 (W_hi rows 32 r ..)
+constexpr int kB1WBytes = 3 * 8 * kB1WRows * 16;   // one CTA's conv weight image: [tap 3][kchunk 8][96 rows][8] bf16 = 36864
 constexpr int kB1Slab0 = 2 * 7 * kSlabBytes;        // slab0 buffer: [part][7 kchunks][130 rows][16 B] = 29120 (also stages the raw fp32 rows: <= 28128 B)
-constexpr int kB1SmemBytes = 2 * kB1WBytes + 2 * kB1Slab0 + kSlabBytes + 2 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4;
+constexpr int kB1StageRun = (kB1Rows / 2) * 16;     // 62 pooled rows x 16 B: one (part, kchunk) run of the X2 tape
+constexpr int kB1Stage = 16 * kB1StageRun;          // 15872
+constexpr int kB1SmemBytes = 2 * kB1WBytes + 2 * kB1Slab0 + kSlabBytes + 2 * kB1SlabBytes + 256 + 2 * 64 * 4 + 2 * 2 * 64 * 4 + kB1Stage;
 static_assert(kB1SmemBytes <= 232448, "exceeds 227 KB");
 
 struct Block1Params {
@@ -56,7 +73,7 @@ struct Block1Params {
     int out_rows_cap;
     int n_tiles;
     int64_t total_rows;          // stream: rows T of the log (to keep the 16-byte-rounded bulk copies in bounds)
-    int dbg;                     // timing ablations only (results invalid when non-zero)
+    int dbg;                     // timing ablations only (results invalid when non-zero); w1 / w2: [rank 2] images of kB1WBytes
     long long* trace;            // optional: CTA 0 records clock64() per role per tile ([tile][16])
 };
 #define B1_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
@@ -121,27 +138,39 @@ block1_kernel(const Block1Params p) {
     uint64_t* x1_empty = bars + 14;  // [2] commit
     uint64_t* wbar = bars + 16;      // weights landed
     uint64_t* raw_full = bars + 17;  // [2] raw fp32 rows of a tile landed (bulk TMA, bytes)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* st_full = bars + 19;   // 256 epilogue threads left the pooled rows of a tile in the staging tile
+    uint64_t* st_done = bars + 21;   // the copy engine has read them
+    uint64_t* p1_ready = bars + 23;  // [2] leader only: the PEER's slab0[buf] is written and its D1[buf] is free (one remote arrive)
+    uint64_t* p2_ready = bars + 25;  // [2] leader only: the peer's slab1[buf] is written and its D2[buf] is free
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // b1[64], b2[64]
     float* s_nrm = s_bias + 128;     // stream mode: [2 windows][mean 64 | 1/std 64] of the tile being converted
+    uint8_t* stage = reinterpret_cast<uint8_t*>(s_nrm + 256);     // kB1Stage bytes: pooled rows on their way to the X2 tape
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NR = p.n_windows * kRW1;
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // pair j of the grid walks the tile pairs j, j + npairs, ...; rank r of the pair takes tile 2 * (pair tile) + r (an odd
+    // tail tile does not exist: its rows lie beyond the chunk, its operands are zeros, nothing of it is stored)
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+    const int my_tiles = ((p.n_tiles + 1) / 2 - pair + npairs - 1) / npairs;
+    auto tile_of = [&](int k) { return 2 * (pair + k * npairs) + (int)rank; };
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&p1_ready[i], 1); ptx::mbar_init(&p2_ready[i], 1); }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&x0_full[i], 128); ptx::mbar_init(&x0_empty[i], 1);
             ptx::mbar_init(&d1_full[i], 1);   ptx::mbar_init(&d1_empty[i], 8);
             ptx::mbar_init(&d2_full[i], 1);   ptx::mbar_init(&d2_empty[i], 8);
         }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&x1_full[i], 256); ptx::mbar_init(&x1_empty[i], 1); }
+        ptx::mbar_init(st_full, 256); ptx::mbar_init(st_done, 1);
         ptx::mbar_init(wbar, 1);
         ptx::mbar_init(&raw_full[0], 1); ptx::mbar_init(&raw_full[1], 1);
         ptx::fence_barrier_init();
     }
     pdl_launch_dependents();
-    if (warp == 12) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    if (warp == 12) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
     // zero the activation slabs once: the shared zero kchunk and the never-written halo rows of slab1 must not hold
     // NaN bit patterns
     for (int i = threadIdx.x; i < (2 * kB1Slab0 + kSlabBytes + 2 * kB1SlabBytes) / 16; i += kB1Threads)
@@ -152,13 +181,14 @@ block1_kernel(const Block1Params p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::cluster_sync();                                        // the peer's barriers exist before anything remote touches them
     // The X2 tape we overwrite may still be read by the previous step's block2, and the stream-mode statistics come from the
     // kernel before us: converters, epilogues and issuers wait.  The conv weights (warp 12) and the raw input rows (loader,
     // warp 13) are written by no kernel of the step: both are requested while the previous kernel drains.
     if (warp == 12 && ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(wbar, 2 * kB1WBytes);
-        ptx::bulk_g2s(w1s, p.w1, kB1WBytes, wbar);
-        ptx::bulk_g2s(w2s, p.w2, kB1WBytes, wbar);
+        ptx::bulk_g2s(w1s, p.w1 + (size_t)rank * kB1WBytes, kB1WBytes, wbar);
+        ptx::bulk_g2s(w2s, p.w2 + (size_t)rank * kB1WBytes, kB1WBytes, wbar);
     }
     if (warp != 13) pdl_wait();
 
@@ -174,7 +204,7 @@ block1_kernel(const Block1Params p) {
             return r - w * kRW1 < 150;
         };
         for (int k = 0; k < my_tiles; ++k) {
-            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
+            const int r0 = tile_of(k) * kB1Rows - 3;
             const uint32_t buf = k & 1;
             if (warp == 0) B1_TRACE(k, 0);
             const TileSegs sg = tile_segs<STREAM>(p, r0);
@@ -268,7 +298,7 @@ block1_kernel(const Block1Params p) {
         // ===== loader: raw fp32 rows of tile k -> slab0[k & 1] by bulk TMA, as soon as conv1(k-2) has drained it =====
         const uint64_t pol_once = ptx::policy_evict_first();     // the input windows are read exactly once: first out of the L2
         for (int k = 0; k < my_tiles; ++k) {
-            const int r0 = (int)(blockIdx.x + k * gridDim.x) * kB1Rows - 3;
+            const int r0 = tile_of(k) * kB1Rows - 3;
             const uint32_t buf = k & 1;
             const TileSegs sg = tile_segs<STREAM>(p, r0);
             ptx::mbar_wait_relaxed(&x0_empty[buf], ((k >> 1) & 1) ^ 1, 256);
@@ -297,7 +327,7 @@ block1_kernel(const Block1Params p) {
                 }
                 // warm L2 with the tile that will use this buffer next
                 if (k + 2 < my_tiles) {
-                    const TileSegs nx = tile_segs<STREAM>(p, (int)(blockIdx.x + (k + 2) * gridDim.x) * kB1Rows - 3);
+                    const TileSegs nx = tile_segs<STREAM>(p, tile_of(k + 2) * kB1Rows - 3);
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
                         if (nx.bytes[j] > 0)
@@ -309,20 +339,50 @@ block1_kernel(const Block1Params p) {
             }
             __syncwarp();
         }
+    } else if (warp == 15) {
+        // ===== store warp: the 62 pooled rows of tile k, staged as 16 runs (part, kchunk) of 992 B -> X2 tape =====
+        for (int k = 0; k < my_tiles; ++k) {
+            const int tile = tile_of(k);
+            ptx::mbar_wait_relaxed(st_full, k & 1);
+            int rows = p.out_rows_cap - tile * (kB1Rows / 2);
+            rows = rows < kB1Rows / 2 ? rows : kB1Rows / 2;
+            if (lane < 16 && rows > 0 && !(p.dbg & 1)) {
+                const int part = lane >> 3, kc = lane & 7;
+                ptx::bulk_s2g(p.out + (part ? p.out_part_stride : 0) + (size_t)kc * p.out_kch_stride + (size_t)(tile * (kB1Rows / 2) + kGuard) * 16,
+                              stage + lane * kB1StageRun, (uint32_t)rows * 16);
+                ptx::bulk_commit_group();
+                ptx::bulk_wait_group_read0();                         // the staging tile may be overwritten
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(st_done);
+        }
+        if (lane < 16) ptx::bulk_wait_group0();                        // every write has been performed before the CTA exits
     } else if (warp == 12 || warp == 14) {
         // ===== MMA issuers (warp-uniform control flow; one elected lane issues): warp 12 = conv1, warp 14 = conv2.
         // Two issuers so that one's serial code between tiles (mbarrier probes, fences, descriptors: ~500 cycles, more
         // than the tensor pipe's short queue covers) is filled by the other's MMAs; each accumulator keeps one issuer.
         {
             ptx::mbar_wait(wbar, 0);
-            constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(128, 128);
-            constexpr uint32_t idesc64 = ptx::make_idesc_bf16_f32(128, 64);
+            if (rank != 0) {
+                // ===== peer CTA: no MMA is issued here.  Each issuer warp tells the leader, once per tile, that this CTA's operand slab
+                // is written and its accumulator buffer is free
+                const bool one = ptx::elect_one();
+                for (int k = 0; k < my_tiles; ++k) {
+                    const uint32_t buf = k & 1, ph = (k >> 1) & 1;
+                    if (warp == 12) { ptx::mbar_wait(&x0_full[buf], ph); ptx::mbar_wait(&d1_empty[buf], ph ^ 1); }
+                    else            { ptx::mbar_wait(&x1_full[buf], ph); ptx::mbar_wait(&d2_empty[buf], ph ^ 1); }
+                    if (one) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(warp == 12 ? &p1_ready[buf] : &p2_ready[buf]), 0));
+                    __syncwarp();
+                }
+            } else {
+            constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(256, 128);
+            constexpr uint32_t idesc64 = ptx::make_idesc_bf16_f32(256, 64);
             const uint32_t w1a = ptx::smem_u32(w1s), w2a = ptx::smem_u32(w2s);
             const uint32_t s0a = ptx::smem_u32(slab0), s1a = ptx::smem_u32(slab1), za = ptx::smem_u32(zchunk);
 
-            // 24 MMAs: 3 taps x 4 kchunk pairs x (A_hi x [W_hi ; W_lo] at N = 128, A_lo x W_hi at N = 64); then the two
-            // completion commits.  KCH = kchunks per part of the A image; with KCH = 7 the pair (6, 7) takes kchunk 7
-            // from the shared zero chunk through its leading-dimension offset.
+            // 24 MMAs of M = 256 (both CTAs): 3 taps x 4 kchunk pairs x (A_hi x [W_hi ; W_lo] at N = 128, A_lo x W_hi at N = 64); then
+            // the two completion commits, multicast to both CTAs.  KCH = kchunks per part of the A image; with KCH = 7 the pair
+            // (6, 7) takes kchunk 7 from the shared zero chunk through its leading-dimension offset.
             auto conv_mmas = [&](uint32_t a_base, int kch, uint32_t w_base, uint32_t d, uint64_t* bar_a, uint64_t* bar_b) {
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -334,13 +394,15 @@ block1_kernel(const Block1Params p) {
                             const bool zpair = (kch == 7 && kk == 3);
                             const uint64_t da_hi = ptx::make_smem_desc(a_hi, zpair ? (za + tap * 16 - a_hi) : (uint32_t)kSlabBytes, 128);
                             const uint64_t da_lo = ptx::make_smem_desc(a_lo, zpair ? (za + tap * 16 - a_lo) : (uint32_t)kSlabBytes, 128);
-                            const uint64_t db = ptx::make_smem_desc(w_base + (tap * 8 + 2 * kk) * 2048, 2048, 128);
-                            ptx::umma_bf16_ss(d, da_hi, db, idesc128, (tap | kk) ? 1u : 0u);
-                            ptx::umma_bf16_ss(d, da_lo, db, idesc64, 1u);
+                            const uint32_t wb = w_base + (tap * 8 + 2 * kk) * (kB1WRows * 16);
+                            const uint64_t db1 = ptx::make_smem_desc(wb, kB1WRows * 16, 128);               // this CTA's 64 rows of [W_hi ; W_lo]
+                            const uint64_t db2 = ptx::make_smem_desc(wb + 64 * 16, kB1WRows * 16, 128);     // this CTA's 32 rows of W_hi
+                            ptx::umma_bf16_ss_pair(d, da_hi, db1, idesc128, (tap | kk) ? 1u : 0u);
+                            ptx::umma_bf16_ss_pair(d, da_lo, db2, idesc64, 1u);
                         }
                     }
-                    ptx::umma_commit(bar_a);
-                    ptx::umma_commit(bar_b);
+                    ptx::umma_commit_pair(bar_a, (uint16_t)0x3);
+                    ptx::umma_commit_pair(bar_b, (uint16_t)0x3);
                 }
                 __syncwarp();
             };
@@ -348,6 +410,7 @@ block1_kernel(const Block1Params p) {
                 const uint32_t buf = k & 1, ph = (k >> 1) & 1;
                 ptx::mbar_wait(&x0_full[buf], ph);
                 ptx::mbar_wait(&d1_empty[buf], ph ^ 1);
+                ptx::mbar_wait_cluster(&p1_ready[buf], ph);
                 ptx::tc_fence_after_sync();
                 B1_TRACE(k, 4);
                 conv_mmas(s0a + buf * kB1Slab0, 7, w1a, tmem_base + buf * 128, &x0_empty[buf], &d1_full[buf]);
@@ -356,12 +419,14 @@ block1_kernel(const Block1Params p) {
                 const uint32_t buf = k & 1, ph = (k >> 1) & 1;
                 ptx::mbar_wait(&x1_full[buf], ph);
                 ptx::mbar_wait(&d2_empty[buf], ph ^ 1);
+                ptx::mbar_wait_cluster(&p2_ready[buf], ph);
                 ptx::tc_fence_after_sync();
                 B1_TRACE(k, 5);
                 conv_mmas(s1a + buf * kB1SlabBytes, 8, w2a, tmem_base + 256 + buf * 128, &x1_empty[buf], &d2_full[buf]);
             };
             if (warp == 12) { for (int k = 0; k < my_tiles; ++k) issue_c1(k); }
             else            { for (int k = 0; k < my_tiles; ++k) issue_c2(k); }
+            }
         }
     } else {
         // ===== epilogue warps 4..11 =====
@@ -373,7 +438,7 @@ block1_kernel(const Block1Params p) {
         const uint32_t tq = tmem_base + h * 32 + ((uint32_t)(q * 32) << 16);
 
         auto epi1 = [&](int k) {
-            const int tile = blockIdx.x + k * gridDim.x;
+            const int tile = tile_of(k);
             const uint32_t buf = k & 1, ph = (k >> 1) & 1;
             const int r = tile * kB1Rows - 2 + rit;           // X1 row
             const bool valid = r >= 0 && pos_mod(r, kRW1) < 150;
@@ -417,12 +482,11 @@ block1_kernel(const Block1Params p) {
             if (warp == 4) B1_TRACE(k, 10);
         };
         auto epi2 = [&](int k) {
-            const int tile = blockIdx.x + k * gridDim.x;
+            const int tile = tile_of(k);
             const uint32_t buf = k & 1, ph = (k >> 1) & 1;
             const int r = tile * kB1Rows - 2 + rit;           // conv2 output row (X1 row space)
-            const int orow = r >> 1;                          // pooled row (arithmetic shift: -2,-1 -> -1)
             const bool valid = r >= 0 && (pos_mod(r, kRW1) >> 1) < 75;
-            const bool store = ((rit >= 2 && rit < 126) || (tile == 0 && rit < 2)) && orow < p.out_rows_cap;
+            const bool store = rit >= 2 && rit < 126;         // pooled rows 0..61 of the tile
             if (warp == 4) B1_TRACE(k, 11);
             ptx::mbar_wait_relaxed(&d2_full[buf], ph);
             if (warp == 4) B1_TRACE(k, 12);
@@ -434,7 +498,7 @@ block1_kernel(const Block1Params p) {
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&d2_empty[buf]);
-            if (p.dbg & 8) return;
+            if (p.dbg & 8) { ptx::mbar_arrive(st_full); return; }
             // MaxPool1d(2,2) first (bias and ReLU commute with max): the two lanes of a pool pair exchange halves, the even
             // lane finishes columns [0,16) of this warp's 32, the odd lane [16,32)
             float y[16];
@@ -453,16 +517,30 @@ block1_kernel(const Block1Params p) {
                 y[i + 2] = valid ? relu_nan(y[i + 2] + b4.z) : 0.f;
                 y[i + 3] = valid ? relu_nan(y[i + 3] + b4.w) : 0.f;
             }
-            if (store && !(p.dbg & 1)) {
-                uint8_t* base = p.out + (size_t)(orow + kGuard) * 16 + (size_t)(h * 4 + odd * 2) * p.out_kch_stride;
+            uint4 ghi[2], glo[2];
+#pragma unroll
+            for (int qd = 0; qd < 2; ++qd) split8(y + qd * 8, ghi[qd], glo[qd]);
+            ptx::mbar_wait_relaxed(st_done, (k & 1) ^ 1);     // the previous tile's rows have left the staging tile
+            if (store) {
+                uint8_t* base = stage + (h * 4 + odd * 2) * kB1StageRun + ((rit >> 1) - 1) * 16;      // [part][kchunk][pooled row][16 B]
 #pragma unroll
                 for (int qd = 0; qd < 2; ++qd) {
-                    uint4 hi, lo;
-                    split8(y + qd * 8, hi, lo);
-                    *reinterpret_cast<uint4*>(base + (size_t)qd * p.out_kch_stride) = hi;
-                    *reinterpret_cast<uint4*>(base + (size_t)qd * p.out_kch_stride + p.out_part_stride) = lo;
+                    *reinterpret_cast<uint4*>(base + qd * kB1StageRun) = ghi[qd];
+                    *reinterpret_cast<uint4*>(base + qd * kB1StageRun + 8 * kB1StageRun) = glo[qd];
                 }
             }
+            if (tile == 0 && rit < 2) {
+                // the tape's leading guard row (X2 row -1: conv3's zero padding in front of window 0).  The tape's place in the
+                // workspace depends on the chunk size, so the row may hold another call's data: written with every tile 0
+                uint8_t* g = p.out + (size_t)(kGuard - 1) * 16 + (size_t)(h * 4 + odd * 2) * p.out_kch_stride;
+#pragma unroll
+                for (int qd = 0; qd < 2; ++qd) {
+                    *reinterpret_cast<uint4*>(g + (size_t)qd * p.out_kch_stride) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(g + (size_t)qd * p.out_kch_stride + p.out_part_stride) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            ptx::fence_proxy_async_smem();                    // generic-proxy writes -> visible to the copy engine
+            ptx::mbar_arrive(st_full);
             if (warp == 4) B1_TRACE(k, 13);
         };
         for (int k = 0; k < my_tiles; ++k) {
@@ -474,7 +552,8 @@ block1_kernel(const Block1Params p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 12) ptx::tmem_dealloc(tmem_base, 512);
+    ptx::cluster_sync();              // no CTA leaves (or frees its TMEM) while its peer's MMAs / arrives may still reach it
+    if (warp == 12) ptx::tmem_dealloc_pair(tmem_base, 512);
 }
 
 }  // namespace tc

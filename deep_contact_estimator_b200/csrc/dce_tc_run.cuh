@@ -87,11 +87,13 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             b.out = x2; b.out_part_stride = W.x2.part_stride; b.out_kch_stride = W.x2.kch_stride; b.out_rows_cap = W.x2.m_tiles * 128;
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = opt.block1_dbg; b.trace = (opt.trace_layer < 0) ? opt.trace : nullptr;
-            const int grid = b.n_tiles < sm_count ? b.n_tiles : sm_count;
+            int pairs = (b.n_tiles + 1) / 2 < sm_count / 2 ? (b.n_tiles + 1) / 2 : sm_count / 2;     // CTA pairs: two tiles in lockstep
+            if (pairs < 1) pairs = 1;
+            const int grid = 2 * pairs;
             if (stream_mode)
-                DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
+                DCE_KL(ctx, "tc_block1_stream", { cudaError_t le_ = launch_pdl_pairs(block1_kernel<true>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
             else
-                DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl(block1_kernel<false>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
+                DCE_KL(ctx, "tc_block1", { cudaError_t le_ = launch_pdl_pairs(block1_kernel<false>, dim3(grid), dim3(kB1Threads), kB1SmemBytes, s, b); (void)le_; });
         } else {
         // ---- ingest (a2/a3/a4): windows -> X0 tape
         const int iblocks = W.x0.m_tiles * 4;
