@@ -136,7 +136,11 @@ __host__ __device__ constexpr int tapgemm_threads(int MT) { return (kEpiWarps + 
 // re-stream the same few weight blocks from the same L2 lines for every tile, which hot-spots L2.
 // AT = 1: the A operand is row-major in global memory ([part][row][K] bf16: what block2 can write in whole lines) and
 // arrives by tensor-map TMA, one box of 128 rows x 64 B (KSA = 4 kchunks) per M-tile and part, in the 64-byte swizzle.
-template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1, int WST = 0, int AT = 0>
+// KS = 2 (fc.3, MT = 1): TWO issuer warps share one tile along K — issuer i takes the K-stages i, i + 2, ... into its own
+// accumulator, the epilogue adds the two.  A single issuer at N = 128 spends ~93 cycles per 64-cycle MMA (mbarrier probe,
+// descriptors, commit per stage, and the pipe queues only an MMA or two ahead); two issuers fill each other's gaps exactly
+// as fc.0's two accumulators do, and every accumulator still sees its MMAs in one fixed order (bit-reproducible).
+template <int BN, int TAPS, int KSA, int NSTAGE, int MT = 1, int WST = 0, int AT = 0, int KS = 1>
 struct TapGemmCfg {
     static constexpr int A_PART = AT ? 128 * KSA * 16 : KSA * kSlabBytes;
     static constexpr int A_TILE = 2 * A_PART;                 // hi + lo slabs of one M-tile
@@ -149,8 +153,10 @@ struct TapGemmCfg {
     // BN = 240 (fc.0: 2048 = 8 x 240 + 128 output features -> 9 n-tiles x 16 M-tile pairs = 144 tiles for 148 SMs instead of
     // 128): the MMA is N = 240, the accumulator keeps a 256-column pitch, and the epilogue masks the columns that do not exist
     static constexpr int ACC_COLS = (BN == 240) ? 256 : BN;
-    static constexpr int NBUF = (2 * MT * ACC_COLS <= 512) ? 2 : 1;   // accumulator buffers (epilogue / MMA overlap)
-    static constexpr int TMEM_COLS = NBUF * MT * ACC_COLS;
+    static constexpr int ACCS = MT * KS;                              // accumulators (= issuer warps) per tile
+    static constexpr int NBUF = (2 * ACCS * ACC_COLS <= 512) ? 2 : 1; // accumulator buffers (epilogue / MMA overlap)
+    static constexpr int TMEM_COLS = NBUF * ACCS * ACC_COLS;
+    static_assert(KS == 1 || (KS == 2 && MT == 1 && WST == 0), "K-split issuers: one M-tile, streamed weights");
     static constexpr int BAR_BYTES = (2 * NSTAGE + 5) * 8 + 8;
     static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_BYTES = RING_BYTES + WRES_BYTES + BAR_BYTES + kEpiWarps * (ACC_COLS / 2) * 4;
@@ -166,11 +172,12 @@ struct TapGemmCfg {
 #endif
 #define TG_TRACE(k, ev) do { if (DCE_TRACE && p.trace && blockIdx.x == 0 && (k) < 60 && (threadIdx.x & 31) == 0) p.trace[(k) * 16 + (ev)] = clock64(); } while (0)
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0>
-__global__ void __launch_bounds__(tapgemm_threads(MT), 1)
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0, int KS = 1>
+__global__ void __launch_bounds__(tapgemm_threads(MT * KS), 1)
 tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
-    constexpr int kProducerWarp0 = kEpiWarps + MT;
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT>;
+    constexpr int kProducerWarp0 = kEpiWarps + MT * KS;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT, KS>;
+    constexpr int ACCS = Cfg::ACCS;
     constexpr int NBUF = Cfg::NBUF;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wres = smem + Cfg::RING_BYTES;                       // resident weight image (WST > 0)
@@ -190,8 +197,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     const int total_tiles = (p.m_tiles / MT) * p.n_tiles;      // p.m_tiles is a multiple of MT (make_tape)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], MT); }
-        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], MT); ptx::mbar_init(&tempty[b], kEpiWarps); }
+        for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(&full[i], kProdWarps); ptx::mbar_init(&empty[i], MT); }   // KS = 2: a slot belongs to ONE issuer (MT = 1)
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], ACCS); ptx::mbar_init(&tempty[b], kEpiWarps); }
         ptx::mbar_init(wbar, 1);
         ptx::fence_barrier_init();
     }
@@ -270,30 +277,32 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
         // current stage's MMAs, where the pipe still has queued work.
         {
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
-            const int mt = warp - kMmaWarp;
+            const int iw = warp - kMmaWarp;                      // issuer = accumulator index
+            const int mt = KS > 1 ? 0 : iw, ks = KS > 1 ? iw : 0;
             const bool leader = ptx::elect_one();
             const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             const uint32_t total_stages = (uint32_t)my_tiles * p.stages;
             if (WST) ptx::mbar_wait(wbar, 0);
-            uint32_t it = 0;
+            uint32_t it = ks;
             if (my_tiles > 0) {
                 ptx::mbar_wait(&tempty[0], 1);                       // fresh barrier: passes
-                ptx::mbar_wait(&full[0], 0);
+                ptx::mbar_wait(&full[ks % NSTAGE], 0);
                 ptx::tc_fence_after_sync();
             }
             for (int tcount = 0; tcount < my_tiles; ++tcount) {
                 const uint32_t buf = tcount % NBUF;
-                if (mt == 0) TG_TRACE(tcount, 2);
-                const uint32_t d = tmem_base + buf * (MT * ACC) + mt * ACC;
+                if (iw == 0) TG_TRACE(tcount, 2);
+                const uint32_t d = tmem_base + buf * (ACCS * ACC) + iw * ACC;
                 // A single accumulator buffer (fc.0: 2 x 256 columns fill the TMEM): the epilogue that frees it cannot start
                 // before this issuer's own `tfull` commit of the previous tile, so the buffer is awaited here, at the top of
                 // the tile, not by the mid-stage probe below (which would wait for it BEFORE that commit: a deadlock found
                 // by tools/simulate_block2_protocol.py).
                 if (NBUF == 1 && tcount > 0) { ptx::mbar_wait(&tempty[0], (tcount & 1) ^ 1); ptx::tc_fence_after_sync(); }
-                for (int s = 0; s < p.stages; ++s, ++it) {
+                for (int s = ks; s < p.stages; s += KS, it += KS) {     // p.stages is a multiple of KS
                     const uint32_t slot = it % NSTAGE;
-                    if (mt == 0 && s == 0) TG_TRACE(tcount, 4);
-                    if (mt == 0 && s == p.stages - 1) TG_TRACE(tcount, 5);
+                    const bool last_stage = s + KS >= p.stages;       // this issuer's last stage of the tile
+                    if (iw == 0 && s == 0) TG_TRACE(tcount, 4);
+                    if (iw == 0 && last_stage) TG_TRACE(tcount, 5);
                     const uint32_t a0 = ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + mt * Cfg::A_TILE;
                     const uint32_t b0 = WST ? ptx::smem_u32(wres) + s * Cfg::B_BYTES : ptx::smem_u32(smem + slot * Cfg::STAGE_BYTES) + Cfg::A_BYTES;
 #pragma unroll
@@ -304,7 +313,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                             const uint32_t b_hi = b0 + (tap * KSA + 2 * kk) * Cfg::B_TAPCH;
                             const uint64_t db_hi = ptx::make_smem_desc(b_hi, Cfg::B_TAPCH, 128);
                             const uint64_t db_lo = ptx::make_smem_desc(b_hi + Cfg::B_PART, Cfg::B_TAPCH, 128);
-                            const uint32_t first = (s == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                            const uint32_t first = (s == ks && tap == 0 && kk == 0) ? 0u : 1u;
                             const uint32_t a_hi = AT ? a0 + kk * 32 : a0 + (2 * kk) * kSlabBytes + arow * 16;
                             const uint64_t da_hi = AT ? ptx::make_smem_desc_sw64(a_hi) : ptx::make_smem_desc(a_hi, kSlabBytes, 128);
                             const uint64_t da_lo = AT ? ptx::make_smem_desc_sw64(a_hi + Cfg::A_PART) : ptx::make_smem_desc(a_hi + Cfg::A_PART, kSlabBytes, 128);
@@ -314,19 +323,19 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                                 ptx::umma_bf16_ss(d, da_hi, db_hi, idesc, 1u);
                             }
                             // mid-stage: probe what the NEXT stage needs while MMAs of this one are still queued
-                            if (tap == (TAPS - 1) / 2 && kk == (KSA / 2 - 1) / 2 && it + 1 < total_stages) {
-                                if (NBUF > 1 && s == p.stages - 1) {           // next stage opens the next tile
+                            if (tap == (TAPS - 1) / 2 && kk == (KSA / 2 - 1) / 2 && it + KS < total_stages) {
+                                if (NBUF > 1 && last_stage) {                  // next stage opens the next tile
                                     const uint32_t nt = tcount + 1;
                                     ptx::mbar_wait(&tempty[nt % NBUF], ((nt / NBUF) & 1) ^ 1);
                                 }
-                                ptx::mbar_wait(&full[(it + 1) % NSTAGE], ((it + 1) / NSTAGE) & 1);
+                                ptx::mbar_wait(&full[(it + KS) % NSTAGE], ((it + KS) / NSTAGE) & 1);
                                 ptx::tc_fence_after_sync();
                             }
                         }
                     }
                     if (leader) {
                         ptx::umma_commit(&empty[slot]);          // this issuer's MMAs on the slot have retired
-                        if (s == p.stages - 1) ptx::umma_commit(&tfull[buf]);   // this accumulator is complete
+                        if (last_stage) ptx::umma_commit(&tfull[buf]);          // this accumulator is complete
                     }
                 }
             }
@@ -392,7 +401,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
             }
             constexpr int CPM = HALF / 32;                   // 32-column chunks per M-tile for this warp
             constexpr int NCH = MT * CPM;
-            const uint32_t taddr0 = tmem_base + buf * (MT * ACC) + h * HALF + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr0 = tmem_base + buf * (ACCS * ACC) + h * HALF + ((uint32_t)(q * 32) << 16);
             auto chunk_addr = [&](int ci) { return taddr0 + (ci / CPM) * ACC + (ci % CPM) * 32; };
 
             float lg[16];                                    // EPI_FC_LOGITS: this thread's share of its row's 16 logits
@@ -471,6 +480,16 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                 }
             };
 
+            // KS = 2: the second issuer's accumulator (the odd K-stages) sits ACC columns further: added here
+            auto fold = [&](uint32_t (&v)[32], int ci) {
+                if (KS > 1) {
+                    uint32_t w[32];
+                    ptx::tmem_ld32(chunk_addr(ci) + ACC, w);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                }
+            };
             // software pipeline over the chunks: the TMEM load of chunk i+1 is in flight while chunk i is processed
             if (!(p.dbg & 2)) {
                 uint32_t va[32], vb[32];
@@ -479,10 +498,12 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                 for (int ci = 0; ci < NCH; ci += 2) {
                     ptx::tmem_ld_wait();
                     if (ci + 1 < NCH) ptx::tmem_ld32(chunk_addr(ci + 1), vb);
+                    fold(va, ci);
                     process(va, ci);
                     if (ci + 1 < NCH) {
                         ptx::tmem_ld_wait();
                         if (ci + 2 < NCH) ptx::tmem_ld32(chunk_addr(ci + 2), va);
+                        fold(vb, ci + 1);
                         process(vb, ci + 1);
                     }
                 }
@@ -792,10 +813,11 @@ inline size_t workspace_bytes(int64_t max_windows) {
     return make_workspace(max_windows < kChunk ? max_windows : kChunk).end;
 }
 
-template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0>
+template <int BN, int TAPS, int KSA, int NSTAGE, int EPI, int MT = 1, int WST = 0, int AT = 0, int KS = 1>
 inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmParams& p) {
-    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT>;
-    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, AT>;
+    using Cfg = TapGemmCfg<BN, TAPS, KSA, NSTAGE, MT, WST, AT, KS>;
+    auto kern = tapgemm_kernel<BN, TAPS, KSA, NSTAGE, EPI, MT, WST, AT, KS>;
+    if (KS > 1 && p.stages % KS) return DCE_EINVAL;
     if (WST && (p.stages != WST || p.n_tiles != 1)) return DCE_EINVAL;
     constexpr int kSmem = Cfg::SMEM_BYTES + (EPI == EPI_FC_LOGITS ? BN * 64 : 0);      // + [BN][16] fp32 of the next layer
     static_assert(kSmem <= 232448, "exceeds 227 KB");
@@ -806,7 +828,7 @@ inline int launch_layer(Ctx& ctx, const char* name, int sm_count, const TapGemmP
     }
     const int tiles = (p.m_tiles / MT) * p.n_tiles;
     const int grid = tiles < sm_count ? tiles : sm_count;         // persistent: a CTA walks tiles blockIdx.x, + gridDim.x, ...
-    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT)), kSmem, ctx.stream, p); (void)le_; });
+    DCE_KL(ctx, name, { cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(tapgemm_threads(MT * KS)), kSmem, ctx.stream, p); (void)le_; });
     return DCE_OK;
 }
 

@@ -214,10 +214,10 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
                 // that finishes an M-tile's last n-tile does them
                 p.tickets = reinterpret_cast<unsigned*>(ws + W.o_tickets); p.b3 = bp.b[6];
                 p.logits = logits ? logits + c0 * 16 : nullptr; p.cls = cls ? cls + c0 : nullptr; p.bits = bits ? bits + c0 * 4 : nullptr;
-                if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3_argmax", sm_count, p)) != DCE_OK) return rc;
+                if ((rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 0, 2>(ctx, "tc_fc2_fc3_argmax", sm_count, p)) != DCE_OK) return rc;
                 continue;
             }
-            rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1>(ctx, "tc_fc2_fc3", sm_count, p);
+            rc = launch_layer<128, 1, 4, 6, EPI_FC_LOGITS, 1, 0, 0, 2>(ctx, "tc_fc2_fc3", sm_count, p);
             if (rc != DCE_OK) return rc;
             DCE_KL(ctx, "logits_argmax_bits", { cudaError_t le_ = launch_pdl(fp32::logit_shares_argmax_kernel, dim3((m + 127) / 128), dim3(128), 0, s,
                 (const float*)h2, bp.b[6], (int64_t)m, 2 * kLayers[5].n_tiles, logits ? logits + c0 * 16 : nullptr, cls ? cls + c0 : nullptr,
