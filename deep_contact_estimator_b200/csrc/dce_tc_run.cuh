@@ -74,10 +74,25 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
         if (opt.fuse_block1) {
             // ---- fused ingest + conv1 + conv2 + pool (a2-a6): windows -> X2
             static DeviceOnce attr_once;
+            static int max_pairs[64] = {};                   // per device: how many 2-CTA clusters of this kernel are resident at once
+            int dev_ = 0;
+            cudaGetDevice(&dev_);
+            dev_ &= 63;
             if (auto first_ = attr_once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1SmemBytes);
-                if (e != cudaSuccess) { first_.fail(); ctx.err = e; return DCE_ECUDA; }
+                int n_ = 0;
+                if (e == cudaSuccess) {
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3(2); cfg.blockDim = dim3(kB1Threads); cfg.dynamicSmemBytes = kB1SmemBytes;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    e = cudaOccupancyMaxActiveClusters(&n_, block1_kernel<false>, &cfg);
+                }
+                if (e != cudaSuccess || n_ < 1) { first_.fail(); ctx.err = (e != cudaSuccess) ? e : cudaErrorLaunchOutOfResources; return DCE_ECUDA; }
+                max_pairs[dev_] = n_;
             }
             Block1Params b{};
             b.x = stream_mode ? src : src + (size_t)c0 * 150 * 54; b.first = first + c0; b.n_windows = m; b.total_rows = total_rows;
@@ -88,6 +103,7 @@ inline int run(const char* buf, const PackedLayout& L, const BiasPtrs& bp, const
             b.n_tiles = (m * kRW1 + kB1Rows - 1) / kB1Rows;
             b.dbg = opt.block1_dbg; b.trace = (opt.trace_layer < 0) ? opt.trace : nullptr;
             int pairs = (b.n_tiles + 1) / 2 < sm_count / 2 ? (b.n_tiles + 1) / 2 : sm_count / 2;     // CTA pairs: two tiles in lockstep
+            if (pairs > max_pairs[dev_]) pairs = max_pairs[dev_];       // a TPC with one SM fused off hosts no pair: never queue a persistent cluster behind another
             if (pairs < 1) pairs = 1;
             const int grid = 2 * pairs;
             if (stream_mode)
