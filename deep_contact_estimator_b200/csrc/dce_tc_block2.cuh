@@ -190,15 +190,20 @@ block2_kernel(const Block2Params p) {
         // The next block's barrier is probed in the middle of this block's MMAs.
         const uint32_t total_blocks = (uint32_t)my_tiles * 12;
         if (my_tiles > 0) { ptx::mbar_wait(&wfull[0], 0); ptx::tc_fence_after_sync(); }
-        auto stage_mmas = [&](uint32_t slab, int kch_total, int s, uint32_t d, bool first_stage) {
+        // Descriptors are built by ADDING 16-byte units to the low word of a constant descriptor (start addresses stay below
+        // 2^18, so no carry reaches the LBO field at bit 16): one uniform add per descriptor instead of shift / mask / or — the
+        // thread that issues the MMAs is the kernel's critical path, the pipe queues only an MMA or two ahead of it
+        const uint64_t kDA = ptx::make_smem_desc(0, kSlabBytes, 128), kDB = ptx::make_smem_desc(0, 4096, 128);
+        const uint32_t sa16 = sa >> 4, sb16 = sb >> 4, rg16 = rg >> 4;
+        auto stage_mmas = [&](uint32_t slab16, int kch_total, int s, uint32_t d, bool first_stage) {
             const uint32_t slot = it % kB2Ring;
-            const uint32_t b0 = rg + slot * kB2WBlock;
+            const uint32_t b16 = rg16 + slot * (kB2WBlock >> 4);
+            const uint32_t a16 = slab16 + (uint32_t)(s * 2) * (kSlabBytes >> 4);
 #pragma unroll
             for (int tap = 0; tap < 3; ++tap) {
-                const uint32_t a_hi = slab + (uint32_t)(s * 2) * kSlabBytes + tap * 16;
-                const uint64_t db = ptx::make_smem_desc(b0 + tap * 8192, 4096, 128);
-                const uint64_t da_hi = ptx::make_smem_desc(a_hi, kSlabBytes, 128);
-                const uint64_t da_lo = ptx::make_smem_desc(a_hi + (uint32_t)kch_total * kSlabBytes, kSlabBytes, 128);
+                const uint64_t db = kDB + (uint64_t)(b16 + tap * (8192 >> 4));
+                const uint64_t da_hi = kDA + (uint64_t)(a16 + tap);
+                const uint64_t da_lo = kDA + (uint64_t)(a16 + tap + (uint32_t)kch_total * (kSlabBytes >> 4));
                 if (leader) {
                     ptx::umma_bf16_ss(d, da_hi, db, idesc256, (first_stage && tap == 0) ? 0u : 1u);
                     ptx::umma_bf16_ss(d, da_lo, db, idesc128, 1u);
@@ -217,7 +222,7 @@ block2_kernel(const Block2Params p) {
             ptx::mbar_wait(d3_empty, (k & 1) ^ 1);               // epilogue 1 of tile k-1 holds D3 in registers
             ptx::tc_fence_after_sync();
             B2_TRACE(k, 1);
-            for (int s = 0; s < 4; ++s) stage_mmas(sa, 8, s, tmem_base, s == 0);
+            for (int s = 0; s < 4; ++s) stage_mmas(sa16, 8, s, tmem_base, s == 0);
             if (leader) { ptx::umma_commit(a_empty); ptx::umma_commit(d3_full); }
         };
         auto issue_c4 = [&](int k) {
@@ -226,7 +231,7 @@ block2_kernel(const Block2Params p) {
             ptx::mbar_wait(d4_empty, (k & 1) ^ 1);               // epilogue 2 of tile k-1 holds D4 in registers
             ptx::tc_fence_after_sync();
             B2_TRACE(k, 3);
-            for (int s = 0; s < 8; ++s) stage_mmas(sb, 16, s, tmem_base + 256, s == 0);
+            for (int s = 0; s < 8; ++s) stage_mmas(sb16, 16, s, tmem_base + 256, s == 0);
             if (leader) { ptx::umma_commit(x3_empty); ptx::umma_commit(d4_full); }
             B2_TRACE(k, 4);
         };
