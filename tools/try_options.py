@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of handle options on the GPU: bit-equality of the results against the default kernels at several batch sizes,
 then the batch-4096 step and per-kernel CUDA-event times, two passes (the second runs power-capped).  Run under a timeout:
-    timeout 180 python tools/try_options.py fc_pair=1 [key=value ...]  [-- second set ...]"""
+    timeout 180 python tools/try_options.py block2_dbg=2 [key=value ...]  [-- second set ...]"""
 import os
 import sys
 
