@@ -71,4 +71,4 @@ def test_fused_kernel_protocols_simulated():
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
     n, missed = sim.check(runs=60)
-    assert n == 60 * 4 * 2 and missed == []
+    assert n == 60 * 4 * 2 + 3 * 60 * 3 and missed == []

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Randomised discrete-event simulation of the mbarrier protocols of the two fused convolution kernels
-(csrc/dce_tc_block2.cuh, csrc/dce_tc_block1.cuh): every warp role is a coroutine that waits on / arrives at mbarriers
+(csrc/dce_tc_block2.cuh, csrc/dce_tc_block1.cuh) and of tapgemm_kernel (csrc/dce_tc.cuh: fc.0 with two accumulators in one
+TMEM buffer, fc.3 with two issuers on alternating K-stages, the layer-wise convolutions): every warp role is a coroutine that waits on / arrives at mbarriers
 exactly as the kernel does, the tensor pipe is an in-order queue whose tcgen05.commit entries arrive when everything
 before them has retired, bulk copies land after a random latency.  Durations are drawn at random, so many interleavings
 are explored.  Checked on every run:
@@ -457,6 +458,81 @@ def simulate_block1(seed, tiles=7, mutate=None, epi_warps=2):
     return sim.now
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# tapgemm_kernel (fc.0: MT = 2 issuers, ONE accumulator buffer; fc.3: KS = 2 issuers on alternating K-stages, two buffers):
+# 4 producer warps fill a ring of NSTAGE slots, the issuers probe the NEXT stage's barrier (and, with two buffers, the next
+# tile's accumulator) in the middle of the current stage, i.e. before they commit it; with one buffer the accumulator is
+# awaited at the top of the tile (the order that does not deadlock: DESIGN.md, round 1)
+# ---------------------------------------------------------------------------------------------------------------
+def simulate_tapgemm(seed, tiles=3, MT=1, KS=1, NBUF=2, NSTAGE=4, stages=6, mutate=None, epi_warps=4, prod_warps=2):
+    rng = random.Random(seed)
+    sim = Sim(rng, pipe_depth=3)
+    R = lambda lo, hi: rng.uniform(lo, hi)
+    skip = lambda tag: mutate == tag
+    ACCS = MT * KS
+    ring = [[Res(f"ring{i}.{p}") for p in range(prod_warps)] for i in range(NSTAGE)]
+    acc = [[Res(f"acc{b}.{i}") for i in range(ACCS)] for b in range(2)]
+    full = [Bar(f"full{i}", prod_warps) for i in range(NSTAGE)]
+    empty = [Bar(f"empty{i}", MT) for i in range(NSTAGE)]
+    tfull = [Bar(f"tfull{b}", ACCS) for b in range(2)]
+    tempty = [Bar(f"tempty{b}", epi_warps) for b in range(2)]
+    total = tiles * stages
+
+    def producer(pw):
+        for it in range(total):
+            slot = it % NSTAGE
+            if not skip("empty"):
+                yield ("wait", empty[slot], it // NSTAGE - 1)
+            yield ("copy", R(30, 400), (ring[slot][pw], it), None, full[slot])
+            yield ("delay", R(1, 10))
+
+    def issuer(iw):
+        mt, ks = (0, iw) if KS > 1 else (iw, 0)
+        it = ks
+        if tiles:
+            yield ("wait", tempty[0], -1)
+            yield ("wait", full[ks % NSTAGE], 0)
+        for t in range(tiles):
+            buf = t % NBUF
+            if NBUF == 1 and t > 0 and not skip("tempty"):
+                yield ("wait", tempty[0], t - 1)
+            for s_ in range(ks, stages, KS):
+                slot = it % NSTAGE
+                last = s_ + KS >= stages
+                reads = [(r, it) for r in ring[slot]]
+                yield ("mma", R(6, 14), reads, [(acc[buf][iw], t)])
+                if it + KS < total:
+                    if NBUF > 1 and last and not skip("tempty"):
+                        nt = t + 1
+                        yield ("wait", tempty[nt % NBUF], nt // NBUF - 1)
+                    if not skip("full"):
+                        yield ("wait", full[(it + KS) % NSTAGE], (it + KS) // NSTAGE)
+                yield ("mma", R(6, 14), reads, [(acc[buf][iw], t)])
+                yield ("commit", [empty[slot]] + ([tfull[buf]] if last else []))
+                it += KS
+
+    def epilogue(w):
+        for t in range(tiles):
+            buf = t % NBUF
+            yield ("wait", tfull[buf], t // NBUF)
+            yield ("rw", R(20, 300) if rng.random() < 0.7 else R(300, 4000), [(a, t) for a in acc[buf]], [])
+            yield ("arrive", tempty[buf])
+
+    for pw in range(prod_warps):
+        sim.spawn(f"producer{pw}", producer(pw))
+    for iw in range(ACCS):
+        sim.spawn(f"issuer{iw}", issuer(iw))
+    for w in range(epi_warps):
+        sim.spawn(f"epi{w}", epilogue(w))
+    sim.run()
+    return sim.now
+
+
+TAPGEMM_CONFIGS = [dict(MT=2, KS=1, NBUF=1, NSTAGE=3, stages=6),      # fc.0: two accumulators fill the TMEM, one buffer
+                   dict(MT=1, KS=2, NBUF=2, NSTAGE=6, stages=8),      # fc.3: two issuers on alternating K-stages
+                   dict(MT=1, KS=1, NBUF=2, NSTAGE=4, stages=5)]      # the layer-wise convolutions
+TAPGEMM_MUTATIONS = ["empty", "tempty", "full"]
+
 BLOCK2_MUTATIONS = ["wempty", "a_empty", "d3_empty", "d4_empty", "x3_empty", "st_empty"]
 # (block1's waits on d2_empty and x1_empty are implied by the order in which the eight epilogue warps work — epilogue 1 of
 # tile k comes after epilogue 2 of tile k-2, which waited for conv2 of tile k-2 — so removing them changes nothing
@@ -473,6 +549,21 @@ def check(runs=200, tiles=(1, 2, 3, 7)):
             simulate_block1(seed * 11 + t, tiles=t)
             n += 2
     missed = []
+    for ci, cfg in enumerate(TAPGEMM_CONFIGS):
+        for seed in range(runs):
+            for t in tiles[:3]:
+                simulate_tapgemm(seed * 13 + t, tiles=t, **cfg)
+                n += 1
+        for m in TAPGEMM_MUTATIONS:
+            caught = False
+            for seed in range(max(60, runs // 2)):
+                try:
+                    simulate_tapgemm(seed, tiles=4, mutate=m, **cfg)
+                except Violation:
+                    caught = True
+                    break
+            if not caught:
+                missed.append(f"tapgemm{ci}:{m}")
     for name, fn, muts in (("block2", simulate_block2, BLOCK2_MUTATIONS), ("block1", simulate_block1, BLOCK1_MUTATIONS)):
         for m in muts:
             caught = False
