@@ -399,6 +399,12 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     out_off[mt] = (size_t)(row + kGuard) * 16;
                 }
             }
+            // the chunk loop below is a real loop (its body must stay in the instruction cache: see there), so the per-M-tile
+            // values are picked with selects, never by indexing a register array with a runtime value
+            auto pick_i = [&](const int (&a)[MT], int mt) { return MT == 1 ? a[0] : (mt ? a[MT - 1] : a[0]); };
+            auto pick_b = [&](const bool (&a)[MT], int mt) { return MT == 1 ? a[0] : (mt ? a[MT - 1] : a[0]); };
+            auto pick_z = [&](const size_t (&a)[MT], int mt) { return MT == 1 ? a[0] : (mt ? a[MT - 1] : a[0]); };
+            static_assert(MT <= 2, "pick_*: two M-tiles at most");
             constexpr int CPM = HALF / 32;                   // 32-column chunks per M-tile for this warp
             constexpr int NCH = MT * CPM;
             const uint32_t taddr0 = tmem_base + buf * (ACCS * ACC) + h * HALF + ((uint32_t)(q * 32) << 16);
@@ -420,7 +426,10 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     y[i + 3] = relu_nan(__uint_as_float(v[i + 3]) + b4.w);
                 }
                 if (EPI == EPI_FC_LOGITS) {
-                    // fc.6 folded into fc.3's epilogue: H2 never leaves the registers (smem reads are warp broadcasts)
+                    // fc.6 folded into fc.3's epilogue: H2 never leaves the registers (smem reads are warp broadcasts).  This layer's
+                    // thread has two chunks, i.e. ONE pass of the loop below: straight-line code.  A short loop over eight columns
+                    // (re-used instructions, software-pipelined TMEM loads) was measured too: 14.4 k cycles instead of 8.2 k — the
+                    // 256 broadcast LDS.128 per thread want the deep interleaving the unrolled form gives them
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float4* wr = s_w3 + (h * HALF + c0 + i) * 4;
@@ -436,8 +445,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     return;
                 }
                 if (EPI == EPI_FC_F32) {
-                    if (rows[mt] < p.n_valid) {
-                        float* dst = p.out_f32 + (size_t)rows[mt] * p.N + n0 + c0;
+                    if (pick_i(rows, mt) < p.n_valid) {
+                        float* dst = p.out_f32 + (size_t)pick_i(rows, mt) * p.N + n0 + c0;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
@@ -450,7 +459,7 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     for (int i = 0; i < 32; ++i) y[i] = max_nan(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));
                 }
                 if (EPI == EPI_TAPE || EPI == EPI_POOL_TAPE) {
-                    if (!valid[mt]) {
+                    if (!pick_b(valid, mt)) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) y[i] = 0.f;                  // guard rows stay zero
                     }
@@ -462,19 +471,19 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     const int kch = (n0 + c0) / 8 + qd;
                     if (BN == 240 && (h * HALF + c0 + qd * 8 >= BN || n0 + c0 + qd * 8 >= p.N)) continue;   // columns of the pitch / of the last n-tile that do not exist
                     if (EPI == EPI_TAPE || EPI == EPI_FC_TAPE) {
-                        uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + out_off[mt];
+                        uint8_t* dst = p.out + (size_t)kch * p.out_kch_stride + pick_z(out_off, mt);
                         *reinterpret_cast<uint4*>(dst) = hi;
                         *reinterpret_cast<uint4*>(dst + p.out_part_stride) = lo;
-                        if (EPI == EPI_TAPE && zero_prev[mt]) {
+                        if (EPI == EPI_TAPE && pick_b(zero_prev, mt)) {
                             *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
                             *reinterpret_cast<uint4*>(dst + p.out_part_stride - 16) = make_uint4(0, 0, 0, 0);
                         }
                     } else {
                         // pooled: even lane writes the hi part, odd lane the lo part of the pooled row
-                        if (out_off[mt] != (size_t)-1) {
-                            uint8_t* dst = p.out + (EPI == EPI_POOL_FC ? (size_t)kch * 16 : (size_t)kch * p.out_kch_stride) + out_off[mt] + ((lane & 1) ? p.out_part_stride : 0);
+                        if (pick_z(out_off, mt) != (size_t)-1) {
+                            uint8_t* dst = p.out + (EPI == EPI_POOL_FC ? (size_t)kch * 16 : (size_t)kch * p.out_kch_stride) + pick_z(out_off, mt) + ((lane & 1) ? p.out_part_stride : 0);
                             *reinterpret_cast<uint4*>(dst) = (lane & 1) ? lo : hi;
-                            if (EPI == EPI_POOL_TAPE && zero_prev[mt]) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
+                            if (EPI == EPI_POOL_TAPE && pick_b(zero_prev, mt)) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0, 0, 0, 0);
                         }
                     }
                 }
@@ -490,11 +499,14 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
                 }
             };
-            // software pipeline over the chunks: the TMEM load of chunk i+1 is in flight while chunk i is processed
+            // software pipeline over the chunks: the TMEM load of chunk i+1 is in flight while chunk i is processed.  NOT
+            // unrolled: a CTA runs this epilogue once or a few times per launch, so unrolled (fc.0: 8 chunks = 42 KB of
+            // straight-line code) every instruction line is a cold instruction-cache miss — measured 3 500 cycles per
+            // 330-instruction chunk, 28 k cycles per tile, 10 % of the kernel; as a loop the second pass on hits
             if (!(p.dbg & 2)) {
                 uint32_t va[32], vb[32];
                 ptx::tmem_ld32(chunk_addr(0), va);
-#pragma unroll
+#pragma unroll 1
                 for (int ci = 0; ci < NCH; ci += 2) {
                     ptx::tmem_ld_wait();
                     if (ci + 1 < NCH) ptx::tmem_ld32(chunk_addr(ci + 1), vb);
