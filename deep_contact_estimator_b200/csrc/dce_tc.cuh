@@ -208,7 +208,13 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+#if DCE_TRACE
+    if (p.trace && blockIdx.x < 60 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[blockIdx.x * 16 + 12] = (long long)t_; }
+#endif
     pdl_wait();                                                 // everything the previous kernel wrote is visible from here on
+#if DCE_TRACE
+    if (p.trace && blockIdx.x < 60 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[blockIdx.x * 16 + 13] = (long long)t_; }
+#endif
 
     if (warp >= kProducerWarp0) {
         // ===== TMA producers (warp-uniform loops; one elected lane per warp issues) =====
@@ -567,6 +573,9 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
 
     ptx::tc_fence_before_sync();
     __syncthreads();
+#if DCE_TRACE
+    if (p.trace && blockIdx.x < 60 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[blockIdx.x * 16 + 14] = (long long)t_; }
+#endif
     if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

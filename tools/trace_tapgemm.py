@@ -21,3 +21,11 @@ for k in range(0, 10):
     print(f"{k:4d} " + " ".join(f"{(t[k, e] - t0) if t[k, e] else 0:10d}" for e in range(15)))
 k1 = max(k for k in range(60) if t[k, 2] > 0)
 print("tiles", k1 + 1, "SM clock during kernel: %.3f GHz" % ((t[k1, 2] - t[1, 2]) / (t[k1, 15] - t[1, 15])), " tile period cycles %.0f, ns %.0f" % ((t[k1, 2] - t[1, 2]) / (k1 - 1), (t[k1, 15] - t[1, 15]) / (k1 - 1)))
+
+# per-CTA wall clock (globaltimer, ns): kernel entry, after griddepcontrol.wait, exit — CTAs 0..59
+ent, dep, ext = t[:, 12], t[:, 13], t[:, 14]
+ok = ext > 0
+if ok.any():
+    z = ent[ok].min()
+    print("CTAs traced:", int(ok.sum()), " entry spread %.1f us, dependency wait ends %.1f .. %.1f us after the first entry, exits %.1f .. %.1f us, CTA 0 exit %.1f us"
+          % ((ent[ok].max() - z) / 1e3, (dep[ok].min() - z) / 1e3, (dep[ok].max() - z) / 1e3, (ext[ok].min() - z) / 1e3, (ext[ok].max() - z) / 1e3, (ext[0] - z) / 1e3))
